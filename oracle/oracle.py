@@ -1,0 +1,173 @@
+"""TEST INFRASTRUCTURE ONLY: ctypes loader for the CPU oracle (oracle/evp_oracle.c).
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference
+legs may import this module.  PARITY UNPINNED for evp() outputs (see evp_oracle.h).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+from typing import Dict, Optional
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+c_dp = C.POINTER(C.c_double)
+c_ip = C.POINTER(C.c_int32)
+
+
+class OrcGrid(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in
+                ("nx_block", "ny_block", "ilo", "ihi", "jlo", "jhi", "ew_boundary", "ns_boundary")]
+
+
+class OrcParams(C.Structure):
+    _fields_ = ([(n, C.c_double) for n in ("dtei", "ecci", "dte2T", "denom1", "denom2", "rcon")] +
+                [("ndte", C.c_int32), ("evp_damping", C.c_int32)] +
+                [(n, C.c_double) for n in ("rhoi", "rhos", "rhow", "dragio", "gravit", "puny", "cosw", "sinw")] +
+                [(n, C.c_int32) for n in ("auscom", "coupled", "use_ocnslope", "access_wind",
+                                          "kstrength", "krdg_partic", "krdg_redist")] +
+                [("mu_rdg", C.c_double), ("ncat", C.c_int32)])
+
+
+_D_STATIC = ["dxt", "dyt", "dxhy", "dyhx", "cxp", "cyp", "cxm", "cym",
+             "tarea", "tarear", "tinyarea", "uarea", "uarear", "fcor"]
+_I_STATIC = ["tmask", "umask"]
+_D_INPUT = ["aice", "vice", "vsno", "strairxT", "strairyT", "strax", "stray",
+            "uocn", "vocn", "ss_tltx", "ss_tlty", "aice0", "aicen", "vicen", "strength_in"]
+STATE_D = ["uvel", "vvel",
+           "stressp_1", "stressp_2", "stressp_3", "stressp_4",
+           "stressm_1", "stressm_2", "stressm_3", "stressm_4",
+           "stress12_1", "stress12_2", "stress12_3", "stress12_4"]
+_I_STATE = ["iceumask"]
+OUT_D = ["strength", "strairx", "strairy", "strtltx", "strtlty", "strintx", "strinty",
+         "strocnx", "strocny", "strocnxT", "strocnyT", "fm", "prs_sig",
+         "divu", "shear", "rdg_conv", "rdg_shear", "sicemass"]
+_I_OUT = ["icetmask"]
+SCRATCH_D = ["tmass", "umass", "aiu", "umassdtei", "waterx", "watery", "forcex", "forcey"]
+
+
+class OrcFields(C.Structure):
+    _fields_ = ([(n, c_dp) for n in _D_STATIC] + [(n, c_ip) for n in _I_STATIC] +
+                [(n, c_dp) for n in _D_INPUT] +
+                [(n, c_dp) for n in STATE_D] + [(n, c_ip) for n in _I_STATE] +
+                [(n, c_dp) for n in OUT_D] + [(n, c_ip) for n in _I_OUT] +
+                [(n, c_dp) for n in SCRATCH_D])
+
+
+def build(force: bool = False) -> None:
+    """Compile the oracle libraries with oracle/Makefile (gcc only)."""
+    if force:
+        subprocess.check_call(["make", "-C", HERE, "clean"], stdout=subprocess.DEVNULL)
+    subprocess.check_call(["make", "-C", HERE], stdout=subprocess.DEVNULL)
+
+
+_libs: Dict[str, C.CDLL] = {}
+
+
+def lib(kind: str = "strict") -> C.CDLL:
+    if kind not in _libs:
+        path = os.path.join(HERE, f"liboracle_{kind}.so")
+        if not os.path.exists(path):
+            build()
+        L = C.CDLL(path)
+        L.orc_evp.restype = C.c_int
+        L.orc_evp.argtypes = [C.POINTER(OrcGrid), C.POINTER(OrcParams), C.POINTER(OrcFields), c_dp]
+        L.orc_subcycle_only.restype = C.c_int
+        L.orc_subcycle_only.argtypes = [C.POINTER(OrcGrid), C.POINTER(OrcParams), C.POINTER(OrcFields),
+                                        C.c_int, c_dp]
+        L.orc_set_evp_parameters.argtypes = [C.POINTER(OrcParams), C.c_double, C.c_int]
+        L.orc_default_params.argtypes = [C.POINTER(OrcParams)]
+        L.orc_halo_r8.argtypes = [c_dp, C.POINTER(OrcGrid), C.c_int, C.c_int, C.c_double]
+        L.orc_halo_i4.argtypes = [c_ip, C.POINTER(OrcGrid), C.c_int, C.c_int, C.c_int32]
+        L.orc_principal_stress.argtypes = [C.c_int, C.c_int, c_dp, c_dp, c_dp, c_dp, C.c_double, c_dp, c_dp]
+        _libs[kind] = L
+    return _libs[kind]
+
+
+def make_params(dt: float = 3600.0, ndte: int = 120, kind: str = "strict", **over) -> OrcParams:
+    p = OrcParams()
+    L = lib(kind)
+    L.orc_default_params(C.byref(p))
+    for k, v in over.items():
+        setattr(p, k, v)
+    L.orc_set_evp_parameters(C.byref(p), dt, ndte)
+    return p
+
+
+def make_grid(nx_block: int, ny_block: int, ew: int, ns: int) -> OrcGrid:
+    return OrcGrid(nx_block, ny_block, 2, nx_block - 1, 2, ny_block - 1, ew, ns)
+
+
+def _ptr(a: Optional[np.ndarray], ip: bool = False):
+    if a is None:
+        return None
+    assert a.flags.f_contiguous, "oracle arrays must be Fortran-ordered"
+    assert a.dtype == (np.int32 if ip else np.float64)
+    return a.ctypes.data_as(c_ip if ip else c_dp)
+
+
+def halo_r8(a: np.ndarray, ew: int, ns: int, loc: int, kind: int, lib_kind: str = "strict") -> None:
+    g = make_grid(a.shape[0], a.shape[1], ew, ns)
+    lib(lib_kind).orc_halo_r8(_ptr(a), C.byref(g), loc, kind, 0.0)
+
+
+def principal_stress(sp1, sm1, s12, prs, puny=1e-11, lib_kind="strict"):
+    sig1 = np.zeros_like(sp1, order="F")
+    sig2 = np.zeros_like(sp1, order="F")
+    lib(lib_kind).orc_principal_stress(sp1.shape[0], sp1.shape[1], _ptr(sp1), _ptr(sm1), _ptr(s12),
+                                       _ptr(prs), puny, _ptr(sig1), _ptr(sig2))
+    return sig1, sig2
+
+
+class Fields:
+    """Owns every array of one oracle run and the ctypes view onto them."""
+
+    def __init__(self, grid_fields: Dict[str, np.ndarray], inputs: Dict[str, np.ndarray],
+                 state: Dict[str, np.ndarray], strength_in: Optional[np.ndarray] = None):
+        nxb, nyb = grid_fields["dxt"].shape
+        self.shape = (nxb, nyb)
+        self.arr: Dict[str, Optional[np.ndarray]] = {}
+        for n in _D_STATIC + _I_STATIC:
+            self.arr[n] = grid_fields[n]
+        for n in _D_INPUT:
+            self.arr[n] = inputs.get(n)
+        self.arr["strength_in"] = strength_in
+        for n in STATE_D + _I_STATE:
+            self.arr[n] = state[n]
+        for n in OUT_D + SCRATCH_D:
+            self.arr[n] = np.zeros((nxb, nyb), order="F")
+        self.arr["icetmask"] = np.zeros((nxb, nyb), dtype=np.int32, order="F")
+        self.c = OrcFields()
+        for n, _t in OrcFields._fields_:
+            a = self.arr[n]
+            setattr(self.c, n, _ptr(a, ip=(a is not None and a.dtype == np.int32)))
+
+    def __getitem__(self, k):
+        return self.arr[k]
+
+
+def run_evp(grid, inputs, state, params: Optional[OrcParams] = None, strength_in=None,
+            lib_kind: str = "strict"):
+    """One `evp(dt)` call.  `grid` is cice4_b200.grid.Grid; `state` arrays are updated
+    in place.  Returns (Fields, subcycle_seconds)."""
+    p = params if params is not None else make_params(kind=lib_kind)
+    f = Fields(grid.f, inputs, state, strength_in)
+    g = make_grid(grid.nx_block, grid.ny_block, grid.ew, grid.ns)
+    sec = C.c_double(0.0)
+    rc = lib(lib_kind).orc_evp(C.byref(g), C.byref(p), C.byref(f.c), C.byref(sec))
+    if rc != 0:
+        raise RuntimeError("orc_evp failed")
+    return f, sec.value
+
+
+def time_subcycles(grid, fields: Fields, params: OrcParams, nsub: int, lib_kind: str = "fast") -> float:
+    """Seconds for `nsub` subcycles (stress+stepu+2 halos) on already-prepared fields."""
+    g = make_grid(grid.nx_block, grid.ny_block, grid.ew, grid.ns)
+    sec = C.c_double(0.0)
+    rc = lib(lib_kind).orc_subcycle_only(C.byref(g), C.byref(params), C.byref(fields.c), nsub, C.byref(sec))
+    if rc != 0:
+        raise RuntimeError("orc_subcycle_only failed")
+    return sec.value
