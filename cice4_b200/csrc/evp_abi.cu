@@ -1,0 +1,705 @@
+// evp_abi.cu -- the C ABI of libevp_b200.so (include/evp_b200.h): handle, device memory,
+// marshalling and the evp() sequence of source/ice_dyn_evp.F90:119-432 on one B200.
+// There is no CPU fallback anywhere in this file: every compute entry needs a CUDA device.
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "../../include/evp_b200.h"
+#include "evp_aux.cuh"
+#include "evp_common.cuh"
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const char *fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return code;
+}
+
+#define CU(call)                                                                                   \
+    do {                                                                                           \
+        cudaError_t e_ = (call);                                                                   \
+        if (e_ != cudaSuccess)                                                                     \
+            return fail(EVP_B200_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), \
+                        __FILE__, __LINE__);                                                       \
+    } while (0)
+
+// names of the double planes held on the device
+enum PlaneId {
+    // static grid
+    P_DXT, P_DYT, P_DXHY, P_DYHX, P_CXP, P_CYP, P_CXM, P_CYM, P_TAREA, P_TAREAR, P_TINYAREA,
+    P_UAREA, P_UAREAR, P_FCOR,
+    // inputs
+    P_AICE, P_VICE, P_VSNO, P_UOCN, P_VOCN, P_SSTLTX, P_SSTLTY, P_AICE0,
+    // scratch (locals of evp, :170-178) and work1 of ice_work
+    P_TMASS, P_UMASS, P_AIU, P_UMASSDTEI, P_WATERX, P_WATERY, P_FORCEX, P_FORCEY, P_WRKX, P_WRKY,
+    // outputs
+    P_STRAIRX, P_STRAIRY, P_STRTLTX, P_STRTLTY, P_STRINTX, P_STRINTY, P_STROCNX, P_STROCNY,
+    P_STROCNXT, P_STROCNYT, P_FM, P_PRS_SIG, P_DIVU, P_SHEAR, P_RDG_CONV, P_RDG_SHEAR, P_STRENGTH,
+    P_SIG1, P_SIG2,
+    // ping-pong state: u, v, 12 stresses, two copies each
+    P_U0, P_U1, P_V0, P_V1, P_S0, P_S1 = P_S0 + EVP_NSTRESS, P_COUNT = P_S1 + EVP_NSTRESS
+};
+enum MaskId { M_TMASK, M_UMASK, M_TMPHM, M_ICETMASK, M_ICEUMASK, M_COUNT };
+
+struct Timer {
+    cudaEvent_t ev[8];
+};
+
+} // namespace
+
+struct evp_b200_handle {
+    evp_b200_dims dims;
+    evp_b200_params par;
+    std::vector<int32_t> blk_tab; // host copy of the per-block table
+    int *d_blk_tab = nullptr;
+    BlockGeom bg;
+    PlaneGeom pg;
+    size_t blocked_elems = 0; // nx_block*ny_block*max_blocks
+    // derived scalars (set_evp_parameters, source/ice_dyn_evp.F90:563-575)
+    double dtei, ecci, dte2T, denom1, denom2, rcon, dragw;
+    int device = 0;
+    cudaStream_t st = nullptr;
+    double *pool = nullptr;
+    double *pl[P_COUNT];
+    double *cat = nullptr; // aicen, vicen planes (2*ncat), allocated on first device ice_strength
+    uint8_t *mpool = nullptr;
+    uint8_t *mk[M_COUNT];
+    // staging in the caller's block layout
+    double *stage = nullptr; // n_stage slots of blocked_elems doubles
+    int n_stage = 0;
+    int32_t *stage_i = nullptr; // 2 slots of blocked_elems int32
+    double *stage_cat = nullptr;
+    cudaEvent_t ev[8];
+    cudaGraph_t graph = nullptr;
+    cudaGraphExec_t graph_exec = nullptr;
+    int cur = 0; // which ping-pong copy holds the current state
+    bool prepared = false, resident = false;
+    evp_b200_timings tm;
+    std::unordered_map<const void *, size_t> pinned;
+    int grid_x = 0, grid_y = 0, threads = 128, strip_w = 0, rows = 0;
+    int sub_launches_per_loop = 0;
+};
+
+namespace {
+
+void pin(evp_b200_handle *h, const void *p, size_t bytes) {
+    if (!h->par.pin_host || !p) return;
+    auto it = h->pinned.find(p);
+    if (it != h->pinned.end() && it->second >= bytes) return;
+    if (it != h->pinned.end()) cudaHostUnregister(const_cast<void *>(p));
+    if (cudaHostRegister(const_cast<void *>(p), bytes, cudaHostRegisterDefault) == cudaSuccess)
+        h->pinned[p] = bytes;
+    else
+        cudaGetLastError(); // pageable copy still works
+}
+
+int upload_r8(evp_b200_handle *h, const double *host, int slot, double *plane) {
+    if (!host) return fail(EVP_B200_ERR_ARG, "required host array is NULL (stage slot %d)", slot);
+    double *stg = h->stage + (size_t)slot * h->blocked_elems;
+    const size_t bytes = h->blocked_elems * sizeof(double);
+    pin(h, host, bytes);
+    CU(cudaMemcpyAsync(stg, host, bytes, cudaMemcpyHostToDevice, h->st));
+    aux_unblock_r8(h->bg, h->pg, stg, plane, h->st);
+    return 0;
+}
+
+int upload_mask(evp_b200_handle *h, const int32_t *host, int slot, uint8_t *plane) {
+    if (!host) return fail(EVP_B200_ERR_ARG, "required host mask is NULL");
+    int32_t *stg = h->stage_i + (size_t)slot * h->blocked_elems;
+    const size_t bytes = h->blocked_elems * sizeof(int32_t);
+    pin(h, host, bytes);
+    CU(cudaMemcpyAsync(stg, host, bytes, cudaMemcpyHostToDevice, h->st));
+    aux_unblock_mask(h->bg, h->pg, stg, plane, h->st);
+    return 0;
+}
+
+// fresh = the staging slot does not hold the caller's current values: fill it from the host
+// first for KEEP policies (not needed for state fields, whose slot was uploaded this call)
+int download_r8(evp_b200_handle *h, double *host, int slot, const double *plane, int policy) {
+    if (!host) return 0;
+    double *stg = h->stage + (size_t)slot * h->blocked_elems;
+    const size_t bytes = h->blocked_elems * sizeof(double);
+    pin(h, host, bytes);
+    aux_block_r8(h->bg, h->pg, plane, h->mk[M_ICETMASK], stg, policy, h->st);
+    CU(cudaMemcpyAsync(host, stg, bytes, cudaMemcpyDeviceToHost, h->st));
+    return 0;
+}
+
+int download_mask(evp_b200_handle *h, int32_t *host, int slot, const uint8_t *plane, int policy) {
+    if (!host) return 0;
+    int32_t *stg = h->stage_i + (size_t)slot * h->blocked_elems;
+    const size_t bytes = h->blocked_elems * sizeof(int32_t);
+    pin(h, host, bytes);
+    aux_block_mask(h->bg, h->pg, plane, stg, policy, h->st);
+    CU(cudaMemcpyAsync(host, stg, bytes, cudaMemcpyDeviceToHost, h->st));
+    return 0;
+}
+
+// staging slots
+enum {
+    SL_AICE, SL_VICE, SL_VSNO, SL_STRAIRX, SL_STRAIRY, SL_UOCN, SL_VOCN, SL_SSTLTX, SL_SSTLTY, SL_AICE0,
+    SL_STRENGTH, SL_U, SL_V, SL_S0, SL_OUT0 = SL_S0 + EVP_NSTRESS, SL_COUNT = SL_OUT0 + 20
+};
+
+void fill_subargs(evp_b200_handle *h, SubArgs &a, int cur) {
+    double **p = h->pl;
+    a.dxt = p[P_DXT]; a.dyt = p[P_DYT]; a.dxhy = p[P_DXHY]; a.dyhx = p[P_DYHX];
+    a.cxp = p[P_CXP]; a.cyp = p[P_CYP]; a.cxm = p[P_CXM]; a.cym = p[P_CYM];
+    a.tinyarea = p[P_TINYAREA]; a.tarear = p[P_TAREAR]; a.strength = p[P_STRENGTH];
+    a.aiu = p[P_AIU]; a.uocn = p[P_UOCN]; a.vocn = p[P_VOCN]; a.waterx = p[P_WATERX]; a.watery = p[P_WATERY];
+    a.forcex = p[P_FORCEX]; a.forcey = p[P_FORCEY]; a.umassdtei = p[P_UMASSDTEI]; a.fm = p[P_FM];
+    a.uarear = p[P_UAREAR];
+    a.icetmask = h->mk[M_ICETMASK]; a.iceumask = h->mk[M_ICEUMASK];
+    a.u_old = p[cur ? P_U1 : P_U0]; a.v_old = p[cur ? P_V1 : P_V0];
+    a.u_new = p[cur ? P_U0 : P_U1]; a.v_new = p[cur ? P_V0 : P_V1];
+    for (int k = 0; k < EVP_NSTRESS; ++k) {
+        a.s_old[k] = p[(cur ? P_S1 : P_S0) + k];
+        a.s_new[k] = p[(cur ? P_S0 : P_S1) + k];
+    }
+    a.divu = p[P_DIVU]; a.shear = p[P_SHEAR]; a.rdg_conv = p[P_RDG_CONV]; a.rdg_shear = p[P_RDG_SHEAR];
+    a.prs_sig = p[P_PRS_SIG]; a.strintx = p[P_STRINTX]; a.strinty = p[P_STRINTY];
+    a.strocnx = p[P_STROCNX]; a.strocny = p[P_STROCNY];
+    a.nx = h->pg.nx; a.nyl = h->pg.nyl; a.pitch = h->pg.pitch;
+    a.ew_cyclic = h->pg.ew_cyclic;
+    a.strip_w = h->strip_w; a.rows = h->rows;
+    a.evp_damping = h->par.evp_damping; a.hemisphere_turning = h->par.hemisphere_turning;
+    a.ecci = h->ecci; a.dte2T = h->dte2T; a.denom1 = h->denom1; a.denom2 = h->denom2; a.rcon = h->rcon;
+    a.dragw = h->dragw; a.cosw = h->par.cosw; a.sinw = h->par.sinw;
+}
+
+// one subcycle: fused stress+stepu (+ east-west halo), then the north-south part of
+// ice_HaloUpdate(uvel), ice_HaloUpdate(vvel) (:397-402).  Returns kernels launched.
+int launch_subcycle(evp_b200_handle *h, int cur, bool last) {
+    SubArgs a;
+    fill_subargs(h, a, cur);
+    subcycle_launch_fn fn = h->par.math_mode == 1 ? evp_subcycle_launch_fast : evp_subcycle_launch_strict;
+    fn(a, last, h->par.kernel_variant, h->threads, (unsigned)h->grid_x, (unsigned)h->grid_y, (void *)h->st);
+    int n = 1;
+    if (h->pg.ns_cyclic) n += 2;
+    if (h->pg.tripole) n += 1;
+    aux_halo_uv_ns(h->pg, a.u_new, a.v_new, h->st);
+    return n;
+}
+
+int run_subcycle_loop(evp_b200_handle *h) {
+    const int ndte = h->par.ndte;
+    if (h->cur != 0) return fail(EVP_B200_ERR_STATE, "subcycle loop must start from state copy 0");
+    if (h->par.use_graph) {
+        if (!h->graph_exec) {
+            CU(cudaStreamBeginCapture(h->st, cudaStreamCaptureModeThreadLocal));
+            int cur = 0, n = 0;
+            for (int k = 1; k <= ndte; ++k) {
+                n += launch_subcycle(h, cur, k == ndte);
+                cur ^= 1;
+            }
+            h->sub_launches_per_loop = n;
+            CU(cudaStreamEndCapture(h->st, &h->graph));
+            CU(cudaGraphInstantiate(&h->graph_exec, h->graph, 0));
+        }
+        CU(cudaGraphLaunch(h->graph_exec, h->st));
+        h->cur = ndte & 1;
+    } else {
+        int n = 0;
+        for (int k = 1; k <= ndte; ++k) {
+            n += launch_subcycle(h, h->cur, k == ndte);
+            h->cur ^= 1;
+        }
+        h->sub_launches_per_loop = n;
+    }
+    CU(cudaGetLastError());
+    if (h->cur != 0) { // odd ndte: bring the result back to copy 0 so the next loop starts there
+        const size_t bytes = h->pg.cells * sizeof(double);
+        CU(cudaMemcpyAsync(h->pl[P_U0], h->pl[P_U1], bytes, cudaMemcpyDeviceToDevice, h->st));
+        CU(cudaMemcpyAsync(h->pl[P_V0], h->pl[P_V1], bytes, cudaMemcpyDeviceToDevice, h->st));
+        for (int k = 0; k < EVP_NSTRESS; ++k)
+            CU(cudaMemcpyAsync(h->pl[P_S0 + k], h->pl[P_S1 + k], bytes, cudaMemcpyDeviceToDevice, h->st));
+        h->cur = 0;
+    }
+    return 0;
+}
+
+void choose_tiling(evp_b200_handle *h) {
+    int sms = 148;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device);
+    const int nx = h->pg.nx, nyl = h->pg.nyl;
+    int nt = h->par.tile_threads > 0 ? h->par.tile_threads : 128;
+    if (nt != 64 && nt != 128 && nt != 256) nt = 128;
+    // balanced strips: ncx strips of strip_w U columns, strip_w + 1 <= nt threads hold T columns
+    const int ncx = (nx + (nt - 1) - 1) / (nt - 1);
+    const int strip_w = (nx + ncx - 1) / ncx;
+    int rows = h->par.tile_rows;
+    if (rows <= 0) {
+        // one wave: about (CTAs per SM) * SMs CTAs in total
+        const int per_sm = (nt == 256) ? 1 : (nt == 128 ? 2 : 4);
+        int target = per_sm * sms;
+        if ((h->par.kernel_variant & 1) == 1) target = target * 3 / 2; // no-prefetch build: fewer registers
+        int ncy = target / ncx;
+        if (ncy < 1) ncy = 1;
+        rows = (nyl + ncy - 1) / ncy;
+        if (rows < 4) rows = 4;
+    }
+    if (rows > nyl) rows = nyl;
+    h->threads = nt;
+    h->strip_w = strip_w;
+    h->rows = rows;
+    h->grid_x = ncx;
+    h->grid_y = (nyl + rows - 1) / rows;
+}
+
+} // namespace
+
+extern "C" {
+
+int evp_b200_abi_version(void) { return EVP_B200_ABI_VERSION; }
+
+const char *evp_b200_last_error(void) { return g_err.c_str(); }
+
+void evp_b200_default_params(evp_b200_params *p) {
+    memset(p, 0, sizeof(*p));
+    p->dt = 3600.0;
+    p->ndte = 120;          // source/ice_init.F90:216
+    p->evp_damping = 0;     // :217
+    p->dragio = 0.00536;    // drivers/cice4/ice_constants.F90:59
+    p->cosw = 1.0;          // source/ice_dyn_evp.F90:84-85
+    p->sinw = 0.0;
+    p->rhoi = 917.0;
+    p->rhos = 330.0;
+    p->rhow = 1026.0;
+    p->gravit = 9.80616;
+    p->puny = 1.0e-11;
+    p->kstrength = 1;       // source/ice_init.F90:219-222
+    p->krdg_partic = 1;
+    p->krdg_redist = 1;
+    p->mu_rdg = 3.0;
+    p->ncat = 5;
+    p->math_mode = 0;
+    p->pin_host = 0;
+    p->use_graph = 1;
+}
+
+int evp_b200_init(const evp_b200_dims *d, const evp_b200_params *p, const evp_b200_static_fields *g,
+                  evp_b200_handle **out) {
+    if (!d || !p || !g || !out) return fail(EVP_B200_ERR_ARG, "NULL argument");
+    *out = nullptr;
+    if (d->nblocks < 1 || d->nblocks > d->max_blocks) return fail(EVP_B200_ERR_ARG, "bad nblocks");
+    if (d->nx_block < 3 || d->ny_block < 3) return fail(EVP_B200_ERR_ARG, "bad block size");
+    if (!d->ilo || !d->ihi || !d->jlo || !d->jhi || !d->iglob_lo || !d->jglob_lo)
+        return fail(EVP_B200_ERR_ARG, "block index arrays are NULL");
+    if (d->ns_boundary > EVP_B200_BND_TRIPOLE || d->ew_boundary > EVP_B200_BND_CYCLIC || d->ew_boundary < 0 ||
+        d->ns_boundary < 0)
+        return fail(EVP_B200_ERR_UNSUPPORTED, "boundary type not supported (tripoleT is not implemented)");
+    if (d->nranks != 1 || d->rank != 0)
+        return fail(EVP_B200_ERR_UNSUPPORTED, "multi-rank slabs need evp_b200_comm_init (not in this build)");
+    if (d->slab_jlo != 1 || d->slab_jhi != d->ny_global) return fail(EVP_B200_ERR_ARG, "slab must span the domain when nranks == 1");
+    if (p->ndte < 1 || !(p->dt > 0.0)) return fail(EVP_B200_ERR_ARG, "bad dt/ndte");
+    if (p->ncat < 1 || p->ncat > 16) return fail(EVP_B200_ERR_ARG, "ncat out of range");
+    if (d->ns_boundary == EVP_B200_BND_TRIPOLE && d->nx_global + 2 > 8 * 1024)
+        return fail(EVP_B200_ERR_UNSUPPORTED, "tripole fold kernel supports nx_global <= 8190");
+
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev < 1) {
+        cudaGetLastError();
+        return fail(EVP_B200_ERR_CUDA, "no CUDA device: libevp_b200 has no CPU fallback");
+    }
+    evp_b200_handle *h = new evp_b200_handle();
+    h->dims = *d;
+    h->par = *p;
+    if (d->device >= 0) {
+        CU(cudaSetDevice(d->device));
+        h->device = d->device;
+    } else {
+        CU(cudaGetDevice(&h->device));
+    }
+    // block table + coverage check
+    const int nyl = d->slab_jhi - d->slab_jlo + 1;
+    h->blk_tab.resize((size_t)d->nblocks * 6);
+    long covered = 0;
+    for (int b = 0; b < d->nblocks; ++b) {
+        if (d->ilo[b] < 2 || d->jlo[b] < 2 || d->ihi[b] > d->nx_block - 1 || d->jhi[b] > d->ny_block - 1 ||
+            d->ihi[b] < d->ilo[b] || d->jhi[b] < d->jlo[b]) {
+            delete h;
+            return fail(EVP_B200_ERR_ARG, "block %d: bad ilo/ihi/jlo/jhi (nghost must be 1)", b);
+        }
+        h->blk_tab[b * 6 + 0] = d->ilo[b];
+        h->blk_tab[b * 6 + 1] = d->ihi[b];
+        h->blk_tab[b * 6 + 2] = d->jlo[b];
+        h->blk_tab[b * 6 + 3] = d->jhi[b];
+        h->blk_tab[b * 6 + 4] = d->iglob_lo[b] - d->ilo[b];
+        h->blk_tab[b * 6 + 5] = d->jglob_lo[b] - d->jlo[b] - (d->slab_jlo - 1);
+        const int ig1 = d->iglob_lo[b] + (d->ihi[b] - d->ilo[b]);
+        const int jg1 = d->jglob_lo[b] + (d->jhi[b] - d->jlo[b]);
+        if (d->iglob_lo[b] < 1 || ig1 > d->nx_global || d->jglob_lo[b] < d->slab_jlo || jg1 > d->slab_jhi) {
+            delete h;
+            return fail(EVP_B200_ERR_ARG, "block %d lies outside the slab", b);
+        }
+        covered += (long)(d->ihi[b] - d->ilo[b] + 1) * (d->jhi[b] - d->jlo[b] + 1);
+    }
+    if (covered != (long)d->nx_global * nyl) {
+        delete h;
+        return fail(EVP_B200_ERR_ARG, "blocks cover %ld cells, slab has %ld (land-block elimination is not supported)",
+                    covered, (long)d->nx_global * nyl);
+    }
+
+    // set_evp_parameters, source/ice_dyn_evp.F90:563-575
+    {
+        const double eyc = 0.36;
+        const double dte = p->dt / (double)p->ndte;
+        h->dtei = 1.0 / dte;
+        const double ecc = 4.0;
+        h->ecci = 0.25;
+        const double tdamp2 = 2.0 * eyc * p->dt;
+        h->dte2T = dte / tdamp2;
+        h->denom1 = 1.0 / (1.0 + h->dte2T);
+        h->denom2 = 1.0 / (1.0 + h->dte2T * ecc);
+        h->rcon = 1230.0 * eyc * p->dt * (h->dtei * h->dtei);
+        h->dragw = p->dragio * p->rhow; // :78 / :1382
+    }
+
+    PlaneGeom &pg = h->pg;
+    pg.nx = d->nx_global;
+    pg.nyl = nyl;
+    pg.pitch = ((pg.nx + 2 + 15) / 16) * 16;
+    pg.ew_cyclic = d->ew_boundary == EVP_B200_BND_CYCLIC;
+    pg.ns_cyclic = d->ns_boundary == EVP_B200_BND_CYCLIC;
+    pg.tripole = d->ns_boundary == EVP_B200_BND_TRIPOLE;
+    pg.cells = (size_t)pg.pitch * (pg.nyl + 2);
+    h->blocked_elems = (size_t)d->nx_block * d->ny_block * d->max_blocks;
+
+    CU(cudaStreamCreateWithFlags(&h->st, cudaStreamNonBlocking));
+    for (auto &e : h->ev) CU(cudaEventCreate(&e));
+    CU(cudaMalloc(&h->pool, sizeof(double) * pg.cells * P_COUNT));
+    CU(cudaMemsetAsync(h->pool, 0, sizeof(double) * pg.cells * P_COUNT, h->st));
+    for (int k = 0; k < P_COUNT; ++k) h->pl[k] = h->pool + (size_t)k * pg.cells;
+    CU(cudaMalloc(&h->mpool, pg.cells * M_COUNT));
+    CU(cudaMemsetAsync(h->mpool, 0, pg.cells * M_COUNT, h->st));
+    for (int k = 0; k < M_COUNT; ++k) h->mk[k] = h->mpool + (size_t)k * pg.cells;
+    h->n_stage = SL_COUNT;
+    CU(cudaMalloc(&h->stage, sizeof(double) * h->blocked_elems * h->n_stage));
+    CU(cudaMalloc(&h->stage_i, sizeof(int32_t) * h->blocked_elems * 2));
+    CU(cudaMalloc(&h->d_blk_tab, sizeof(int) * h->blk_tab.size()));
+    CU(cudaMemcpyAsync(h->d_blk_tab, h->blk_tab.data(), sizeof(int) * h->blk_tab.size(), cudaMemcpyHostToDevice, h->st));
+    h->bg.nx_block = d->nx_block;
+    h->bg.ny_block = d->ny_block;
+    h->bg.nblocks = d->nblocks;
+    h->bg.tab = h->d_blk_tab;
+
+    // static fields
+    struct { const double *src; int id; } statics[] = {
+        {g->dxt, P_DXT}, {g->dyt, P_DYT}, {g->dxhy, P_DXHY}, {g->dyhx, P_DYHX}, {g->cxp, P_CXP}, {g->cyp, P_CYP},
+        {g->cxm, P_CXM}, {g->cym, P_CYM}, {g->tarea, P_TAREA}, {g->tarear, P_TAREAR}, {g->tinyarea, P_TINYAREA},
+        {g->uarea, P_UAREA}, {g->uarear, P_UAREAR}, {g->fcor, P_FCOR}};
+    int slot = 0;
+    for (auto &s : statics) {
+        int rc = upload_r8(h, s.src, slot++, h->pl[s.id]);
+        if (rc) { evp_b200_finalize(h); return rc; }
+    }
+    int rc = upload_mask(h, g->tmask, 0, h->mk[M_TMASK]);
+    if (!rc) rc = upload_mask(h, g->umask, 1, h->mk[M_UMASK]);
+    if (rc) { evp_b200_finalize(h); return rc; }
+    CU(cudaStreamSynchronize(h->st));
+    choose_tiling(h);
+    memset(&h->tm, 0, sizeof(h->tm));
+    *out = h;
+    return EVP_B200_OK;
+}
+
+static int do_prep(evp_b200_handle *h, const evp_b200_inputs *in, evp_b200_state *st, int32_t *icetmask_out) {
+    if (!h || !in || !st) return fail(EVP_B200_ERR_ARG, "NULL argument");
+    CU(cudaSetDevice(h->device));
+    const PlaneGeom &pg = h->pg;
+    double **p = h->pl;
+    const size_t pbytes = pg.cells * sizeof(double);
+    CU(cudaEventRecord(h->ev[0], h->st));
+    // ---- upload inputs and state --------------------------------------------------------------
+    int rc = 0;
+    if ((rc = upload_r8(h, in->aice, SL_AICE, p[P_AICE]))) return rc;
+    if ((rc = upload_r8(h, in->vice, SL_VICE, p[P_VICE]))) return rc;
+    if ((rc = upload_r8(h, in->vsno, SL_VSNO, p[P_VSNO]))) return rc;
+    // strairx = strairxT (:668-669) or strax (:273-274): uploaded straight into work1 of t2ugrid_vector
+    if ((rc = upload_r8(h, in->strairxT, SL_STRAIRX, p[P_WRKX]))) return rc;
+    if ((rc = upload_r8(h, in->strairyT, SL_STRAIRY, p[P_WRKY]))) return rc;
+    if ((rc = upload_r8(h, in->uocn, SL_UOCN, p[P_UOCN]))) return rc;
+    if ((rc = upload_r8(h, in->vocn, SL_VOCN, p[P_VOCN]))) return rc;
+    const bool need_slope = h->par.coupled_tilt && !(h->par.hemisphere_turning && !h->par.use_ocnslope);
+    if (need_slope) {
+        if ((rc = upload_r8(h, in->ss_tltx, SL_SSTLTX, p[P_SSTLTX]))) return rc;
+        if ((rc = upload_r8(h, in->ss_tlty, SL_SSTLTY, p[P_SSTLTY]))) return rc;
+    }
+    if ((rc = upload_r8(h, st->uvel, SL_U, p[P_U0]))) return rc;
+    if ((rc = upload_r8(h, st->vvel, SL_V, p[P_V0]))) return rc;
+    double *sh[EVP_NSTRESS] = {st->stressp_1, st->stressp_2, st->stressp_3, st->stressp_4,
+                               st->stressm_1, st->stressm_2, st->stressm_3, st->stressm_4,
+                               st->stress12_1, st->stress12_2, st->stress12_3, st->stress12_4};
+    for (int k = 0; k < EVP_NSTRESS; ++k)
+        if ((rc = upload_r8(h, sh[k], SL_S0 + k, p[P_S0 + k]))) return rc;
+    if ((rc = upload_mask(h, st->iceumask, 0, h->mk[M_ICEUMASK]))) return rc;
+    CU(cudaEventRecord(h->ev[1], h->st));
+
+    // ---- :214-224 and init_history_dyn (source/ice_flux.F90:585-602) ---------------------------
+    const int zero_ids[] = {P_RDG_CONV, P_RDG_SHEAR, P_DIVU, P_SHEAR, P_PRS_SIG, P_STRTLTX, P_STRTLTY,
+                            P_STRINTX, P_STRINTY, P_STROCNX, P_STROCNY, P_FM};
+    for (int id : zero_ids) CU(cudaMemsetAsync(p[id], 0, pbytes, h->st));
+
+    PrepArgs a;
+    memset(&a, 0, sizeof(a));
+    a.tarea = p[P_TAREA]; a.uarea = p[P_UAREA]; a.fcor = p[P_FCOR];
+    a.tmask = h->mk[M_TMASK]; a.umask = h->mk[M_UMASK];
+    a.aice = p[P_AICE]; a.vice = p[P_VICE]; a.vsno = p[P_VSNO]; a.uocn = p[P_UOCN]; a.vocn = p[P_VOCN];
+    a.ss_tltx = p[P_SSTLTX]; a.ss_tlty = p[P_SSTLTY];
+    a.tmass = p[P_TMASS]; a.umass = p[P_UMASS]; a.aiu = p[P_AIU]; a.umassdtei = p[P_UMASSDTEI];
+    a.waterx = p[P_WATERX]; a.watery = p[P_WATERY]; a.forcex = p[P_FORCEX]; a.forcey = p[P_FORCEY];
+    a.strairx = p[P_STRAIRX]; a.strairy = p[P_STRAIRY]; a.strtltx = p[P_STRTLTX]; a.strtlty = p[P_STRTLTY];
+    a.strintx = p[P_STRINTX]; a.strinty = p[P_STRINTY]; a.strocnx = p[P_STROCNX]; a.strocny = p[P_STROCNY];
+    a.fm = p[P_FM]; a.uvel = p[P_U0]; a.vvel = p[P_V0];
+    for (int k = 0; k < EVP_NSTRESS; ++k) a.stress[k] = p[P_S0 + k];
+    a.tmphm = h->mk[M_TMPHM]; a.icetmask = h->mk[M_ICETMASK]; a.iceumask = h->mk[M_ICEUMASK];
+    a.rhoi = h->par.rhoi; a.rhos = h->par.rhos; a.dtei = h->dtei; a.cosw = h->par.cosw; a.sinw = h->par.sinw;
+    a.gravit = h->par.gravit;
+    a.hemisphere_turning = h->par.hemisphere_turning; a.coupled_tilt = h->par.coupled_tilt;
+    a.use_ocnslope = h->par.use_ocnslope;
+
+    aux_prep1(pg, a, h->st);                                             // :236-242
+    aux_icetmask(pg, a, h->st);
+    aux_halo_u8(pg, h->mk[M_ICETMASK], h->st);                           // :250-253
+    aux_to_ugrid(pg, p[P_TMASS], p[P_TAREA], p[P_UAREA], p[P_UMASS], h->st); // :259-260
+    aux_to_ugrid(pg, p[P_AICE], p[P_TAREA], p[P_UAREA], p[P_AIU], h->st);
+    aux_halo_r8(pg, p[P_WRKX], 1, -1, h->st);                            // t2ugrid_vector, :276-277
+    aux_halo_r8(pg, p[P_WRKY], 1, -1, h->st);
+    aux_to_ugrid(pg, p[P_WRKX], p[P_TAREA], p[P_UAREA], p[P_STRAIRX], h->st);
+    aux_to_ugrid(pg, p[P_WRKY], p[P_TAREA], p[P_UAREA], p[P_STRAIRY], h->st);
+    aux_prep2(pg, a, h->st);                                             // :292-316
+    CU(cudaGetLastError());
+    CU(cudaEventRecord(h->ev[2], h->st));
+    h->tm.kernel_launches = 0;
+    if (icetmask_out) {
+        if ((rc = download_mask(h, icetmask_out, 1, h->mk[M_ICETMASK], PACK_FULL))) return rc;
+        CU(cudaStreamSynchronize(h->st));
+    }
+    h->prepared = true;
+    h->resident = false;
+    h->cur = 0;
+    return 0;
+}
+
+static int do_run(evp_b200_handle *h, const evp_b200_inputs *in, const double *strength, evp_b200_state *st,
+                  evp_b200_outputs *out) {
+    if (!h || !st) return fail(EVP_B200_ERR_ARG, "NULL argument");
+    if (!h->prepared) return fail(EVP_B200_ERR_STATE, "evp_b200_run called before evp_b200_prep");
+    CU(cudaSetDevice(h->device));
+    const PlaneGeom &pg = h->pg;
+    double **p = h->pl;
+    const size_t pbytes = pg.cells * sizeof(double);
+    int rc = 0;
+    // ---- ice strength (:322-332) ----------------------------------------------------------------
+    if (strength) {
+        if ((rc = upload_r8(h, strength, SL_STRENGTH, p[P_STRENGTH]))) return rc;
+    } else {
+        if (!in || !in->aice0 || !in->aicen || !in->vicen)
+            return fail(EVP_B200_ERR_ARG, "strength == NULL needs aice0/aicen/vicen for the device ice_strength");
+        const int ncat = h->par.ncat;
+        if (!h->cat) {
+            CU(cudaMalloc(&h->cat, pbytes * 2 * ncat));
+            CU(cudaMemsetAsync(h->cat, 0, pbytes * 2 * ncat, h->st));
+            CU(cudaMalloc(&h->stage_cat, sizeof(double) * h->blocked_elems));
+        }
+        if ((rc = upload_r8(h, in->aice0, SL_AICE0, p[P_AICE0]))) return rc;
+        // (nx_block, ny_block, ncat, max_blocks): category n of block b is a strided set of planes;
+        // with max_blocks == 1 it is contiguous.  General case: copy per (block, category).
+        const size_t be = (size_t)h->dims.nx_block * h->dims.ny_block;
+        for (int which = 0; which < 2; ++which) {
+            const double *src = which == 0 ? in->aicen : in->vicen;
+            pin(h, src, be * ncat * h->dims.max_blocks * sizeof(double));
+            for (int n = 0; n < ncat; ++n) {
+                for (int b = 0; b < h->dims.nblocks; ++b)
+                    CU(cudaMemcpyAsync(h->stage_cat + (size_t)b * be, src + ((size_t)b * ncat + n) * be,
+                                       be * sizeof(double), cudaMemcpyHostToDevice, h->st));
+                aux_unblock_r8(h->bg, pg, h->stage_cat, h->cat + (size_t)(which * ncat + n) * pg.cells, h->st);
+            }
+        }
+        StrengthArgs sa;
+        sa.aice = p[P_AICE]; sa.vice = p[P_VICE]; sa.aice0 = p[P_AICE0];
+        sa.aicen = h->cat; sa.vicen = h->cat + (size_t)ncat * pg.cells;
+        sa.icetmask = h->mk[M_ICETMASK]; sa.strength = p[P_STRENGTH];
+        sa.ncat = ncat; sa.kstrength = h->par.kstrength; sa.krdg_partic = h->par.krdg_partic;
+        sa.krdg_redist = h->par.krdg_redist; sa.mu_rdg = h->par.mu_rdg; sa.puny = h->par.puny;
+        sa.gravit = h->par.gravit; sa.rhow = h->par.rhow; sa.rhoi = h->par.rhoi;
+        aux_ice_strength(pg, sa, h->st);
+    }
+    // ---- :336-344 ------------------------------------------------------------------------------
+    aux_halo_r8(pg, p[P_STRENGTH], 1, 1, h->st);
+    aux_halo_r8(pg, p[P_U0], 2, -1, h->st);
+    aux_halo_r8(pg, p[P_V0], 2, -1, h->st);
+    // second ping-pong copy: same ghost / masked-out values as copy 0; stresses outside the T list are 0
+    CU(cudaMemcpyAsync(p[P_U1], p[P_U0], pbytes, cudaMemcpyDeviceToDevice, h->st));
+    CU(cudaMemcpyAsync(p[P_V1], p[P_V0], pbytes, cudaMemcpyDeviceToDevice, h->st));
+    CU(cudaMemsetAsync(p[P_S1], 0, pbytes * EVP_NSTRESS, h->st));
+    h->cur = 0;
+    CU(cudaEventRecord(h->ev[3], h->st));
+    // ---- :347-404 ------------------------------------------------------------------------------
+    if ((rc = run_subcycle_loop(h))) return rc;
+    CU(cudaEventRecord(h->ev[4], h->st));
+    h->resident = true;
+    // ---- evp_finish + u2tgrid_vector (:410-428) -------------------------------------------------
+    FinishArgs fa;
+    fa.uvel = p[P_U0]; fa.vvel = p[P_V0]; fa.uocn = p[P_UOCN]; fa.vocn = p[P_VOCN]; fa.aiu = p[P_AIU];
+    fa.fm = p[P_FM]; fa.iceumask = h->mk[M_ICEUMASK];
+    fa.strocnx = p[P_STROCNX]; fa.strocny = p[P_STROCNY]; fa.strocnxT = p[P_WRKX]; fa.strocnyT = p[P_WRKY];
+    fa.dragw = h->dragw; fa.cosw = h->par.cosw; fa.sinw = h->par.sinw;
+    fa.hemisphere_turning = h->par.hemisphere_turning;
+    aux_finish(pg, fa, h->st);
+    // work1 = strocnxT; HALO(work1); to_tgrid(work1, strocnxT): the ghosts of strocnxT keep the 0 of :1512
+    CU(cudaMemsetAsync(p[P_STROCNXT], 0, pbytes, h->st));
+    CU(cudaMemsetAsync(p[P_STROCNYT], 0, pbytes, h->st));
+    aux_halo_r8(pg, p[P_WRKX], 2, -1, h->st);
+    aux_halo_r8(pg, p[P_WRKY], 2, -1, h->st);
+    aux_to_tgrid(pg, p[P_WRKX], p[P_TAREA], p[P_UAREA], p[P_STROCNXT], h->st);
+    aux_to_tgrid(pg, p[P_WRKY], p[P_TAREA], p[P_UAREA], p[P_STROCNYT], h->st);
+    if (out && (out->sig1 || out->sig2))
+        aux_principal_stress(pg.cells, p[P_S0], p[P_S0 + 4], p[P_S0 + 8], p[P_PRS_SIG], h->par.puny,
+                             p[P_SIG1], p[P_SIG2], h->st);
+    CU(cudaGetLastError());
+    CU(cudaEventRecord(h->ev[5], h->st));
+    // ---- download ------------------------------------------------------------------------------
+    if ((rc = download_r8(h, st->uvel, SL_U, p[P_U0], PACK_FULL))) return rc;
+    if ((rc = download_r8(h, st->vvel, SL_V, p[P_V0], PACK_FULL))) return rc;
+    double *sh[EVP_NSTRESS] = {st->stressp_1, st->stressp_2, st->stressp_3, st->stressp_4,
+                               st->stressm_1, st->stressm_2, st->stressm_3, st->stressm_4,
+                               st->stress12_1, st->stress12_2, st->stress12_3, st->stress12_4};
+    for (int k = 0; k < EVP_NSTRESS; ++k)
+        if ((rc = download_r8(h, sh[k], SL_S0 + k, p[P_S0 + k], PACK_TNE_KEEP))) return rc;
+    if ((rc = download_mask(h, st->iceumask, 0, h->mk[M_ICEUMASK], PACK_INT_KEEP))) return rc;
+    if (out) {
+        struct { double *dst; int id; int policy; } outs[] = {
+            {out->strairx, P_STRAIRX, PACK_INT_ZERO}, {out->strairy, P_STRAIRY, PACK_INT_ZERO},
+            {out->strtltx, P_STRTLTX, PACK_INT_ZERO}, {out->strtlty, P_STRTLTY, PACK_INT_ZERO},
+            {out->strintx, P_STRINTX, PACK_INT_ZERO}, {out->strinty, P_STRINTY, PACK_INT_ZERO},
+            {out->strocnx, P_STROCNX, PACK_INT_ZERO}, {out->strocny, P_STROCNY, PACK_INT_ZERO},
+            {out->strocnxT, P_STROCNXT, PACK_INT_ZERO}, {out->strocnyT, P_STROCNYT, PACK_INT_ZERO},
+            {out->fm, P_FM, PACK_INT_ZERO}, {out->prs_sig, P_PRS_SIG, PACK_TNE_ZERO},
+            {out->divu, P_DIVU, PACK_TNE_ZERO}, {out->shear, P_SHEAR, PACK_TNE_ZERO},
+            {out->rdg_conv, P_RDG_CONV, PACK_TNE_ZERO}, {out->rdg_shear, P_RDG_SHEAR, PACK_TNE_ZERO},
+            {out->strength, P_STRENGTH, PACK_FULL}, {out->sicemass, P_TMASS, PACK_FULL},
+            {out->sig1, P_SIG1, PACK_FULL}, {out->sig2, P_SIG2, PACK_FULL}};
+        int slot = SL_OUT0;
+        for (auto &o : outs) {
+            if ((rc = download_r8(h, o.dst, slot, p[o.id], o.policy))) return rc;
+            ++slot;
+        }
+    }
+    CU(cudaEventRecord(h->ev[6], h->st));
+    CU(cudaStreamSynchronize(h->st));
+    CU(cudaEventElapsedTime(&h->tm.upload_ms, h->ev[0], h->ev[1]));
+    CU(cudaEventElapsedTime(&h->tm.prep_ms, h->ev[1], h->ev[3]));
+    CU(cudaEventElapsedTime(&h->tm.subcycle_ms, h->ev[3], h->ev[4]));
+    CU(cudaEventElapsedTime(&h->tm.finish_ms, h->ev[4], h->ev[5]));
+    CU(cudaEventElapsedTime(&h->tm.download_ms, h->ev[5], h->ev[6]));
+    CU(cudaEventElapsedTime(&h->tm.total_ms, h->ev[0], h->ev[6]));
+    h->tm.subcycle_launches = h->sub_launches_per_loop;
+    h->prepared = false;
+    return 0;
+}
+
+int evp_b200_prep(evp_b200_handle *h, const evp_b200_inputs *in, evp_b200_state *st, int32_t *icetmask_out) {
+    return do_prep(h, in, st, icetmask_out);
+}
+
+int evp_b200_run(evp_b200_handle *h, const double *strength, evp_b200_state *st, evp_b200_outputs *out) {
+    if (!strength) return fail(EVP_B200_ERR_ARG, "evp_b200_run needs the strength array (use evp_b200_step for the device ice_strength)");
+    return do_run(h, nullptr, strength, st, out);
+}
+
+int evp_b200_step(evp_b200_handle *h, const evp_b200_inputs *in, const double *strength, evp_b200_state *st,
+                  evp_b200_outputs *out) {
+    int rc = do_prep(h, in, st, nullptr);
+    if (rc) return rc;
+    return do_run(h, in, strength, st, out);
+}
+
+int evp_b200_subcycle_resident(evp_b200_handle *h, int32_t repeats, float *ms_per_loop) {
+    if (!h || repeats < 1) return fail(EVP_B200_ERR_ARG, "bad argument");
+    if (!h->resident) return fail(EVP_B200_ERR_STATE, "no device-resident state: call evp_b200_step/run first");
+    CU(cudaSetDevice(h->device));
+    CU(cudaEventRecord(h->ev[3], h->st));
+    for (int r = 0; r < repeats; ++r) {
+        int rc = run_subcycle_loop(h);
+        if (rc) return rc;
+    }
+    CU(cudaEventRecord(h->ev[4], h->st));
+    CU(cudaStreamSynchronize(h->st));
+    float ms = 0.f;
+    CU(cudaEventElapsedTime(&ms, h->ev[3], h->ev[4]));
+    if (ms_per_loop) *ms_per_loop = ms / (float)repeats;
+    return 0;
+}
+
+int evp_b200_principal_stress(evp_b200_handle *h, const double *sp1, const double *sm1, const double *s12,
+                              const double *prs, double *sig1, double *sig2) {
+    if (!h || !sp1 || !sm1 || !s12 || !prs || !sig1 || !sig2) return fail(EVP_B200_ERR_ARG, "NULL argument");
+    CU(cudaSetDevice(h->device));
+    // pointwise over the whole block array (source/ice_dyn_evp.F90:1593-1607): no layout change needed
+    const size_t n = h->blocked_elems, bytes = n * sizeof(double);
+    double *s = h->stage;
+    const double *src[4] = {sp1, sm1, s12, prs};
+    for (int k = 0; k < 4; ++k) CU(cudaMemcpyAsync(s + k * n, src[k], bytes, cudaMemcpyHostToDevice, h->st));
+    aux_principal_stress(n, s, s + n, s + 2 * n, s + 3 * n, h->par.puny, s + 4 * n, s + 5 * n, h->st);
+    CU(cudaMemcpyAsync(sig1, s + 4 * n, bytes, cudaMemcpyDeviceToHost, h->st));
+    CU(cudaMemcpyAsync(sig2, s + 5 * n, bytes, cudaMemcpyDeviceToHost, h->st));
+    CU(cudaStreamSynchronize(h->st));
+    return 0;
+}
+
+int evp_b200_get_timings(const evp_b200_handle *h, evp_b200_timings *t) {
+    if (!h || !t) return fail(EVP_B200_ERR_ARG, "NULL argument");
+    *t = h->tm;
+    return 0;
+}
+
+int evp_b200_comm_unique_id(uint8_t id[128]) {
+    (void)id;
+    return fail(EVP_B200_ERR_UNSUPPORTED, "multi-rank exchange is not in this build");
+}
+
+int evp_b200_comm_init(evp_b200_handle *h, const uint8_t id[128]) {
+    (void)h;
+    (void)id;
+    return fail(EVP_B200_ERR_UNSUPPORTED, "multi-rank exchange is not in this build");
+}
+
+int evp_b200_finalize(evp_b200_handle *h) {
+    if (!h) return EVP_B200_OK;
+    cudaSetDevice(h->device);
+    if (h->st) cudaStreamSynchronize(h->st);
+    for (auto &kv : h->pinned) cudaHostUnregister(const_cast<void *>(kv.first));
+    if (h->graph_exec) cudaGraphExecDestroy(h->graph_exec);
+    if (h->graph) cudaGraphDestroy(h->graph);
+    cudaFree(h->pool);
+    cudaFree(h->cat);
+    cudaFree(h->mpool);
+    cudaFree(h->stage);
+    cudaFree(h->stage_i);
+    cudaFree(h->stage_cat);
+    cudaFree(h->d_blk_tab);
+    for (auto &e : h->ev)
+        if (e) cudaEventDestroy(e);
+    if (h->st) cudaStreamDestroy(h->st);
+    cudaGetLastError();
+    delete h;
+    return EVP_B200_OK;
+}
+
+} // extern "C"

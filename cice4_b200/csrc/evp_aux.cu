@@ -1,0 +1,491 @@
+// evp_aux.cu -- once-per-call kernels of libevp_b200: host-layout marshalling, evp_prep1/2,
+// T<->U grid operators, halo updates (east-west wrap, north-south cyclic, tripole u-fold),
+// evp_finish, principal_stress and the device ice_strength.
+// Compiled with -fmad=false: these kernels always use unfused IEEE arithmetic in the
+// reference's operation order, so their results are bit-identical to the unfused CPU oracle
+// (ice_strength excepted: it calls exp()).
+#include "evp_aux.cuh"
+
+#include <cmath>
+
+namespace {
+
+constexpr int TPB = 256;
+inline unsigned nblk(size_t n, int tpb = TPB) { return (unsigned)((n + tpb - 1) / tpb); }
+
+// ---------------------------------------------------------------------------------------------
+// host block layout <-> slab plane
+// ---------------------------------------------------------------------------------------------
+struct Loc {
+    int i, j, pi, pj;
+    bool pad, phys, tne, ighost, jghost;
+};
+
+__device__ __forceinline__ Loc locate(const BlockGeom &bg, int b, int cell) {
+    Loc L;
+    const int *t = bg.tab + b * 6;
+    const int ilo = t[0], ihi = t[1], jlo = t[2], jhi = t[3];
+    L.i = cell % bg.nx_block + 1;
+    L.j = cell / bg.nx_block + 1;
+    L.pi = L.i + t[4];
+    L.pj = L.j + t[5];
+    L.pad = (L.i > ihi + 1) || (L.j > jhi + 1) || (L.i < ilo - 1) || (L.j < jlo - 1);
+    L.ighost = (L.i < ilo) || (L.i > ihi);
+    L.jghost = (L.j < jlo) || (L.j > jhi);
+    L.phys = !L.ighost && !L.jghost;
+    L.tne = (L.i >= ilo) && (L.i <= ihi + 1) && (L.j >= jlo) && (L.j <= jhi + 1);
+    return L;
+}
+
+// a block cell is a source for the plane if it is physical, or a ghost cell that lands on the
+// plane's own ghost ring in every direction in which it is a ghost (domain boundary or the row
+// owned by the neighbouring slab); interior ghost cells duplicate another block's physical cell.
+template <typename TS, typename TD>
+__global__ void k_unblock(BlockGeom bg, PlaneGeom pg, const TS *__restrict__ blocked, TD *__restrict__ plane) {
+    const int cell = blockIdx.x * blockDim.x + threadIdx.x;
+    const int b = blockIdx.y;
+    if (cell >= bg.nx_block * bg.ny_block) return;
+    const Loc L = locate(bg, b, cell);
+    if (L.pad) return;
+    const bool ring_i = (L.pi == 0) || (L.pi == pg.nx + 1);
+    const bool ring_j = (L.pj == 0) || (L.pj == pg.nyl + 1);
+    if ((L.ighost && !ring_i) || (L.jghost && !ring_j)) return;
+    if (L.pi < 0 || L.pi > pg.nx + 1 || L.pj < 0 || L.pj > pg.nyl + 1) return;
+    const TS v = blocked[(size_t)b * bg.nx_block * bg.ny_block + cell];
+    plane[(size_t)L.pj * pg.pitch + L.pi] = (TD)v;
+}
+
+template <typename TS, typename TD>
+__global__ void k_block(BlockGeom bg, PlaneGeom pg, const TS *__restrict__ plane,
+                        const uint8_t *__restrict__ icetmask, TD *__restrict__ blocked, int policy) {
+    const int cell = blockIdx.x * blockDim.x + threadIdx.x;
+    const int b = blockIdx.y;
+    if (cell >= bg.nx_block * bg.ny_block) return;
+    const Loc L = locate(bg, b, cell);
+    if (L.pad) return;
+    if (L.pi < 0 || L.pi > pg.nx + 1 || L.pj < 0 || L.pj > pg.nyl + 1) return;
+    const size_t pidx = (size_t)L.pj * pg.pitch + L.pi;
+    TD *dst = blocked + (size_t)b * bg.nx_block * bg.ny_block + cell;
+    const TD v = (TD)plane[pidx];
+    switch (policy) {
+    case PACK_FULL: *dst = v; break;
+    case PACK_TNE_KEEP:
+        if (L.tne) *dst = v;
+        else if (icetmask[pidx] == 0) *dst = (TD)0;
+        break;
+    case PACK_TNE_ZERO: *dst = L.tne ? v : (TD)0; break;
+    case PACK_INT_ZERO: *dst = L.phys ? v : (TD)0; break;
+    case PACK_INT_KEEP:
+        if (L.phys) *dst = v;
+        break;
+    default: break;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// halo updates on a slab plane (serial/ice_boundary.F90:591-873; address lists :3494-4202)
+// ---------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void k_halo_ew(PlaneGeom pg, T *__restrict__ a) {
+    const int j = 1 + blockIdx.x * blockDim.x + threadIdx.x;
+    if (j > pg.nyl) return;
+    const size_t r = (size_t)j * pg.pitch;
+    a[r] = a[r + pg.nx];         // 'east' message: east edge -> west ghost column (:3629-3643)
+    a[r + pg.nx + 1] = a[r + 1]; // 'west' message (:3654-3668)
+}
+
+template <typename T>
+__global__ void k_halo_ns_cyclic(PlaneGeom pg, T *__restrict__ a, int with_corners) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x; // 0..nx+1
+    if (i > pg.nx + 1) return;
+    if (!with_corners && (i == 0 || i == pg.nx + 1)) return;
+    const size_t top = (size_t)pg.nyl * pg.pitch, gn = (size_t)(pg.nyl + 1) * pg.pitch;
+    // columns 0 and nx+1 hold the east-west wrap already, so copying them fills the corner cells
+    a[i] = a[top + i];                // 'north' message -> south ghost row (:3681-3695)
+    a[gn + i] = a[(size_t)pg.pitch + i]; // 'south' message (:3774-3788)
+}
+
+// Tripole u-fold for up to 2 planes (blockIdx.x selects).  One CTA per plane: all reads of the
+// top physical rows happen before the barrier, all writes after it, so the in-place update of
+// row nyl is safe.  loc 1 = centre (ghost row only), 2 = NE corner (symmetrise + overwrite the
+// top physical row, :777-800, :837-866).
+constexpr int TRIP_MAXC = 8;
+template <typename T>
+__global__ void __launch_bounds__(1024) k_halo_tripole(PlaneGeom pg, T *a0, T *a1, int loc, int isign) {
+    T *a = blockIdx.x == 0 ? a0 : a1;
+    const int nx = pg.nx, nyl = pg.nyl;
+    const size_t rtop = (size_t)nyl * pg.pitch, rbelow = (size_t)(nyl - 1) * pg.pitch,
+                 rghost = (size_t)(nyl + 1) * pg.pitch;
+    T vtop[TRIP_MAXC], vghost[TRIP_MAXC];
+#pragma unroll
+    for (int c = 0; c < TRIP_MAXC; ++c) {
+        const int i = threadIdx.x + c * 1024; // plane column 0..nx+1
+        vtop[c] = (T)0;
+        vghost[c] = (T)0;
+        if (i > nx + 1) continue;
+        int ig = i; // i_glob of the column (source/ice_blocks.F90:291-330)
+        if (i == 0) ig = pg.ew_cyclic ? nx : 1;
+        if (i == nx + 1) ig = pg.ew_cyclic ? 1 : nx;
+        if (loc == 2) {
+            int k = nx - ig; // iSrc = nxGlobal - i_glob + 1 - ioffset, ioffset = 1
+            if (k == 0) k = nx;
+            // bufTripole(k, 2) after symmetrisation of the top physical row
+            T x;
+            if (k >= 1 && k <= nx / 2 - 1) {
+                const T x1 = a[rtop + k], x2 = a[rtop + (nx - k)];
+                x = (T)(0.5 * (x1 + isign * x2));
+            } else if (k >= nx - (nx / 2 - 1) && k <= nx - 1) {
+                const int kk = nx - k; // the partner index i of the loop at :793-800
+                const T x1 = a[rtop + kk], x2 = a[rtop + k];
+                x = (T)(isign * (T)(0.5 * (x1 + isign * x2)));
+            } else {
+                x = a[rtop + k];
+            }
+            vtop[c] = (T)(isign * x);                  // j=1: row jhi   <- isign*buf(iSrc, 2)
+            vghost[c] = (T)(isign * a[rbelow + k]);    // j=2: row jhi+1 <- isign*buf(iSrc, 1)
+        } else {
+            int k = nx - ig + 1; // ioffset = 0
+            if (k > nx) k -= nx;
+            vghost[c] = (T)(isign * a[rtop + k]);      // j=2: jSrc = 2; j=1 skipped (jSrc = 3)
+        }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int c = 0; c < TRIP_MAXC; ++c) {
+        const int i = threadIdx.x + c * 1024;
+        if (i > nx + 1) continue;
+        if (loc == 2) a[rtop + i] = vtop[c];
+        a[rghost + i] = vghost[c];
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// evp_prep1 (source/ice_dyn_evp.F90:643-691)
+// ---------------------------------------------------------------------------------------------
+__global__ void k_prep1(PlaneGeom pg, PrepArgs a) {
+    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= pg.cells) return;
+    const double a_min = 0.001, m_min = 0.01;
+    double tmass = 0.0;
+    const bool tm = a.tmask[idx] != 0;
+    if (tm) tmass = (a.rhoi * a.vice[idx] + a.rhos * a.vsno[idx]); // :652
+    a.tmass[idx] = tmass;
+    a.tmphm[idx] = (tm && (a.aice[idx] > a_min) && (tmass > m_min)) ? 1 : 0; // :660
+    a.icetmask[idx] = 0; // :674
+}
+
+__global__ void k_icetmask(PlaneGeom pg, PrepArgs a) {
+    const int i = 1 + blockIdx.x * blockDim.x + threadIdx.x;
+    const int j = 1 + blockIdx.y;
+    if (i > pg.nx || j > pg.nyl) return;
+    const size_t idx = (size_t)j * pg.pitch + i;
+    const uint8_t *m = a.tmphm;
+    const size_t p = pg.pitch;
+    uint8_t any = m[idx - 1 + p] | m[idx + p] | m[idx + 1 + p] | m[idx - 1] | m[idx] | m[idx + 1] |
+                  m[idx - 1 - p] | m[idx - p] | m[idx + 1 - p]; // :683-687
+    if (!a.tmask[idx]) any = 0;                                  // :689
+    a.icetmask[idx] = any ? 1 : 0;
+}
+
+// to_ugrid (source/ice_grid.F90:1612-1631): zero everywhere, 4-point area-weighted mean inside
+__global__ void k_to_ugrid(PlaneGeom pg, const double *__restrict__ w1, const double *__restrict__ tarea,
+                           const double *__restrict__ uarea, double *__restrict__ w2) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int j = blockIdx.y;
+    if (i >= pg.pitch) return;
+    const size_t idx = (size_t)j * pg.pitch + i, p = pg.pitch;
+    double r = 0.0;
+    if (i >= 1 && i <= pg.nx && j >= 1 && j <= pg.nyl)
+        r = 0.25 * (w1[idx] * tarea[idx] + w1[idx + 1] * tarea[idx + 1] + w1[idx + p] * tarea[idx + p] +
+                    w1[idx + p + 1] * tarea[idx + p + 1]) / uarea[idx];
+    w2[idx] = r;
+}
+
+// to_tgrid (source/ice_grid.F90:1720-1730): interior only, ghosts of w2 untouched
+__global__ void k_to_tgrid(PlaneGeom pg, const double *__restrict__ w1, const double *__restrict__ tarea,
+                           const double *__restrict__ uarea, double *__restrict__ w2) {
+    const int i = 1 + blockIdx.x * blockDim.x + threadIdx.x;
+    const int j = 1 + blockIdx.y;
+    if (i > pg.nx || j > pg.nyl) return;
+    const size_t idx = (size_t)j * pg.pitch + i, p = pg.pitch;
+    w2[idx] = 0.25 * (w1[idx] * uarea[idx] + w1[idx - 1] * uarea[idx - 1] + w1[idx - p] * uarea[idx - p] +
+                      w1[idx - p - 1] * uarea[idx - p - 1]) / tarea[idx];
+}
+
+// evp_prep2 (source/ice_dyn_evp.F90:819-936), dense: the index lists become the masks themselves
+__global__ void k_prep2(PlaneGeom pg, PrepArgs a) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int j = blockIdx.y;
+    if (i > pg.nx + 1) return;
+    const size_t idx = (size_t)j * pg.pitch + i;
+    const double a_min = 0.001, m_min = 0.01;
+    double waterx = 0.0, watery = 0.0, forcex = 0.0, forcey = 0.0, umassdtei = 0.0; // :821-825
+    if (a.icetmask[idx] == 0) { // :827-840
+#pragma unroll
+        for (int k = 0; k < EVP_NSTRESS; ++k) a.stress[k][idx] = 0.0;
+    }
+    if (i >= 1 && i <= pg.nx && j >= 1 && j <= pg.nyl) {
+        const bool old = a.iceumask[idx] != 0; // :872-874
+        const double aiu = a.aiu[idx], umass = a.umass[idx];
+        const bool now = (a.umask[idx] != 0) && (aiu > a_min) && (umass > m_min);
+        a.iceumask[idx] = now ? 1 : 0;
+        if (now) {
+            const double uocn = a.uocn[idx], vocn = a.vocn[idx];
+            if (!old) { // :882-885
+                a.uvel[idx] = uocn;
+                a.vvel[idx] = vocn;
+            }
+            umassdtei = umass * a.dtei;           // :906
+            const double fm = a.fcor[idx] * umass; // :907
+            a.fm[idx] = fm;
+            if (a.hemisphere_turning) { // :912-913, sign(1., real(fm))
+                const double sg = signbit(__double2float_rn(fm)) ? -1.0 : 1.0;
+                waterx = uocn * a.cosw - vocn * a.sinw * sg;
+                watery = vocn * a.cosw + uocn * a.sinw * sg;
+            } else { // :915-916
+                waterx = uocn * a.cosw - vocn * a.sinw;
+                watery = vocn * a.cosw + uocn * a.sinw;
+            }
+            double tx, ty;
+            if (!a.coupled_tilt) { // :921-922
+                tx = -fm * vocn;
+                ty = fm * uocn;
+            } else { // :924-925
+                tx = -a.gravit * umass * a.ss_tltx[idx];
+                ty = -a.gravit * umass * a.ss_tlty[idx];
+            }
+            if (a.hemisphere_turning && !a.use_ocnslope) { // :929-932 (AusCOM)
+                tx = -fm * vocn;
+                ty = fm * uocn;
+            }
+            a.strtltx[idx] = tx;
+            a.strtlty[idx] = ty;
+            forcex = a.strairx[idx] + tx; // :934-935
+            forcey = a.strairy[idx] + ty;
+        } else { // :888-893
+            a.uvel[idx] = 0.0;
+            a.vvel[idx] = 0.0;
+            a.strintx[idx] = 0.0;
+            a.strinty[idx] = 0.0;
+            a.strocnx[idx] = 0.0;
+            a.strocny[idx] = 0.0;
+        }
+    }
+    a.waterx[idx] = waterx;
+    a.watery[idx] = watery;
+    a.forcex[idx] = forcex;
+    a.forcey[idx] = forcey;
+    a.umassdtei[idx] = umassdtei;
+}
+
+// evp_finish (source/ice_dyn_evp.F90:1510-1547)
+__global__ void k_finish(PlaneGeom pg, FinishArgs a) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int j = blockIdx.y;
+    if (i > pg.nx + 1) return;
+    const size_t idx = (size_t)j * pg.pitch + i;
+    double xT = 0.0, yT = 0.0; // :1512-1513
+    if (i >= 1 && i <= pg.nx && j >= 1 && j <= pg.nyl && a.iceumask[idx]) {
+        const double u = a.uvel[idx], v = a.vvel[idx], aiu = a.aiu[idx];
+        const double du = a.uocn[idx] - u, dv = a.vocn[idx] - v;
+        const double vrel = a.dragw * sqrt(du * du + dv * dv); // :1522
+        double sx = a.strocnx[idx], sy = a.strocny[idx];
+        if (a.hemisphere_turning && a.fm[idx] < 0.0) { // :1525-1530
+            sx = sx - vrel * (u * a.cosw + v * a.sinw) * aiu;
+            sy = sy - vrel * (v * a.cosw - u * a.sinw) * aiu;
+        } else { // :1532-1541
+            sx = sx - vrel * (u * a.cosw - v * a.sinw) * aiu;
+            sy = sy - vrel * (v * a.cosw + u * a.sinw) * aiu;
+        }
+        a.strocnx[idx] = sx;
+        a.strocny[idx] = sy;
+        xT = sx / aiu; // :1545-1546
+        yT = sy / aiu;
+    }
+    a.strocnxT[idx] = xT;
+    a.strocnyT[idx] = yT;
+}
+
+// principal_stress (source/ice_dyn_evp.F90:1593-1607)
+__global__ void k_principal_stress(size_t n, const double *__restrict__ sp1, const double *__restrict__ sm1,
+                                   const double *__restrict__ s12, const double *__restrict__ prs,
+                                   double puny, double *__restrict__ sig1, double *__restrict__ sig2) {
+    const size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    double r1 = 1.0e30, r2 = 1.0e30; // spval_dbl
+    const double p = prs[k];
+    if (p > puny) {
+        const double rt = sqrt(sm1[k] * sm1[k] + 4.0 * (s12[k] * s12[k]));
+        r1 = (0.5 * (sp1[k] + rt)) / p;
+        r2 = (0.5 * (sp1[k] - rt)) / p;
+    }
+    sig1[k] = r1;
+    sig2[k] = r2;
+}
+
+// ice_strength (source/ice_mechred.F90:1869-2036 with ridge_itd :773-1081) for one T cell of the
+// T list (icetmask == 1 on [1..nx+1] x [1..nyl+1]); 0 elsewhere (:1942).
+constexpr int MAXCAT = 16;
+__global__ void k_ice_strength(PlaneGeom pg, StrengthArgs a) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int j = blockIdx.y;
+    if (i > pg.nx + 1) return;
+    const size_t idx = (size_t)j * pg.pitch + i;
+    double result = 0.0;
+    const int ncat = a.ncat;
+    if (a.kstrength == 1) {
+        if (i >= 1 && j >= 1 && a.icetmask[idx]) {
+            const double puny = a.puny;
+            const double Cf = 17.0;
+            const double Cp = 0.5 * a.gravit * (a.rhow - a.rhoi) * a.rhoi / a.rhow;
+            const double Gstar = 0.15, astar = 0.05, maxraft = 1.0, Hstar = 25.0;
+            const double Gstari = 1.0 / Gstar, astari = 1.0 / astar;
+            double Gs[MAXCAT + 2], apartic[MAXCAT + 1], hrmin[MAXCAT + 1], hrmax[MAXCAT + 1],
+                hrexp[MAXCAT + 1], krdg[MAXCAT + 1];
+            double *Gsum = Gs + 1;
+            Gsum[-1] = 0.0;
+            apartic[0] = 0.0;
+            for (int n = 1; n <= ncat; ++n) {
+                apartic[n] = 0.0; hrmin[n] = 0.0; hrmax[n] = 0.0; hrexp[n] = 0.0; krdg[n] = 1.0;
+            }
+            const double a0 = a.aice0[idx];
+            Gsum[0] = (a0 > puny) ? a0 : Gsum[-1];
+            for (int n = 1; n <= ncat; ++n) {
+                const double an = a.aicen[(size_t)(n - 1) * pg.cells + idx];
+                Gsum[n] = (an > puny) ? Gsum[n - 1] + an : Gsum[n - 1];
+            }
+            const double work = 1.0 / Gsum[ncat];
+            for (int n = 0; n <= ncat; ++n) Gsum[n] = Gsum[n] * work;
+            if (a.krdg_partic == 0) {
+                for (int n = 0; n <= ncat; ++n) {
+                    if (Gsum[n] < Gstar)
+                        apartic[n] = Gstari * (Gsum[n] - Gsum[n - 1]) * (2.0 - (Gsum[n - 1] + Gsum[n]) * Gstari);
+                    else if (Gsum[n - 1] < Gstar)
+                        apartic[n] = Gstari * (Gstar - Gsum[n - 1]) * (2.0 - (Gsum[n - 1] + Gstar) * Gstari);
+                }
+            } else {
+                const double xtmp = 1.0 / (1.0 - exp(-astari));
+                for (int n = -1; n <= ncat; ++n) Gsum[n] = exp(-Gsum[n] * astari) * xtmp;
+                for (int n = 0; n <= ncat; ++n) apartic[n] = Gsum[n - 1] - Gsum[n];
+            }
+            for (int n = 1; n <= ncat; ++n) {
+                const double an = a.aicen[(size_t)(n - 1) * pg.cells + idx];
+                const double vn = a.vicen[(size_t)(n - 1) * pg.cells + idx];
+                if (an > puny) {
+                    double hi = vn / an;
+                    if (a.krdg_redist == 0) {
+                        hrmin[n] = fmin(2.0 * hi, hi + maxraft);
+                        hrmax[n] = 2.0 * sqrt(Hstar * hi);
+                        hrmax[n] = fmax(hrmax[n], hrmin[n] + puny);
+                        const double hrmean = 0.5 * (hrmin[n] + hrmax[n]);
+                        krdg[n] = hrmean / hi;
+                    } else {
+                        hi = fmax(hi, puny);
+                        hrmin[n] = fmin(2.0 * hi, hi + maxraft);
+                        hrexp[n] = a.mu_rdg * sqrt(hi);
+                        krdg[n] = (hrmin[n] + hrexp[n]) / hi;
+                    }
+                }
+            }
+            double aksum = apartic[0];
+            for (int n = 1; n <= ncat; ++n) aksum = aksum + apartic[n] * (1.0 - 1.0 / krdg[n]);
+            double s = 0.0;
+            for (int n = 1; n <= ncat; ++n) {
+                const double an = a.aicen[(size_t)(n - 1) * pg.cells + idx];
+                const double vn = a.vicen[(size_t)(n - 1) * pg.cells + idx];
+                if (an > puny && apartic[n] > 0.0) {
+                    const double hi = vn / an;
+                    double h2rdg;
+                    if (a.krdg_redist == 0)
+                        h2rdg = (1.0 / 3.0) * (hrmax[n] * hrmax[n] * hrmax[n] - hrmin[n] * hrmin[n] * hrmin[n]) /
+                                (hrmax[n] - hrmin[n]);
+                    else
+                        h2rdg = hrmin[n] * hrmin[n] + 2.0 * hrmin[n] * hrexp[n] + 2.0 * hrexp[n] * hrexp[n];
+                    const double dh2rdg = -hi * hi + h2rdg / krdg[n];
+                    s = s + apartic[n] * dh2rdg;
+                }
+            }
+            result = Cf * Cp * s / aksum;
+        }
+    } else {
+        if (i >= 1 && i <= pg.nx && j >= 1 && j <= pg.nyl)
+            result = 2.75e4 * a.vice[idx] * exp(-20.0 * (1.0 - a.aice[idx]));
+    }
+    a.strength[idx] = result;
+}
+
+} // namespace
+
+// ---------------------------------------------------------------------------------------------
+// launchers
+// ---------------------------------------------------------------------------------------------
+void aux_unblock_r8(const BlockGeom &bg, const PlaneGeom &pg, const double *blocked, double *plane, cudaStream_t s) {
+    dim3 grid(nblk((size_t)bg.nx_block * bg.ny_block), bg.nblocks);
+    k_unblock<double, double><<<grid, TPB, 0, s>>>(bg, pg, blocked, plane);
+}
+void aux_unblock_mask(const BlockGeom &bg, const PlaneGeom &pg, const int32_t *blocked, uint8_t *plane, cudaStream_t s) {
+    dim3 grid(nblk((size_t)bg.nx_block * bg.ny_block), bg.nblocks);
+    k_unblock<int32_t, uint8_t><<<grid, TPB, 0, s>>>(bg, pg, blocked, plane);
+}
+void aux_block_r8(const BlockGeom &bg, const PlaneGeom &pg, const double *plane, const uint8_t *icetmask,
+                  double *blocked, int policy, cudaStream_t s) {
+    dim3 grid(nblk((size_t)bg.nx_block * bg.ny_block), bg.nblocks);
+    k_block<double, double><<<grid, TPB, 0, s>>>(bg, pg, plane, icetmask, blocked, policy);
+}
+void aux_block_mask(const BlockGeom &bg, const PlaneGeom &pg, const uint8_t *plane, int32_t *blocked,
+                    int policy, cudaStream_t s) {
+    dim3 grid(nblk((size_t)bg.nx_block * bg.ny_block), bg.nblocks);
+    k_block<uint8_t, int32_t><<<grid, TPB, 0, s>>>(bg, pg, plane, nullptr, blocked, policy);
+}
+
+void aux_halo_r8(const PlaneGeom &pg, double *plane, int loc, int isign, cudaStream_t s) {
+    if (pg.ew_cyclic) k_halo_ew<double><<<nblk(pg.nyl), TPB, 0, s>>>(pg, plane);
+    if (pg.ns_cyclic) k_halo_ns_cyclic<double><<<nblk(pg.nx + 2), TPB, 0, s>>>(pg, plane, pg.ew_cyclic);
+    if (pg.tripole) k_halo_tripole<double><<<1, 1024, 0, s>>>(pg, plane, plane, loc, isign);
+}
+void aux_halo_u8(const PlaneGeom &pg, uint8_t *plane, cudaStream_t s) {
+    if (pg.ew_cyclic) k_halo_ew<uint8_t><<<nblk(pg.nyl), TPB, 0, s>>>(pg, plane);
+    if (pg.ns_cyclic) k_halo_ns_cyclic<uint8_t><<<nblk(pg.nx + 2), TPB, 0, s>>>(pg, plane, pg.ew_cyclic);
+    if (pg.tripole) k_halo_tripole<uint8_t><<<1, 1024, 0, s>>>(pg, plane, plane, 1, 1);
+}
+void aux_halo_uv_ns(const PlaneGeom &pg, double *u, double *v, cudaStream_t s) {
+    if (pg.ns_cyclic) {
+        k_halo_ns_cyclic<double><<<nblk(pg.nx + 2), TPB, 0, s>>>(pg, u, pg.ew_cyclic);
+        k_halo_ns_cyclic<double><<<nblk(pg.nx + 2), TPB, 0, s>>>(pg, v, pg.ew_cyclic);
+    }
+    if (pg.tripole) k_halo_tripole<double><<<2, 1024, 0, s>>>(pg, u, v, 2, -1);
+}
+
+void aux_prep1(const PlaneGeom &pg, const PrepArgs &a, cudaStream_t s) {
+    k_prep1<<<nblk(pg.cells), TPB, 0, s>>>(pg, a);
+}
+void aux_icetmask(const PlaneGeom &pg, const PrepArgs &a, cudaStream_t s) {
+    dim3 grid(nblk(pg.nx), pg.nyl);
+    k_icetmask<<<grid, TPB, 0, s>>>(pg, a);
+}
+void aux_to_ugrid(const PlaneGeom &pg, const double *w1, const double *tarea, const double *uarea,
+                  double *w2, cudaStream_t s) {
+    dim3 grid(nblk(pg.pitch), pg.nyl + 2);
+    k_to_ugrid<<<grid, TPB, 0, s>>>(pg, w1, tarea, uarea, w2);
+}
+void aux_to_tgrid(const PlaneGeom &pg, const double *w1, const double *tarea, const double *uarea,
+                  double *w2, cudaStream_t s) {
+    dim3 grid(nblk(pg.nx), pg.nyl);
+    k_to_tgrid<<<grid, TPB, 0, s>>>(pg, w1, tarea, uarea, w2);
+}
+void aux_prep2(const PlaneGeom &pg, const PrepArgs &a, cudaStream_t s) {
+    dim3 grid(nblk(pg.nx + 2), pg.nyl + 2);
+    k_prep2<<<grid, TPB, 0, s>>>(pg, a);
+}
+void aux_finish(const PlaneGeom &pg, const FinishArgs &a, cudaStream_t s) {
+    dim3 grid(nblk(pg.nx + 2), pg.nyl + 2);
+    k_finish<<<grid, TPB, 0, s>>>(pg, a);
+}
+void aux_principal_stress(size_t n, const double *sp1, const double *sm1, const double *s12,
+                          const double *prs, double puny, double *sig1, double *sig2, cudaStream_t s) {
+    k_principal_stress<<<nblk(n), TPB, 0, s>>>(n, sp1, sm1, s12, prs, puny, sig1, sig2);
+}
+void aux_ice_strength(const PlaneGeom &pg, const StrengthArgs &a, cudaStream_t s) {
+    dim3 grid(nblk(pg.nx + 2), pg.nyl + 2);
+    k_ice_strength<<<grid, TPB, 0, s>>>(pg, a);
+}

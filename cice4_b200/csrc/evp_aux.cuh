@@ -1,0 +1,92 @@
+// evp_aux.cuh -- launchers of the once-per-call kernels (marshalling, prep, halo, finish).
+#pragma once
+
+#include <cuda_runtime.h>
+
+#include <cstdint>
+
+#include "evp_common.cuh"
+
+// geometry of one handle's slab planes
+struct PlaneGeom {
+    int nx, nyl, pitch;
+    int ew_cyclic, ns_cyclic;
+    int tripole;   // 1 when this slab holds the tripole fold (top rank, ns = tripole)
+    size_t cells;  // pitch * (nyl + 2)
+};
+
+// block layout of the caller's host arrays; device copy of per-block ints:
+// tab[b*6 + {0..5}] = ilo, ihi, jlo, jhi (1-based), ishift, jshift with
+// plane_i = local_i(1-based) + ishift, plane_j = local_j(1-based) + jshift
+struct BlockGeom {
+    int nx_block, ny_block, nblocks;
+    const int *tab;
+};
+
+// download policies (which cells of a block the reference's evp defines)
+enum {
+    PACK_FULL = 0,        // every cell of the block (uvel, vvel, icetmask, tmass, strength)
+    PACK_TNE_KEEP = 1,    // [ilo..ihi+1]x[jlo..jhi+1]; elsewhere 0 where icetmask==0, else untouched (stresses)
+    PACK_TNE_ZERO = 2,    // [ilo..ihi+1]x[jlo..jhi+1]; elsewhere 0 (prs_sig, divu, shear, rdg_*)
+    PACK_INT_ZERO = 3,    // interior; elsewhere 0 (U-point outputs, strocnxT)
+    PACK_INT_KEEP = 4     // interior; elsewhere untouched (iceumask)
+};
+
+void aux_unblock_r8(const BlockGeom &bg, const PlaneGeom &pg, const double *blocked, double *plane, cudaStream_t s);
+void aux_unblock_mask(const BlockGeom &bg, const PlaneGeom &pg, const int32_t *blocked, uint8_t *plane, cudaStream_t s);
+void aux_block_r8(const BlockGeom &bg, const PlaneGeom &pg, const double *plane, const uint8_t *icetmask,
+                  double *blocked, int policy, cudaStream_t s);
+void aux_block_mask(const BlockGeom &bg, const PlaneGeom &pg, const uint8_t *plane, int32_t *blocked,
+                    int policy, cudaStream_t s);
+
+// ice_HaloUpdate for a slab plane: east-west wrap, north-south cyclic, tripole u-fold.
+// loc: 1 centre, 2 NE corner; isign: +1 scalar, -1 vector.  (slab-to-slab rows are exchanged by the caller)
+void aux_halo_r8(const PlaneGeom &pg, double *plane, int loc, int isign, cudaStream_t s);
+void aux_halo_u8(const PlaneGeom &pg, uint8_t *plane, cudaStream_t s);
+// uvel+vvel together (NE corner, vector): north-south part only (east-west is done by the subcycle kernel)
+void aux_halo_uv_ns(const PlaneGeom &pg, double *u, double *v, cudaStream_t s);
+
+struct PrepArgs {
+    // static
+    const double *tarea, *uarea, *fcor;
+    const uint8_t *tmask, *umask;
+    // inputs
+    const double *aice, *vice, *vsno, *uocn, *vocn, *ss_tltx, *ss_tlty;
+    // scratch / outputs
+    double *tmass, *umass, *aiu, *umassdtei, *waterx, *watery, *forcex, *forcey;
+    double *strairx, *strairy, *strtltx, *strtlty, *strintx, *strinty, *strocnx, *strocny, *fm;
+    double *uvel, *vvel;
+    double *stress[EVP_NSTRESS];
+    uint8_t *tmphm, *icetmask, *iceumask;
+    double rhoi, rhos, dtei, cosw, sinw, gravit;
+    int hemisphere_turning, coupled_tilt, use_ocnslope;
+};
+
+void aux_prep1(const PlaneGeom &pg, const PrepArgs &a, cudaStream_t s);      // tmass, tmphm   (:643-677)
+void aux_icetmask(const PlaneGeom &pg, const PrepArgs &a, cudaStream_t s);   // icetmask       (:679-691)
+void aux_to_ugrid(const PlaneGeom &pg, const double *w1, const double *tarea, const double *uarea,
+                  double *w2, cudaStream_t s);                               // ice_grid.F90:1612-1631
+void aux_to_tgrid(const PlaneGeom &pg, const double *w1, const double *tarea, const double *uarea,
+                  double *w2, cudaStream_t s);                               // ice_grid.F90:1720-1730
+void aux_prep2(const PlaneGeom &pg, const PrepArgs &a, cudaStream_t s);      // :819-936
+
+struct FinishArgs {
+    const double *uvel, *vvel, *uocn, *vocn, *aiu, *fm;
+    const uint8_t *iceumask;
+    double *strocnx, *strocny, *strocnxT, *strocnyT;
+    double dragw, cosw, sinw;
+    int hemisphere_turning;
+};
+void aux_finish(const PlaneGeom &pg, const FinishArgs &a, cudaStream_t s);   // :1510-1547
+
+void aux_principal_stress(size_t n, const double *sp1, const double *sm1, const double *s12,
+                          const double *prs, double puny, double *sig1, double *sig2, cudaStream_t s);
+
+struct StrengthArgs {
+    const double *aice, *vice, *aice0, *aicen, *vicen; // aicen/vicen: ncat planes, stride `cells`
+    const uint8_t *icetmask;
+    double *strength;
+    int ncat, kstrength, krdg_partic, krdg_redist;
+    double mu_rdg, puny, gravit, rhow, rhoi;
+};
+void aux_ice_strength(const PlaneGeom &pg, const StrengthArgs &a, cudaStream_t s); // ice_mechred.F90:1869-2036

@@ -1,0 +1,46 @@
+// evp_common.cuh -- shared declarations of libevp_b200 (device layout + kernel argument blocks).
+//
+// Device layout ("plane"): one padded slab per field, i fastest, index
+//   idx(i, j) = j * pitch + i,   i in [0, nx+1],  j in [0, nyl+1]
+// where nx = nx_global, nyl = rows of this handle's y-slab, (0 / nx+1 / 0 / nyl+1) is the
+// 1-cell ghost ring (domain boundary or neighbouring slab) and pitch is nx+2 rounded up to 16
+// doubles.  Plane (i, j) is Fortran (i+1, j+1) of a single whole-slab block, so indices map
+// 1:1 to source/ice_dyn_evp.F90.
+#pragma once
+
+#include <cstddef>
+#include <cstdint>
+
+#define EVP_NSTRESS 12
+
+// argument block of the fused stress+stepu subcycle kernel
+struct SubArgs {
+    // T-cell statics (source/ice_dyn_evp.F90:992-1005)
+    const double *dxt, *dyt, *dxhy, *dyhx, *cxp, *cyp, *cxm, *cym, *tinyarea, *tarear, *strength;
+    // U-cell statics (:1339-1349)
+    const double *aiu, *uocn, *vocn, *waterx, *watery, *forcex, *forcey, *umassdtei, *fm, *uarear;
+    const uint8_t *icetmask, *iceumask;
+    // ping-pong state
+    const double *u_old, *v_old;
+    double *u_new, *v_new;
+    const double *s_old[EVP_NSTRESS]; // stressp_1..4, stressm_1..4, stress12_1..4
+    double *s_new[EVP_NSTRESS];
+    // written on the last subcycle only (ksub == ndte, :1103-1115; :1415-1418,:1434-1435)
+    double *divu, *shear, *rdg_conv, *rdg_shear, *prs_sig, *strintx, *strinty, *strocnx, *strocny;
+    int nx, nyl, pitch;
+    int ew_cyclic;
+    int strip_w;   // U columns produced per CTA (threads 0..strip_w hold T columns)
+    int rows;      // U rows marched per CTA
+    int evp_damping, hemisphere_turning;
+    double ecci, dte2T, denom1, denom2, rcon, dragw, cosw, sinw;
+};
+
+typedef void (*subcycle_launch_fn)(const SubArgs &a, bool last, int variant, int threads,
+                                   unsigned grid_x, unsigned grid_y, void *stream);
+
+// defined in evp_subcycle_strict.cu (-fmad=false) and evp_subcycle_fast.cu (-fmad=true)
+void evp_subcycle_launch_strict(const SubArgs &a, bool last, int variant, int threads,
+                                unsigned grid_x, unsigned grid_y, void *stream);
+void evp_subcycle_launch_fast(const SubArgs &a, bool last, int variant, int threads,
+                              unsigned grid_x, unsigned grid_y, void *stream);
+int evp_subcycle_max_threads(void);

@@ -1,0 +1,364 @@
+// evp_subcycle_body.cuh -- the fused stress + stepu subcycle kernel (one EVP subcycle per launch).
+//
+// Included by evp_subcycle_strict.cu (nvcc -fmad=false: unfused IEEE arithmetic, bit-identical to
+// the unfused CPU oracle) and evp_subcycle_fast.cu (-fmad=true: nvcc contracts a*b+c into DFMA).
+// EVP_SUB_LAUNCH names the exported launcher.
+//
+// What it replaces: `stress` (source/ice_dyn_evp.F90:947-1293) and `stepu` (:1302-1443) for one
+// ksub, plus the east-west part of the two ice_HaloUpdate calls (:397-402).  The reference writes
+// str(nx_block,ny_block,8) to memory in `stress` and reads it back in `stepu`; here the eight
+// stress combinations never leave the SM:
+//
+//   * a CTA owns a strip of `strip_w` U columns and marches north over `rows` U rows;
+//     thread t holds T column i0+t and U column i0+t (threads 0..strip_w are active, the last
+//     one only supplies the T column east of the strip);
+//   * for T row j a thread computes the four-corner strain rates / Delta / stress update of its
+//     T cell from u,v at (i-1..i, j-1..j) -- west values by an offset load that hits L1, south
+//     values carried in registers from the previous row -- and forms str(1:8);
+//   * str(2,4,7,8) of the east neighbour arrive through a double-buffered shared-memory line
+//     (one __syncthreads per row), str(1,5) (+ east 2,7) of the row below are carried in
+//     registers, so U(i, j-1) is finished in the same iteration with the reference's summation
+//     order  ((s1 + s2) + s3) + s4  and  ((s5 + s6) + s7) + s8  (:1415-1418);
+//   * u,v and the 12 stresses are ping-ponged (read `old`, write `new`): the first T row of the
+//     CTA above and the T column east of the strip are recomputed redundantly from `old` values,
+//     exactly like the reference's redundant N/E ghost-cell stresses (:846-859), so results do
+//     not depend on the tiling;
+//   * loads for T row j+1 are issued before the arithmetic of row j (software prefetch), the
+//     U-row loads before the stress arithmetic whose result they are combined with.
+//
+// Algorithmic traffic per active cell and subcycle: 12+12 stresses, 2+2 velocities, strength +
+// 9 T metrics, 10 U fields = 48 fp64 words = 384 B (+2 mask bytes).
+#include <cuda_runtime.h>
+
+#include "evp_common.cuh"
+
+namespace EVP_SUB_NS {
+
+struct TRow {
+    double s[EVP_NSTRESS];
+    double strength, dxt, dyt, dxhy, dyhx, cxp, cyp, cxm, cym, tiny, tarear;
+    double u, v, uw, vw;
+    bool act;
+};
+
+struct URow {
+    double aiu, uocn, vocn, waterx, watery, forcex, forcey, umassdtei, fm, uarear;
+    bool act;
+};
+
+template <bool LAST>
+__device__ __forceinline__ void load_T(const SubArgs &a, TRow &t, int i, int j, bool colT) {
+    const size_t idx = (size_t)j * a.pitch + i;
+    t.act = colT && (__ldg(a.icetmask + idx) != 0);
+    if (colT) {
+        t.u = __ldg(a.u_old + idx);
+        t.v = __ldg(a.v_old + idx);
+        t.uw = __ldg(a.u_old + idx - 1);
+        t.vw = __ldg(a.v_old + idx - 1);
+    } else {
+        t.u = t.v = t.uw = t.vw = 0.0;
+    }
+    if (t.act) {
+#pragma unroll
+        for (int k = 0; k < EVP_NSTRESS; ++k) t.s[k] = __ldg(a.s_old[k] + idx);
+        t.strength = __ldg(a.strength + idx);
+        t.dxt = __ldg(a.dxt + idx);
+        t.dyt = __ldg(a.dyt + idx);
+        t.dxhy = __ldg(a.dxhy + idx);
+        t.dyhx = __ldg(a.dyhx + idx);
+        t.cxp = __ldg(a.cxp + idx);
+        t.cyp = __ldg(a.cyp + idx);
+        t.cxm = __ldg(a.cxm + idx);
+        t.cym = __ldg(a.cym + idx);
+        t.tiny = __ldg(a.tinyarea + idx);
+        if (LAST) t.tarear = __ldg(a.tarear + idx);
+    }
+}
+
+__device__ __forceinline__ void load_U(const SubArgs &a, URow &u, int i, int j, bool colU) {
+    const size_t idx = (size_t)j * a.pitch + i;
+    u.act = colU && (__ldg(a.iceumask + idx) != 0);
+    if (u.act) {
+        u.aiu = __ldg(a.aiu + idx);
+        u.uocn = __ldg(a.uocn + idx);
+        u.vocn = __ldg(a.vocn + idx);
+        u.waterx = __ldg(a.waterx + idx);
+        u.watery = __ldg(a.watery + idx);
+        u.forcex = __ldg(a.forcex + idx);
+        u.forcey = __ldg(a.forcey + idx);
+        u.umassdtei = __ldg(a.umassdtei + idx);
+        u.fm = __ldg(a.fm + idx);
+        u.uarear = __ldg(a.uarear + idx);
+    }
+}
+
+// source/ice_dyn_evp.F90:1056-1291 for one T cell.  (un,vn)=(i,j) (uw,vw)=(i-1,j) (us,vs)=(i,j-1)
+// (usw,vsw)=(i-1,j-1).  Operation order is the Fortran's.
+template <bool LAST>
+__device__ __forceinline__ void stress_cell(const SubArgs &a, const TRow &t, double us, double vs,
+                                            double usw, double vsw, size_t idx, bool store,
+                                            double (&str)[8]) {
+    const double p5 = 0.5, p25 = 0.25, c4 = 4.0;
+    const double p166 = 1.0 / 6.0, p333 = 1.0 / 3.0, p111 = 1.0 / 9.0;
+    const double p055 = p111 * 0.5, p027 = p055 * 0.5, p222 = 2.0 / 9.0;
+    const double un = t.u, vn = t.v, uw = t.uw, vw = t.vw;
+    const double cyp = t.cyp, cxp = t.cxp, cym = t.cym, cxm = t.cxm, dxt = t.dxt, dyt = t.dyt;
+
+    // :1065-1072
+    const double divune = cyp * un - dyt * uw + cxp * vn - dxt * vs;
+    const double divunw = cym * uw + dyt * un + cxp * vw - dxt * vsw;
+    const double divusw = cym * usw + dyt * us + cxm * vsw + dxt * vw;
+    const double divuse = cyp * us - dyt * usw + cxm * vs + dxt * vn;
+    // :1075-1082
+    const double tensionne = -cym * un - dyt * uw + cxm * vn + dxt * vs;
+    const double tensionnw = -cyp * uw + dyt * un + cxm * vw + dxt * vsw;
+    const double tensionsw = -cyp * usw + dyt * us + cxp * vsw - dxt * vw;
+    const double tensionse = -cym * us - dyt * usw + cxp * vs - dxt * vn;
+    // :1085-1092
+    const double shearne = -cym * vn - dyt * vw - cxm * un - dxt * us;
+    const double shearnw = -cyp * vw + dyt * vn - cxm * uw - dxt * usw;
+    const double shearsw = -cyp * vsw + dyt * vs - cxp * usw + dxt * uw;
+    const double shearse = -cym * vs - dyt * vsw - cxp * us + dxt * un;
+    // :1095-1098
+    const double Deltane = sqrt(divune * divune + a.ecci * (tensionne * tensionne + shearne * shearne));
+    const double Deltanw = sqrt(divunw * divunw + a.ecci * (tensionnw * tensionnw + shearnw * shearnw));
+    const double Deltase = sqrt(divuse * divuse + a.ecci * (tensionse * tensionse + shearse * shearse));
+    const double Deltasw = sqrt(divusw * divusw + a.ecci * (tensionsw * tensionsw + shearsw * shearsw));
+
+    if (LAST && store) { // :1103-1115
+        const double divu = p25 * (divune + divunw + divuse + divusw) * t.tarear;
+        const double tmp = p25 * (Deltane + Deltanw + Deltase + Deltasw) * t.tarear;
+        a.divu[idx] = divu;
+        a.rdg_conv[idx] = -fmin(divu, 0.0);
+        a.rdg_shear[idx] = p5 * (tmp - fabs(divu));
+        const double tsum = tensionne + tensionnw + tensionse + tensionsw;
+        const double ssum = shearne + shearnw + shearse + shearsw;
+        a.shear[idx] = p25 * t.tarear * sqrt(tsum * tsum + ssum * ssum);
+    }
+
+    double c0ne, c0nw, c0sw, c0se;
+    if (a.evp_damping) { // :1121-1128
+        const double t4 = c4 * t.tiny;
+        c0ne = fmin(t.strength / fmax(Deltane, t4), a.rcon);
+        c0nw = fmin(t.strength / fmax(Deltanw, t4), a.rcon);
+        c0sw = fmin(t.strength / fmax(Deltasw, t4), a.rcon);
+        c0se = fmin(t.strength / fmax(Deltase, t4), a.rcon);
+        if (LAST && store) a.prs_sig[idx] = t.strength * Deltane / fmax(Deltane, t4);
+    } else { // :1131-1135
+        c0ne = t.strength / fmax(Deltane, t.tiny);
+        c0nw = t.strength / fmax(Deltanw, t.tiny);
+        c0sw = t.strength / fmax(Deltasw, t.tiny);
+        c0se = t.strength / fmax(Deltase, t.tiny);
+        if (LAST && store) a.prs_sig[idx] = c0ne * Deltane;
+    }
+    const double c1ne = c0ne * a.dte2T; // :1138-1141
+    const double c1nw = c0nw * a.dte2T;
+    const double c1sw = c0sw * a.dte2T;
+    const double c1se = c0se * a.dte2T;
+
+    // :1148-1165
+    const double sp1 = (t.s[0] + c1ne * (divune - Deltane)) * a.denom1;
+    const double sp2 = (t.s[1] + c1nw * (divunw - Deltanw)) * a.denom1;
+    const double sp3 = (t.s[2] + c1sw * (divusw - Deltasw)) * a.denom1;
+    const double sp4 = (t.s[3] + c1se * (divuse - Deltase)) * a.denom1;
+    const double sm1 = (t.s[4] + c1ne * tensionne) * a.denom2;
+    const double sm2 = (t.s[5] + c1nw * tensionnw) * a.denom2;
+    const double sm3 = (t.s[6] + c1sw * tensionsw) * a.denom2;
+    const double sm4 = (t.s[7] + c1se * tensionse) * a.denom2;
+    const double s121 = (t.s[8] + c1ne * shearne * p5) * a.denom2;
+    const double s122 = (t.s[9] + c1nw * shearnw * p5) * a.denom2;
+    const double s123 = (t.s[10] + c1sw * shearsw * p5) * a.denom2;
+    const double s124 = (t.s[11] + c1se * shearse * p5) * a.denom2;
+
+    if (store) {
+        a.s_new[0][idx] = sp1; a.s_new[1][idx] = sp2; a.s_new[2][idx] = sp3; a.s_new[3][idx] = sp4;
+        a.s_new[4][idx] = sm1; a.s_new[5][idx] = sm2; a.s_new[6][idx] = sm3; a.s_new[7][idx] = sm4;
+        a.s_new[8][idx] = s121; a.s_new[9][idx] = s122; a.s_new[10][idx] = s123; a.s_new[11][idx] = s124;
+    }
+
+    // :1196-1215
+    const double ssigpn = sp1 + sp2, ssigps = sp3 + sp4, ssigpe = sp1 + sp4, ssigpw = sp2 + sp3;
+    const double ssigp1 = (sp1 + sp3) * p055, ssigp2 = (sp2 + sp4) * p055;
+    const double ssigmn = sm1 + sm2, ssigms = sm3 + sm4, ssigme = sm1 + sm4, ssigmw = sm2 + sm3;
+    const double ssigm1 = (sm1 + sm3) * p055, ssigm2 = (sm2 + sm4) * p055;
+    const double ssig12n = s121 + s122, ssig12s = s123 + s124, ssig12e = s121 + s124, ssig12w = s122 + s123;
+    const double ssig121 = (s121 + s123) * p111, ssig122 = (s122 + s124) * p111;
+    // :1217-1234
+    const double csigpne = p111 * sp1 + ssigp2 + p027 * sp3;
+    const double csigpnw = p111 * sp2 + ssigp1 + p027 * sp4;
+    const double csigpsw = p111 * sp3 + ssigp2 + p027 * sp1;
+    const double csigpse = p111 * sp4 + ssigp1 + p027 * sp2;
+    const double csigmne = p111 * sm1 + ssigm2 + p027 * sm3;
+    const double csigmnw = p111 * sm2 + ssigm1 + p027 * sm4;
+    const double csigmsw = p111 * sm3 + ssigm2 + p027 * sm1;
+    const double csigmse = p111 * sm4 + ssigm1 + p027 * sm2;
+    const double csig12ne = p222 * s121 + ssig122 + p055 * s123;
+    const double csig12nw = p222 * s122 + ssig121 + p055 * s124;
+    const double csig12sw = p222 * s123 + ssig122 + p055 * s121;
+    const double csig12se = p222 * s124 + ssig121 + p055 * s122;
+    // :1236-1239
+    const double str12ew = p5 * dxt * (p333 * ssig12e + p166 * ssig12w);
+    const double str12we = p5 * dxt * (p333 * ssig12w + p166 * ssig12e);
+    const double str12ns = p5 * dyt * (p333 * ssig12n + p166 * ssig12s);
+    const double str12sn = p5 * dyt * (p333 * ssig12s + p166 * ssig12n);
+    // :1244-1264
+    double strp_tmp = p25 * dyt * (p333 * ssigpn + p166 * ssigps);
+    double strm_tmp = p25 * dyt * (p333 * ssigmn + p166 * ssigms);
+    str[0] = -strp_tmp - strm_tmp - str12ew + t.dxhy * (-csigpne + csigmne) + t.dyhx * csig12ne;
+    str[1] = strp_tmp + strm_tmp - str12we + t.dxhy * (-csigpnw + csigmnw) + t.dyhx * csig12nw;
+    strp_tmp = p25 * dyt * (p333 * ssigps + p166 * ssigpn);
+    strm_tmp = p25 * dyt * (p333 * ssigms + p166 * ssigmn);
+    str[2] = -strp_tmp - strm_tmp + str12ew + t.dxhy * (-csigpse + csigmse) + t.dyhx * csig12se;
+    str[3] = strp_tmp + strm_tmp + str12we + t.dxhy * (-csigpsw + csigmsw) + t.dyhx * csig12sw;
+    // :1269-1289
+    strp_tmp = p25 * dxt * (p333 * ssigpe + p166 * ssigpw);
+    strm_tmp = p25 * dxt * (p333 * ssigme + p166 * ssigmw);
+    str[4] = -strp_tmp + strm_tmp - str12ns - t.dyhx * (csigpne + csigmne) + t.dxhy * csig12ne;
+    str[5] = strp_tmp - strm_tmp - str12sn - t.dyhx * (csigpse + csigmse) + t.dxhy * csig12se;
+    strp_tmp = p25 * dxt * (p333 * ssigpw + p166 * ssigpe);
+    strm_tmp = p25 * dxt * (p333 * ssigmw + p166 * ssigme);
+    str[6] = -strp_tmp + strm_tmp + str12ns - t.dyhx * (csigpnw + csigmnw) + t.dxhy * csig12nw;
+    str[7] = strp_tmp - strm_tmp + str12sn - t.dyhx * (csigpsw + csigmsw) + t.dxhy * csig12sw;
+}
+
+// source/ice_dyn_evp.F90:1386-1441 for one U cell; sx, sy are the two str sums of :1415-1418
+template <bool LAST>
+__device__ __forceinline__ void stepu_cell(const SubArgs &a, const URow &u, double uold, double vold,
+                                           double sx, double sy, int i, size_t idx) {
+    const double du = u.uocn - uold, dv = u.vocn - vold;
+    const double vrel = u.aiu * a.dragw * sqrt(du * du + dv * dv); // :1394
+    const double taux = vrel * u.waterx;                            // :1397-1398
+    const double tauy = vrel * u.watery;
+    const double cca = u.umassdtei + vrel * a.cosw;                 // :1401
+    double ccb;
+    if (a.hemisphere_turning && u.fm < 0.0)                         // :1403-1410
+        ccb = u.fm - vrel * a.sinw;
+    else
+        ccb = u.fm + vrel * a.sinw;
+    const double ab2 = cca * cca + ccb * ccb;                       // :1412
+    const double strintx = u.uarear * sx;                           // :1415-1418
+    const double strinty = u.uarear * sy;
+    const double cc1 = strintx + u.forcex + taux + u.umassdtei * uold; // :1421-1424
+    const double cc2 = strinty + u.forcey + tauy + u.umassdtei * vold;
+    const double unew = (cca * cc1 + ccb * cc2) / ab2;              // :1426-1427
+    const double vnew = (cca * cc2 - ccb * cc1) / ab2;
+    a.u_new[idx] = unew;
+    a.v_new[idx] = vnew;
+    if (a.ew_cyclic) { // east-west part of ice_HaloUpdate(uvel/vvel), serial/ice_boundary.F90:3629-3668
+        if (i == a.nx) {
+            a.u_new[idx - a.nx] = unew;
+            a.v_new[idx - a.nx] = vnew;
+        }
+        if (i == 1) {
+            a.u_new[idx + a.nx] = unew;
+            a.v_new[idx + a.nx] = vnew;
+        }
+    }
+    if (LAST) { // only the last subcycle's values are observable (:1415-1418,:1434-1435)
+        a.strintx[idx] = strintx;
+        a.strinty[idx] = strinty;
+        a.strocnx[idx] = taux;
+        a.strocny[idx] = tauy;
+    }
+}
+
+template <int NT, bool LAST, bool PREFETCH>
+__global__ void __launch_bounds__(NT) k_subcycle(const __grid_constant__ SubArgs a) {
+    __shared__ double xch[2][4][NT];
+    const int tid = threadIdx.x;
+    const int i = 1 + blockIdx.x * a.strip_w + tid;
+    const int j0 = 1 + blockIdx.y * a.rows;
+    const int jlast = min(j0 + a.rows, a.nyl + 1); // last T row of this CTA
+    const bool colT = (tid <= a.strip_w) && (i <= a.nx + 1);
+    const bool colU = (tid < a.strip_w) && (i <= a.nx);
+    const bool ownT = colT && (tid < a.strip_w || i == a.nx + 1);
+
+    double us = 0.0, vs = 0.0, usw = 0.0, vsw = 0.0;
+    if (colT) {
+        const size_t idx = (size_t)(j0 - 1) * a.pitch + i;
+        us = __ldg(a.u_old + idx);
+        vs = __ldg(a.v_old + idx);
+        usw = __ldg(a.u_old + idx - 1);
+        vsw = __ldg(a.v_old + idx - 1);
+    }
+    double px = 0.0, s5c = 0.0, s7c = 0.0;
+    TRow t;
+    load_T<LAST>(a, t, i, j0, colT);
+    int par = 0;
+
+    for (int j = j0; j <= jlast; ++j) {
+        TRow tn;
+        URow uc;
+        if (PREFETCH) {
+            if (j < jlast) load_T<LAST>(a, tn, i, j + 1, colT);
+        }
+        uc.act = false;
+        if (j > j0) load_U(a, uc, i, j - 1, colU);
+
+        const size_t idx = (size_t)j * a.pitch + i;
+        double str[8];
+        if (t.act) {
+            const bool store = ownT && (j < j0 + a.rows || j == a.nyl + 1);
+            stress_cell<LAST>(a, t, us, vs, usw, vsw, idx, store, str);
+        } else {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) str[k] = 0.0; // str(:,:,:) = c0, :1051
+        }
+        xch[par][0][tid] = str[1];
+        xch[par][1][tid] = str[3];
+        xch[par][2][tid] = str[6];
+        xch[par][3][tid] = str[7];
+        __syncthreads();
+        double s2r = 0.0, s4r = 0.0, s7r = 0.0, s8r = 0.0;
+        if (tid < NT - 1) {
+            s2r = xch[par][0][tid + 1];
+            s4r = xch[par][1][tid + 1];
+            s7r = xch[par][2][tid + 1];
+            s8r = xch[par][3][tid + 1];
+        }
+        par ^= 1;
+
+        if (uc.act) {
+            const double sx = px + str[2] + s4r;          // ((s1 + s2) + s3) + s4
+            const double sy = s5c + str[5] + s7c + s8r;    // ((s5 + s6) + s7) + s8
+            stepu_cell<LAST>(a, uc, us, vs, sx, sy, i, idx - a.pitch);
+        }
+        px = str[0] + s2r;
+        s5c = str[4];
+        s7c = s7r;
+        us = t.u;
+        vs = t.v;
+        usw = t.uw;
+        vsw = t.vw;
+        if (PREFETCH) {
+            t = tn;
+        } else {
+            if (j < jlast) load_T<LAST>(a, t, i, j + 1, colT);
+        }
+    }
+}
+
+template <int NT>
+static void launch_nt(const SubArgs &a, bool last, int variant, unsigned gx, unsigned gy, cudaStream_t s) {
+    dim3 grid(gx, gy), block(NT);
+    const bool prefetch = (variant & 1) == 0;
+    if (last) {
+        if (prefetch) k_subcycle<NT, true, true><<<grid, block, 0, s>>>(a);
+        else k_subcycle<NT, true, false><<<grid, block, 0, s>>>(a);
+    } else {
+        if (prefetch) k_subcycle<NT, false, true><<<grid, block, 0, s>>>(a);
+        else k_subcycle<NT, false, false><<<grid, block, 0, s>>>(a);
+    }
+}
+
+} // namespace EVP_SUB_NS
+
+void EVP_SUB_LAUNCH(const SubArgs &a, bool last, int variant, int threads, unsigned grid_x,
+                    unsigned grid_y, void *stream) {
+    cudaStream_t s = (cudaStream_t)stream;
+    switch (threads) {
+    case 64: EVP_SUB_NS::launch_nt<64>(a, last, variant, grid_x, grid_y, s); break;
+    case 256: EVP_SUB_NS::launch_nt<256>(a, last, variant, grid_x, grid_y, s); break;
+    default: EVP_SUB_NS::launch_nt<128>(a, last, variant, grid_x, grid_y, s); break;
+    }
+}

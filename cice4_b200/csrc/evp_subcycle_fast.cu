@@ -1,0 +1,5 @@
+// FMA-contracted build of the subcycle kernel: compiled with -fmad=true.  Differences from the
+// unfused build are rounding-level only (DESIGN.md states the measured bound).
+#define EVP_SUB_NS evp_sub_fast
+#define EVP_SUB_LAUNCH evp_subcycle_launch_fast
+#include "evp_subcycle_body.cuh"

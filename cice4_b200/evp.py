@@ -1,0 +1,417 @@
+"""Host-side mirror of `module ice_dyn_evp` over the C ABI of libevp_b200.so.
+
+The reference is Fortran and no Fortran compiler exists in this image, so the host side above
+the C ABI is written here in Python with the reference's names and call order
+(/root/reference/source/ice_dyn_evp.F90): module variables `kdyn, ndte, evp_damping,
+yield_curve, dragio, cosw, sinw` (:64-97), `init_evp(dt)` (:441-526), `evp(dt)` (:119-432),
+`principal_stress` (:1558-1609) and `set_evp_parameters` (:535-577).  The module arrays of
+ice_state / ice_flux that `evp` reads and writes are numpy arrays in Fortran order
+`(nx_block, ny_block, max_blocks)` held in `self.state`, `self.flux`.
+
+The Fortran shim a CICE maintainer would compile instead is cice4_b200/fortran/ice_dyn_evp_b200.F90
+(see INTEGRATION.md); both bind exactly the entry points declared in include/evp_b200.h.
+
+There is NO CPU fallback: importing works without a GPU (so that symbols can be checked), but
+every compute call fails with EvpB200Error when the library or a CUDA device is missing.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Dict, Optional, Sequence
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "lib", "libevp_b200.so")
+
+c_dp = C.POINTER(C.c_double)
+c_ip = C.POINTER(C.c_int32)
+
+BND = {"open": 0, "closed": 1, "cyclic": 2, "tripole": 3}
+
+EXPORTS = [
+    "evp_b200_abi_version", "evp_b200_last_error", "evp_b200_default_params", "evp_b200_init",
+    "evp_b200_prep", "evp_b200_run", "evp_b200_step", "evp_b200_subcycle_resident",
+    "evp_b200_principal_stress", "evp_b200_get_timings", "evp_b200_comm_unique_id",
+    "evp_b200_comm_init", "evp_b200_finalize",
+]
+
+
+class EvpB200Error(RuntimeError):
+    pass
+
+
+class Dims(C.Structure):
+    _fields_ = ([(n, C.c_int32) for n in ("nx_block", "ny_block", "max_blocks", "nblocks", "nx_global",
+                                          "ny_global", "ew_boundary", "ns_boundary")] +
+                [(n, c_ip) for n in ("ilo", "ihi", "jlo", "jhi", "iglob_lo", "jglob_lo")] +
+                [(n, C.c_int32) for n in ("slab_jlo", "slab_jhi", "rank", "nranks", "device")])
+
+
+class Params(C.Structure):
+    _fields_ = [("dt", C.c_double), ("ndte", C.c_int32), ("evp_damping", C.c_int32),
+                ("dragio", C.c_double), ("cosw", C.c_double), ("sinw", C.c_double),
+                ("rhoi", C.c_double), ("rhos", C.c_double), ("rhow", C.c_double),
+                ("gravit", C.c_double), ("puny", C.c_double),
+                ("coupled_tilt", C.c_int32), ("use_ocnslope", C.c_int32),
+                ("hemisphere_turning", C.c_int32), ("wind_from_strax", C.c_int32),
+                ("kstrength", C.c_int32), ("krdg_partic", C.c_int32), ("krdg_redist", C.c_int32),
+                ("ncat", C.c_int32), ("mu_rdg", C.c_double),
+                ("math_mode", C.c_int32), ("pin_host", C.c_int32), ("use_graph", C.c_int32),
+                ("tile_threads", C.c_int32), ("tile_rows", C.c_int32), ("kernel_variant", C.c_int32)]
+
+
+STATIC_D = ["dxt", "dyt", "dxhy", "dyhx", "cxp", "cyp", "cxm", "cym",
+            "tarea", "tarear", "tinyarea", "uarea", "uarear", "fcor"]
+STATIC_I = ["tmask", "umask"]
+INPUT_D = ["aice", "vice", "vsno", "strairxT", "strairyT", "uocn", "vocn", "ss_tltx", "ss_tlty",
+           "aice0", "aicen", "vicen"]
+STATE_D = ["uvel", "vvel",
+           "stressp_1", "stressp_2", "stressp_3", "stressp_4",
+           "stressm_1", "stressm_2", "stressm_3", "stressm_4",
+           "stress12_1", "stress12_2", "stress12_3", "stress12_4"]
+OUTPUT_D = ["strairx", "strairy", "strtltx", "strtlty", "strintx", "strinty",
+            "strocnx", "strocny", "strocnxT", "strocnyT", "fm", "prs_sig",
+            "divu", "shear", "rdg_conv", "rdg_shear", "strength", "sicemass", "sig1", "sig2"]
+
+
+class StaticFields(C.Structure):
+    _fields_ = [(n, c_dp) for n in STATIC_D] + [(n, c_ip) for n in STATIC_I]
+
+
+class Inputs(C.Structure):
+    _fields_ = [(n, c_dp) for n in INPUT_D]
+
+
+class State(C.Structure):
+    _fields_ = [(n, c_dp) for n in STATE_D] + [("iceumask", c_ip)]
+
+
+class Outputs(C.Structure):
+    _fields_ = [(n, c_dp) for n in OUTPUT_D]
+
+
+class Timings(C.Structure):
+    _fields_ = [(n, C.c_float) for n in ("upload_ms", "prep_ms", "subcycle_ms", "finish_ms",
+                                         "download_ms", "total_ms")] + \
+               [("kernel_launches", C.c_int32), ("subcycle_launches", C.c_int32)]
+
+
+_lib: Optional[C.CDLL] = None
+
+
+def load_library(path: str = LIB_PATH) -> C.CDLL:
+    """dlopen libevp_b200.so and declare the prototypes of include/evp_b200.h."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(path):
+        raise EvpB200Error(f"{path} is missing: build it with `python -m cice4_b200.build` "
+                           "(there is no CPU fallback)")
+    L = C.CDLL(path)
+    H = C.c_void_p
+    L.evp_b200_abi_version.restype = C.c_int
+    L.evp_b200_last_error.restype = C.c_char_p
+    L.evp_b200_default_params.argtypes = [C.POINTER(Params)]
+    L.evp_b200_default_params.restype = None
+    L.evp_b200_init.argtypes = [C.POINTER(Dims), C.POINTER(Params), C.POINTER(StaticFields), C.POINTER(H)]
+    L.evp_b200_prep.argtypes = [H, C.POINTER(Inputs), C.POINTER(State), c_ip]
+    L.evp_b200_run.argtypes = [H, c_dp, C.POINTER(State), C.POINTER(Outputs)]
+    L.evp_b200_step.argtypes = [H, C.POINTER(Inputs), c_dp, C.POINTER(State), C.POINTER(Outputs)]
+    L.evp_b200_subcycle_resident.argtypes = [H, C.c_int32, C.POINTER(C.c_float)]
+    L.evp_b200_principal_stress.argtypes = [H, c_dp, c_dp, c_dp, c_dp, c_dp, c_dp]
+    L.evp_b200_get_timings.argtypes = [H, C.POINTER(Timings)]
+    L.evp_b200_comm_unique_id.argtypes = [C.POINTER(C.c_uint8)]
+    L.evp_b200_comm_init.argtypes = [H, C.POINTER(C.c_uint8)]
+    L.evp_b200_finalize.argtypes = [H]
+    for n in EXPORTS:
+        if n not in ("evp_b200_last_error", "evp_b200_default_params"):
+            getattr(L, n).restype = C.c_int
+    _lib = L
+    return L
+
+
+def _check(rc: int) -> None:
+    if rc != 0:
+        msg = load_library().evp_b200_last_error().decode(errors="replace")
+        raise EvpB200Error(f"libevp_b200 error {rc}: {msg}")
+
+
+def _dptr(a: Optional[np.ndarray]):
+    if a is None:
+        return None
+    if a.dtype != np.float64 or not a.flags.f_contiguous:
+        raise EvpB200Error("arrays must be float64 in Fortran order (nx_block, ny_block, max_blocks)")
+    return a.ctypes.data_as(c_dp)
+
+
+def _iptr(a: Optional[np.ndarray]):
+    if a is None:
+        return None
+    if a.dtype != np.int32 or not a.flags.f_contiguous:
+        raise EvpB200Error("masks must be int32 in Fortran order")
+    return a.ctypes.data_as(c_ip)
+
+
+def default_params(**over) -> Params:
+    p = Params()
+    load_library().evp_b200_default_params(C.byref(p))
+    for k, v in over.items():
+        if not hasattr(p, k):
+            raise EvpB200Error(f"unknown parameter {k}")
+        setattr(p, k, v)
+    return p
+
+
+class BlockLayout:
+    """`ice_blocks` for the caller's arrays: nx_block, ny_block, max_blocks and, per local block,
+    ilo/ihi/jlo/jhi and the global index of the first physical cell
+    (/root/reference/source/ice_blocks.F90:133-350)."""
+
+    def __init__(self, nx_global: int, ny_global: int, nx_block: int, ny_block: int,
+                 ilo: Sequence[int], ihi: Sequence[int], jlo: Sequence[int], jhi: Sequence[int],
+                 iglob_lo: Sequence[int], jglob_lo: Sequence[int], max_blocks: Optional[int] = None):
+        self.nx_global, self.ny_global = nx_global, ny_global
+        self.nx_block, self.ny_block = nx_block, ny_block
+        self.nblocks = len(ilo)
+        self.max_blocks = max_blocks or self.nblocks
+        mk = lambda v: np.ascontiguousarray(np.asarray(v, dtype=np.int32))
+        self.ilo, self.ihi, self.jlo, self.jhi = mk(ilo), mk(ihi), mk(jlo), mk(jhi)
+        self.iglob_lo, self.jglob_lo = mk(iglob_lo), mk(jglob_lo)
+
+    @classmethod
+    def single_block(cls, nx: int, ny: int) -> "BlockLayout":
+        """One block spanning the domain (BLCKX=NXGLOB, BLCKY=NYGLOB, as bld/config.ubuntu)."""
+        return cls(nx, ny, nx + 2, ny + 2, [2], [nx + 1], [2], [ny + 1], [1], [1])
+
+    @classmethod
+    def cartesian(cls, nx: int, ny: int, bx: int, by: int) -> "BlockLayout":
+        """create_blocks (/root/reference/source/ice_blocks.F90:196-222): blocks of bx x by,
+        j-outer / i-inner numbering, padded at the east/north edge when sizes do not divide."""
+        nbx = (nx - 1) // bx + 1
+        nby = (ny - 1) // by + 1
+        ilo, ihi, jlo, jhi, ig, jg = [], [], [], [], [], []
+        for jb in range(nby):
+            js = jb * by + 1
+            je = min(js + by - 1, ny)
+            for ib in range(nbx):
+                is_ = ib * bx + 1
+                ie = min(is_ + bx - 1, nx)
+                ilo.append(2)
+                ihi.append(2 + (ie - is_))
+                jlo.append(2)
+                jhi.append(2 + (je - js))
+                ig.append(is_)
+                jg.append(js)
+        return cls(nx, ny, bx + 2, by + 2, ilo, ihi, jlo, jhi, ig, jg)
+
+    @property
+    def shape(self):
+        return (self.nx_block, self.ny_block, self.max_blocks)
+
+
+class IceDynEvp:
+    """`module ice_dyn_evp` on one B200 (one y-slab)."""
+
+    def __init__(self, layout: BlockLayout, ew_boundary: str = "cyclic", ns_boundary: str = "open",
+                 device: int = -1, **params):
+        # namelist / module variables, source/ice_dyn_evp.F90:64-97
+        self.kdyn = 1
+        self.yield_curve = "ellipse"
+        self.layout = layout
+        self.ew_boundary, self.ns_boundary = ew_boundary, ns_boundary
+        self.device = device
+        self._param_over = dict(params)
+        self.params: Optional[Params] = None
+        self._h = C.c_void_p(None)
+        self._keep = []
+        # module state of ice_state / ice_flux that evp owns across steps
+        sh = layout.shape
+        self.state: Dict[str, np.ndarray] = {n: np.zeros(sh, order="F") for n in STATE_D}
+        self.state["iceumask"] = np.zeros(sh, dtype=np.int32, order="F")
+        self.flux: Dict[str, np.ndarray] = {}
+
+    # --- module variables -----------------------------------------------------------------
+    @property
+    def ndte(self) -> int:
+        return self.params.ndte if self.params is not None else self._param_over.get("ndte", 120)
+
+    @property
+    def evp_damping(self) -> bool:
+        return bool(self.params.evp_damping) if self.params is not None else bool(self._param_over.get("evp_damping", 0))
+
+    def set_evp_parameters(self, dt: float) -> Dict[str, float]:
+        """source/ice_dyn_evp.F90:535-577 (host copy; the library computes the same scalars)."""
+        ndte = self.ndte
+        eyc = 0.36
+        dte = dt / float(ndte)
+        dtei = 1.0 / dte
+        ecc = 4.0
+        tdamp2 = 2.0 * eyc * dt
+        dte2T = dte / tdamp2
+        return dict(dte=dte, dtei=dtei, ecci=0.25, tdamp=eyc * dt, dte2T=dte2T,
+                    denom1=1.0 / (1.0 + dte2T), denom2=1.0 / (1.0 + dte2T * ecc),
+                    rcon=1230.0 * eyc * dt * dtei ** 2)
+
+    # --- init_evp -------------------------------------------------------------------------
+    def init_evp(self, dt: float, grid_fields: Dict[str, np.ndarray]) -> None:
+        """source/ice_dyn_evp.F90:441-526.  `grid_fields` are the module ice_grid arrays
+        (block layout) plus fcor; velocities, stresses and iceumask are zeroed as :487-524."""
+        L = load_library()
+        self.finalize()
+        lay = self.layout
+        p = default_params(**self._param_over)
+        p.dt = dt
+        self.params = p
+        d = Dims()
+        d.nx_block, d.ny_block, d.max_blocks, d.nblocks = lay.nx_block, lay.ny_block, lay.max_blocks, lay.nblocks
+        d.nx_global, d.ny_global = lay.nx_global, lay.ny_global
+        d.ew_boundary, d.ns_boundary = BND[self.ew_boundary], BND[self.ns_boundary]
+        d.ilo, d.ihi, d.jlo, d.jhi = _iptr(lay.ilo), _iptr(lay.ihi), _iptr(lay.jlo), _iptr(lay.jhi)
+        d.iglob_lo, d.jglob_lo = _iptr(lay.iglob_lo), _iptr(lay.jglob_lo)
+        d.slab_jlo, d.slab_jhi = 1, lay.ny_global
+        d.rank, d.nranks, d.device = 0, 1, self.device
+        sf = StaticFields()
+        keep = []
+        for n in STATIC_D:
+            a = self._as_block(grid_fields[n], np.float64)
+            keep.append(a)
+            setattr(sf, n, _dptr(a))
+        for n in STATIC_I:
+            a = self._as_block(grid_fields[n], np.int32)
+            keep.append(a)
+            setattr(sf, n, _iptr(a))
+        h = C.c_void_p(None)
+        _check(L.evp_b200_init(C.byref(d), C.byref(p), C.byref(sf), C.byref(h)))
+        self._h = h
+        for n in STATE_D:
+            self.state[n][...] = 0.0
+        self.state["iceumask"][...] = 0
+
+    def _as_block(self, a: np.ndarray, dtype) -> np.ndarray:
+        sh = self.layout.shape
+        if a.ndim == 2:
+            a = a.reshape(a.shape[0], a.shape[1], 1, order="F")
+        if a.shape != sh:
+            raise EvpB200Error(f"array shape {a.shape} does not match the block layout {sh}")
+        return np.asfortranarray(a, dtype=dtype)
+
+    # --- evp ------------------------------------------------------------------------------
+    def evp(self, dt: float, inputs: Dict[str, np.ndarray], strength: Optional[np.ndarray] = None,
+            want: Optional[Sequence[str]] = None, two_phase: bool = False) -> Dict[str, np.ndarray]:
+        """One dynamics step, source/ice_dyn_evp.F90:119-432.  `dt` is unused at run time exactly as
+        in the reference (the parameters are frozen by init_evp, :195-197).  Updates `self.state` in
+        place and returns the output fields named in `want` (default: all of include/evp_b200.h's
+        evp_b200_outputs except sig1/sig2).  `strength=None` runs ice_strength on the device.
+        `two_phase` uses evp_b200_prep + evp_b200_run (what the Fortran shim does when ice_strength
+        stays on the host) and returns the halo-updated icetmask as outputs['icetmask']."""
+        if not self._h:
+            raise EvpB200Error("init_evp has not been called")
+        L = load_library()
+        sh = self.layout.shape
+        inp = Inputs()
+        keep = []
+        for n in INPUT_D:
+            a = inputs.get(n)
+            if a is None:
+                continue
+            if n in ("aicen", "vicen"):
+                if a.ndim == 3:
+                    a = a.reshape(a.shape[0], a.shape[1], a.shape[2], 1, order="F")
+                a = np.asfortranarray(a, dtype=np.float64)
+            else:
+                a = self._as_block(a, np.float64)
+            keep.append(a)
+            setattr(inp, n, _dptr(a))
+        st = State()
+        for n in STATE_D:
+            setattr(st, n, _dptr(self.state[n]))
+        st.iceumask = _iptr(self.state["iceumask"])
+        names = list(want) if want is not None else [n for n in OUTPUT_D if n not in ("sig1", "sig2")]
+        out = Outputs()
+        res: Dict[str, np.ndarray] = {}
+        for n in names:
+            res[n] = np.zeros(sh, order="F")
+            setattr(out, n, _dptr(res[n]))
+        sp = None
+        if strength is not None:
+            sarr = self._as_block(strength, np.float64)
+            keep.append(sarr)
+            sp = _dptr(sarr)
+        if two_phase:
+            if sp is None:
+                raise EvpB200Error("two_phase needs a host strength array")
+            icet = np.zeros(sh, dtype=np.int32, order="F")
+            _check(L.evp_b200_prep(self._h, C.byref(inp), C.byref(st), _iptr(icet)))
+            _check(L.evp_b200_run(self._h, sp, C.byref(st), C.byref(out)))
+            res["icetmask"] = icet
+        else:
+            _check(L.evp_b200_step(self._h, C.byref(inp), sp, C.byref(st), C.byref(out)))
+        self.flux.update(res)
+        return res
+
+    def principal_stress(self, stressp_1, stressm_1, stress12_1, prs_sig):
+        """source/ice_dyn_evp.F90:1558-1609 -> (sig1, sig2)."""
+        if not self._h:
+            raise EvpB200Error("init_evp has not been called")
+        a = [self._as_block(x, np.float64) for x in (stressp_1, stressm_1, stress12_1, prs_sig)]
+        sig1 = np.zeros(self.layout.shape, order="F")
+        sig2 = np.zeros(self.layout.shape, order="F")
+        _check(load_library().evp_b200_principal_stress(self._h, *[_dptr(x) for x in a], _dptr(sig1), _dptr(sig2)))
+        return sig1, sig2
+
+    # --- measurement hooks (the reference's timer_dynamics, mpi/ice_timers.F90) -------------
+    def subcycle_resident(self, repeats: int = 1) -> float:
+        """Mean device milliseconds of one ndte subcycle loop on the resident state."""
+        ms = C.c_float(0.0)
+        _check(load_library().evp_b200_subcycle_resident(self._h, repeats, C.byref(ms)))
+        return ms.value
+
+    def timings(self) -> Dict[str, float]:
+        t = Timings()
+        _check(load_library().evp_b200_get_timings(self._h, C.byref(t)))
+        return {n: getattr(t, n) for n, _ in Timings._fields_}
+
+    def finalize(self) -> None:
+        if self._h:
+            load_library().evp_b200_finalize(self._h)
+            self._h = C.c_void_p(None)
+
+    def __del__(self):
+        try:
+            self.finalize()
+        except Exception:
+            pass
+
+
+def split_blocks(a: np.ndarray, layout: BlockLayout, ew: str, ns: str) -> np.ndarray:
+    """Padded single-block array (nx+2, ny+2[, k]) -> block layout, ghost cells taken from the
+    neighbouring cells of the padded array (what scatter_global + ice_HaloUpdate leave in a
+    multi-block run).  Host helper for tests and the harness."""
+    extra = a.shape[2:]
+    out = np.zeros((layout.nx_block, layout.ny_block) + extra + (layout.max_blocks,), dtype=a.dtype, order="F")
+    for b in range(layout.nblocks):
+        ni = layout.ihi[b] - layout.ilo[b] + 1
+        nj = layout.jhi[b] - layout.jlo[b] + 1
+        i0 = layout.iglob_lo[b] - 1   # padded index of the west ghost column of this block
+        j0 = layout.jglob_lo[b] - 1
+        out[0:ni + 2, 0:nj + 2, ..., b] = a[i0:i0 + ni + 2, j0:j0 + nj + 2, ...]
+    return out
+
+
+def merge_blocks(blk: np.ndarray, layout: BlockLayout, base: Optional[np.ndarray] = None) -> np.ndarray:
+    """Block layout -> padded single-block array: physical cells from every block, the outer
+    ghost ring from the edge blocks.  Inverse of split_blocks for consistent arrays."""
+    nx, ny = layout.nx_global, layout.ny_global
+    out = np.zeros((nx + 2, ny + 2), dtype=blk.dtype, order="F") if base is None else base.copy(order="F")
+    for b in range(layout.nblocks):
+        ni = layout.ihi[b] - layout.ilo[b] + 1
+        nj = layout.jhi[b] - layout.jlo[b] + 1
+        ig, jg = layout.iglob_lo[b], layout.jglob_lo[b]
+        w = 0 if ig == 1 else 1
+        e = ni + 2 if ig + ni - 1 == nx else ni + 1
+        s = 0 if jg == 1 else 1
+        n = nj + 2 if jg + nj - 1 == ny else nj + 1
+        out[ig - 1 + w:ig - 1 + e, jg - 1 + s:jg - 1 + n] = blk[w:e, s:n, b]
+    return out

@@ -1,0 +1,195 @@
+/*
+ * evp_b200.h -- C ABI of libevp_b200.so: the B200 (sm_100a) implementation of
+ * CICE4's elastic-viscous-plastic dynamics step.
+ *
+ * This is the drop-in boundary for ONE path of COSIMA/cice4: `subroutine evp(dt)`
+ * (source/ice_dyn_evp.F90:119-432) with `init_evp` (:441-526) and
+ * `principal_stress` (:1558-1609).  The reference has no FFI of its own; a
+ * replacement ice_dyn_evp.F90 (cice4_b200/fortran/ice_dyn_evp_b200.F90, see
+ * INTEGRATION.md) keeps the module's public names and marshals `c_loc` pointers
+ * of the module arrays of ice_state / ice_flux / ice_grid into these calls.
+ *
+ * Conventions
+ *  - every array pointer is CALLER-OWNED HOST memory, fp64 unless stated,
+ *    Fortran order (nx_block, ny_block, max_blocks) contiguous, valid for the
+ *    duration of the call only; the library owns all device memory;
+ *  - Fortran `logical` arrays (tmask, umask, iceumask) are passed as int32 0/1;
+ *  - ghost cells of inputs are inputs (evp_prep1 reads aice/vice/vsno on the whole
+ *    block, source/ice_dyn_evp.F90:643-677); the library performs only the halo
+ *    updates evp itself performs (:250-253,:276-277,:336-344,:397-402,:427-428);
+ *  - every function returns 0 on success, an EVP_B200_ERR_* code otherwise;
+ *    evp_b200_last_error() returns a thread-local message.  No CPU fallback
+ *    exists: without a CUDA device every compute entry fails with
+ *    EVP_B200_ERR_CUDA.
+ *  - one handle is driven by one host thread (the reference has no threads).
+ */
+#ifndef EVP_B200_H
+#define EVP_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define EVP_B200_ABI_VERSION 1
+
+enum {
+    EVP_B200_OK = 0,
+    EVP_B200_ERR_ARG = 1,         /* bad argument / inconsistent dims */
+    EVP_B200_ERR_CUDA = 2,        /* CUDA runtime error or no device */
+    EVP_B200_ERR_UNSUPPORTED = 3, /* valid in the reference, not implemented here */
+    EVP_B200_ERR_STATE = 4,       /* call order violated (run before prep, ...) */
+    EVP_B200_ERR_COMM = 5         /* inter-GPU exchange failed */
+};
+
+/* ew_boundary_type / ns_boundary_type of domain_nml (source/ice_domain.F90:126-131,
+ * index maps source/ice_blocks.F90:237-343).  'tripole' is the u-fold;
+ * 'tripoleT' is not implemented (EVP_B200_ERR_UNSUPPORTED). */
+enum { EVP_B200_BND_OPEN = 0, EVP_B200_BND_CLOSED = 1, EVP_B200_BND_CYCLIC = 2, EVP_B200_BND_TRIPOLE = 3 };
+
+/* Replaces: nx_block/ny_block/max_blocks (source/ice_blocks.F90:56-61,
+ * source/ice_domain_size.F90:34-64), nblocks + blocks_ice (source/ice_domain.F90),
+ * type block (source/ice_blocks.F90:32-45) and the y-slab re-mapping of
+ * ice_distribution for GPUs. */
+typedef struct {
+    int32_t nx_block, ny_block; /* block size incl. the 1-cell ghost ring */
+    int32_t max_blocks;         /* 3rd extent of every host array */
+    int32_t nblocks;            /* local blocks actually used (<= max_blocks) */
+    int32_t nx_global, ny_global;
+    int32_t ew_boundary, ns_boundary;
+    /* per local block, length nblocks, Fortran 1-based: this_block%ilo..jhi and the
+     * global index of the first physical cell, this_block%i_glob(ilo), %j_glob(jlo) */
+    const int32_t *ilo, *ihi, *jlo, *jhi;
+    const int32_t *iglob_lo, *jglob_lo;
+    /* rows of the global domain owned by this handle (1-based, inclusive); the local
+     * blocks must tile [1..nx_global] x [slab_jlo..slab_jhi] exactly */
+    int32_t slab_jlo, slab_jhi;
+    int32_t rank, nranks;       /* position in the south->north chain of y-slabs */
+    int32_t device;             /* CUDA device ordinal, -1 = current */
+} evp_b200_dims;
+
+/* Replaces the scalars of module ice_dyn_evp (source/ice_dyn_evp.F90:64-103), the
+ * constants it uses (drivers/cice4/ice_constants.F90:50-60,65-66) and the CPP
+ * variants AusCOM / coupled / ACCESS as run-time flags (bld/Macros.nci:56-82). */
+typedef struct {
+    double dt;              /* dynamics time step passed to init_evp (s) */
+    int32_t ndte;           /* subcycles, namelist ice_nml */
+    int32_t evp_damping;    /* namelist ice_nml */
+    double dragio;          /* ice-ocean drag coefficient */
+    double cosw, sinw;      /* ocean turning angle */
+    double rhoi, rhos, rhow, gravit, puny;
+    int32_t coupled_tilt;       /* #ifdef coupled: tilt = -gravit*umass*ss_tlt (:924-925) */
+    int32_t use_ocnslope;       /* AusCOM namelist; 0 reverts to geostrophic tilt (:928-933) */
+    int32_t hemisphere_turning; /* #ifdef AusCOM/ACCICE: sign(1.,real(fm)) turning (:912-913,:1403-1408,:1525-1536) */
+    int32_t wind_from_strax;    /* #ifdef ACCESS: strairx = strax (:271-275) */
+    /* ice_strength options (source/ice_init.F90:219-222); only used when the library
+     * computes strength itself (strength == NULL in evp_b200_step) */
+    int32_t kstrength, krdg_partic, krdg_redist, ncat;
+    double mu_rdg;
+    /* library knobs */
+    int32_t math_mode;      /* 0 = unfused IEEE (bit-exact vs the unfused CPU oracle); 1 = FMA-contracted */
+    int32_t pin_host;       /* 1 = cudaHostRegister caller arrays on first use */
+    int32_t use_graph;      /* 1 = replay the ndte loop as one CUDA graph */
+    int32_t tile_threads;   /* 0 = default; threads per CTA of the subcycle kernel */
+    int32_t tile_rows;      /* 0 = default; U rows marched per CTA */
+    int32_t kernel_variant; /* 0 = default */
+} evp_b200_params;
+
+/* module ice_grid arrays read by evp (source/ice_grid.F90:58-85,114-123) + fcor_blk
+ * (source/ice_dyn_evp.F90:105-106,503).  Uploaded once by evp_b200_init. */
+typedef struct {
+    const double *dxt, *dyt, *dxhy, *dyhx, *cxp, *cyp, *cxm, *cym;
+    const double *tarea, *tarear, *tinyarea, *uarea, *uarear, *fcor;
+    const int32_t *tmask, *umask;
+} evp_b200_static_fields;
+
+/* per-call inputs (source/ice_state.F90:66-89, source/ice_flux.F90:45-56) */
+typedef struct {
+    const double *aice, *vice, *vsno;
+    const double *strairxT, *strairyT; /* or strax/stray when wind_from_strax */
+    const double *uocn, *vocn;
+    const double *ss_tltx, *ss_tlty;   /* may be NULL unless coupled_tilt && use_ocnslope */
+    /* only for the device ice_strength (strength == NULL): (nx_block,ny_block,ncat,max_blocks) */
+    const double *aice0, *aicen, *vicen;
+} evp_b200_inputs;
+
+/* persistent module state, in/out (source/ice_state.F90:132-134, source/ice_flux.F90:85-93) */
+typedef struct {
+    double *uvel, *vvel;
+    double *stressp_1, *stressp_2, *stressp_3, *stressp_4;
+    double *stressm_1, *stressm_2, *stressm_3, *stressm_4;
+    double *stress12_1, *stress12_2, *stress12_3, *stress12_4;
+    int32_t *iceumask;
+} evp_b200_state;
+
+/* outputs; any pointer may be NULL = not downloaded.  Cells evp never writes are 0,
+ * as after init_history_dyn (source/ice_flux.F90:585-602) in step_dynamics. */
+typedef struct {
+    double *strairx, *strairy, *strtltx, *strtlty, *strintx, *strinty;
+    double *strocnx, *strocny, *strocnxT, *strocnyT, *fm, *prs_sig;
+    double *divu, *shear, *rdg_conv, *rdg_shear;
+    double *strength;  /* halo-updated strength as left by evp (:337-338) */
+    double *sicemass;  /* AusCOM: = tmass (:246-248) */
+    double *sig1, *sig2; /* principal_stress epilogue (source/ice_history.F90:1939-1945) */
+} evp_b200_outputs;
+
+/* device timings of the last call, milliseconds, CUDA events on the library stream */
+typedef struct {
+    float upload_ms, prep_ms, subcycle_ms, finish_ms, download_ms, total_ms;
+    int32_t kernel_launches;   /* kernels launched (graph nodes count) in the last call */
+    int32_t subcycle_launches; /* of which inside the ndte loop */
+} evp_b200_timings;
+
+typedef struct evp_b200_handle evp_b200_handle;
+
+int evp_b200_abi_version(void);
+const char *evp_b200_last_error(void);
+void evp_b200_default_params(evp_b200_params *p);
+
+/* init_evp (source/ice_dyn_evp.F90:441-526): set_evp_parameters, device allocation,
+ * static-field upload.  Velocity/stress zeroing stays with the caller's module arrays. */
+int evp_b200_init(const evp_b200_dims *dims, const evp_b200_params *params,
+                  const evp_b200_static_fields *grid, evp_b200_handle **out);
+
+/* source/ice_dyn_evp.F90:214-316: zero diagnostics, evp_prep1, HALO icetmask, to_ugrid x2,
+ * t2ugrid_vector x2, evp_prep2.  icetmask_out (int32, block layout, halo-updated) lets the
+ * Fortran shim rebuild icellt/indxti/indxtj (:850-859) for its own ice_strength call. */
+int evp_b200_prep(evp_b200_handle *h, const evp_b200_inputs *in, evp_b200_state *st,
+                  int32_t *icetmask_out);
+
+/* source/ice_dyn_evp.F90:336-428: HALO strength,u,v; ndte x (stress, stepu, HALO u,v);
+ * evp_finish; u2tgrid_vector x2; download of state and outputs. */
+int evp_b200_run(evp_b200_handle *h, const double *strength, evp_b200_state *st,
+                 evp_b200_outputs *out);
+
+/* prep + run in one call; strength == NULL computes ice_strength on the device
+ * (source/ice_mechred.F90:1869-2036; needs aice0/aicen/vicen). */
+int evp_b200_step(evp_b200_handle *h, const evp_b200_inputs *in, const double *strength,
+                  evp_b200_state *st, evp_b200_outputs *out);
+
+/* Re-run the ndte subcycle loop `repeats` times on the device-resident fields left by the
+ * last prep/run (no host traffic); ms_per_loop = mean device time of one ndte loop.  This is
+ * the timed region of the headline metric (grid-cell-subcycles/s). */
+int evp_b200_subcycle_resident(evp_b200_handle *h, int32_t repeats, float *ms_per_loop);
+
+/* principal_stress (source/ice_dyn_evp.F90:1558-1609) on caller arrays */
+int evp_b200_principal_stress(evp_b200_handle *h, const double *stressp_1, const double *stressm_1,
+                              const double *stress12_1, const double *prs_sig,
+                              double *sig1, double *sig2);
+
+int evp_b200_get_timings(const evp_b200_handle *h, evp_b200_timings *t);
+
+/* multi-GPU: one handle per rank (y-slab).  id is the 128-byte ncclUniqueId made by rank 0
+ * (evp_b200_comm_unique_id) and broadcast by the host (MPI_Bcast in the Fortran world,
+ * torch.distributed in the Python harness).  Replaces the per-subcycle ice_HaloUpdate of
+ * mpi/ice_boundary.F90:1028-1417 between tasks. */
+int evp_b200_comm_unique_id(uint8_t id[128]);
+int evp_b200_comm_init(evp_b200_handle *h, const uint8_t id[128]);
+
+int evp_b200_finalize(evp_b200_handle *h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,56 @@
+"""Shared helpers of the parity tests: run the oracle and the CUDA path on the same case."""
+import copy
+
+import numpy as np
+
+from cice4_b200 import evp as E
+from cice4_b200 import synth
+
+STATE = E.STATE_D + ["iceumask"]
+OUT_CMP = ["strairx", "strairy", "strtltx", "strtlty", "strintx", "strinty", "strocnx", "strocny",
+           "strocnxT", "strocnyT", "fm", "prs_sig", "divu", "shear", "rdg_conv", "rdg_shear"]
+
+
+def oracle_steps(O, case, nsteps=1, strength_from_oracle=True, **pover):
+    """nsteps consecutive evp calls with the oracle; returns (state, fields of last call, strengths)."""
+    g = case.grid
+    st = synth.zero_state(g.nx_block, g.ny_block)
+    dt = pover.pop("dt", 3600.0)
+    ndte = pover.pop("ndte", 120)
+    p = O.make_params(dt=dt, ndte=ndte, **pover)
+    f = None
+    strengths = []
+    for _ in range(nsteps):
+        f, _sec = O.run_evp(g, case.inputs, st, p)
+        strengths.append(f["strength"].copy(order="F"))
+    return st, f, strengths, p
+
+
+def cuda_steps(case, nsteps=1, strengths=None, layout=None, two_phase=False, want=None, **params):
+    """Same through the C ABI.  strengths: list of host strength arrays (pre-halo values are fine:
+    evp halo-updates strength itself) or None for the device ice_strength."""
+    g = case.grid
+    lay = layout or E.BlockLayout.single_block(g.nx, g.ny)
+    ew = {v: k for k, v in E.BND.items()}[g.ew]
+    ns = {v: k for k, v in E.BND.items()}[g.ns]
+    dt = params.pop("dt", 3600.0)
+    dyn = E.IceDynEvp(lay, ew, ns, **params)
+    gf = {n: E.split_blocks(g.f[n], lay, ew, ns) for n in E.STATIC_D + E.STATIC_I}
+    dyn.init_evp(dt, gf)
+    inputs = {k: E.split_blocks(v, lay, ew, ns) for k, v in case.inputs.items()}
+    out = None
+    for k in range(nsteps):
+        s = None
+        if strengths is not None:
+            s = E.split_blocks(strengths[k], lay, ew, ns)
+        out = dyn.evp(dt, inputs, strength=s, two_phase=two_phase, want=want)
+    return dyn, out
+
+
+def maxabs(a, b):
+    return float(np.max(np.abs(np.asarray(a) - np.asarray(b)))) if a.size else 0.0
+
+
+def relerr(a, b):
+    scale = float(np.max(np.abs(b)))
+    return maxabs(a, b) / scale if scale > 0 else maxabs(a, b)

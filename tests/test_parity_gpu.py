@@ -1,0 +1,205 @@
+"""GPU parity tests: the CUDA path, called through the C ABI (ctypes over libevp_b200.so),
+against the CPU oracle on the same seeded inputs.
+
+Tolerances (BASELINE.json north_star): after a full ndte = 120 timestep
+    max |du|, |dv| <= 1e-10 m/s,   relative stress error <= 1e-10.
+math_mode = 0 (unfused) is additionally required to be BIT-EXACT against the unfused oracle for
+every field; math_mode = 1 (FMA-contracted) must stay within the tolerance.
+"""
+import numpy as np
+import pytest
+
+from cice4_b200 import evp as E
+from cice4_b200 import synth
+from conftest import GX3_FIXTURE
+from helpers import OUT_CMP, STATE, cuda_steps, maxabs, oracle_steps, relerr
+
+pytestmark = pytest.mark.gpu
+
+TOL_U = 1e-10      # m/s
+TOL_S = 1e-10      # relative
+
+
+def _merge(dyn_or_arr, lay):
+    return E.merge_blocks(dyn_or_arr, lay)
+
+
+def _compare_exact(dyn, out, st, f, lay, names_out=OUT_CMP):
+    bad = []
+    for n in STATE:
+        a = _merge(dyn.state[n], lay)
+        if not np.array_equal(a, st[n]):
+            bad.append((n, maxabs(a, st[n])))
+    for n in names_out:
+        a = _merge(out[n], lay)
+        if not np.array_equal(a, f[n]):
+            bad.append((n, maxabs(a, f[n])))
+    assert not bad, f"not bit-exact: {bad}"
+
+
+def _compare_tol(dyn, out, st, f, lay):
+    for n in ("uvel", "vvel"):
+        assert maxabs(_merge(dyn.state[n], lay), st[n]) <= TOL_U, n
+    for n in STATE[2:14]:
+        assert relerr(_merge(dyn.state[n], lay), st[n]) <= TOL_S, n
+    assert np.array_equal(_merge(dyn.state["iceumask"], lay), st["iceumask"])
+    for n in OUT_CMP:
+        assert relerr(_merge(out[n], lay), f[n]) <= 1e-9, n
+
+
+CASES = [
+    ("gx3-real-grid", dict(name="gx3", realistic=True, gx3_fixture=GX3_FIXTURE)),
+    ("gx3-dense", dict(name="gx3", realistic=False, gx3_fixture=GX3_FIXTURE)),
+    ("tripole-64x48", dict(name="om1deg", nx=64, ny=48)),
+    ("tripole-130x70-realistic", dict(name="om1deg", nx=130, ny=70, realistic=True)),
+    ("cyclic-cyclic-40x33", dict(name="x", nx=40, ny=33, ew="cyclic", ns="cyclic")),
+    ("open-open-37x29", dict(name="x", nx=37, ny=29, ew="open", ns="open")),
+]
+
+
+@pytest.mark.parametrize("label,kw", CASES, ids=[c[0] for c in CASES])
+def test_bit_exact_vs_oracle_two_steps(oracle, evp_lib, label, kw):
+    """Cold start + warm second call (the timed configuration), unfused math: bit-exact."""
+    case = synth.make_case(**kw)
+    st, f, strengths, _ = oracle_steps(oracle, case, nsteps=2)
+    lay = E.BlockLayout.single_block(case.grid.nx, case.grid.ny)
+    dyn, out = cuda_steps(case, nsteps=2, strengths=strengths, math_mode=0)
+    _compare_exact(dyn, out, st, f, lay)
+    assert np.abs(st["uvel"]).max() > 1e-3   # the case is not trivially zero
+
+
+@pytest.mark.parametrize("label,kw", CASES[:4], ids=[c[0] for c in CASES[:4]])
+def test_fma_mode_within_tolerance(oracle, evp_lib, label, kw):
+    case = synth.make_case(**kw)
+    st, f, strengths, _ = oracle_steps(oracle, case, nsteps=2)
+    lay = E.BlockLayout.single_block(case.grid.nx, case.grid.ny)
+    dyn, out = cuda_steps(case, nsteps=2, strengths=strengths, math_mode=1)
+    _compare_tol(dyn, out, st, f, lay)
+
+
+@pytest.mark.parametrize("threads,rows,variant", [(64, 5, 0), (128, 7, 1), (256, 0, 0), (128, 1000, 0)])
+def test_tiling_invariance(oracle, evp_lib, threads, rows, variant):
+    """Strip width, rows per CTA and the prefetch variant must not change a single bit."""
+    case = synth.make_case("om1deg", nx=300, ny=90)
+    st, f, strengths, _ = oracle_steps(oracle, case, nsteps=1, ndte=40)
+    lay = E.BlockLayout.single_block(300, 90)
+    dyn, out = cuda_steps(case, strengths=strengths, ndte=40, tile_threads=threads, tile_rows=rows,
+                          kernel_variant=variant)
+    _compare_exact(dyn, out, st, f, lay)
+
+
+def test_graph_and_stream_launch_agree(oracle, evp_lib):
+    case = synth.make_case("om1deg", nx=64, ny=48)
+    st, f, strengths, _ = oracle_steps(oracle, case, nsteps=1, ndte=30)
+    lay = E.BlockLayout.single_block(64, 48)
+    for use_graph in (0, 1):
+        dyn, out = cuda_steps(case, strengths=strengths, ndte=30, use_graph=use_graph)
+        _compare_exact(dyn, out, st, f, lay)
+
+
+def test_odd_ndte(oracle, evp_lib):
+    case = synth.make_case("gx3", nx=50, ny=40, ew="cyclic", ns="open")
+    st, f, strengths, _ = oracle_steps(oracle, case, nsteps=2, ndte=7)
+    lay = E.BlockLayout.single_block(50, 40)
+    dyn, out = cuda_steps(case, nsteps=2, strengths=strengths, ndte=7)
+    _compare_exact(dyn, out, st, f, lay)
+
+
+@pytest.mark.parametrize("bx,by", [(16, 12), (64, 7), (10, 48), (23, 19)])
+def test_block_decomposition_invariance(oracle, evp_lib, bx, by):
+    """Reference block layouts (incl. padded edge blocks) give the single-block answer
+    (doc/cicedoc.pdf 4.6: bit-for-bit regardless of decomposition)."""
+    case = synth.make_case("om1deg", nx=64, ny=48, realistic=True)
+    st, f, strengths, _ = oracle_steps(oracle, case, nsteps=2)
+    lay = E.BlockLayout.cartesian(64, 48, bx, by)
+    dyn, out = cuda_steps(case, nsteps=2, strengths=strengths, layout=lay)
+    _compare_exact(dyn, out, st, f, lay)
+    # ghost cells of every block hold the neighbour's values after the final halo update
+    ublk = dyn.state["uvel"]
+    want = E.split_blocks(st["uvel"], lay, "cyclic", "tripole")
+    for b in range(lay.nblocks):
+        ni, nj = lay.ihi[b] - lay.ilo[b] + 3, lay.jhi[b] - lay.jlo[b] + 3
+        np.testing.assert_array_equal(ublk[:ni, :nj, b], want[:ni, :nj, b])
+
+
+def test_two_phase_prep_run(oracle, evp_lib):
+    """evp_b200_prep + evp_b200_run (host ice_strength in between, as the Fortran shim does)."""
+    case = synth.make_case("om1deg", nx=64, ny=48, realistic=True)
+    st, f, strengths, _ = oracle_steps(oracle, case, nsteps=1)
+    lay = E.BlockLayout.single_block(64, 48)
+    dyn, out = cuda_steps(case, strengths=strengths, two_phase=True)
+    _compare_exact(dyn, out, st, f, lay)
+    np.testing.assert_array_equal(_merge(out["icetmask"], lay), f["icetmask"])
+
+
+def test_device_ice_strength(oracle, evp_lib):
+    """strength == NULL: ice_strength on the device.  exp() differs from glibc in the last
+    bits, so the comparison is by tolerance (relative 1e-12 on strength itself)."""
+    case = synth.make_case("om1deg", nx=64, ny=48, realistic=True)
+    st, f, strengths, _ = oracle_steps(oracle, case, nsteps=1)
+    lay = E.BlockLayout.single_block(64, 48)
+    dyn, out = cuda_steps(case, strengths=None)
+    assert relerr(_merge(out["strength"], lay), f["strength"]) <= 1e-12
+    _compare_tol(dyn, out, st, f, lay)
+
+
+@pytest.mark.parametrize("pover", [
+    dict(evp_damping=1),
+    dict(auscom=1, coupled=1, use_ocnslope=0, cosw=0.9063077870366499, sinw=0.42261826174069944),
+    dict(auscom=1, coupled=1, use_ocnslope=1),
+    dict(coupled=1),
+], ids=["evp_damping", "auscom-turning", "auscom-ocnslope", "coupled"])
+def test_namelist_and_cpp_variants(oracle, evp_lib, pover):
+    case = synth.make_case("om1deg", nx=48, ny=40)
+    rng = np.random.default_rng(5)
+    case.inputs["ss_tltx"][...] = 1e-6 * rng.standard_normal(case.inputs["ss_tltx"].shape)
+    case.inputs["ss_tlty"][...] = 1e-6 * rng.standard_normal(case.inputs["ss_tlty"].shape)
+    st, f, strengths, _ = oracle_steps(oracle, case, nsteps=1, **dict(pover))
+    lay = E.BlockLayout.single_block(48, 40)
+    cpar = {}
+    for k, v in pover.items():
+        cpar[{"auscom": "hemisphere_turning", "coupled": "coupled_tilt"}.get(k, k)] = v
+    want = OUT_CMP + (["sicemass"] if pover.get("auscom") else [])
+    dyn, out = cuda_steps(case, strengths=strengths, want=want + ["strength"], **cpar)
+    _compare_exact(dyn, out, st, f, lay, names_out=want)
+
+
+def test_principal_stress(oracle, evp_lib):
+    case = synth.make_case("om1deg", nx=48, ny=40)
+    st, f, strengths, _ = oracle_steps(oracle, case, nsteps=1)
+    lay = E.BlockLayout.single_block(48, 40)
+    dyn, out = cuda_steps(case, strengths=strengths, want=["prs_sig", "sig1", "sig2"])
+    s1, s2 = oracle.principal_stress(st["stressp_1"], st["stressm_1"], st["stress12_1"], f["prs_sig"])
+    np.testing.assert_array_equal(_merge(out["sig1"], lay), s1)
+    np.testing.assert_array_equal(_merge(out["sig2"], lay), s2)
+    g1, g2 = dyn.principal_stress(dyn.state["stressp_1"], dyn.state["stressm_1"], dyn.state["stress12_1"],
+                                  out["prs_sig"])
+    np.testing.assert_array_equal(_merge(g1, lay), s1)
+    np.testing.assert_array_equal(_merge(g2, lay), s2)
+
+
+def test_full_size_properties_om025(evp_lib):
+    """BASELINE metric size (1440 x 1080, tripole): size-independent properties instead of the
+    (slow) oracle: tripole symmetry, masked cells stay zero, unfused vs FMA within tolerance,
+    tiling invariance bit-exact, finite and plausible magnitudes."""
+    case = synth.make_case("om025", realistic=True)
+    nx, ny = 1440, 1080
+    lay = E.BlockLayout.single_block(nx, ny)
+    res = {}
+    for tag, par in (("a", dict(math_mode=0)), ("b", dict(math_mode=0, tile_threads=256, tile_rows=19)),
+                     ("c", dict(math_mode=1))):
+        dyn, out = cuda_steps(case, strengths=None, want=["strength", "divu", "prs_sig"], **par)
+        res[tag] = ({k: v[:, :, 0].copy() for k, v in dyn.state.items()}, out)
+        dyn.finalize()
+    sa, sb, sc = res["a"][0], res["b"][0], res["c"][0]
+    u = sa["uvel"]
+    assert np.isfinite(u).all() and 0.01 < np.abs(u).max() < 3.0
+    for i in range(1, nx // 2):
+        assert u[i, ny] == -u[nx - i, ny]
+    I = (slice(1, nx + 1), slice(1, ny + 1))
+    assert np.all(u[I][sa["iceumask"][I] == 0] == 0.0)
+    for n in STATE:
+        assert np.array_equal(sa[n], sb[n]), f"tiling changed {n}"
+    assert maxabs(sa["uvel"], sc["uvel"]) <= TOL_U and maxabs(sa["vvel"], sc["vvel"]) <= TOL_U
+    for n in STATE[2:14]:
+        assert relerr(sc[n], sa[n]) <= TOL_S, n
