@@ -245,9 +245,11 @@ void choose_tiling(evp_b200_handle *h) {
     int rows = h->par.tile_rows;
     if (rows <= 0) {
         // one wave: about (CTAs per SM) * SMs CTAs in total
-        const int per_sm = (nt == 256) ? 1 : (nt == 128 ? 2 : 4);
-        int target = per_sm * sms;
-        if ((h->par.kernel_variant & 1) == 1) target = target * 3 / 2; // no-prefetch build: fewer registers
+        // resident CTAs per SM by register use: 2 x 128 threads by default, 3 with the
+        // register-capped build (kernel_variant bit 1)
+        const bool tight = (h->par.kernel_variant & 2) != 0;
+        const int per_sm = (nt == 256) ? (tight ? 2 : 1) : (nt == 128 ? (tight ? 3 : 2) : (tight ? 6 : 4));
+        const int target = per_sm * sms;
         int ncy = target / ncx;
         if (ncy < 1) ncy = 1;
         rows = (nyl + ncy - 1) / ncy;

@@ -46,10 +46,12 @@ struct URow {
     bool act;
 };
 
+// `act` comes from a mask byte that was loaded one iteration earlier, so the data loads below
+// are issued without waiting on a dependent mask load.
 template <bool LAST>
-__device__ __forceinline__ void load_T(const SubArgs &a, TRow &t, int i, int j, bool colT) {
+__device__ __forceinline__ void load_T(const SubArgs &a, TRow &t, int i, int j, bool colT, bool act) {
     const size_t idx = (size_t)j * a.pitch + i;
-    t.act = colT && (__ldg(a.icetmask + idx) != 0);
+    t.act = act;
     if (colT) {
         t.u = __ldg(a.u_old + idx);
         t.v = __ldg(a.v_old + idx);
@@ -75,9 +77,9 @@ __device__ __forceinline__ void load_T(const SubArgs &a, TRow &t, int i, int j, 
     }
 }
 
-__device__ __forceinline__ void load_U(const SubArgs &a, URow &u, int i, int j, bool colU) {
+__device__ __forceinline__ void load_U(const SubArgs &a, URow &u, int i, int j, bool act) {
     const size_t idx = (size_t)j * a.pitch + i;
-    u.act = colU && (__ldg(a.iceumask + idx) != 0);
+    u.act = act;
     if (u.act) {
         u.aiu = __ldg(a.aiu + idx);
         u.uocn = __ldg(a.uocn + idx);
@@ -262,8 +264,8 @@ __device__ __forceinline__ void stepu_cell(const SubArgs &a, const URow &u, doub
     }
 }
 
-template <int NT, bool LAST, bool PREFETCH>
-__global__ void __launch_bounds__(NT) k_subcycle(const __grid_constant__ SubArgs a) {
+template <int NT, bool LAST, bool PREFETCH, int MINB>
+__global__ void __launch_bounds__(NT, MINB) k_subcycle(const __grid_constant__ SubArgs a) {
     __shared__ double xch[2][4][NT];
     const int tid = threadIdx.x;
     const int i = 1 + blockIdx.x * a.strip_w + tid;
@@ -282,18 +284,27 @@ __global__ void __launch_bounds__(NT) k_subcycle(const __grid_constant__ SubArgs
         vsw = __ldg(a.v_old + idx - 1);
     }
     double px = 0.0, s5c = 0.0, s7c = 0.0;
+    // mask bytes run two rows (T) / one row (U) ahead of the data they gate
+    const uint8_t *tmk = a.icetmask + (size_t)j0 * a.pitch + i;
+    const uint8_t *umk = a.iceumask + (size_t)j0 * a.pitch + i;
+    bool tm_next = colT && (j0 + 1 <= jlast) && (__ldg(tmk + a.pitch) != 0); // T row j0+1
+    bool um_cur = false;                                                      // U row j-1
     TRow t;
-    load_T<LAST>(a, t, i, j0, colT);
+    load_T<LAST>(a, t, i, j0, colT, colT && (__ldg(tmk) != 0));
     int par = 0;
 
     for (int j = j0; j <= jlast; ++j) {
         TRow tn;
         URow uc;
+        const bool tm_next2 = colT && (j + 2 <= jlast) && (__ldg(tmk + 2 * (size_t)a.pitch) != 0);
+        const bool um_next = colU && (j + 1 <= jlast) && (__ldg(umk) != 0); // U row j
+        tmk += a.pitch;
+        umk += a.pitch;
         if (PREFETCH) {
-            if (j < jlast) load_T<LAST>(a, tn, i, j + 1, colT);
+            if (j < jlast) load_T<LAST>(a, tn, i, j + 1, colT, tm_next);
         }
         uc.act = false;
-        if (j > j0) load_U(a, uc, i, j - 1, colU);
+        if (j > j0) load_U(a, uc, i, j - 1, um_cur);
 
         const size_t idx = (size_t)j * a.pitch + i;
         double str[8];
@@ -333,21 +344,25 @@ __global__ void __launch_bounds__(NT) k_subcycle(const __grid_constant__ SubArgs
         if (PREFETCH) {
             t = tn;
         } else {
-            if (j < jlast) load_T<LAST>(a, t, i, j + 1, colT);
+            if (j < jlast) load_T<LAST>(a, t, i, j + 1, colT, tm_next);
         }
+        tm_next = tm_next2;
+        um_cur = um_next;
     }
 }
 
-template <int NT>
+// variant bit 0: 1 = no register prefetch of the next T row; bit 1: 1 = cap registers for one
+// more resident CTA per SM (launch bounds)
+template <int NT, int MINB>
 static void launch_nt(const SubArgs &a, bool last, int variant, unsigned gx, unsigned gy, cudaStream_t s) {
     dim3 grid(gx, gy), block(NT);
     const bool prefetch = (variant & 1) == 0;
     if (last) {
-        if (prefetch) k_subcycle<NT, true, true><<<grid, block, 0, s>>>(a);
-        else k_subcycle<NT, true, false><<<grid, block, 0, s>>>(a);
+        if (prefetch) k_subcycle<NT, true, true, MINB><<<grid, block, 0, s>>>(a);
+        else k_subcycle<NT, true, false, MINB><<<grid, block, 0, s>>>(a);
     } else {
-        if (prefetch) k_subcycle<NT, false, true><<<grid, block, 0, s>>>(a);
-        else k_subcycle<NT, false, false><<<grid, block, 0, s>>>(a);
+        if (prefetch) k_subcycle<NT, false, true, MINB><<<grid, block, 0, s>>>(a);
+        else k_subcycle<NT, false, false, MINB><<<grid, block, 0, s>>>(a);
     }
 }
 
@@ -356,9 +371,19 @@ static void launch_nt(const SubArgs &a, bool last, int variant, unsigned gx, uns
 void EVP_SUB_LAUNCH(const SubArgs &a, bool last, int variant, int threads, unsigned grid_x,
                     unsigned grid_y, void *stream) {
     cudaStream_t s = (cudaStream_t)stream;
+    const bool tight = (variant & 2) != 0;
     switch (threads) {
-    case 64: EVP_SUB_NS::launch_nt<64>(a, last, variant, grid_x, grid_y, s); break;
-    case 256: EVP_SUB_NS::launch_nt<256>(a, last, variant, grid_x, grid_y, s); break;
-    default: EVP_SUB_NS::launch_nt<128>(a, last, variant, grid_x, grid_y, s); break;
+    case 64:
+        if (tight) EVP_SUB_NS::launch_nt<64, 6>(a, last, variant, grid_x, grid_y, s);
+        else EVP_SUB_NS::launch_nt<64, 1>(a, last, variant, grid_x, grid_y, s);
+        break;
+    case 256:
+        if (tight) EVP_SUB_NS::launch_nt<256, 2>(a, last, variant, grid_x, grid_y, s);
+        else EVP_SUB_NS::launch_nt<256, 1>(a, last, variant, grid_x, grid_y, s);
+        break;
+    default:
+        if (tight) EVP_SUB_NS::launch_nt<128, 3>(a, last, variant, grid_x, grid_y, s);
+        else EVP_SUB_NS::launch_nt<128, 1>(a, last, variant, grid_x, grid_y, s);
+        break;
     }
 }
