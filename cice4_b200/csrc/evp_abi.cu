@@ -3,6 +3,7 @@
 // There is no CPU fallback anywhere in this file: every compute entry needs a CUDA device.
 #include <cuda_runtime.h>
 #include <dlfcn.h>
+#include <nccl.h> // types only: libnccl.so.2 is dlopen()ed by evp_b200_comm_init, never linked
 
 #include <cmath>
 #include <cstdarg>
@@ -93,6 +94,16 @@ struct evp_b200_handle {
     std::unordered_map<const void *, size_t> pinned;
     int grid_x = 0, grid_y = 0, threads = 128, strip_w = 0, rows = 0;
     int sub_launches_per_loop = 0;
+    // y-slab chain: neighbour ranks (-1 = none) and the NCCL communicator (dlopen()ed entry points)
+    int north = -1, south = -1;
+    void *nccl_lib = nullptr;
+    ncclComm_t comm = nullptr;
+    ncclResult_t (*pGroupStart)() = nullptr;
+    ncclResult_t (*pGroupEnd)() = nullptr;
+    ncclResult_t (*pSend)(const void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*pRecv)(void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*pCommDestroy)(ncclComm_t) = nullptr;
+    const char *(*pGetErrorString)(ncclResult_t) = nullptr;
 };
 
 namespace {
@@ -156,6 +167,39 @@ enum {
     SL_STRENGTH, SL_U, SL_V, SL_S0, SL_OUT0 = SL_S0 + EVP_NSTRESS, SL_COUNT = SL_OUT0 + 20
 };
 
+// Slab-to-slab part of ice_HaloUpdate (replaces the MPI_ISEND/IRECV of mpi/ice_boundary.F90:1145-1215
+// between tasks): whole padded rows -- columns 0 and nx+1 already hold the east-west wrap, so the
+// corner cells travel with the row -- straight out of / into the planes, one grouped NCCL call for
+// all planes.  Row nyl -> north neighbour's row 0, row 1 -> south neighbour's row nyl+1.
+int exchange_rows(evp_b200_handle *h, void *const *planes, int n, size_t elem) {
+    if (h->dims.nranks == 1) return 0;
+    if (!h->comm) return fail(EVP_B200_ERR_STATE, "nranks > 1 but evp_b200_comm_init has not been called");
+    const PlaneGeom &pg = h->pg;
+    const size_t rowb = (size_t)pg.pitch * elem, cnt = (size_t)(pg.nx + 2) * elem;
+    ncclResult_t r = h->pGroupStart();
+    for (int k = 0; k < n && r == ncclSuccess; ++k) {
+        char *p = (char *)planes[k];
+        if (h->north >= 0) {
+            r = h->pSend(p + rowb * pg.nyl, cnt, ncclChar, h->north, h->comm, h->st);
+            if (r == ncclSuccess) r = h->pRecv(p + rowb * (pg.nyl + 1), cnt, ncclChar, h->north, h->comm, h->st);
+        }
+        if (h->south >= 0 && r == ncclSuccess) {
+            r = h->pSend(p + rowb, cnt, ncclChar, h->south, h->comm, h->st);
+            if (r == ncclSuccess) r = h->pRecv(p, cnt, ncclChar, h->south, h->comm, h->st);
+        }
+    }
+    ncclResult_t r2 = h->pGroupEnd();
+    if (r == ncclSuccess) r = r2;
+    if (r != ncclSuccess) return fail(EVP_B200_ERR_COMM, "NCCL row exchange failed: %s", h->pGetErrorString(r));
+    return 0;
+}
+
+int halo_r8(evp_b200_handle *h, double *plane, int loc, int isign) {
+    aux_halo_r8(h->pg, plane, loc, isign, h->st);
+    void *pp[1] = {plane};
+    return exchange_rows(h, pp, 1, sizeof(double));
+}
+
 void fill_subargs(evp_b200_handle *h, SubArgs &a, int cur) {
     double **p = h->pl;
     a.dxt = p[P_DXT]; a.dyt = p[P_DYT]; a.dxhy = p[P_DXHY]; a.dyhx = p[P_DYHX];
@@ -193,6 +237,11 @@ int launch_subcycle(evp_b200_handle *h, int cur, bool last) {
     if (h->pg.ns_cyclic) n += 2;
     if (h->pg.tripole) n += 1;
     aux_halo_uv_ns(h->pg, a.u_new, a.v_new, h->st);
+    if (h->dims.nranks > 1) {
+        void *pp[2] = {a.u_new, a.v_new};
+        if (exchange_rows(h, pp, 2, sizeof(double))) return -1;
+        n += 1;
+    }
     return n;
 }
 
@@ -203,12 +252,16 @@ int run_subcycle_loop(evp_b200_handle *h) {
         if (!h->graph_exec) {
             CU(cudaStreamBeginCapture(h->st, cudaStreamCaptureModeThreadLocal));
             int cur = 0, n = 0;
+            bool bad = false;
             for (int k = 1; k <= ndte; ++k) {
-                n += launch_subcycle(h, cur, k == ndte);
+                const int m = launch_subcycle(h, cur, k == ndte);
+                if (m < 0) bad = true;
+                n += m;
                 cur ^= 1;
             }
             h->sub_launches_per_loop = n;
             CU(cudaStreamEndCapture(h->st, &h->graph));
+            if (bad) return EVP_B200_ERR_COMM;
             CU(cudaGraphInstantiate(&h->graph_exec, h->graph, 0));
         }
         CU(cudaGraphLaunch(h->graph_exec, h->st));
@@ -216,7 +269,9 @@ int run_subcycle_loop(evp_b200_handle *h) {
     } else {
         int n = 0;
         for (int k = 1; k <= ndte; ++k) {
-            n += launch_subcycle(h, h->cur, k == ndte);
+            const int m = launch_subcycle(h, h->cur, k == ndte);
+            if (m < 0) return EVP_B200_ERR_COMM;
+            n += m;
             h->cur ^= 1;
         }
         h->sub_launches_per_loop = n;
@@ -305,9 +360,15 @@ int evp_b200_init(const evp_b200_dims *d, const evp_b200_params *p, const evp_b2
     if (d->ns_boundary > EVP_B200_BND_TRIPOLE || d->ew_boundary > EVP_B200_BND_CYCLIC || d->ew_boundary < 0 ||
         d->ns_boundary < 0)
         return fail(EVP_B200_ERR_UNSUPPORTED, "boundary type not supported (tripoleT is not implemented)");
-    if (d->nranks != 1 || d->rank != 0)
-        return fail(EVP_B200_ERR_UNSUPPORTED, "multi-rank slabs need evp_b200_comm_init (not in this build)");
-    if (d->slab_jlo != 1 || d->slab_jhi != d->ny_global) return fail(EVP_B200_ERR_ARG, "slab must span the domain when nranks == 1");
+    if (d->nranks < 1 || d->rank < 0 || d->rank >= d->nranks) return fail(EVP_B200_ERR_ARG, "bad rank/nranks");
+    if (d->slab_jlo < 1 || d->slab_jhi > d->ny_global || d->slab_jhi - d->slab_jlo + 1 < 2)
+        return fail(EVP_B200_ERR_ARG, "bad slab rows (each slab needs at least 2 rows)");
+    if (d->nranks == 1 && (d->slab_jlo != 1 || d->slab_jhi != d->ny_global))
+        return fail(EVP_B200_ERR_ARG, "slab must span the domain when nranks == 1");
+    if (d->nranks > 1 && d->ns_boundary == EVP_B200_BND_CYCLIC)
+        return fail(EVP_B200_ERR_UNSUPPORTED, "north-south cyclic domains are single-slab only");
+    if (d->nranks > 1 && ((d->rank == 0) != (d->slab_jlo == 1) || (d->rank == d->nranks - 1) != (d->slab_jhi == d->ny_global)))
+        return fail(EVP_B200_ERR_ARG, "slabs must be ordered south to north by rank");
     if (p->ndte < 1 || !(p->dt > 0.0)) return fail(EVP_B200_ERR_ARG, "bad dt/ndte");
     if (p->ncat < 1 || p->ncat > 16) return fail(EVP_B200_ERR_ARG, "ncat out of range");
     if (d->ns_boundary == EVP_B200_BND_TRIPOLE && d->nx_global + 2 > 8 * 1024)
@@ -378,7 +439,9 @@ int evp_b200_init(const evp_b200_dims *d, const evp_b200_params *p, const evp_b2
     pg.pitch = ((pg.nx + 2 + 15) / 16) * 16;
     pg.ew_cyclic = d->ew_boundary == EVP_B200_BND_CYCLIC;
     pg.ns_cyclic = d->ns_boundary == EVP_B200_BND_CYCLIC;
-    pg.tripole = d->ns_boundary == EVP_B200_BND_TRIPOLE;
+    pg.tripole = d->ns_boundary == EVP_B200_BND_TRIPOLE && d->rank == d->nranks - 1;
+    h->north = (d->rank < d->nranks - 1) ? d->rank + 1 : -1;
+    h->south = (d->rank > 0) ? d->rank - 1 : -1;
     pg.cells = (size_t)pg.pitch * (pg.nyl + 2);
     h->blocked_elems = (size_t)d->nx_block * d->ny_block * d->max_blocks;
 
@@ -478,10 +541,14 @@ static int do_prep(evp_b200_handle *h, const evp_b200_inputs *in, evp_b200_state
     aux_prep1(pg, a, h->st);                                             // :236-242
     aux_icetmask(pg, a, h->st);
     aux_halo_u8(pg, h->mk[M_ICETMASK], h->st);                           // :250-253
+    {
+        void *pp[1] = {h->mk[M_ICETMASK]};
+        if ((rc = exchange_rows(h, pp, 1, 1))) return rc;
+    }
     aux_to_ugrid(pg, p[P_TMASS], p[P_TAREA], p[P_UAREA], p[P_UMASS], h->st); // :259-260
     aux_to_ugrid(pg, p[P_AICE], p[P_TAREA], p[P_UAREA], p[P_AIU], h->st);
-    aux_halo_r8(pg, p[P_WRKX], 1, -1, h->st);                            // t2ugrid_vector, :276-277
-    aux_halo_r8(pg, p[P_WRKY], 1, -1, h->st);
+    if ((rc = halo_r8(h, p[P_WRKX], 1, -1))) return rc;                  // t2ugrid_vector, :276-277
+    if ((rc = halo_r8(h, p[P_WRKY], 1, -1))) return rc;
     aux_to_ugrid(pg, p[P_WRKX], p[P_TAREA], p[P_UAREA], p[P_STRAIRX], h->st);
     aux_to_ugrid(pg, p[P_WRKY], p[P_TAREA], p[P_UAREA], p[P_STRAIRY], h->st);
     aux_prep2(pg, a, h->st);                                             // :292-316
@@ -543,9 +610,9 @@ static int do_run(evp_b200_handle *h, const evp_b200_inputs *in, const double *s
         aux_ice_strength(pg, sa, h->st);
     }
     // ---- :336-344 ------------------------------------------------------------------------------
-    aux_halo_r8(pg, p[P_STRENGTH], 1, 1, h->st);
-    aux_halo_r8(pg, p[P_U0], 2, -1, h->st);
-    aux_halo_r8(pg, p[P_V0], 2, -1, h->st);
+    if ((rc = halo_r8(h, p[P_STRENGTH], 1, 1))) return rc;
+    if ((rc = halo_r8(h, p[P_U0], 2, -1))) return rc;
+    if ((rc = halo_r8(h, p[P_V0], 2, -1))) return rc;
     // second ping-pong copy: same ghost / masked-out values as copy 0; stresses outside the T list are 0
     CU(cudaMemcpyAsync(p[P_U1], p[P_U0], pbytes, cudaMemcpyDeviceToDevice, h->st));
     CU(cudaMemcpyAsync(p[P_V1], p[P_V0], pbytes, cudaMemcpyDeviceToDevice, h->st));
@@ -567,8 +634,8 @@ static int do_run(evp_b200_handle *h, const evp_b200_inputs *in, const double *s
     // work1 = strocnxT; HALO(work1); to_tgrid(work1, strocnxT): the ghosts of strocnxT keep the 0 of :1512
     CU(cudaMemsetAsync(p[P_STROCNXT], 0, pbytes, h->st));
     CU(cudaMemsetAsync(p[P_STROCNYT], 0, pbytes, h->st));
-    aux_halo_r8(pg, p[P_WRKX], 2, -1, h->st);
-    aux_halo_r8(pg, p[P_WRKY], 2, -1, h->st);
+    if ((rc = halo_r8(h, p[P_WRKX], 2, -1))) return rc;
+    if ((rc = halo_r8(h, p[P_WRKY], 2, -1))) return rc;
     aux_to_tgrid(pg, p[P_WRKX], p[P_TAREA], p[P_UAREA], p[P_STROCNXT], h->st);
     aux_to_tgrid(pg, p[P_WRKY], p[P_TAREA], p[P_UAREA], p[P_STROCNYT], h->st);
     if (out && (out->sig1 || out->sig2))
@@ -671,15 +738,50 @@ int evp_b200_get_timings(const evp_b200_handle *h, evp_b200_timings *t) {
     return 0;
 }
 
+static void *open_nccl() {
+    void *lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+    if (!lib) lib = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+    return lib;
+}
+
 int evp_b200_comm_unique_id(uint8_t id[128]) {
-    (void)id;
-    return fail(EVP_B200_ERR_UNSUPPORTED, "multi-rank exchange is not in this build");
+    if (!id) return fail(EVP_B200_ERR_ARG, "NULL argument");
+    void *lib = open_nccl();
+    if (!lib) return fail(EVP_B200_ERR_COMM, "cannot dlopen libnccl.so.2: %s", dlerror());
+    auto fn = (ncclResult_t(*)(ncclUniqueId *))dlsym(lib, "ncclGetUniqueId");
+    if (!fn) return fail(EVP_B200_ERR_COMM, "ncclGetUniqueId not found");
+    static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId is 128 bytes");
+    ncclUniqueId uid;
+    ncclResult_t r = fn(&uid);
+    if (r != ncclSuccess) return fail(EVP_B200_ERR_COMM, "ncclGetUniqueId failed (%d)", (int)r);
+    memcpy(id, &uid, 128);
+    return 0;
 }
 
 int evp_b200_comm_init(evp_b200_handle *h, const uint8_t id[128]) {
-    (void)h;
-    (void)id;
-    return fail(EVP_B200_ERR_UNSUPPORTED, "multi-rank exchange is not in this build");
+    if (!h || !id) return fail(EVP_B200_ERR_ARG, "NULL argument");
+    if (h->dims.nranks == 1) return 0;
+    if (h->comm) return 0;
+    CU(cudaSetDevice(h->device));
+    h->nccl_lib = open_nccl();
+    if (!h->nccl_lib) return fail(EVP_B200_ERR_COMM, "cannot dlopen libnccl.so.2: %s", dlerror());
+    auto initRank = (ncclResult_t(*)(ncclComm_t *, int, ncclUniqueId, int))dlsym(h->nccl_lib, "ncclCommInitRank");
+    h->pGroupStart = (ncclResult_t(*)())dlsym(h->nccl_lib, "ncclGroupStart");
+    h->pGroupEnd = (ncclResult_t(*)())dlsym(h->nccl_lib, "ncclGroupEnd");
+    h->pSend = (decltype(h->pSend))dlsym(h->nccl_lib, "ncclSend");
+    h->pRecv = (decltype(h->pRecv))dlsym(h->nccl_lib, "ncclRecv");
+    h->pCommDestroy = (decltype(h->pCommDestroy))dlsym(h->nccl_lib, "ncclCommDestroy");
+    h->pGetErrorString = (decltype(h->pGetErrorString))dlsym(h->nccl_lib, "ncclGetErrorString");
+    if (!initRank || !h->pGroupStart || !h->pGroupEnd || !h->pSend || !h->pRecv || !h->pCommDestroy || !h->pGetErrorString)
+        return fail(EVP_B200_ERR_COMM, "libnccl lacks a required entry point");
+    ncclUniqueId uid;
+    memcpy(&uid, id, 128);
+    ncclResult_t r = initRank(&h->comm, h->dims.nranks, uid, h->dims.rank);
+    if (r != ncclSuccess) {
+        h->comm = nullptr;
+        return fail(EVP_B200_ERR_COMM, "ncclCommInitRank failed: %s", h->pGetErrorString(r));
+    }
+    return 0;
 }
 
 int evp_b200_finalize(evp_b200_handle *h) {
@@ -687,6 +789,7 @@ int evp_b200_finalize(evp_b200_handle *h) {
     cudaSetDevice(h->device);
     if (h->st) cudaStreamSynchronize(h->st);
     for (auto &kv : h->pinned) cudaHostUnregister(const_cast<void *>(kv.first));
+    if (h->comm && h->pCommDestroy) h->pCommDestroy(h->comm);
     if (h->graph_exec) cudaGraphExecDestroy(h->graph_exec);
     if (h->graph) cudaGraphDestroy(h->graph);
     cudaFree(h->pool);

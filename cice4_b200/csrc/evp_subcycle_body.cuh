@@ -284,11 +284,13 @@ __global__ void __launch_bounds__(NT, MINB) k_subcycle(const __grid_constant__ S
         vsw = __ldg(a.v_old + idx - 1);
     }
     double px = 0.0, s5c = 0.0, s7c = 0.0;
-    // mask bytes run two rows (T) / one row (U) ahead of the data they gate
+    // Mask bytes run two rows (T) / one row (U) ahead of the data they gate and are kept RAW in a
+    // register: the compare that consumes a byte sits one iteration after its load, so no data load
+    // ever waits on a mask load.
     const uint8_t *tmk = a.icetmask + (size_t)j0 * a.pitch + i;
     const uint8_t *umk = a.iceumask + (size_t)j0 * a.pitch + i;
-    bool tm_next = colT && (j0 + 1 <= jlast) && (__ldg(tmk + a.pitch) != 0); // T row j0+1
-    bool um_cur = false;                                                      // U row j-1
+    unsigned tm_raw = (colT && j0 + 1 <= jlast) ? __ldg(tmk + a.pitch) : 0u; // T row j+1
+    unsigned um_raw = 0u;                                                     // U row j-1
     TRow t;
     load_T<LAST>(a, t, i, j0, colT, colT && (__ldg(tmk) != 0));
     int par = 0;
@@ -296,8 +298,10 @@ __global__ void __launch_bounds__(NT, MINB) k_subcycle(const __grid_constant__ S
     for (int j = j0; j <= jlast; ++j) {
         TRow tn;
         URow uc;
-        const bool tm_next2 = colT && (j + 2 <= jlast) && (__ldg(tmk + 2 * (size_t)a.pitch) != 0);
-        const bool um_next = colU && (j + 1 <= jlast) && (__ldg(umk) != 0); // U row j
+        const bool tm_next = tm_raw != 0u;
+        const bool um_cur = um_raw != 0u;
+        const unsigned tm_raw2 = (colT && j + 2 <= jlast) ? __ldg(tmk + 2 * (size_t)a.pitch) : 0u;
+        const unsigned um_raw1 = (colU && j + 1 <= jlast) ? __ldg(umk) : 0u; // U row j
         tmk += a.pitch;
         umk += a.pitch;
         if (PREFETCH) {
@@ -346,8 +350,8 @@ __global__ void __launch_bounds__(NT, MINB) k_subcycle(const __grid_constant__ S
         } else {
             if (j < jlast) load_T<LAST>(a, t, i, j + 1, colT, tm_next);
         }
-        tm_next = tm_next2;
-        um_cur = um_next;
+        tm_raw = tm_raw2;
+        um_raw = um_raw1;
     }
 }
 

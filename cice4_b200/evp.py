@@ -215,13 +215,17 @@ class IceDynEvp:
     """`module ice_dyn_evp` on one B200 (one y-slab)."""
 
     def __init__(self, layout: BlockLayout, ew_boundary: str = "cyclic", ns_boundary: str = "open",
-                 device: int = -1, **params):
+                 device: int = -1, rank: int = 0, nranks: int = 1, slab: Optional[Sequence[int]] = None,
+                 **params):
         # namelist / module variables, source/ice_dyn_evp.F90:64-97
         self.kdyn = 1
         self.yield_curve = "ellipse"
         self.layout = layout
         self.ew_boundary, self.ns_boundary = ew_boundary, ns_boundary
         self.device = device
+        # y-slab of the global domain owned by this rank (1-based inclusive rows), SURVEY 8(e)
+        self.rank, self.nranks = rank, nranks
+        self.slab = tuple(slab) if slab is not None else (1, layout.ny_global)
         self._param_over = dict(params)
         self.params: Optional[Params] = None
         self._h = C.c_void_p(None)
@@ -270,8 +274,8 @@ class IceDynEvp:
         d.ew_boundary, d.ns_boundary = BND[self.ew_boundary], BND[self.ns_boundary]
         d.ilo, d.ihi, d.jlo, d.jhi = _iptr(lay.ilo), _iptr(lay.ihi), _iptr(lay.jlo), _iptr(lay.jhi)
         d.iglob_lo, d.jglob_lo = _iptr(lay.iglob_lo), _iptr(lay.jglob_lo)
-        d.slab_jlo, d.slab_jhi = 1, lay.ny_global
-        d.rank, d.nranks, d.device = 0, 1, self.device
+        d.slab_jlo, d.slab_jhi = self.slab
+        d.rank, d.nranks, d.device = self.rank, self.nranks, self.device
         sf = StaticFields()
         keep = []
         for n in STATIC_D:
@@ -288,6 +292,21 @@ class IceDynEvp:
         for n in STATE_D:
             self.state[n][...] = 0.0
         self.state["iceumask"][...] = 0
+
+    # --- multi-GPU: NCCL communicator over the chain of y-slabs ---------------------------------
+    @staticmethod
+    def comm_unique_id() -> bytes:
+        """ncclUniqueId (128 bytes) made on rank 0; broadcast it with the host's own transport
+        (MPI_Bcast in the Fortran world, torch.distributed in the Python harness)."""
+        buf = (C.c_uint8 * 128)()
+        _check(load_library().evp_b200_comm_unique_id(buf))
+        return bytes(buf)
+
+    def comm_init(self, uid: bytes) -> None:
+        if not self._h:
+            raise EvpB200Error("init_evp has not been called")
+        buf = (C.c_uint8 * 128).from_buffer_copy(uid)
+        _check(load_library().evp_b200_comm_init(self._h, buf))
 
     def _as_block(self, a: np.ndarray, dtype) -> np.ndarray:
         sh = self.layout.shape
