@@ -148,6 +148,7 @@ def run_b200(args):
     import torch
     from cice4_b200 import build as B
     from cice4_b200 import evp as E
+    from cice4_b200 import slab, synth
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device (the b200 arm has no CPU fallback)")
     rank = int(os.environ.get("RANK", "0"))
@@ -155,36 +156,76 @@ def run_b200(args):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     if world != args.gpus:
         raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
-    if world > 1:
-        raise SystemExit("bench.py: multi-GPU slabs are not in this build")
     torch.cuda.set_device(local_rank)
-    B.build()
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    if rank == 0:
+        B.build()
+    if dist:
+        dist.barrier()
+
+    def allmax(x):
+        if not dist:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def allsum(x):
+        if not dist:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t.item())
+
+    def barrier():
+        torch.cuda.synchronize()
+        if dist:
+            dist.barrier()
+            torch.cuda.synchronize()
+
     case = build_case(args.workload, args.realistic)
     g = case.grid
     nx, ny, ndte = g.nx, g.ny, args.ndte
+    dt = synth.CONFIG_DT.get(case.name, 3600.0)
     ew = {v: k for k, v in E.BND.items()}[g.ew]
     ns = {v: k for k, v in E.BND.items()}[g.ns]
-    lay = E.BlockLayout.single_block(nx, ny)
-    dyn = E.IceDynEvp(lay, ew, ns, device=local_rank, ndte=ndte, math_mode=args.math_mode, pin_host=1,
-                      tile_threads=args.tile_threads, tile_rows=args.tile_rows, kernel_variant=args.variant)
+    # y-slab of this rank (strong scaling: the named grid is split over the GPUs)
+    lay = slab.slab_layout(nx, ny, world, rank)
+    rows = slab.layout_rows(lay)
+    dyn = E.IceDynEvp(lay, ew, ns, device=local_rank, rank=rank, nranks=world, slab=rows, ndte=ndte,
+                      math_mode=args.math_mode, pin_host=1, tile_threads=args.tile_threads,
+                      tile_rows=args.tile_rows, kernel_variant=args.variant)
     gf = {n: E.split_blocks(g.f[n], lay, ew, ns) for n in E.STATIC_D + E.STATIC_I}
-    dyn.init_evp(3600.0, gf)
+    dyn.init_evp(dt, gf)
+    if dist:
+        uid = torch.zeros(128, dtype=torch.uint8, device="cuda")
+        if rank == 0:
+            uid.copy_(torch.tensor(list(E.IceDynEvp.comm_unique_id()), dtype=torch.uint8))
+        dist.broadcast(uid, 0)
+        dyn.comm_init(bytes(uid.cpu().tolist()))
     inputs = {k: E.split_blocks(v, lay, ew, ns) for k, v in case.inputs.items()}
     want = [n for n in E.OUTPUT_D if n not in ("sig1", "sig2", "sicemass")]
     # cold start (iceumask = .false. => u = uocn), then warm calls are what is timed
-    out = dyn.evp(3600.0, inputs, strength=None, want=want)
+    out = dyn.evp(dt, inputs, strength=None, want=want)
     strength = out["strength"].copy(order="F")
-    out = dyn.evp(3600.0, inputs, strength=strength, want=want, two_phase=True)
-    icellt = int(E.merge_blocks(out["icetmask"], lay)[1:, 1:].sum())
-    icellu = int(dyn.state["iceumask"].sum())
+    out = dyn.evp(dt, inputs, strength=strength, want=want, two_phase=True)
+    nyl = rows[1] - rows[0] + 1
+    top = nyl + 2 if rank == world - 1 else nyl + 1        # the domain's north ghost row belongs to the last slab
+    icellt = int(allsum(float(out["icetmask"][1:, 1:top, 0].sum())))
+    icellu = int(allsum(float(dyn.state["iceumask"].sum())))
     bytes_per_sub = BYTES_T * icellt + BYTES_U * icellu
 
     # ---- device-resident subcycle loop: the headline value ---------------------------------------
     for _ in range(max(3, args.warmup)):
         dyn.subcycle_resident(1)
+    barrier()
     with ClockSampler(local_rank) as cs:
         t0 = time.perf_counter()
-        ms_loop = dyn.subcycle_resident(args.steps)
+        ms_loop = allmax(dyn.subcycle_resident(args.steps))
+        barrier()
         wall = time.perf_counter() - t0
         if wall < 1.5:   # give nvidia-smi a few samples under the same load (not part of the number)
             dyn.subcycle_resident(max(1, int(1.5 / max(ms_loop * 1e-3, 1e-4))))
@@ -193,46 +234,57 @@ def run_b200(args):
     value = nx * ny * ndte / (ms_loop * 1e-3)
     kernel_s = ms_loop * 1e-3 / ndte
     peak, peak_src = measured_peaks()
-    achieved = bytes_per_sub / kernel_s / 1e9
+    achieved = bytes_per_sub / kernel_s / 1e9        # whole job, all GPUs
 
     # ---- end to end through the public call, host buffers ----------------------------------------
     for _ in range(2):
-        dyn.evp(3600.0, inputs, strength=strength, want=want)
+        dyn.evp(dt, inputs, strength=strength, want=want)
+    barrier()
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        dyn.evp(3600.0, inputs, strength=strength, want=want)
-    e2e_s = (time.perf_counter() - t0) / args.steps
+        dyn.evp(dt, inputs, strength=strength, want=want)
+    barrier()
+    e2e_s = allmax((time.perf_counter() - t0) / args.steps)
     tme = dyn.timings()
     plane = lay.nx_block * lay.ny_block * lay.max_blocks
-    h2d = (7 + 14 + 1) * plane * 8 + plane * 4          # inputs + state + strength, iceumask
-    d2h = (14 + len(want)) * plane * 8 + plane * 4
+    h2d = int(allsum((7 + 14 + 1) * plane * 8 + plane * 4))          # inputs + state + strength, iceumask
+    d2h = int(allsum((14 + len(want)) * plane * 8 + plane * 4))
 
-    base, _, _ = cpu_baseline(case, ndte) if not args.no_cpu_baseline else ({"value": None}, 0, 0)
+    base = {"value": None}
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        base, _, _ = cpu_baseline(case, ndte)
     dyn.finalize()
+    if dist:
+        dist.barrier()
+        dist.destroy_process_group()
+    if rank != 0:
+        return
 
     line = {
-        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": 1, "steps": args.steps, "warmup": max(3, args.warmup),
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
         "ms_per_step": ms_loop, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"{case.name} {nx}x{ny} ndte={ndte} {'realistic' if args.realistic else 'dense'} mask, "
+        "config": {"workload": f"{case.name} {nx}x{ny} ndte={ndte} dt={dt:g}s {'realistic' if args.realistic else 'dense'} mask, "
                                f"ew={ew} ns={ns}, warm second call",
                    "step": "one ndte subcycle loop (stress+stepu+halo) on device-resident fields",
                    "active_T_cells": icellt, "active_U_cells": icellu,
-                   "l2": f"working set {bytes_per_sub / 1e6:.0f} MB per subcycle vs 126 MB L2: inputs larger than L2"
-                         if bytes_per_sub > 2.0e8 else "working set fits L2: effective bandwidth, latency-bound",
-                   "math_mode": "fma-contracted" if args.math_mode else "unfused (bit-exact vs oracle)",
+                   "l2": f"working set {bytes_per_sub / world / 1e6:.0f} MB per subcycle per GPU vs 126 MB L2: "
+                         + ("inputs larger than L2" if bytes_per_sub / world > 2.0e8 else
+                            "fits L2 -> effective bandwidth, latency-bound"),
+                   "math_mode": "fma-contracted (<=1e-10 of the unfused oracle)" if args.math_mode else "unfused (bit-exact vs oracle)",
                    "tile": {"threads": args.tile_threads, "rows": args.tile_rows, "variant": args.variant},
-                   "parallelism": "1 GPU"},
-        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": None, "peak_source": peak_src,
-                     "kernel": "k_subcycle (fused stress+stepu)", "kernel_us": kernel_s * 1e6,
-                     "algorithmic_bytes_per_launch": bytes_per_sub,
-                     "frac_of_nominal_8TBs": achieved / 8000.0},
+                   "parallelism": f"{world} y-slab(s), one process per GPU"
+                                  + (", NCCL row exchange every subcycle" if world > 1 else "")},
+        "roofline": {"bound": "hbm", "achieved": achieved / world, "peak": peak, "unit": "GB/s",
+                     "frac": achieved / world / peak, "traffic": None, "peak_source": peak_src,
+                     "per": "GPU", "kernel": "k_subcycle (fused stress+stepu)", "kernel_us": kernel_s * 1e6,
+                     "algorithmic_bytes_per_launch": bytes_per_sub / world,
+                     "frac_of_nominal_8TBs": achieved / world / 8000.0},
         "cpu_baseline": base,
         "e2e": {"value": nx * ny * ndte / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "ms_per_call": e2e_s * 1e3,
-                "device_breakdown_ms": {k: round(v, 3) for k, v in tme.items() if k.endswith("_ms")}},
-        "gpu_launches": int(tm["subcycle_launches"]) * args.steps,
+                "device_breakdown_ms_rank0": {k: round(v, 3) for k, v in tme.items() if k.endswith("_ms")}},
+        "gpu_launches": int(tm["subcycle_launches"]) * args.steps * world,
         "clocks": clocks,
     }
     print(json.dumps(line), flush=True)

@@ -382,6 +382,9 @@ int evp_b200_init(const evp_b200_dims *d, const evp_b200_params *p, const evp_b2
     evp_b200_handle *h = new evp_b200_handle();
     h->dims = *d;
     h->par = *p;
+    // NCCL send/recv inside a captured graph dead-locked on 2 x B200 (NCCL 2.28.9): multi-rank
+    // handles launch the subcycle loop on the stream instead
+    if (d->nranks > 1) h->par.use_graph = 0;
     if (d->device >= 0) {
         CU(cudaSetDevice(d->device));
         h->device = d->device;
@@ -456,6 +459,9 @@ int evp_b200_init(const evp_b200_dims *d, const evp_b200_params *p, const evp_b2
     h->n_stage = SL_COUNT;
     CU(cudaMalloc(&h->stage, sizeof(double) * h->blocked_elems * h->n_stage));
     CU(cudaMalloc(&h->stage_i, sizeof(int32_t) * h->blocked_elems * 2));
+    // padding cells of padded blocks / unused blocks are never written by the pack kernels: keep them 0
+    CU(cudaMemsetAsync(h->stage, 0, sizeof(double) * h->blocked_elems * h->n_stage, h->st));
+    CU(cudaMemsetAsync(h->stage_i, 0, sizeof(int32_t) * h->blocked_elems * 2, h->st));
     CU(cudaMalloc(&h->d_blk_tab, sizeof(int) * h->blk_tab.size()));
     CU(cudaMemcpyAsync(h->d_blk_tab, h->blk_tab.data(), sizeof(int) * h->blk_tab.size(), cudaMemcpyHostToDevice, h->st));
     h->bg.nx_block = d->nx_block;

@@ -333,8 +333,8 @@ class IceDynEvp:
         keep = []
         for n in INPUT_D:
             a = inputs.get(n)
-            if a is None:
-                continue
+            if a is None or (strength is not None and n in ("aice0", "aicen", "vicen")):
+                continue   # the category arrays feed only the device ice_strength
             if n in ("aicen", "vicen"):
                 if a.ndim == 3:
                     a = a.reshape(a.shape[0], a.shape[1], a.shape[2], 1, order="F")
@@ -351,8 +351,14 @@ class IceDynEvp:
         out = Outputs()
         res: Dict[str, np.ndarray] = {}
         for n in names:
-            res[n] = np.zeros(sh, order="F")
-            setattr(out, n, _dptr(res[n]))
+            # module arrays of ice_flux: allocated once and reused, like the Fortran module variables
+            # (their addresses stay stable, so the library pins them once)
+            a = self.flux.get(n)
+            if a is None or a.shape != sh:
+                a = np.zeros(sh, order="F")
+                self.flux[n] = a
+            res[n] = a
+            setattr(out, n, _dptr(a))
         sp = None
         if strength is not None:
             sarr = self._as_block(strength, np.float64)

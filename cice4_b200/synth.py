@@ -26,6 +26,13 @@ CONFIGS = {
 }
 
 
+# dynamics time step per config (s): the elastic subcycle dte = dt/ndte must shrink with the
+# grid spacing or the EVP iteration amplifies rounding noise (DESIGN.md "FMA contraction");
+# 1 deg and coarser use the reference's dt = 3600 s (input_templates/gx3/ice_in), 0.25 deg
+# dt = 1800 s and 0.1 deg dt = 600 s as the ACCESS-OM2 configurations of those grids do.
+CONFIG_DT = {"gx3": 3600.0, "gx1": 3600.0, "om1deg": 3600.0, "om025": 1800.0, "p01": 600.0}
+
+
 def hin_max(ncat: int = NCAT) -> np.ndarray:
     """Category bounds, kcatbound=0, kitd=1 (/root/reference/source/ice_itd.F90:162-186).
     Known answers: ice.log.Linux.LANL.coyote:185-190."""

@@ -188,7 +188,8 @@ def test_full_size_properties_om025(evp_lib):
     res = {}
     for tag, par in (("a", dict(math_mode=0)), ("b", dict(math_mode=0, tile_threads=256, tile_rows=19)),
                      ("c", dict(math_mode=1))):
-        dyn, out = cuda_steps(case, strengths=None, want=["strength", "divu", "prs_sig"], **par)
+        dyn, out = cuda_steps(case, strengths=None, want=["strength", "divu", "prs_sig"],
+                              dt=synth.CONFIG_DT["om025"], **par)
         res[tag] = ({k: v[:, :, 0].copy() for k, v in dyn.state.items()}, out)
         dyn.finalize()
     sa, sb, sc = res["a"][0], res["b"][0], res["c"][0]
