@@ -83,6 +83,19 @@ def lib(kind: str = "strict") -> C.CDLL:
         L.orc_halo_r8.argtypes = [c_dp, C.POINTER(OrcGrid), C.c_int, C.c_int, C.c_double]
         L.orc_halo_i4.argtypes = [c_ip, C.POINTER(OrcGrid), C.c_int, C.c_int, C.c_int32]
         L.orc_principal_stress.argtypes = [C.c_int, C.c_int, c_dp, c_dp, c_dp, c_dp, C.c_double, c_dp, c_dp]
+        # primitives, for the slab (multi-rank) restatement in tests/test_slab_gloo.py
+        G_, P_, F_ = C.POINTER(OrcGrid), C.POINTER(OrcParams), C.POINTER(OrcFields)
+        L.orc_evp_prep1.argtypes = [G_, P_, F_]
+        L.orc_evp_prep2.argtypes = [G_, P_, F_, c_ip, c_ip, c_ip, c_ip, c_ip, c_ip]
+        L.orc_ice_strength.argtypes = [G_, P_, F_, C.c_int32, c_ip, c_ip]
+        L.orc_stress.argtypes = [G_, P_, F_, C.c_int, C.c_int32, c_ip, c_ip, c_dp]
+        L.orc_stepu.argtypes = [G_, P_, F_, C.c_int32, c_ip, c_ip, c_dp]
+        L.orc_evp_finish.argtypes = [G_, P_, F_, C.c_int32, c_ip, c_ip]
+        L.orc_to_ugrid.argtypes = [G_, c_dp, c_dp, c_dp, c_dp]
+        L.orc_to_tgrid.argtypes = [G_, c_dp, c_dp, c_dp, c_dp]
+        for fn in ("orc_evp_prep1", "orc_evp_prep2", "orc_ice_strength", "orc_stress", "orc_stepu",
+                   "orc_evp_finish", "orc_to_ugrid", "orc_to_tgrid", "orc_halo_r8", "orc_halo_i4"):
+            getattr(L, fn).restype = None
         _libs[kind] = L
     return _libs[kind]
 

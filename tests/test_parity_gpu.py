@@ -204,3 +204,20 @@ def test_full_size_properties_om025(evp_lib):
     assert maxabs(sa["uvel"], sc["uvel"]) <= TOL_U and maxabs(sa["vvel"], sc["vvel"]) <= TOL_U
     for n in STATE[2:14]:
         assert relerr(sc[n], sa[n]) <= TOL_S, n
+
+
+def test_two_gpus_bit_exact_vs_oracle(evp_lib):
+    """y-slabs on 2 GPUs with the NCCL row exchange (skipped on a single-GPU box; run by hand with
+    `gpurun --gpus 2`, see tests/multigpu_parity.py)."""
+    import os
+    import subprocess
+    import sys
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+           "--master-addr", "127.0.0.1", "--master-port", "29533", os.path.join(root, "tests", "multigpu_parity.py"),
+           "--realistic"]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=240)
+    assert r.returncode == 0 and "BIT-EXACT" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
