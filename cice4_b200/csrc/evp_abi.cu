@@ -104,6 +104,13 @@ struct evp_b200_handle {
     ncclResult_t (*pRecv)(void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
     ncclResult_t (*pCommDestroy)(ncclComm_t) = nullptr;
     const char *(*pGetErrorString)(ncclResult_t) = nullptr;
+    // peer-to-peer halo (exchange_mode 0): neighbours' plane pools and sync blocks mapped via CUDA IPC
+    int *sync = nullptr;              // local sync block (64 ints): see SubArgs::sync
+    bool p2p = false;
+    double *peer_pool[2] = {nullptr, nullptr}; // [0] north, [1] south
+    int *peer_sync[2] = {nullptr, nullptr};
+    int peer_nyl[2] = {0, 0};
+    size_t peer_cells[2] = {0, 0};
 };
 
 namespace {
@@ -224,6 +231,24 @@ void fill_subargs(evp_b200_handle *h, SubArgs &a, int cur) {
     a.evp_damping = h->par.evp_damping; a.hemisphere_turning = h->par.hemisphere_turning;
     a.ecci = h->ecci; a.dte2T = h->dte2T; a.denom1 = h->denom1; a.denom2 = h->denom2; a.rcon = h->rcon;
     a.dragw = h->dragw; a.cosw = h->par.cosw; a.sinw = h->par.sinw;
+    a.peer_n_u = a.peer_n_v = a.peer_s_u = a.peer_s_v = nullptr;
+    a.peer_n_flag = a.peer_s_flag = nullptr;
+    a.sync = h->sync;
+    a.p2p = h->p2p ? 1 : 0;
+    if (h->p2p) {
+        const int pu = cur ? P_U0 : P_U1, pv = cur ? P_V0 : P_V1; // the neighbours' `new` copies
+        if (h->north >= 0) { // north neighbour's south ghost row = its row 0
+            a.peer_n_u = h->peer_pool[0] + (size_t)pu * h->peer_cells[0];
+            a.peer_n_v = h->peer_pool[0] + (size_t)pv * h->peer_cells[0];
+            a.peer_n_flag = h->peer_sync[0] + 3;
+        }
+        if (h->south >= 0) { // south neighbour's north ghost row = its row nyl+1
+            const size_t off = (size_t)(h->peer_nyl[1] + 1) * h->pg.pitch;
+            a.peer_s_u = h->peer_pool[1] + (size_t)pu * h->peer_cells[1] + off;
+            a.peer_s_v = h->peer_pool[1] + (size_t)pv * h->peer_cells[1] + off;
+            a.peer_s_flag = h->peer_sync[1] + 2;
+        }
+    }
 }
 
 // one subcycle: fused stress+stepu (+ east-west halo), then the north-south part of
@@ -237,7 +262,7 @@ int launch_subcycle(evp_b200_handle *h, int cur, bool last) {
     if (h->pg.ns_cyclic) n += 2;
     if (h->pg.tripole) n += 1;
     aux_halo_uv_ns(h->pg, a.u_new, a.v_new, h->st);
-    if (h->dims.nranks > 1) {
+    if (h->dims.nranks > 1 && !h->p2p) {
         void *pp[2] = {a.u_new, a.v_new};
         if (exchange_rows(h, pp, 2, sizeof(double))) return -1;
         n += 1;
@@ -248,7 +273,10 @@ int launch_subcycle(evp_b200_handle *h, int cur, bool last) {
 int run_subcycle_loop(evp_b200_handle *h) {
     const int ndte = h->par.ndte;
     if (h->cur != 0) return fail(EVP_B200_ERR_STATE, "subcycle loop must start from state copy 0");
-    if (h->par.use_graph) {
+    // NCCL send/recv inside a captured graph dead-locked on 2 x B200 (NCCL 2.28.9): with the NCCL
+    // exchange the loop is launched on the stream; the peer-to-peer exchange has no host calls
+    const bool graph_ok = h->par.use_graph && (h->dims.nranks == 1 || h->p2p);
+    if (graph_ok) {
         if (!h->graph_exec) {
             CU(cudaStreamBeginCapture(h->st, cudaStreamCaptureModeThreadLocal));
             int cur = 0, n = 0;
@@ -277,6 +305,9 @@ int run_subcycle_loop(evp_b200_handle *h) {
         h->sub_launches_per_loop = n;
     }
     CU(cudaGetLastError());
+    // peer-to-peer halo: the ghost rows of the final copy are complete once both neighbours have
+    // published the epoch of their last subcycle kernel
+    if (h->p2p) aux_wait_peers(h->sync, h->north >= 0, h->south >= 0, h->st);
     if (h->cur != 0) { // odd ndte: bring the result back to copy 0 so the next loop starts there
         const size_t bytes = h->pg.cells * sizeof(double);
         CU(cudaMemcpyAsync(h->pl[P_U0], h->pl[P_U1], bytes, cudaMemcpyDeviceToDevice, h->st));
@@ -382,9 +413,6 @@ int evp_b200_init(const evp_b200_dims *d, const evp_b200_params *p, const evp_b2
     evp_b200_handle *h = new evp_b200_handle();
     h->dims = *d;
     h->par = *p;
-    // NCCL send/recv inside a captured graph dead-locked on 2 x B200 (NCCL 2.28.9): multi-rank
-    // handles launch the subcycle loop on the stream instead
-    if (d->nranks > 1) h->par.use_graph = 0;
     if (d->device >= 0) {
         CU(cudaSetDevice(d->device));
         h->device = d->device;
@@ -462,6 +490,8 @@ int evp_b200_init(const evp_b200_dims *d, const evp_b200_params *p, const evp_b2
     // padding cells of padded blocks / unused blocks are never written by the pack kernels: keep them 0
     CU(cudaMemsetAsync(h->stage, 0, sizeof(double) * h->blocked_elems * h->n_stage, h->st));
     CU(cudaMemsetAsync(h->stage_i, 0, sizeof(int32_t) * h->blocked_elems * 2, h->st));
+    CU(cudaMalloc(&h->sync, sizeof(int) * 64));
+    CU(cudaMemsetAsync(h->sync, 0, sizeof(int) * 64, h->st));
     CU(cudaMalloc(&h->d_blk_tab, sizeof(int) * h->blk_tab.size()));
     CU(cudaMemcpyAsync(h->d_blk_tab, h->blk_tab.data(), sizeof(int) * h->blk_tab.size(), cudaMemcpyHostToDevice, h->st));
     h->bg.nx_block = d->nx_block;
@@ -623,6 +653,12 @@ static int do_run(evp_b200_handle *h, const evp_b200_inputs *in, const double *s
     CU(cudaMemcpyAsync(p[P_U1], p[P_U0], pbytes, cudaMemcpyDeviceToDevice, h->st));
     CU(cudaMemcpyAsync(p[P_V1], p[P_V0], pbytes, cudaMemcpyDeviceToDevice, h->st));
     CU(cudaMemsetAsync(p[P_S1], 0, pbytes * EVP_NSTRESS, h->st));
+    if (h->p2p) {
+        // the neighbours store into the ghost rows of copy 1 from their first subcycle kernel on:
+        // exchanging those rows once more (same values) orders their stores after the copy above
+        void *pp[2] = {p[P_U1], p[P_V1]};
+        if ((rc = exchange_rows(h, pp, 2, sizeof(double)))) return rc;
+    }
     h->cur = 0;
     CU(cudaEventRecord(h->ev[3], h->st));
     // ---- :347-404 ------------------------------------------------------------------------------
@@ -685,6 +721,7 @@ static int do_run(evp_b200_handle *h, const evp_b200_inputs *in, const double *s
     CU(cudaEventElapsedTime(&h->tm.download_ms, h->ev[5], h->ev[6]));
     CU(cudaEventElapsedTime(&h->tm.total_ms, h->ev[0], h->ev[6]));
     h->tm.subcycle_launches = h->sub_launches_per_loop;
+    h->tm.exchange_mode_used = h->dims.nranks == 1 ? -1 : (h->p2p ? 0 : 1);
     h->prepared = false;
     return 0;
 }
@@ -787,6 +824,53 @@ int evp_b200_comm_init(evp_b200_handle *h, const uint8_t id[128]) {
         h->comm = nullptr;
         return fail(EVP_B200_ERR_COMM, "ncclCommInitRank failed: %s", h->pGetErrorString(r));
     }
+    if (h->par.exchange_mode == 0) {
+        // Peer-to-peer halo: swap CUDA IPC handles of the plane pool and the sync block with both
+        // neighbours (through the communicator just made), map them, and let the subcycle kernel
+        // store its boundary rows straight into the neighbours' ghost rows.
+        struct PeerInfo {
+            cudaIpcMemHandle_t pool, sync;
+            int nyl, pitch;
+            unsigned long long cells;
+        } mine, theirs[2];
+        memset(&mine, 0, sizeof(mine));
+        memset(theirs, 0, sizeof(theirs));
+        CU(cudaIpcGetMemHandle(&mine.pool, h->pool));
+        CU(cudaIpcGetMemHandle(&mine.sync, h->sync));
+        mine.nyl = h->pg.nyl;
+        mine.pitch = h->pg.pitch;
+        mine.cells = h->pg.cells;
+        char *d = nullptr;
+        CU(cudaMalloc(&d, 3 * sizeof(PeerInfo)));
+        CU(cudaMemcpyAsync(d, &mine, sizeof(PeerInfo), cudaMemcpyHostToDevice, h->st));
+        ncclResult_t q = h->pGroupStart();
+        const int nb[2] = {h->north, h->south};
+        for (int k = 0; k < 2 && q == ncclSuccess; ++k)
+            if (nb[k] >= 0) {
+                q = h->pSend(d, sizeof(PeerInfo), ncclChar, nb[k], h->comm, h->st);
+                if (q == ncclSuccess) q = h->pRecv(d + (k + 1) * sizeof(PeerInfo), sizeof(PeerInfo), ncclChar, nb[k], h->comm, h->st);
+            }
+        ncclResult_t q2 = h->pGroupEnd();
+        if (q == ncclSuccess) q = q2;
+        if (q != ncclSuccess) return fail(EVP_B200_ERR_COMM, "IPC handle exchange failed: %s", h->pGetErrorString(q));
+        CU(cudaMemcpyAsync(theirs, d + sizeof(PeerInfo), 2 * sizeof(PeerInfo), cudaMemcpyDeviceToHost, h->st));
+        CU(cudaStreamSynchronize(h->st));
+        cudaFree(d);
+        bool ok = true;
+        for (int k = 0; k < 2 && ok; ++k)
+            if (nb[k] >= 0) {
+                if (theirs[k].pitch != h->pg.pitch) ok = false;
+                void *pp = nullptr, *ps = nullptr;
+                if (ok && cudaIpcOpenMemHandle(&pp, theirs[k].pool, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) ok = false;
+                if (ok && cudaIpcOpenMemHandle(&ps, theirs[k].sync, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) ok = false;
+                h->peer_pool[k] = (double *)pp;
+                h->peer_sync[k] = (int *)ps;
+                h->peer_nyl[k] = theirs[k].nyl;
+                h->peer_cells[k] = (size_t)theirs[k].cells;
+            }
+        cudaGetLastError();
+        h->p2p = ok;   // on failure the NCCL exchange stays in use (evp_b200_get_timings reports the mode)
+    }
     return 0;
 }
 
@@ -795,6 +879,11 @@ int evp_b200_finalize(evp_b200_handle *h) {
     cudaSetDevice(h->device);
     if (h->st) cudaStreamSynchronize(h->st);
     for (auto &kv : h->pinned) cudaHostUnregister(const_cast<void *>(kv.first));
+    for (int k = 0; k < 2; ++k) {
+        if (h->peer_pool[k]) cudaIpcCloseMemHandle(h->peer_pool[k]);
+        if (h->peer_sync[k]) cudaIpcCloseMemHandle(h->peer_sync[k]);
+    }
+    cudaFree(h->sync);
     if (h->comm && h->pCommDestroy) h->pCommDestroy(h->comm);
     if (h->graph_exec) cudaGraphExecDestroy(h->graph_exec);
     if (h->graph) cudaGraphDestroy(h->graph);

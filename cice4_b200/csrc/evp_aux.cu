@@ -414,6 +414,15 @@ __global__ void k_ice_strength(PlaneGeom pg, StrengthArgs a) {
     a.strength[idx] = result;
 }
 
+__global__ void k_wait_peers(int *sync, int has_north, int has_south) {
+    const int e = *(volatile int *)(sync + 1);
+    if (has_north)
+        while (*(volatile int *)(sync + 2) < e) __nanosleep(50);
+    if (has_south)
+        while (*(volatile int *)(sync + 3) < e) __nanosleep(50);
+    __threadfence_system();
+}
+
 } // namespace
 
 // ---------------------------------------------------------------------------------------------
@@ -488,4 +497,7 @@ void aux_principal_stress(size_t n, const double *sp1, const double *sm1, const 
 void aux_ice_strength(const PlaneGeom &pg, const StrengthArgs &a, cudaStream_t s) {
     dim3 grid(nblk(pg.nx + 2), pg.nyl + 2);
     k_ice_strength<<<grid, TPB, 0, s>>>(pg, a);
+}
+void aux_wait_peers(int *sync, int has_north, int has_south, cudaStream_t s) {
+    k_wait_peers<<<1, 1, 0, s>>>(sync, has_north, has_south);
 }

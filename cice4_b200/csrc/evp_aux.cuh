@@ -90,3 +90,6 @@ struct StrengthArgs {
     double mu_rdg, puny, gravit, rhow, rhoi;
 };
 void aux_ice_strength(const PlaneGeom &pg, const StrengthArgs &a, cudaStream_t s); // ice_mechred.F90:1869-2036
+
+// spin until both neighbours have published at least this rank's epoch (see SubArgs::sync)
+void aux_wait_peers(int *sync, int has_north, int has_south, cudaStream_t s);

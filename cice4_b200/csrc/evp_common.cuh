@@ -33,6 +33,15 @@ struct SubArgs {
     int rows;      // U rows marched per CTA
     int evp_damping, hemisphere_turning;
     double ecci, dte2T, denom1, denom2, rcon, dragw, cosw, sinw;
+    // ---- multi-rank peer-to-peer velocity halo (exchange_mode 0); all null/0 on one rank -------
+    // ghost rows of the neighbours' u_new/v_new planes, mapped through CUDA IPC:
+    // peer_n_* = row 0 of the north neighbour, peer_s_* = row nyl+1 of the south neighbour
+    double *peer_n_u, *peer_n_v, *peer_s_u, *peer_s_v;
+    // sync block in local memory: [0] CTAs finished (counter), [1] subcycle kernels completed on this
+    // rank (epoch), [2] epoch published by the north neighbour, [3] by the south neighbour
+    int *sync;
+    int *peer_n_flag, *peer_s_flag; // where this rank publishes its epoch: north's sync[3], south's sync[2]
+    int p2p;                         // 1 = the above are in use
 };
 
 typedef void (*subcycle_launch_fn)(const SubArgs &a, bool last, int variant, int threads,

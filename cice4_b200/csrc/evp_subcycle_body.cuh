@@ -226,7 +226,7 @@ __device__ __forceinline__ void stress_cell(const SubArgs &a, const TRow &t, dou
 // source/ice_dyn_evp.F90:1386-1441 for one U cell; sx, sy are the two str sums of :1415-1418
 template <bool LAST>
 __device__ __forceinline__ void stepu_cell(const SubArgs &a, const URow &u, double uold, double vold,
-                                           double sx, double sy, int i, size_t idx) {
+                                           double sx, double sy, int i, int j, size_t idx) {
     const double du = u.uocn - uold, dv = u.vocn - vold;
     const double vrel = u.aiu * a.dragw * sqrt(du * du + dv * dv); // :1394
     const double taux = vrel * u.waterx;                            // :1397-1398
@@ -256,6 +256,25 @@ __device__ __forceinline__ void stepu_cell(const SubArgs &a, const URow &u, doub
             a.v_new[idx + a.nx] = vnew;
         }
     }
+    if (a.p2p) {
+        // slab-to-slab part of the halo update: the top / bottom physical row goes straight into the
+        // neighbour GPU's ghost row over NVLink (whole padded row: the wrap columns travel with it)
+        double *pu = nullptr, *pv = nullptr;
+        if (j == a.nyl && a.peer_n_u) { pu = a.peer_n_u; pv = a.peer_n_v; }
+        if (j == 1 && a.peer_s_u) {
+            if (pu) { // one-row slab: both neighbours
+                pu[i] = unew; pv[i] = vnew;
+                if (a.ew_cyclic && i == a.nx) { pu[0] = unew; pv[0] = vnew; }
+                if (a.ew_cyclic && i == 1) { pu[a.nx + 1] = unew; pv[a.nx + 1] = vnew; }
+            }
+            pu = a.peer_s_u; pv = a.peer_s_v;
+        }
+        if (pu) {
+            pu[i] = unew; pv[i] = vnew;
+            if (a.ew_cyclic && i == a.nx) { pu[0] = unew; pv[0] = vnew; }
+            if (a.ew_cyclic && i == 1) { pu[a.nx + 1] = unew; pv[a.nx + 1] = vnew; }
+        }
+    }
     if (LAST) { // only the last subcycle's values are observable (:1415-1418,:1434-1435)
         a.strintx[idx] = strintx;
         a.strinty[idx] = strinty;
@@ -269,7 +288,29 @@ __global__ void __launch_bounds__(NT, MINB) k_subcycle(const __grid_constant__ S
     __shared__ double xch[2][4][NT];
     const int tid = threadIdx.x;
     const int i = 1 + blockIdx.x * a.strip_w + tid;
-    const int j0 = 1 + blockIdx.y * a.rows;
+    // Row chunks are issued boundary-first: blockIdx.y 0 -> southernmost chunk, 1 -> northernmost, the
+    // interior after them, so that with the peer-to-peer halo the rows the neighbours wait for are
+    // produced first and the wait for the neighbours' rows overlaps with nothing else pending.
+    int chunk = blockIdx.y;
+    if (gridDim.y > 1) chunk = (blockIdx.y == 0) ? 0 : (blockIdx.y == 1 ? (int)gridDim.y - 1 : (int)blockIdx.y - 1);
+    const int j0 = 1 + chunk * a.rows;
+    if (a.p2p) {
+        // Before reading the ghost rows the neighbours stored during their previous subcycle kernel,
+        // and before storing into their ghost rows of the buffer they read during that kernel, wait
+        // until they have published at least as many completed subcycles as this rank has.
+        const bool top = (chunk == (int)gridDim.y - 1), bot = (chunk == 0);
+        if ((top && a.peer_n_flag) || (bot && a.peer_s_flag)) {
+            if (tid == 0) {
+                const int e = *(volatile int *)(a.sync + 1);
+                if (top && a.peer_n_flag)
+                    while (*(volatile int *)(a.sync + 2) < e) __nanosleep(20);
+                if (bot && a.peer_s_flag)
+                    while (*(volatile int *)(a.sync + 3) < e) __nanosleep(20);
+                __threadfence_system();
+            }
+            __syncthreads();
+        }
+    }
     const int jlast = min(j0 + a.rows, a.nyl + 1); // last T row of this CTA
     const bool colT = (tid <= a.strip_w) && (i <= a.nx + 1);
     const bool colU = (tid < a.strip_w) && (i <= a.nx);
@@ -336,7 +377,7 @@ __global__ void __launch_bounds__(NT, MINB) k_subcycle(const __grid_constant__ S
         if (uc.act) {
             const double sx = px + str[2] + s4r;          // ((s1 + s2) + s3) + s4
             const double sy = s5c + str[5] + s7c + s8r;    // ((s5 + s6) + s7) + s8
-            stepu_cell<LAST>(a, uc, us, vs, sx, sy, i, idx - a.pitch);
+            stepu_cell<LAST>(a, uc, us, vs, sx, sy, i, j - 1, idx - a.pitch);
         }
         px = str[0] + s2r;
         s5c = str[4];
@@ -352,6 +393,24 @@ __global__ void __launch_bounds__(NT, MINB) k_subcycle(const __grid_constant__ S
         }
         tm_raw = tm_raw2;
         um_raw = um_raw1;
+    }
+    if (a.p2p) {
+        // Publish completion: every CTA makes its (peer) stores visible system-wide, the last one to
+        // finish bumps this rank's epoch and writes it into both neighbours' sync blocks.
+        __syncthreads();
+        if (tid == 0) {
+            __threadfence_system();
+            const unsigned total = gridDim.x * gridDim.y;
+            const unsigned prev = atomicAdd((unsigned *)a.sync, 1u);
+            if (prev == total - 1) {
+                a.sync[0] = 0;
+                const int e = a.sync[1] + 1;
+                a.sync[1] = e;
+                __threadfence_system();
+                if (a.peer_n_flag) *(volatile int *)a.peer_n_flag = e;
+                if (a.peer_s_flag) *(volatile int *)a.peer_s_flag = e;
+            }
+        }
     }
 }
 

@@ -59,7 +59,8 @@ class Params(C.Structure):
                 ("kstrength", C.c_int32), ("krdg_partic", C.c_int32), ("krdg_redist", C.c_int32),
                 ("ncat", C.c_int32), ("mu_rdg", C.c_double),
                 ("math_mode", C.c_int32), ("pin_host", C.c_int32), ("use_graph", C.c_int32),
-                ("tile_threads", C.c_int32), ("tile_rows", C.c_int32), ("kernel_variant", C.c_int32)]
+                ("tile_threads", C.c_int32), ("tile_rows", C.c_int32), ("kernel_variant", C.c_int32),
+                ("exchange_mode", C.c_int32)]
 
 
 STATIC_D = ["dxt", "dyt", "dxhy", "dyhx", "cxp", "cyp", "cxm", "cym",
@@ -95,7 +96,8 @@ class Outputs(C.Structure):
 class Timings(C.Structure):
     _fields_ = [(n, C.c_float) for n in ("upload_ms", "prep_ms", "subcycle_ms", "finish_ms",
                                          "download_ms", "total_ms")] + \
-               [("kernel_launches", C.c_int32), ("subcycle_launches", C.c_int32)]
+               [("kernel_launches", C.c_int32), ("subcycle_launches", C.c_int32),
+                ("exchange_mode_used", C.c_int32), ("reserved", C.c_int32)]
 
 
 _lib: Optional[C.CDLL] = None

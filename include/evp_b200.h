@@ -94,6 +94,9 @@ typedef struct {
     int32_t tile_threads;   /* 0 = default; threads per CTA of the subcycle kernel */
     int32_t tile_rows;      /* 0 = default; U rows marched per CTA */
     int32_t kernel_variant; /* 0 = default */
+    int32_t exchange_mode;  /* multi-rank velocity halo inside the ndte loop: 0 = peer-to-peer stores from the
+                               subcycle kernel into the neighbour's ghost rows (CUDA IPC over NVLink, flags for
+                               ordering), 1 = NCCL send/recv after every subcycle */
 } evp_b200_params;
 
 /* module ice_grid arrays read by evp (source/ice_grid.F90:58-85,114-123) + fcor_blk
@@ -139,6 +142,8 @@ typedef struct {
     float upload_ms, prep_ms, subcycle_ms, finish_ms, download_ms, total_ms;
     int32_t kernel_launches;   /* kernels launched (graph nodes count) in the last call */
     int32_t subcycle_launches; /* of which inside the ndte loop */
+    int32_t exchange_mode_used; /* multi-rank: 0 = peer-to-peer stores, 1 = NCCL per subcycle; -1 = single rank */
+    int32_t reserved;
 } evp_b200_timings;
 
 typedef struct evp_b200_handle evp_b200_handle;

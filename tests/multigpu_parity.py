@@ -33,6 +33,7 @@ def main():
     ap.add_argument("--realistic", action="store_true")
     ap.add_argument("--math-mode", type=int, default=0)
     ap.add_argument("--use-graph", type=int, default=1)
+    ap.add_argument("--exchange-mode", type=int, default=0)
     ap.add_argument("--blocks", default="", help="bx,by: reference block layout regrouped into slabs")
     args = ap.parse_args()
 
@@ -58,7 +59,7 @@ def main():
     rows = slab.layout_rows(lay)
 
     dyn = E.IceDynEvp(lay, ew, ns, device=local, rank=rank, nranks=world, slab=rows, ndte=args.ndte,
-                      math_mode=args.math_mode, use_graph=args.use_graph)
+                      math_mode=args.math_mode, use_graph=args.use_graph, exchange_mode=args.exchange_mode)
     gf = {n: E.split_blocks(g.f[n], lay, ew, ns) for n in E.STATIC_D + E.STATIC_I}
     dyn.init_evp(3600.0, gf)
     uid = torch.zeros(128, dtype=torch.uint8, device="cuda")
@@ -104,7 +105,8 @@ def main():
                 ok = False
                 print(f"MISMATCH {n}: max abs diff {np.abs(full[I] - ref[I]).max():.3e}")
         print(f"multigpu_parity: world={world} {args.case} {nx}x{ny} steps={args.steps} blocks='{args.blocks}' "
-              f"graph={args.use_graph}: {'BIT-EXACT vs oracle' if ok else 'FAILED'}; "
+              f"graph={args.use_graph} exchange_mode_used={dyn.timings()['exchange_mode_used']}: "
+              f"{'BIT-EXACT vs oracle' if ok else 'FAILED'}; "
               f"resident loop {ms:.3f} ms on rank 0", flush=True)
     flag = torch.tensor([1 if ok else 0], device="cuda")
     dist.broadcast(flag, 0)

@@ -45,7 +45,7 @@ def test_struct_sizes_match_header():
     assert C.sizeof(E.Inputs) == 12 * 8
     assert C.sizeof(E.State) == 15 * 8
     assert C.sizeof(E.Outputs) == 20 * 8
-    assert C.sizeof(E.Timings) == 8 * 4
+    assert C.sizeof(E.Timings) == 10 * 4
 
 
 def test_bad_arguments_are_rejected(evp_lib):
