@@ -106,6 +106,8 @@ struct evp_b200_handle {
     const char *(*pGetErrorString)(ncclResult_t) = nullptr;
     // peer-to-peer halo (exchange_mode 0): neighbours' plane pools and sync blocks mapped via CUDA IPC
     int *sync = nullptr;              // local sync block (64 ints): see SubArgs::sync
+    double *fold_scratch = nullptr;   // 2 * pitch doubles
+    bool fold_in_kernel = false;      // tripole fold done by the subcycle kernel (else k_halo_tripole)
     bool p2p = false;
     double *peer_pool[2] = {nullptr, nullptr}; // [0] north, [1] south
     int *peer_sync[2] = {nullptr, nullptr};
@@ -231,6 +233,8 @@ void fill_subargs(evp_b200_handle *h, SubArgs &a, int cur) {
     a.evp_damping = h->par.evp_damping; a.hemisphere_turning = h->par.hemisphere_turning;
     a.ecci = h->ecci; a.dte2T = h->dte2T; a.denom1 = h->denom1; a.denom2 = h->denom2; a.rcon = h->rcon;
     a.dragw = h->dragw; a.cosw = h->par.cosw; a.sinw = h->par.sinw;
+    a.fold = h->fold_in_kernel ? 1 : 0;
+    a.fold_scratch = h->fold_scratch;
     a.peer_n_u = a.peer_n_v = a.peer_s_u = a.peer_s_v = nullptr;
     a.peer_n_flag = a.peer_s_flag = nullptr;
     a.sync = h->sync;
@@ -260,8 +264,8 @@ int launch_subcycle(evp_b200_handle *h, int cur, bool last) {
     fn(a, last, h->par.kernel_variant, h->threads, (unsigned)h->grid_x, (unsigned)h->grid_y, (void *)h->st);
     int n = 1;
     if (h->pg.ns_cyclic) n += 2;
-    if (h->pg.tripole) n += 1;
-    aux_halo_uv_ns(h->pg, a.u_new, a.v_new, h->st);
+    if (h->pg.tripole && !h->fold_in_kernel) n += 1;
+    if (!h->fold_in_kernel) aux_halo_uv_ns(h->pg, a.u_new, a.v_new, h->st);
     if (h->dims.nranks > 1 && !h->p2p) {
         void *pp[2] = {a.u_new, a.v_new};
         if (exchange_rows(h, pp, 2, sizeof(double))) return -1;
@@ -339,6 +343,11 @@ void choose_tiling(evp_b200_handle *h) {
         int ncy = target / ncx;
         if (ncy < 1) ncy = 1;
         rows = (nyl + ncy - 1) / ncy;
+        if (h->pg.tripole && ncy > 1 && (h->par.kernel_variant & 4) == 0) {
+            // in-kernel tripole fold: give the northernmost chunk about half the rows of the others
+            // so that its CTAs finish early and the fold overlaps with the rest of the grid
+            rows = (int)((2.0 * nyl) / (2.0 * ncy - 1.0) + 0.999);
+        }
         if (rows < 4) rows = 4;
     }
     if (rows > nyl) rows = nyl;
@@ -347,6 +356,9 @@ void choose_tiling(evp_b200_handle *h) {
     h->rows = rows;
     h->grid_x = ncx;
     h->grid_y = (nyl + rows - 1) / rows;
+    // in-kernel tripole fold needs rows nyl-1 and nyl in the northernmost chunk
+    const int last_rows = nyl - (h->grid_y - 1) * rows;
+    h->fold_in_kernel = h->pg.tripole && last_rows >= 2 && (h->par.kernel_variant & 4) == 0;
 }
 
 } // namespace
@@ -490,6 +502,7 @@ int evp_b200_init(const evp_b200_dims *d, const evp_b200_params *p, const evp_b2
     // padding cells of padded blocks / unused blocks are never written by the pack kernels: keep them 0
     CU(cudaMemsetAsync(h->stage, 0, sizeof(double) * h->blocked_elems * h->n_stage, h->st));
     CU(cudaMemsetAsync(h->stage_i, 0, sizeof(int32_t) * h->blocked_elems * 2, h->st));
+    CU(cudaMalloc(&h->fold_scratch, sizeof(double) * 2 * pg.pitch));
     CU(cudaMalloc(&h->sync, sizeof(int) * 64));
     CU(cudaMemsetAsync(h->sync, 0, sizeof(int) * 64, h->st));
     CU(cudaMalloc(&h->d_blk_tab, sizeof(int) * h->blk_tab.size()));
@@ -884,6 +897,7 @@ int evp_b200_finalize(evp_b200_handle *h) {
         if (h->peer_sync[k]) cudaIpcCloseMemHandle(h->peer_sync[k]);
     }
     cudaFree(h->sync);
+    cudaFree(h->fold_scratch);
     if (h->comm && h->pCommDestroy) h->pCommDestroy(h->comm);
     if (h->graph_exec) cudaGraphExecDestroy(h->graph_exec);
     if (h->graph) cudaGraphDestroy(h->graph);

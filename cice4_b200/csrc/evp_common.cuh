@@ -42,7 +42,32 @@ struct SubArgs {
     int *sync;
     int *peer_n_flag, *peer_s_flag; // where this rank publishes its epoch: north's sync[3], south's sync[2]
     int p2p;                         // 1 = the above are in use
+    // ---- tripole u-fold of u_new/v_new inside the kernel (top slab only) ------------------------
+    int fold;              // 1 = the last CTA of the northernmost chunk to finish applies the fold
+    double *fold_scratch;  // 2 * pitch doubles: copy of the raw top physical row of u_new, v_new
 };
+
+// Tripole u-fold of a NE-corner vector field (serial/ice_boundary.F90:777-800 symmetrisation,
+// :837-866 copy-out) for plane column i in [0, nx+1]: `top` is the raw top physical row (row nyl),
+// `below` row nyl-1.  Returns the new values of rows nyl (vtop) and nyl+1 (vghost).
+__host__ __device__ inline void evp_fold_necorner(const double *top, const double *below, int i, int nx,
+                                                  int ew_cyclic, double isign, double &vtop, double &vghost) {
+    int ig = i; // i_glob of the column (source/ice_blocks.F90:291-330)
+    if (i == 0) ig = ew_cyclic ? nx : 1;
+    if (i == nx + 1) ig = ew_cyclic ? 1 : nx;
+    int k = nx - ig; // iSrc = nxGlobal - i_glob + 1 - ioffset, ioffset = 1
+    if (k == 0) k = nx;
+    double x;
+    if (k >= 1 && k <= nx / 2 - 1) {
+        x = 0.5 * (top[k] + isign * top[nx - k]);
+    } else if (k >= nx - (nx / 2 - 1) && k <= nx - 1) {
+        x = isign * (0.5 * (top[nx - k] + isign * top[k])); // partner of the loop index i = nx - k
+    } else {
+        x = top[k];
+    }
+    vtop = isign * x;          // j=1: row jhi   <- isign*buf(iSrc, 2)
+    vghost = isign * below[k]; // j=2: row jhi+1 <- isign*buf(iSrc, 1)
+}
 
 typedef void (*subcycle_launch_fn)(const SubArgs &a, bool last, int variant, int threads,
                                    unsigned grid_x, unsigned grid_y, void *stream);

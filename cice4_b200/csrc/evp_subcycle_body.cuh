@@ -394,6 +394,76 @@ __global__ void __launch_bounds__(NT, MINB) k_subcycle(const __grid_constant__ S
         tm_raw = tm_raw2;
         um_raw = um_raw1;
     }
+    if (a.fold && chunk == (int)gridDim.y - 1) {
+        // Tripole u-fold (north-south part of the halo update on the top slab): the CTAs of the
+        // northernmost chunk hold rows nyl-1 and nyl; the last of them to finish symmetrises the
+        // top row and fills the ghost row for the whole width.  The raw top row goes through a
+        // scratch copy because the update is in place.
+        __shared__ int is_last;
+        __syncthreads();
+        if (tid == 0) {
+            __threadfence();
+            is_last = (atomicAdd((unsigned *)a.sync + 4, 1u) == gridDim.x - 1) ? 1 : 0;
+        }
+        __syncthreads();
+        if (is_last) {
+            __threadfence();
+            const size_t rtop = (size_t)a.nyl * a.pitch;
+            const int ncol = a.nx + 2;
+            // raw top row of u_new and v_new -> scratch (independent loads, issued in batches)
+            for (int c0 = 0; c0 < 2 * ncol; c0 += 4 * NT) {
+                double val[4];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const int c = c0 + q * NT + tid;
+                    if (c < 2 * ncol) {
+                        const int f = c >= ncol, cc = f ? c - ncol : c;
+                        val[q] = __ldcg((f ? a.v_new : a.u_new) + rtop + cc);
+                    }
+                }
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const int c = c0 + q * NT + tid;
+                    if (c < 2 * ncol) {
+                        const int f = c >= ncol, cc = f ? c - ncol : c;
+                        a.fold_scratch[(size_t)f * a.pitch + cc] = val[q];
+                    }
+                }
+            }
+            __syncthreads();
+            for (int c0 = 0; c0 < 2 * ncol; c0 += 4 * NT) {
+                double vt[4], vg[4];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const int c = c0 + q * NT + tid;
+                    if (c < 2 * ncol) {
+                        const int f = c >= ncol, cc = f ? c - ncol : c;
+                        const double *fld = f ? a.v_new : a.u_new;
+                        int ig = cc;
+                        if (cc == 0) ig = a.ew_cyclic ? a.nx : 1;
+                        if (cc == a.nx + 1) ig = a.ew_cyclic ? 1 : a.nx;
+                        int k = a.nx - ig;
+                        if (k == 0) k = a.nx;
+                        const double *scr = a.fold_scratch + (size_t)f * a.pitch;
+                        double dummy;
+                        evp_fold_necorner(scr, scr, cc, a.nx, a.ew_cyclic, -1.0, vt[q], dummy);
+                        vg[q] = -__ldcg(fld + rtop - a.pitch + k);
+                    }
+                }
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const int c = c0 + q * NT + tid;
+                    if (c < 2 * ncol) {
+                        const int f = c >= ncol, cc = f ? c - ncol : c;
+                        double *fld = f ? a.v_new : a.u_new;
+                        fld[rtop + cc] = vt[q];
+                        fld[rtop + a.pitch + cc] = vg[q];
+                    }
+                }
+            }
+            if (tid == 0) a.sync[4] = 0;
+        }
+    }
     if (a.p2p) {
         // Publish completion: every CTA makes its (peer) stores visible system-wide, the last one to
         // finish bumps this rank's epoch and writes it into both neighbours' sync blocks.
