@@ -198,7 +198,7 @@ def run_b200(args):
     dyn = E.IceDynEvp(lay, ew, ns, device=local_rank, rank=rank, nranks=world, slab=rows, ndte=ndte,
                       math_mode=args.math_mode, pin_host=1, tile_threads=args.tile_threads,
                       tile_rows=args.tile_rows, kernel_variant=args.variant)
-    gf = {n: E.split_blocks(g.f[n], lay, ew, ns) for n in E.STATIC_D + E.STATIC_I}
+    gf = E.grid_fields_in_blocks(g, lay, ew, ns)
     dyn.init_evp(dt, gf)
     if dist:
         uid = torch.zeros(128, dtype=torch.uint8, device="cuda")
@@ -299,7 +299,7 @@ def main():
     ap.add_argument("--workload", default="om025")
     ap.add_argument("--realistic", action="store_true")
     ap.add_argument("--ndte", type=int, default=120)
-    ap.add_argument("--math-mode", type=int, default=1)
+    ap.add_argument("--math-mode", type=int, default=0)
     ap.add_argument("--tile-threads", type=int, default=0)
     ap.add_argument("--tile-rows", type=int, default=0)
     ap.add_argument("--variant", type=int, default=0)

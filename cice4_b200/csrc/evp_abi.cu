@@ -8,6 +8,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <unordered_map>
@@ -43,7 +44,7 @@ int fail(int code, const char *fmt, ...) {
 enum PlaneId {
     // static grid
     P_DXT, P_DYT, P_DXHY, P_DYHX, P_CXP, P_CYP, P_CXM, P_CYM, P_TAREA, P_TAREAR, P_TINYAREA,
-    P_UAREA, P_UAREAR, P_FCOR,
+    P_UAREA, P_UAREAR, P_FCOR, P_HTE, P_HTN,
     // inputs
     P_AICE, P_VICE, P_VSNO, P_UOCN, P_VOCN, P_SSTLTX, P_SSTLTY, P_AICE0,
     // scratch (locals of evp, :170-178) and work1 of ice_work
@@ -106,6 +107,8 @@ struct evp_b200_handle {
     const char *(*pGetErrorString)(ncclResult_t) = nullptr;
     // peer-to-peer halo (exchange_mode 0): neighbours' plane pools and sync blocks mapped via CUDA IPC
     int *sync = nullptr;              // local sync block (64 ints): see SubArgs::sync
+    uint8_t *row_ht = nullptr;        // per-row flag of the 2-plane metric path (nullptr = off)
+    int rows_ht = 0;                  // rows on which it is active
     double *fold_scratch = nullptr;   // 2 * pitch doubles
     bool fold_in_kernel = false;      // tripole fold done by the subcycle kernel (else k_halo_tripole)
     bool p2p = false;
@@ -231,6 +234,10 @@ void fill_subargs(evp_b200_handle *h, SubArgs &a, int cur) {
     a.ew_cyclic = h->pg.ew_cyclic;
     a.strip_w = h->strip_w; a.rows = h->rows;
     a.evp_damping = h->par.evp_damping; a.hemisphere_turning = h->par.hemisphere_turning;
+    a.hte = p[P_HTE]; a.htn = p[P_HTN];
+    // the 2-plane metric path is opt-in (kernel_variant bit 4): it removes 6 of 48 words of DRAM
+    // traffic but the kernel is not purely bandwidth-bound, so it does not run faster
+    a.row_ht = (h->par.kernel_variant & 16) ? h->row_ht : nullptr;
     a.ecci = h->ecci; a.dte2T = h->dte2T; a.denom1 = h->denom1; a.denom2 = h->denom2; a.rcon = h->rcon;
     a.dragw = h->dragw; a.cosw = h->par.cosw; a.sinw = h->par.sinw;
     a.fold = h->fold_in_kernel ? 1 : 0;
@@ -327,7 +334,8 @@ void choose_tiling(evp_b200_handle *h) {
     int sms = 148;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device);
     const int nx = h->pg.nx, nyl = h->pg.nyl;
-    int nt = h->par.tile_threads > 0 ? h->par.tile_threads : 128;
+    // default: 128 threads per CTA; short slabs (multi-GPU) run better with one 256-thread CTA per SM
+    int nt = h->par.tile_threads > 0 ? h->par.tile_threads : (nyl <= 300 ? 256 : 128);
     if (nt != 64 && nt != 128 && nt != 256) nt = 128;
     // balanced strips: ncx strips of strip_w U columns, strip_w + 1 <= nt threads hold T columns
     const int ncx = (nx + (nt - 1) - 1) / (nt - 1);
@@ -335,10 +343,8 @@ void choose_tiling(evp_b200_handle *h) {
     int rows = h->par.tile_rows;
     if (rows <= 0) {
         // one wave: about (CTAs per SM) * SMs CTAs in total
-        // resident CTAs per SM by register use: 2 x 128 threads by default, 3 with the
-        // register-capped build (kernel_variant bit 1)
-        const bool tight = (h->par.kernel_variant & 2) != 0;
-        const int per_sm = (nt == 256) ? (tight ? 2 : 1) : (nt == 128 ? (tight ? 3 : 2) : (tight ? 6 : 4));
+        // resident CTAs per SM at ~227 registers per thread: 256 threads
+        const int per_sm = (nt == 256) ? 1 : (nt == 128 ? 2 : 4);
         const int target = per_sm * sms;
         int ncy = target / ncx;
         if (ncy < 1) ncy = 1;
@@ -486,6 +492,15 @@ int evp_b200_init(const evp_b200_dims *d, const evp_b200_params *p, const evp_b2
     h->north = (d->rank < d->nranks - 1) ? d->rank + 1 : -1;
     h->south = (d->rank > 0) ? d->rank - 1 : -1;
     pg.cells = (size_t)pg.pitch * (pg.nyl + 2);
+    // Plane spacing: consecutive planes are streamed concurrently by the subcycle kernel (~40 of
+    // them); a spacing that is a multiple of 4 KiB puts all streams on the same L2 slice / HBM
+    // channel phase.  Skew the spacing by an odd number of 256-byte segments.
+    {
+        long skew = 1 * 32 + 0; // doubles
+        if (const char *e = getenv("EVP_B200_PLANE_SKEW")) skew = atol(e);
+        if (skew < 0) skew = 0;
+        pg.cells += (size_t)skew;
+    }
     h->blocked_elems = (size_t)d->nx_block * d->ny_block * d->max_blocks;
 
     CU(cudaStreamCreateWithFlags(&h->st, cudaStreamNonBlocking));
@@ -524,6 +539,23 @@ int evp_b200_init(const evp_b200_dims *d, const evp_b200_params *p, const evp_b2
     }
     int rc = upload_mask(h, g->tmask, 0, h->mk[M_TMASK]);
     if (!rc) rc = upload_mask(h, g->umask, 1, h->mk[M_UMASK]);
+    if (!rc && g->HTE && g->HTN) {
+        rc = upload_r8(h, g->HTE, slot++, h->pl[P_HTE]);
+        if (!rc) rc = upload_r8(h, g->HTN, slot++, h->pl[P_HTN]);
+        if (!rc) {
+            CU(cudaMalloc(&h->row_ht, pg.nyl + 2));
+            MetricCheckArgs mc;
+            mc.hte = h->pl[P_HTE]; mc.htn = h->pl[P_HTN];
+            mc.dxt = h->pl[P_DXT]; mc.dyt = h->pl[P_DYT]; mc.dxhy = h->pl[P_DXHY]; mc.dyhx = h->pl[P_DYHX];
+            mc.cxp = h->pl[P_CXP]; mc.cyp = h->pl[P_CYP]; mc.cxm = h->pl[P_CXM]; mc.cym = h->pl[P_CYM];
+            mc.tmask = h->mk[M_TMASK]; mc.row_ht = h->row_ht;
+            aux_check_metrics(pg, mc, h->st);
+            std::vector<uint8_t> flags(pg.nyl + 2);
+            CU(cudaMemcpyAsync(flags.data(), h->row_ht, pg.nyl + 2, cudaMemcpyDeviceToHost, h->st));
+            CU(cudaStreamSynchronize(h->st));
+            for (uint8_t f : flags) h->rows_ht += f ? 1 : 0;
+        }
+    }
     if (rc) { evp_b200_finalize(h); return rc; }
     CU(cudaStreamSynchronize(h->st));
     choose_tiling(h);
@@ -735,6 +767,7 @@ static int do_run(evp_b200_handle *h, const evp_b200_inputs *in, const double *s
     CU(cudaEventElapsedTime(&h->tm.total_ms, h->ev[0], h->ev[6]));
     h->tm.subcycle_launches = h->sub_launches_per_loop;
     h->tm.exchange_mode_used = h->dims.nranks == 1 ? -1 : (h->p2p ? 0 : 1);
+    h->tm.reserved = h->rows_ht; // rows on the 2-plane metric path
     h->prepared = false;
     return 0;
 }
@@ -898,6 +931,7 @@ int evp_b200_finalize(evp_b200_handle *h) {
     }
     cudaFree(h->sync);
     cudaFree(h->fold_scratch);
+    cudaFree(h->row_ht);
     if (h->comm && h->pCommDestroy) h->pCommDestroy(h->comm);
     if (h->graph_exec) cudaGraphExecDestroy(h->graph_exec);
     if (h->graph) cudaGraphDestroy(h->graph);

@@ -414,6 +414,28 @@ __global__ void k_ice_strength(PlaneGeom pg, StrengthArgs a) {
     a.strength[idx] = result;
 }
 
+// one CTA per row: any mismatching ocean cell clears the row's flag
+__global__ void k_check_metrics(PlaneGeom pg, MetricCheckArgs a) {
+    const int j = blockIdx.x; // 0..nyl+1
+    __shared__ int bad;
+    if (threadIdx.x == 0) bad = (j < 1) ? 1 : 0;
+    __syncthreads();
+    if (j >= 1) {
+        for (int i = 1 + threadIdx.x; i <= pg.nx + 1; i += blockDim.x) {
+            const size_t idx = (size_t)j * pg.pitch + i;
+            if (!a.tmask[idx]) continue;
+            const double hte = a.hte[idx], htew = a.hte[idx - 1], htn = a.htn[idx], htns = a.htn[idx - pg.pitch];
+            const bool ok = (a.cyp[idx] == 1.5 * hte - 0.5 * htew) && (a.cxp[idx] == 1.5 * htn - 0.5 * htns) &&
+                            (a.cym[idx] == -(1.5 * htew - 0.5 * hte)) && (a.cxm[idx] == -(1.5 * htns - 0.5 * htn)) &&
+                            (a.dxhy[idx] == 0.5 * (hte - htew)) && (a.dyhx[idx] == 0.5 * (htn - htns)) &&
+                            (a.dxt[idx] == 0.5 * (htn + htns)) && (a.dyt[idx] == 0.5 * (hte + htew));
+            if (!ok) bad = 1;
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) a.row_ht[j] = bad ? 0 : 1;
+}
+
 __global__ void k_wait_peers(int *sync, int has_north, int has_south) {
     const int e = *(volatile int *)(sync + 1);
     if (has_north)
@@ -500,4 +522,7 @@ void aux_ice_strength(const PlaneGeom &pg, const StrengthArgs &a, cudaStream_t s
 }
 void aux_wait_peers(int *sync, int has_north, int has_south, cudaStream_t s) {
     k_wait_peers<<<1, 1, 0, s>>>(sync, has_north, has_south);
+}
+void aux_check_metrics(const PlaneGeom &pg, const MetricCheckArgs &a, cudaStream_t s) {
+    k_check_metrics<<<pg.nyl + 2, 256, 0, s>>>(pg, a);
 }

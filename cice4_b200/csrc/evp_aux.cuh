@@ -93,3 +93,12 @@ void aux_ice_strength(const PlaneGeom &pg, const StrengthArgs &a, cudaStream_t s
 
 // spin until both neighbours have published at least this rank's epoch (see SubArgs::sync)
 void aux_wait_peers(int *sync, int has_north, int has_south, cudaStream_t s);
+
+// row_ht[j] = 1 iff on every ocean T cell (tmask) of row j, columns 1..nx+1, the eight metric planes
+// equal the init_grid2 formulas applied to HTE/HTN bit for bit (rows 1..nyl+1; others 0)
+struct MetricCheckArgs {
+    const double *hte, *htn, *dxt, *dyt, *dxhy, *dyhx, *cxp, *cyp, *cxm, *cym;
+    const uint8_t *tmask;
+    uint8_t *row_ht;
+};
+void aux_check_metrics(const PlaneGeom &pg, const MetricCheckArgs &a, cudaStream_t s);

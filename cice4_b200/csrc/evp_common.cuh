@@ -32,6 +32,10 @@ struct SubArgs {
     int strip_w;   // U columns produced per CTA (threads 0..strip_w hold T columns)
     int rows;      // U rows marched per CTA
     int evp_damping, hemisphere_turning;
+    // 2-plane metric path: on rows where row_ht[j] != 0 the eight metrics are re-derived from the
+    // primary cell widths with the (unfused) init_grid2 formulas instead of being loaded
+    const double *hte, *htn;
+    const uint8_t *row_ht;
     double ecci, dte2T, denom1, denom2, rcon, dragw, cosw, sinw;
     // ---- multi-rank peer-to-peer velocity halo (exchange_mode 0); all null/0 on one rank -------
     // ghost rows of the neighbours' u_new/v_new planes, mapped through CUDA IPC:

@@ -23,8 +23,11 @@
 //     CTA above and the T column east of the strip are recomputed redundantly from `old` values,
 //     exactly like the reference's redundant N/E ghost-cell stresses (:846-859), so results do
 //     not depend on the tiling;
-//   * loads for T row j+1 are issued before the arithmetic of row j (software prefetch), the
-//     U-row loads before the stress arithmetic whose result they are combined with.
+//   * loads for T row j+1 are issued before the arithmetic of row j (software prefetch in
+//     registers), the U-row loads before the stress arithmetic whose result they are combined with;
+//     mask bytes run one more row ahead.  The load sequences are branch-free on purpose: a run-time
+//     branch between them cost 30 % (measured), and staging through shared memory with cp.async
+//     (12 instead of 8 warps per SM) was 50 % slower.
 //
 // Algorithmic traffic per active cell and subcycle: 12+12 stresses, 2+2 velocities, strength +
 // 9 T metrics, 10 U fields = 48 fp64 words = 384 B (+2 mask bytes).
@@ -39,7 +42,25 @@ struct TRow {
     double strength, dxt, dyt, dxhy, dyhx, cxp, cyp, cxm, cym, tiny, tarear;
     double u, v, uw, vw;
     bool act;
+    bool ht; // cyp/cym/cxp/cxm hold raw HTE(i,j), HTE(i-1,j), HTN(i,j), HTN(i,j-1): derive before use
 };
+
+// init_grid2 (source/ice_grid.F90:350-361) and primary_grid_lengths (:1196,:1280) for one T cell,
+// with explicitly unfused arithmetic so that the values equal the host-computed module arrays.
+template <bool HT>
+__device__ __forceinline__ void derive_metrics(TRow &t) {
+    if (!HT || !t.ht) return;
+    const double hte = t.cyp, htew = t.cym, htn = t.cxp, htns = t.cxm;
+    t.cyp = __dsub_rn(__dmul_rn(1.5, hte), __dmul_rn(0.5, htew));
+    t.cxp = __dsub_rn(__dmul_rn(1.5, htn), __dmul_rn(0.5, htns));
+    t.cym = -__dsub_rn(__dmul_rn(1.5, htew), __dmul_rn(0.5, hte));
+    t.cxm = -__dsub_rn(__dmul_rn(1.5, htns), __dmul_rn(0.5, htn));
+    t.dxhy = __dmul_rn(0.5, __dsub_rn(hte, htew));
+    t.dyhx = __dmul_rn(0.5, __dsub_rn(htn, htns));
+    t.dxt = __dmul_rn(0.5, __dadd_rn(htn, htns));
+    t.dyt = __dmul_rn(0.5, __dadd_rn(hte, htew));
+    t.ht = false;
+}
 
 struct URow {
     double aiu, uocn, vocn, waterx, watery, forcex, forcey, umassdtei, fm, uarear;
@@ -48,7 +69,7 @@ struct URow {
 
 // `act` comes from a mask byte that was loaded one iteration earlier, so the data loads below
 // are issued without waiting on a dependent mask load.
-template <bool LAST>
+template <bool LAST, bool HT>
 __device__ __forceinline__ void load_T(const SubArgs &a, TRow &t, int i, int j, bool colT, bool act) {
     const size_t idx = (size_t)j * a.pitch + i;
     t.act = act;
@@ -60,18 +81,27 @@ __device__ __forceinline__ void load_T(const SubArgs &a, TRow &t, int i, int j, 
     } else {
         t.u = t.v = t.uw = t.vw = 0.0;
     }
+    t.ht = false;
     if (t.act) {
 #pragma unroll
         for (int k = 0; k < EVP_NSTRESS; ++k) t.s[k] = __ldg(a.s_old[k] + idx);
         t.strength = __ldg(a.strength + idx);
-        t.dxt = __ldg(a.dxt + idx);
-        t.dyt = __ldg(a.dyt + idx);
-        t.dxhy = __ldg(a.dxhy + idx);
-        t.dyhx = __ldg(a.dyhx + idx);
-        t.cxp = __ldg(a.cxp + idx);
-        t.cyp = __ldg(a.cyp + idx);
-        t.cxm = __ldg(a.cxm + idx);
-        t.cym = __ldg(a.cym + idx);
+        if (HT && __ldg(a.row_ht + j)) { // uniform per row
+            t.ht = true;
+            t.cyp = __ldg(a.hte + idx);
+            t.cym = __ldg(a.hte + idx - 1);
+            t.cxp = __ldg(a.htn + idx);
+            t.cxm = __ldg(a.htn + idx - a.pitch);
+        } else {
+            t.dxt = __ldg(a.dxt + idx);
+            t.dyt = __ldg(a.dyt + idx);
+            t.dxhy = __ldg(a.dxhy + idx);
+            t.dyhx = __ldg(a.dyhx + idx);
+            t.cxp = __ldg(a.cxp + idx);
+            t.cyp = __ldg(a.cyp + idx);
+            t.cxm = __ldg(a.cxm + idx);
+            t.cym = __ldg(a.cym + idx);
+        }
         t.tiny = __ldg(a.tinyarea + idx);
         if (LAST) t.tarear = __ldg(a.tarear + idx);
     }
@@ -283,117 +313,10 @@ __device__ __forceinline__ void stepu_cell(const SubArgs &a, const URow &u, doub
     }
 }
 
-template <int NT, bool LAST, bool PREFETCH, int MINB>
-__global__ void __launch_bounds__(NT, MINB) k_subcycle(const __grid_constant__ SubArgs a) {
-    __shared__ double xch[2][4][NT];
-    const int tid = threadIdx.x;
-    const int i = 1 + blockIdx.x * a.strip_w + tid;
-    // Row chunks are issued boundary-first: blockIdx.y 0 -> southernmost chunk, 1 -> northernmost, the
-    // interior after them, so that with the peer-to-peer halo the rows the neighbours wait for are
-    // produced first and the wait for the neighbours' rows overlaps with nothing else pending.
-    int chunk = blockIdx.y;
-    if (gridDim.y > 1) chunk = (blockIdx.y == 0) ? 0 : (blockIdx.y == 1 ? (int)gridDim.y - 1 : (int)blockIdx.y - 1);
-    const int j0 = 1 + chunk * a.rows;
-    if (a.p2p) {
-        // Before reading the ghost rows the neighbours stored during their previous subcycle kernel,
-        // and before storing into their ghost rows of the buffer they read during that kernel, wait
-        // until they have published at least as many completed subcycles as this rank has.
-        const bool top = (chunk == (int)gridDim.y - 1), bot = (chunk == 0);
-        if ((top && a.peer_n_flag) || (bot && a.peer_s_flag)) {
-            if (tid == 0) {
-                const int e = *(volatile int *)(a.sync + 1);
-                if (top && a.peer_n_flag)
-                    while (*(volatile int *)(a.sync + 2) < e) __nanosleep(20);
-                if (bot && a.peer_s_flag)
-                    while (*(volatile int *)(a.sync + 3) < e) __nanosleep(20);
-                __threadfence_system();
-            }
-            __syncthreads();
-        }
-    }
-    const int jlast = min(j0 + a.rows, a.nyl + 1); // last T row of this CTA
-    const bool colT = (tid <= a.strip_w) && (i <= a.nx + 1);
-    const bool colU = (tid < a.strip_w) && (i <= a.nx);
-    const bool ownT = colT && (tid < a.strip_w || i == a.nx + 1);
-
-    double us = 0.0, vs = 0.0, usw = 0.0, vsw = 0.0;
-    if (colT) {
-        const size_t idx = (size_t)(j0 - 1) * a.pitch + i;
-        us = __ldg(a.u_old + idx);
-        vs = __ldg(a.v_old + idx);
-        usw = __ldg(a.u_old + idx - 1);
-        vsw = __ldg(a.v_old + idx - 1);
-    }
-    double px = 0.0, s5c = 0.0, s7c = 0.0;
-    // Mask bytes run two rows (T) / one row (U) ahead of the data they gate and are kept RAW in a
-    // register: the compare that consumes a byte sits one iteration after its load, so no data load
-    // ever waits on a mask load.
-    const uint8_t *tmk = a.icetmask + (size_t)j0 * a.pitch + i;
-    const uint8_t *umk = a.iceumask + (size_t)j0 * a.pitch + i;
-    unsigned tm_raw = (colT && j0 + 1 <= jlast) ? __ldg(tmk + a.pitch) : 0u; // T row j+1
-    unsigned um_raw = 0u;                                                     // U row j-1
-    TRow t;
-    load_T<LAST>(a, t, i, j0, colT, colT && (__ldg(tmk) != 0));
-    int par = 0;
-
-    for (int j = j0; j <= jlast; ++j) {
-        TRow tn;
-        URow uc;
-        const bool tm_next = tm_raw != 0u;
-        const bool um_cur = um_raw != 0u;
-        const unsigned tm_raw2 = (colT && j + 2 <= jlast) ? __ldg(tmk + 2 * (size_t)a.pitch) : 0u;
-        const unsigned um_raw1 = (colU && j + 1 <= jlast) ? __ldg(umk) : 0u; // U row j
-        tmk += a.pitch;
-        umk += a.pitch;
-        if (PREFETCH) {
-            if (j < jlast) load_T<LAST>(a, tn, i, j + 1, colT, tm_next);
-        }
-        uc.act = false;
-        if (j > j0) load_U(a, uc, i, j - 1, um_cur);
-
-        const size_t idx = (size_t)j * a.pitch + i;
-        double str[8];
-        if (t.act) {
-            const bool store = ownT && (j < j0 + a.rows || j == a.nyl + 1);
-            stress_cell<LAST>(a, t, us, vs, usw, vsw, idx, store, str);
-        } else {
-#pragma unroll
-            for (int k = 0; k < 8; ++k) str[k] = 0.0; // str(:,:,:) = c0, :1051
-        }
-        xch[par][0][tid] = str[1];
-        xch[par][1][tid] = str[3];
-        xch[par][2][tid] = str[6];
-        xch[par][3][tid] = str[7];
-        __syncthreads();
-        double s2r = 0.0, s4r = 0.0, s7r = 0.0, s8r = 0.0;
-        if (tid < NT - 1) {
-            s2r = xch[par][0][tid + 1];
-            s4r = xch[par][1][tid + 1];
-            s7r = xch[par][2][tid + 1];
-            s8r = xch[par][3][tid + 1];
-        }
-        par ^= 1;
-
-        if (uc.act) {
-            const double sx = px + str[2] + s4r;          // ((s1 + s2) + s3) + s4
-            const double sy = s5c + str[5] + s7c + s8r;    // ((s5 + s6) + s7) + s8
-            stepu_cell<LAST>(a, uc, us, vs, sx, sy, i, j - 1, idx - a.pitch);
-        }
-        px = str[0] + s2r;
-        s5c = str[4];
-        s7c = s7r;
-        us = t.u;
-        vs = t.v;
-        usw = t.uw;
-        vsw = t.vw;
-        if (PREFETCH) {
-            t = tn;
-        } else {
-            if (j < jlast) load_T<LAST>(a, t, i, j + 1, colT, tm_next);
-        }
-        tm_raw = tm_raw2;
-        um_raw = um_raw1;
-    }
+// End of a subcycle kernel: tripole fold by the last CTA of the northernmost chunk (top slab), then
+// publication of this rank's epoch to the neighbours (peer-to-peer halo).
+template <int NT>
+__device__ __forceinline__ void k_subcycle_epilogue(const SubArgs &a, int tid, int chunk) {
     if (a.fold && chunk == (int)gridDim.y - 1) {
         // Tripole u-fold (north-south part of the halo update on the top slab): the CTAs of the
         // northernmost chunk hold rows nyl-1 and nyl; the last of them to finish symmetrises the
@@ -484,18 +407,125 @@ __global__ void __launch_bounds__(NT, MINB) k_subcycle(const __grid_constant__ S
     }
 }
 
-// variant bit 0: 1 = no register prefetch of the next T row; bit 1: 1 = cap registers for one
-// more resident CTA per SM (launch bounds)
-template <int NT, int MINB>
-static void launch_nt(const SubArgs &a, bool last, int variant, unsigned gx, unsigned gy, cudaStream_t s) {
+template <int NT, bool LAST, bool HT>
+__global__ void __launch_bounds__(NT) k_subcycle(const __grid_constant__ SubArgs a) {
+    __shared__ double xch[2][4][NT];
+    const int tid = threadIdx.x;
+    const int i = 1 + blockIdx.x * a.strip_w + tid;
+    // Row chunks are issued boundary-first: blockIdx.y 0 -> southernmost chunk, 1 -> northernmost, the
+    // interior after them, so that with the peer-to-peer halo the rows the neighbours wait for are
+    // produced first and the wait for the neighbours' rows overlaps with nothing else pending.
+    int chunk = blockIdx.y;
+    if (gridDim.y > 1) chunk = (blockIdx.y == 0) ? 0 : (blockIdx.y == 1 ? (int)gridDim.y - 1 : (int)blockIdx.y - 1);
+    const int j0 = 1 + chunk * a.rows;
+    if (a.p2p) {
+        // Before reading the ghost rows the neighbours stored during their previous subcycle kernel,
+        // and before storing into their ghost rows of the buffer they read during that kernel, wait
+        // until they have published at least as many completed subcycles as this rank has.
+        const bool top = (chunk == (int)gridDim.y - 1), bot = (chunk == 0);
+        if ((top && a.peer_n_flag) || (bot && a.peer_s_flag)) {
+            if (tid == 0) {
+                const int e = *(volatile int *)(a.sync + 1);
+                if (top && a.peer_n_flag)
+                    while (*(volatile int *)(a.sync + 2) < e) __nanosleep(20);
+                if (bot && a.peer_s_flag)
+                    while (*(volatile int *)(a.sync + 3) < e) __nanosleep(20);
+                __threadfence_system();
+            }
+            __syncthreads();
+        }
+    }
+    const int jlast = min(j0 + a.rows, a.nyl + 1); // last T row of this CTA
+    const bool colT = (tid <= a.strip_w) && (i <= a.nx + 1);
+    const bool colU = (tid < a.strip_w) && (i <= a.nx);
+    const bool ownT = colT && (tid < a.strip_w || i == a.nx + 1);
+
+    double us = 0.0, vs = 0.0, usw = 0.0, vsw = 0.0;
+    if (colT) {
+        const size_t idx = (size_t)(j0 - 1) * a.pitch + i;
+        us = __ldg(a.u_old + idx);
+        vs = __ldg(a.v_old + idx);
+        usw = __ldg(a.u_old + idx - 1);
+        vsw = __ldg(a.v_old + idx - 1);
+    }
+    double px = 0.0, s5c = 0.0, s7c = 0.0;
+    // Mask bytes run two rows (T) / one row (U) ahead of the data they gate and are kept RAW in a
+    // register: the compare that consumes a byte sits one iteration after its load, so no data load
+    // ever waits on a mask load.
+    const uint8_t *tmk = a.icetmask + (size_t)j0 * a.pitch + i;
+    const uint8_t *umk = a.iceumask + (size_t)j0 * a.pitch + i;
+    unsigned tm_raw = (colT && j0 + 1 <= jlast) ? __ldg(tmk + a.pitch) : 0u; // T row j+1
+    unsigned um_raw = 0u;                                                     // U row j-1
+    TRow t;
+    load_T<LAST, HT>(a, t, i, j0, colT, colT && (__ldg(tmk) != 0));
+    int par = 0;
+
+    for (int j = j0; j <= jlast; ++j) {
+        TRow tn;
+        URow uc;
+        const bool tm_next = tm_raw != 0u;
+        const bool um_cur = um_raw != 0u;
+        const unsigned tm_raw2 = (colT && j + 2 <= jlast) ? __ldg(tmk + 2 * (size_t)a.pitch) : 0u;
+        const unsigned um_raw1 = (colU && j + 1 <= jlast) ? __ldg(umk) : 0u; // U row j
+        tmk += a.pitch;
+        umk += a.pitch;
+        if (j < jlast) load_T<LAST, HT>(a, tn, i, j + 1, colT, tm_next); // software prefetch of the next row
+        uc.act = false;
+        if (j > j0) load_U(a, uc, i, j - 1, um_cur);
+
+        const size_t idx = (size_t)j * a.pitch + i;
+        double str[8];
+        if (t.act) {
+            derive_metrics<HT>(t);
+            const bool store = ownT && (j < j0 + a.rows || j == a.nyl + 1);
+            stress_cell<LAST>(a, t, us, vs, usw, vsw, idx, store, str);
+        } else {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) str[k] = 0.0; // str(:,:,:) = c0, :1051
+        }
+        xch[par][0][tid] = str[1];
+        xch[par][1][tid] = str[3];
+        xch[par][2][tid] = str[6];
+        xch[par][3][tid] = str[7];
+        __syncthreads();
+        double s2r = 0.0, s4r = 0.0, s7r = 0.0, s8r = 0.0;
+        if (tid < NT - 1) {
+            s2r = xch[par][0][tid + 1];
+            s4r = xch[par][1][tid + 1];
+            s7r = xch[par][2][tid + 1];
+            s8r = xch[par][3][tid + 1];
+        }
+        par ^= 1;
+
+        if (uc.act) {
+            const double sx = px + str[2] + s4r;          // ((s1 + s2) + s3) + s4
+            const double sy = s5c + str[5] + s7c + s8r;    // ((s5 + s6) + s7) + s8
+            stepu_cell<LAST>(a, uc, us, vs, sx, sy, i, j - 1, idx - a.pitch);
+        }
+        px = str[0] + s2r;
+        s5c = str[4];
+        s7c = s7r;
+        us = t.u;
+        vs = t.v;
+        usw = t.uw;
+        vsw = t.vw;
+        t = tn;
+        tm_raw = tm_raw2;
+        um_raw = um_raw1;
+    }
+    k_subcycle_epilogue<NT>(a, tid, chunk);
+}
+
+// HT (2-plane metric path) is chosen by a.row_ht
+template <int NT>
+static void launch_nt(const SubArgs &a, bool last, unsigned gx, unsigned gy, cudaStream_t s) {
     dim3 grid(gx, gy), block(NT);
-    const bool prefetch = (variant & 1) == 0;
-    if (last) {
-        if (prefetch) k_subcycle<NT, true, true, MINB><<<grid, block, 0, s>>>(a);
-        else k_subcycle<NT, true, false, MINB><<<grid, block, 0, s>>>(a);
+    if (a.row_ht) {
+        if (last) k_subcycle<NT, true, true><<<grid, block, 0, s>>>(a);
+        else k_subcycle<NT, false, true><<<grid, block, 0, s>>>(a);
     } else {
-        if (prefetch) k_subcycle<NT, false, true, MINB><<<grid, block, 0, s>>>(a);
-        else k_subcycle<NT, false, false, MINB><<<grid, block, 0, s>>>(a);
+        if (last) k_subcycle<NT, true, false><<<grid, block, 0, s>>>(a);
+        else k_subcycle<NT, false, false><<<grid, block, 0, s>>>(a);
     }
 }
 
@@ -503,20 +533,11 @@ static void launch_nt(const SubArgs &a, bool last, int variant, unsigned gx, uns
 
 void EVP_SUB_LAUNCH(const SubArgs &a, bool last, int variant, int threads, unsigned grid_x,
                     unsigned grid_y, void *stream) {
+    (void)variant;
     cudaStream_t s = (cudaStream_t)stream;
-    const bool tight = (variant & 2) != 0;
     switch (threads) {
-    case 64:
-        if (tight) EVP_SUB_NS::launch_nt<64, 6>(a, last, variant, grid_x, grid_y, s);
-        else EVP_SUB_NS::launch_nt<64, 1>(a, last, variant, grid_x, grid_y, s);
-        break;
-    case 256:
-        if (tight) EVP_SUB_NS::launch_nt<256, 2>(a, last, variant, grid_x, grid_y, s);
-        else EVP_SUB_NS::launch_nt<256, 1>(a, last, variant, grid_x, grid_y, s);
-        break;
-    default:
-        if (tight) EVP_SUB_NS::launch_nt<128, 3>(a, last, variant, grid_x, grid_y, s);
-        else EVP_SUB_NS::launch_nt<128, 1>(a, last, variant, grid_x, grid_y, s);
-        break;
+    case 64: EVP_SUB_NS::launch_nt<64>(a, last, grid_x, grid_y, s); break;
+    case 256: EVP_SUB_NS::launch_nt<256>(a, last, grid_x, grid_y, s); break;
+    default: EVP_SUB_NS::launch_nt<128>(a, last, grid_x, grid_y, s); break;
     }
 }

@@ -66,6 +66,7 @@ class Params(C.Structure):
 STATIC_D = ["dxt", "dyt", "dxhy", "dyhx", "cxp", "cyp", "cxm", "cym",
             "tarea", "tarear", "tinyarea", "uarea", "uarear", "fcor"]
 STATIC_I = ["tmask", "umask"]
+STATIC_OPT = ["HTE", "HTN"]   # optional: enable the 2-plane metric path of the subcycle kernel
 INPUT_D = ["aice", "vice", "vsno", "strairxT", "strairyT", "uocn", "vocn", "ss_tltx", "ss_tlty",
            "aice0", "aicen", "vicen"]
 STATE_D = ["uvel", "vvel",
@@ -78,7 +79,7 @@ OUTPUT_D = ["strairx", "strairy", "strtltx", "strtlty", "strintx", "strinty",
 
 
 class StaticFields(C.Structure):
-    _fields_ = [(n, c_dp) for n in STATIC_D] + [(n, c_ip) for n in STATIC_I]
+    _fields_ = [(n, c_dp) for n in STATIC_D] + [(n, c_ip) for n in STATIC_I] + [(n, c_dp) for n in STATIC_OPT]
 
 
 class Inputs(C.Structure):
@@ -288,6 +289,11 @@ class IceDynEvp:
             a = self._as_block(grid_fields[n], np.int32)
             keep.append(a)
             setattr(sf, n, _iptr(a))
+        for n in STATIC_OPT:
+            if grid_fields.get(n) is not None:
+                a = self._as_block(grid_fields[n], np.float64)
+                keep.append(a)
+                setattr(sf, n, _dptr(a))
         h = C.c_void_p(None)
         _check(L.evp_b200_init(C.byref(d), C.byref(p), C.byref(sf), C.byref(h)))
         self._h = h
@@ -410,6 +416,13 @@ class IceDynEvp:
             self.finalize()
         except Exception:
             pass
+
+
+def grid_fields_in_blocks(grid, layout: "BlockLayout", ew: str, ns: str, with_ht: bool = True) -> Dict[str, np.ndarray]:
+    """Module ice_grid arrays of a cice4_b200.grid.Grid in the caller's block layout (what
+    init_evp takes); HTE/HTN are included when present so that the 2-plane metric path can be used."""
+    names = STATIC_D + STATIC_I + ([n for n in STATIC_OPT if n in grid.f] if with_ht else [])
+    return {n: split_blocks(grid.f[n], layout, ew, ns) for n in names}
 
 
 def split_blocks(a: np.ndarray, layout: BlockLayout, ew: str, ns: str) -> np.ndarray:

@@ -70,6 +70,7 @@
          type(c_ptr) :: dxt, dyt, dxhy, dyhx, cxp, cyp, cxm, cym
          type(c_ptr) :: tarea, tarear, tinyarea, uarea, uarear, fcor
          type(c_ptr) :: tmask, umask
+         type(c_ptr) :: HTE, HTN
       end type
 
       type, bind(C) :: evp_b200_inputs
@@ -252,6 +253,7 @@
       g%tarea = c_loc(tarea); g%tarear = c_loc(tarear); g%tinyarea = c_loc(tinyarea)
       g%uarea = c_loc(uarea); g%uarear = c_loc(uarear); g%fcor = c_loc(fcor_blk)
       g%tmask = c_loc(tmask_i4); g%umask = c_loc(umask_i4)
+      g%HTE = c_loc(HTE); g%HTN = c_loc(HTN)      ! optional: 2-plane metric path (checked bit for bit at init)
 
       call b200_check(evp_b200_init(d, p, g, b200_handle), 'evp_b200_init')
 

@@ -93,7 +93,8 @@ typedef struct {
     int32_t use_graph;      /* 1 = replay the ndte loop as one CUDA graph */
     int32_t tile_threads;   /* 0 = default; threads per CTA of the subcycle kernel */
     int32_t tile_rows;      /* 0 = default; U rows marched per CTA */
-    int32_t kernel_variant; /* 0 = default */
+    int32_t kernel_variant; /* 0 = default; bit 2 (4): tripole fold as a separate kernel; bit 4 (16): 2-plane
+                               metric path (needs HTE/HTN) */
     int32_t exchange_mode;  /* multi-rank velocity halo inside the ndte loop: 0 = peer-to-peer stores from the
                                subcycle kernel into the neighbour's ghost rows (CUDA IPC over NVLink, flags for
                                ordering), 1 = NCCL send/recv after every subcycle */
@@ -105,6 +106,11 @@ typedef struct {
     const double *dxt, *dyt, *dxhy, *dyhx, *cxp, *cyp, *cxm, *cym;
     const double *tarea, *tarear, *tinyarea, *uarea, *uarear, *fcor;
     const int32_t *tmask, *umask;
+    /* optional (may be NULL): the primary cell widths HTE, HTN of module ice_grid
+     * (source/ice_grid.F90:75-76).  When given, the library checks at init, row by row and bit for
+     * bit, that dxt,dyt,dxhy,dyhx,cxp,cyp,cxm,cym equal the init_grid2 formulas (:350-361,:1196,:1280)
+     * applied to them; on rows where they do, the subcycle kernel streams 2 planes instead of 8. */
+    const double *HTE, *HTN;
 } evp_b200_static_fields;
 
 /* per-call inputs (source/ice_state.F90:66-89, source/ice_flux.F90:45-56) */
@@ -143,7 +149,7 @@ typedef struct {
     int32_t kernel_launches;   /* kernels launched (graph nodes count) in the last call */
     int32_t subcycle_launches; /* of which inside the ndte loop */
     int32_t exchange_mode_used; /* multi-rank: 0 = peer-to-peer stores, 1 = NCCL per subcycle; -1 = single rank */
-    int32_t reserved;
+    int32_t reserved;           /* rows of this slab on the 2-plane metric path (HTE/HTN given and verified) */
 } evp_b200_timings;
 
 typedef struct evp_b200_handle evp_b200_handle;

@@ -35,7 +35,7 @@ def cuda_steps(case, nsteps=1, strengths=None, layout=None, two_phase=False, wan
     ns = {v: k for k, v in E.BND.items()}[g.ns]
     dt = params.pop("dt", 3600.0)
     dyn = E.IceDynEvp(lay, ew, ns, **params)
-    gf = {n: E.split_blocks(g.f[n], lay, ew, ns) for n in E.STATIC_D + E.STATIC_I}
+    gf = E.grid_fields_in_blocks(g, lay, ew, ns)
     dyn.init_evp(dt, gf)
     inputs = {k: E.split_blocks(v, lay, ew, ns) for k, v in case.inputs.items()}
     out = None

@@ -60,7 +60,7 @@ def main():
 
     dyn = E.IceDynEvp(lay, ew, ns, device=local, rank=rank, nranks=world, slab=rows, ndte=args.ndte,
                       math_mode=args.math_mode, use_graph=args.use_graph, exchange_mode=args.exchange_mode)
-    gf = {n: E.split_blocks(g.f[n], lay, ew, ns) for n in E.STATIC_D + E.STATIC_I}
+    gf = E.grid_fields_in_blocks(g, lay, ew, ns)
     dyn.init_evp(3600.0, gf)
     uid = torch.zeros(128, dtype=torch.uint8, device="cuda")
     if rank == 0:

@@ -41,7 +41,7 @@ def test_struct_sizes_match_header():
     """ctypes mirrors must have the C layout (guards against drift between header and mirror)."""
     from cice4_b200 import evp as E
     assert C.sizeof(E.Dims) == 8 * 4 + 6 * 8 + 5 * 4 + 4   # trailing pad to 8
-    assert C.sizeof(E.StaticFields) == 16 * 8
+    assert C.sizeof(E.StaticFields) == 18 * 8
     assert C.sizeof(E.Inputs) == 12 * 8
     assert C.sizeof(E.State) == 15 * 8
     assert C.sizeof(E.Outputs) == 20 * 8
@@ -68,7 +68,7 @@ def test_no_cpu_fallback_without_gpu(evp_lib):
     case = synth.make_case("gx3", nx=12, ny=10, ew="cyclic", ns="open")
     lay = E.BlockLayout.single_block(12, 10)
     dyn = E.IceDynEvp(lay, "cyclic", "open")
-    gf = {n: E.split_blocks(case.grid.f[n], lay, "cyclic", "open") for n in E.STATIC_D + E.STATIC_I}
+    gf = E.grid_fields_in_blocks(case.grid, lay, "cyclic", "open")
     with pytest.raises(E.EvpB200Error, match="error 2"):
         dyn.init_evp(3600.0, gf)
 

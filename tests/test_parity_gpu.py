@@ -77,7 +77,8 @@ def test_fma_mode_within_tolerance(oracle, evp_lib, label, kw):
     _compare_tol(dyn, out, st, f, lay)
 
 
-@pytest.mark.parametrize("threads,rows,variant", [(64, 5, 0), (128, 7, 1), (256, 0, 0), (128, 1000, 0)])
+@pytest.mark.parametrize("threads,rows,variant", [(64, 5, 0), (128, 7, 4), (256, 0, 0), (128, 1000, 0),
+                                                  (128, 0, 16), (64, 9, 16 + 4)])
 def test_tiling_invariance(oracle, evp_lib, threads, rows, variant):
     """Strip width, rows per CTA and the prefetch variant must not change a single bit."""
     case = synth.make_case("om1deg", nx=300, ny=90)
@@ -221,3 +222,27 @@ def test_two_gpus_bit_exact_vs_oracle(evp_lib):
            "--realistic"]
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=240)
     assert r.returncode == 0 and "BIT-EXACT" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
+
+
+def test_two_plane_metric_path_and_fallback(oracle, evp_lib):
+    """HTE/HTN given: rows whose metric planes equal the init_grid2 formulas bit for bit are
+    re-derived in the kernel (2 planes streamed instead of 8); rows that do not (here: a perturbed
+    dxt value, and row 1 whose dxt is extrapolated, ice_grid.F90:1199-1202) fall back to the 8
+    planes.  Either way the result is bit-exact."""
+    case = synth.make_case("om1deg", nx=64, ny=48)
+    lay = E.BlockLayout.single_block(64, 48)
+    st, f, strengths, _ = oracle_steps(oracle, case, nsteps=1)
+    dyn, out = cuda_steps(case, strengths=strengths, kernel_variant=16)
+    rows_on = dyn.timings()["reserved"]
+    assert rows_on >= 45, rows_on
+    _compare_exact(dyn, out, st, f, lay)
+    dyn0, out0 = cuda_steps(case, strengths=strengths, kernel_variant=0)   # default: 8 planes
+    assert dyn0.timings()["reserved"] == rows_on   # still verified, just not used
+    _compare_exact(dyn0, out0, st, f, lay)
+    # perturb one metric value: that row must drop out of the fast path, results follow the arrays
+    case.grid.f["dxt"][20, 30] *= 1.0 + 1e-12
+    st2, f2, strengths2, _ = oracle_steps(oracle, case, nsteps=1)
+    dyn2, out2 = cuda_steps(case, strengths=strengths2, kernel_variant=16)
+    assert dyn2.timings()["reserved"] == rows_on - 1
+    _compare_exact(dyn2, out2, st2, f2, lay)
+    assert not np.array_equal(st2["uvel"], st["uvel"])

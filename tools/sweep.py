@@ -19,16 +19,19 @@ def main():
     ap.add_argument("--realistic", action="store_true")
     ap.add_argument("--ndte", type=int, default=120)
     ap.add_argument("--reps", type=int, default=5)
+    ap.add_argument("--nx", type=int, default=0)
+    ap.add_argument("--ny", type=int, default=0)
     ap.add_argument("--configs", default="1:128:0:0,1:128:0:1,1:128:0:2,1:128:0:3,0:128:0:0")
     args = ap.parse_args()
     B.build()
     fixture = os.path.join(ROOT, "tests", "golden", "gx3_grid.npz") if args.workload == "gx3" else None
-    case = synth.make_case(args.workload, realistic=args.realistic, gx3_fixture=fixture)
+    case = synth.make_case(args.workload, nx=args.nx or None, ny=args.ny or None, realistic=args.realistic,
+                           gx3_fixture=fixture)
     g = case.grid
     ew = {v: k for k, v in E.BND.items()}[g.ew]
     ns = {v: k for k, v in E.BND.items()}[g.ns]
     lay = E.BlockLayout.single_block(g.nx, g.ny)
-    gf = {n: E.split_blocks(g.f[n], lay, ew, ns) for n in E.STATIC_D + E.STATIC_I}
+    gf = E.grid_fields_in_blocks(g, lay, ew, ns)
     inputs = {k: E.split_blocks(v, lay, ew, ns) for k, v in case.inputs.items()}
     ref = None
     print(f"# {args.workload} {g.nx}x{g.ny} ndte={args.ndte} active={case.active_fraction:.3f}")
