@@ -9,6 +9,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
+#include <algorithm>
 #include <cstring>
 #include <string>
 #include <unordered_map>
@@ -94,6 +95,7 @@ struct evp_b200_handle {
     evp_b200_timings tm;
     std::unordered_map<const void *, size_t> pinned;
     int grid_x = 0, grid_y = 0, threads = 128, strip_w = 0, rows = 0;
+    int *d_chunks = nullptr;          // row-chunk table of the subcycle kernel (2 ints per chunk)
     int sub_launches_per_loop = 0;
     // y-slab chain: neighbour ranks (-1 = none) and the NCCL communicator (dlopen()ed entry points)
     int north = -1, south = -1;
@@ -232,7 +234,7 @@ void fill_subargs(evp_b200_handle *h, SubArgs &a, int cur) {
     a.strocnx = p[P_STROCNX]; a.strocny = p[P_STROCNY];
     a.nx = h->pg.nx; a.nyl = h->pg.nyl; a.pitch = h->pg.pitch;
     a.ew_cyclic = h->pg.ew_cyclic;
-    a.strip_w = h->strip_w; a.rows = h->rows;
+    a.strip_w = h->strip_w; a.rows = h->rows; a.chunks = h->d_chunks;
     a.evp_damping = h->par.evp_damping; a.hemisphere_turning = h->par.hemisphere_turning;
     a.hte = p[P_HTE]; a.htn = p[P_HTN];
     // the 2-plane metric path is opt-in (kernel_variant bit 4): it removes 6 of 48 words of DRAM
@@ -330,7 +332,9 @@ int run_subcycle_loop(evp_b200_handle *h) {
     return 0;
 }
 
-void choose_tiling(evp_b200_handle *h) {
+// Tiling of the subcycle kernel: balanced strips in x, one wave of CTAs in total, row chunks in
+// launch order with short boundary chunks.  Returns 0 or a CUDA error code via fail().
+int choose_tiling(evp_b200_handle *h) {
     int sms = 148;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device);
     const int nx = h->pg.nx, nyl = h->pg.nyl;
@@ -340,31 +344,66 @@ void choose_tiling(evp_b200_handle *h) {
     // balanced strips: ncx strips of strip_w U columns, strip_w + 1 <= nt threads hold T columns
     const int ncx = (nx + (nt - 1) - 1) / (nt - 1);
     const int strip_w = (nx + ncx - 1) / ncx;
-    int rows = h->par.tile_rows;
-    if (rows <= 0) {
-        // one wave: about (CTAs per SM) * SMs CTAs in total
-        // resident CTAs per SM at ~227 registers per thread: 256 threads
-        const int per_sm = (nt == 256) ? 1 : (nt == 128 ? 2 : 4);
-        const int target = per_sm * sms;
-        int ncy = target / ncx;
-        if (ncy < 1) ncy = 1;
-        rows = (nyl + ncy - 1) / ncy;
-        if (h->pg.tripole && ncy > 1 && (h->par.kernel_variant & 4) == 0) {
-            // in-kernel tripole fold: give the northernmost chunk about half the rows of the others
-            // so that its CTAs finish early and the fold overlaps with the rest of the grid
-            rows = (int)((2.0 * nyl) / (2.0 * ncy - 1.0) + 0.999);
-        }
-        if (rows < 4) rows = 4;
+    // resident CTAs per SM at ~210 registers per thread: 256 threads
+    const int per_sm = (nt == 256) ? 1 : (nt == 128 ? 2 : 4);
+    int ncy = (per_sm * sms) / ncx; // one wave
+    if (ncy < 1) ncy = 1;
+    if (ncy > nyl) ncy = nyl;
+    const bool fold_wanted = h->pg.tripole && (h->par.kernel_variant & 4) == 0;
+    // relative length of the boundary chunks: the northernmost chunk of the top slab also folds, a
+    // chunk next to another slab waits for that slab's flag at its start
+    const bool multi = h->dims.nranks > 1 && h->par.exchange_mode == 0;
+    double w_top = 1.0, w_bot = 1.0;
+    if (ncy >= 3 && h->par.tile_rows <= 0) {
+        if (fold_wanted) w_top = 0.5;
+        else if (multi && h->north >= 0) w_top = 0.6;
+        if (multi && h->south >= 0) w_bot = 0.6;
     }
-    if (rows > nyl) rows = nyl;
+    std::vector<int> tab; // (j0, n) in launch order: bottom, top, then interior south to north
+    int rows = h->par.tile_rows;
+    if (rows > 0) { // explicit uniform chunks (tests, sweeps)
+        if (rows > nyl) rows = nyl;
+        ncy = (nyl + rows - 1) / rows;
+        std::vector<int> j0s;
+        for (int k = 0; k < ncy; ++k) j0s.push_back(1 + k * rows);
+        auto len = [&](int k) { return std::min(rows, nyl - (j0s[k] - 1)); };
+        tab.push_back(j0s[0]); tab.push_back(len(0));
+        if (ncy > 1) { tab.push_back(j0s[ncy - 1]); tab.push_back(len(ncy - 1)); }
+        for (int k = 1; k < ncy - 1; ++k) { tab.push_back(j0s[k]); tab.push_back(len(k)); }
+    } else {
+        if (ncy < 3) { w_top = w_bot = 1.0; }
+        const double units = (ncy >= 2 ? (ncy - 2) + w_top + w_bot : 1.0);
+        rows = (int)(nyl / units + 0.999);
+        if (rows < 2) rows = 2;
+        int n_bot = ncy >= 2 ? std::max(2, (int)(rows * w_bot + 0.5)) : nyl;
+        int n_top = ncy >= 2 ? std::max(2, (int)(rows * w_top + 0.5)) : 0;
+        if (n_bot + n_top > nyl) { n_bot = nyl; n_top = 0; }
+        const int mid = nyl - n_bot - n_top;
+        int n_mid = mid > 0 ? (mid + rows - 1) / rows : 0;
+        tab.push_back(1); tab.push_back(n_bot);
+        if (n_top > 0) { tab.push_back(nyl - n_top + 1); tab.push_back(n_top); }
+        int j = 1 + n_bot;
+        for (int k = 0; k < n_mid; ++k) { // spread the interior rows evenly
+            const int n = mid / n_mid + (k < mid % n_mid ? 1 : 0);
+            tab.push_back(j); tab.push_back(n);
+            j += n;
+        }
+        ncy = (int)tab.size() / 2;
+    }
     h->threads = nt;
     h->strip_w = strip_w;
     h->rows = rows;
     h->grid_x = ncx;
-    h->grid_y = (nyl + rows - 1) / rows;
+    h->grid_y = ncy;
     // in-kernel tripole fold needs rows nyl-1 and nyl in the northernmost chunk
-    const int last_rows = nyl - (h->grid_y - 1) * rows;
-    h->fold_in_kernel = h->pg.tripole && last_rows >= 2 && (h->par.kernel_variant & 4) == 0;
+    int top_rows = 0;
+    for (int k = 0; k < ncy; ++k)
+        if (tab[2 * k] + tab[2 * k + 1] - 1 == nyl) top_rows = tab[2 * k + 1];
+    h->fold_in_kernel = fold_wanted && top_rows >= 2;
+    if (h->d_chunks) cudaFree(h->d_chunks);
+    CU(cudaMalloc(&h->d_chunks, sizeof(int) * tab.size()));
+    CU(cudaMemcpy(h->d_chunks, tab.data(), sizeof(int) * tab.size(), cudaMemcpyHostToDevice));
+    return 0;
 }
 
 } // namespace
@@ -558,7 +597,7 @@ int evp_b200_init(const evp_b200_dims *d, const evp_b200_params *p, const evp_b2
     }
     if (rc) { evp_b200_finalize(h); return rc; }
     CU(cudaStreamSynchronize(h->st));
-    choose_tiling(h);
+    if (int trc = choose_tiling(h)) { evp_b200_finalize(h); return trc; }
     memset(&h->tm, 0, sizeof(h->tm));
     *out = h;
     return EVP_B200_OK;
@@ -931,6 +970,7 @@ int evp_b200_finalize(evp_b200_handle *h) {
     }
     cudaFree(h->sync);
     cudaFree(h->fold_scratch);
+    cudaFree(h->d_chunks);
     cudaFree(h->row_ht);
     if (h->comm && h->pCommDestroy) h->pCommDestroy(h->comm);
     if (h->graph_exec) cudaGraphExecDestroy(h->graph_exec);

@@ -30,7 +30,10 @@ struct SubArgs {
     int nx, nyl, pitch;
     int ew_cyclic;
     int strip_w;   // U columns produced per CTA (threads 0..strip_w hold T columns)
-    int rows;      // U rows marched per CTA
+    int rows;      // U rows marched per interior CTA (informative; the kernel uses `chunks`)
+    // row chunks in launch order (blockIdx.y): chunks[2k] = first U row, chunks[2k+1] = number of U
+    // rows.  Boundary chunks come first and are shorter (see choose_tiling in evp_abi.cu).
+    const int *chunks;
     int evp_damping, hemisphere_turning;
     // 2-plane metric path: on rows where row_ht[j] != 0 the eight metrics are re-derived from the
     // primary cell widths with the (unfused) init_grid2 formulas instead of being loaded

@@ -316,8 +316,8 @@ __device__ __forceinline__ void stepu_cell(const SubArgs &a, const URow &u, doub
 // End of a subcycle kernel: tripole fold by the last CTA of the northernmost chunk (top slab), then
 // publication of this rank's epoch to the neighbours (peer-to-peer halo).
 template <int NT>
-__device__ __forceinline__ void k_subcycle_epilogue(const SubArgs &a, int tid, int chunk) {
-    if (a.fold && chunk == (int)gridDim.y - 1) {
+__device__ __forceinline__ void k_subcycle_epilogue(const SubArgs &a, int tid, bool top) {
+    if (a.fold && top) {
         // Tripole u-fold (north-south part of the halo update on the top slab): the CTAs of the
         // northernmost chunk hold rows nyl-1 and nyl; the last of them to finish symmetrises the
         // top row and fills the ghost row for the whole width.  The raw top row goes through a
@@ -412,17 +412,17 @@ __global__ void __launch_bounds__(NT) k_subcycle(const __grid_constant__ SubArgs
     __shared__ double xch[2][4][NT];
     const int tid = threadIdx.x;
     const int i = 1 + blockIdx.x * a.strip_w + tid;
-    // Row chunks are issued boundary-first: blockIdx.y 0 -> southernmost chunk, 1 -> northernmost, the
-    // interior after them, so that with the peer-to-peer halo the rows the neighbours wait for are
-    // produced first and the wait for the neighbours' rows overlaps with nothing else pending.
-    int chunk = blockIdx.y;
-    if (gridDim.y > 1) chunk = (blockIdx.y == 0) ? 0 : (blockIdx.y == 1 ? (int)gridDim.y - 1 : (int)blockIdx.y - 1);
-    const int j0 = 1 + chunk * a.rows;
+    // Row chunks come from a table in launch order: the southernmost and northernmost chunk first
+    // (with the peer-to-peer halo the rows the neighbours wait for are produced first), and they are
+    // shorter than the interior ones, so that the wait for the neighbours / the tripole fold at their
+    // end overlaps with the interior CTAs instead of extending the kernel.
+    const int j0 = __ldg(a.chunks + 2 * blockIdx.y);
+    const int nrows = __ldg(a.chunks + 2 * blockIdx.y + 1);
+    const bool top = (j0 + nrows - 1 == a.nyl), bot = (j0 == 1);
     if (a.p2p) {
         // Before reading the ghost rows the neighbours stored during their previous subcycle kernel,
         // and before storing into their ghost rows of the buffer they read during that kernel, wait
         // until they have published at least as many completed subcycles as this rank has.
-        const bool top = (chunk == (int)gridDim.y - 1), bot = (chunk == 0);
         if ((top && a.peer_n_flag) || (bot && a.peer_s_flag)) {
             if (tid == 0) {
                 const int e = *(volatile int *)(a.sync + 1);
@@ -435,7 +435,7 @@ __global__ void __launch_bounds__(NT) k_subcycle(const __grid_constant__ SubArgs
             __syncthreads();
         }
     }
-    const int jlast = min(j0 + a.rows, a.nyl + 1); // last T row of this CTA
+    const int jlast = min(j0 + nrows, a.nyl + 1); // last T row of this CTA
     const bool colT = (tid <= a.strip_w) && (i <= a.nx + 1);
     const bool colU = (tid < a.strip_w) && (i <= a.nx);
     const bool ownT = colT && (tid < a.strip_w || i == a.nx + 1);
@@ -477,7 +477,7 @@ __global__ void __launch_bounds__(NT) k_subcycle(const __grid_constant__ SubArgs
         double str[8];
         if (t.act) {
             derive_metrics<HT>(t);
-            const bool store = ownT && (j < j0 + a.rows || j == a.nyl + 1);
+            const bool store = ownT && (j < j0 + nrows || j == a.nyl + 1);
             stress_cell<LAST>(a, t, us, vs, usw, vsw, idx, store, str);
         } else {
 #pragma unroll
@@ -513,7 +513,7 @@ __global__ void __launch_bounds__(NT) k_subcycle(const __grid_constant__ SubArgs
         tm_raw = tm_raw2;
         um_raw = um_raw1;
     }
-    k_subcycle_epilogue<NT>(a, tid, chunk);
+    k_subcycle_epilogue<NT>(a, tid, top);
 }
 
 // HT (2-plane metric path) is chosen by a.row_ht
