@@ -34,6 +34,7 @@
 #include <cuda_runtime.h>
 
 #include "evp_common.cuh"
+#include "evp_ieee.cuh"
 
 namespace EVP_SUB_NS {
 
@@ -124,6 +125,24 @@ __device__ __forceinline__ void load_U(const SubArgs &a, URow &u, int i, int j, 
     }
 }
 
+// n/d1 .. n/d4: four independent IEEE divisions, interleaved (evp_ieee.cuh); bit-identical to operator/
+__device__ __forceinline__ void div4(double n, double d1, double d2, double d3, double d4, double &q1,
+                                     double &q2, double &q3, double &q4) {
+    bool ok1, ok2, ok3, ok4;
+    const double r1 = evp_ieee::rcp_refined(d1), r2 = evp_ieee::rcp_refined(d2);
+    const double r3 = evp_ieee::rcp_refined(d3), r4 = evp_ieee::rcp_refined(d4);
+    q1 = evp_ieee::div_fast(n, d1, r1, ok1);
+    q2 = evp_ieee::div_fast(n, d2, r2, ok2);
+    q3 = evp_ieee::div_fast(n, d3, r3, ok3);
+    q4 = evp_ieee::div_fast(n, d4, r4, ok4);
+    if (!(ok1 && ok2 && ok3 && ok4)) {
+        q1 = n / d1;
+        q2 = n / d2;
+        q3 = n / d3;
+        q4 = n / d4;
+    }
+}
+
 // source/ice_dyn_evp.F90:1056-1291 for one T cell.  (un,vn)=(i,j) (uw,vw)=(i-1,j) (us,vs)=(i,j-1)
 // (usw,vsw)=(i-1,j-1).  Operation order is the Fortran's.
 template <bool LAST>
@@ -152,10 +171,22 @@ __device__ __forceinline__ void stress_cell(const SubArgs &a, const TRow &t, dou
     const double shearsw = -cyp * vsw + dyt * vs - cxp * usw + dxt * uw;
     const double shearse = -cym * vs - dyt * vsw - cxp * us + dxt * un;
     // :1095-1098
-    const double Deltane = sqrt(divune * divune + a.ecci * (tensionne * tensionne + shearne * shearne));
-    const double Deltanw = sqrt(divunw * divunw + a.ecci * (tensionnw * tensionnw + shearnw * shearnw));
-    const double Deltase = sqrt(divuse * divuse + a.ecci * (tensionse * tensionse + shearse * shearse));
-    const double Deltasw = sqrt(divusw * divusw + a.ecci * (tensionsw * tensionsw + shearsw * shearsw));
+    // four independent IEEE square roots, interleaved (evp_ieee.cuh); bit-identical to sqrt()
+    const double r2ne = divune * divune + a.ecci * (tensionne * tensionne + shearne * shearne);
+    const double r2nw = divunw * divunw + a.ecci * (tensionnw * tensionnw + shearnw * shearnw);
+    const double r2se = divuse * divuse + a.ecci * (tensionse * tensionse + shearse * shearse);
+    const double r2sw = divusw * divusw + a.ecci * (tensionsw * tensionsw + shearsw * shearsw);
+    bool ok1, ok2, ok3, ok4;
+    double Deltane = evp_ieee::sqrt_fast(r2ne, ok1);
+    double Deltanw = evp_ieee::sqrt_fast(r2nw, ok2);
+    double Deltase = evp_ieee::sqrt_fast(r2se, ok3);
+    double Deltasw = evp_ieee::sqrt_fast(r2sw, ok4);
+    if (!(ok1 && ok2 && ok3 && ok4)) {
+        Deltane = sqrt(r2ne);
+        Deltanw = sqrt(r2nw);
+        Deltase = sqrt(r2se);
+        Deltasw = sqrt(r2sw);
+    }
 
     if (LAST && store) { // :1103-1115
         const double divu = p25 * (divune + divunw + divuse + divusw) * t.tarear;
@@ -171,16 +202,16 @@ __device__ __forceinline__ void stress_cell(const SubArgs &a, const TRow &t, dou
     double c0ne, c0nw, c0sw, c0se;
     if (a.evp_damping) { // :1121-1128
         const double t4 = c4 * t.tiny;
-        c0ne = fmin(t.strength / fmax(Deltane, t4), a.rcon);
-        c0nw = fmin(t.strength / fmax(Deltanw, t4), a.rcon);
-        c0sw = fmin(t.strength / fmax(Deltasw, t4), a.rcon);
-        c0se = fmin(t.strength / fmax(Deltase, t4), a.rcon);
+        div4(t.strength, fmax(Deltane, t4), fmax(Deltanw, t4), fmax(Deltasw, t4), fmax(Deltase, t4), c0ne, c0nw,
+             c0sw, c0se);
+        c0ne = fmin(c0ne, a.rcon);
+        c0nw = fmin(c0nw, a.rcon);
+        c0sw = fmin(c0sw, a.rcon);
+        c0se = fmin(c0se, a.rcon);
         if (LAST && store) a.prs_sig[idx] = t.strength * Deltane / fmax(Deltane, t4);
     } else { // :1131-1135
-        c0ne = t.strength / fmax(Deltane, t.tiny);
-        c0nw = t.strength / fmax(Deltanw, t.tiny);
-        c0sw = t.strength / fmax(Deltasw, t.tiny);
-        c0se = t.strength / fmax(Deltase, t.tiny);
+        div4(t.strength, fmax(Deltane, t.tiny), fmax(Deltanw, t.tiny), fmax(Deltasw, t.tiny), fmax(Deltase, t.tiny),
+             c0ne, c0nw, c0sw, c0se);
         if (LAST && store) a.prs_sig[idx] = c0ne * Deltane;
     }
     const double c1ne = c0ne * a.dte2T; // :1138-1141
@@ -272,8 +303,16 @@ __device__ __forceinline__ void stepu_cell(const SubArgs &a, const URow &u, doub
     const double strinty = u.uarear * sy;
     const double cc1 = strintx + u.forcex + taux + u.umassdtei * uold; // :1421-1424
     const double cc2 = strinty + u.forcey + tauy + u.umassdtei * vold;
-    const double unew = (cca * cc1 + ccb * cc2) / ab2;              // :1426-1427
-    const double vnew = (cca * cc2 - ccb * cc1) / ab2;
+    // :1426-1427: two IEEE divisions by the same denominator share the refined reciprocal
+    const double nu = cca * cc1 + ccb * cc2, nv = cca * cc2 - ccb * cc1;
+    bool oku, okv;
+    const double rab = evp_ieee::rcp_refined(ab2);
+    double unew = evp_ieee::div_fast(nu, ab2, rab, oku);
+    double vnew = evp_ieee::div_fast(nv, ab2, rab, okv);
+    if (!(oku && okv)) {
+        unew = nu / ab2;
+        vnew = nv / ab2;
+    }
     a.u_new[idx] = unew;
     a.v_new[idx] = vnew;
     if (a.ew_cyclic) { // east-west part of ice_HaloUpdate(uvel/vvel), serial/ice_boundary.F90:3629-3668

@@ -1,0 +1,86 @@
+// stream_bench.cu -- development micro-benchmark: what DRAM bandwidth does the ACCESS PATTERN of
+// the subcycle kernel allow, without its arithmetic?  NR planes read, NW planes written, fp64.
+//   A: flat 1-D, 8-byte accesses      B: flat 1-D, 16-byte accesses
+//   C: marching strips (one column per thread, rows in a loop, next-row prefetch), 8-byte accesses
+// nvcc -O3 -gencode arch=compute_100a,code=sm_100a tools/stream_bench.cu -o gpurun_out/stream_bench
+#include <cuda_runtime.h>
+#include <cstdio>
+#include <vector>
+constexpr int NR = 37, NW = 14;
+struct P { const double *r[NR]; double *w[NW]; };
+__global__ void kA(P p, size_t n) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double s = 0;
+#pragma unroll
+    for (int k = 0; k < NR; ++k) s += __ldg(p.r[k] + i);
+#pragma unroll
+    for (int k = 0; k < NW; ++k) p.w[k][i] = s + k;
+}
+__global__ void kB(P p, size_t n2) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n2) return;
+    double2 s = make_double2(0, 0);
+#pragma unroll
+    for (int k = 0; k < NR; ++k) { double2 v = __ldg((const double2 *)p.r[k] + i); s.x += v.x; s.y += v.y; }
+#pragma unroll
+    for (int k = 0; k < NW; ++k) ((double2 *)p.w[k])[i] = make_double2(s.x + k, s.y + k);
+}
+template <int NT>
+__global__ void __launch_bounds__(NT) kC(P p, int nx, int ny, int pitch, int strip, int rows) {
+    int i = 1 + blockIdx.x * strip + threadIdx.x;
+    int j0 = 1 + blockIdx.y * rows, j1 = min(j0 + rows, ny + 1);
+    if (threadIdx.x >= strip || i > nx) return;
+    double v[NR];
+    size_t idx = (size_t)j0 * pitch + i;
+#pragma unroll
+    for (int k = 0; k < NR; ++k) v[k] = __ldg(p.r[k] + idx);
+    for (int j = j0; j < j1; ++j) {
+        double nv[NR];
+        size_t nidx = (size_t)(j + 1) * pitch + i;
+        if (j + 1 < j1) {
+#pragma unroll
+            for (int k = 0; k < NR; ++k) nv[k] = __ldg(p.r[k] + nidx);
+        }
+        double s = 0;
+#pragma unroll
+        for (int k = 0; k < NR; ++k) s += v[k];
+        idx = (size_t)j * pitch + i;
+#pragma unroll
+        for (int k = 0; k < NW; ++k) p.w[k][idx] = s + k;
+#pragma unroll
+        for (int k = 0; k < NR; ++k) v[k] = nv[k];
+    }
+}
+int main() {
+    const int nx = 1440, ny = 1080, pitch = 1456;
+    const size_t cells = (size_t)pitch * (ny + 2);
+    double *pool;
+    cudaMalloc(&pool, sizeof(double) * cells * (NR + NW));
+    cudaMemset(pool, 0, sizeof(double) * cells * (NR + NW));
+    P p;
+    for (int k = 0; k < NR; ++k) p.r[k] = pool + (size_t)k * cells;
+    for (int k = 0; k < NW; ++k) p.w[k] = pool + (size_t)(NR + k) * cells;
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0); cudaEventCreate(&e1);
+    const double bytes = 8.0 * cells * (NR + NW);
+    auto time = [&](const char *name, auto launch, double b) {
+        for (int w = 0; w < 3; ++w) launch();
+        cudaEventRecord(e0);
+        const int reps = 20;
+        for (int r = 0; r < reps; ++r) launch();
+        cudaEventRecord(e1);
+        cudaEventSynchronize(e1);
+        float ms; cudaEventElapsedTime(&ms, e0, e1);
+        printf("%-40s %8.2f us  %8.1f GB/s  (%s)\n", name, 1e3 * ms / reps, b / (ms / reps * 1e-3) / 1e9, cudaGetErrorString(cudaGetLastError()));
+    };
+    time("A flat 8B, 256 thr", [&] { kA<<<(unsigned)((cells + 255) / 256), 256>>>(p, cells); }, bytes);
+    time("B flat 16B, 256 thr", [&] { kB<<<(unsigned)((cells / 2 + 255) / 256), 256>>>(p, cells / 2); }, bytes);
+    const double bc = 8.0 * (double)nx * ny * (NR + NW);
+    time("C march 128 thr, strip 120, rows 45", [&] { kC<128><<<dim3(12, 24), 128>>>(p, nx, ny, pitch, 120, 45); }, bc);
+    time("C march 128 thr, strip 120, rows 23", [&] { kC<128><<<dim3(12, 47), 128>>>(p, nx, ny, pitch, 120, 23); }, bc);
+    time("C march 256 thr, strip 240, rows 45", [&] { kC<256><<<dim3(6, 24), 256>>>(p, nx, ny, pitch, 240, 45); }, bc);
+    time("C march 64 thr, strip 60, rows 45", [&] { kC<64><<<dim3(24, 24), 64>>>(p, nx, ny, pitch, 60, 45); }, bc);
+    time("C march 128 thr, strip 120, rows 12", [&] { kC<128><<<dim3(12, 90), 128>>>(p, nx, ny, pitch, 120, 12); }, bc);
+    return 0;
+}
