@@ -92,6 +92,7 @@ struct evp_b200_handle {
     cudaGraphExec_t graph_exec = nullptr;
     int cur = 0; // which ping-pong copy holds the current state
     bool prepared = false, resident = false;
+    bool stress_on_device = false;    // state_residency = 1: copy 0 of the stress planes is current
     evp_b200_timings tm;
     std::unordered_map<const void *, size_t> pinned;
     int grid_x = 0, grid_y = 0, threads = 128, strip_w = 0, rows = 0;
@@ -630,8 +631,9 @@ static int do_prep(evp_b200_handle *h, const evp_b200_inputs *in, evp_b200_state
     double *sh[EVP_NSTRESS] = {st->stressp_1, st->stressp_2, st->stressp_3, st->stressp_4,
                                st->stressm_1, st->stressm_2, st->stressm_3, st->stressm_4,
                                st->stress12_1, st->stress12_2, st->stress12_3, st->stress12_4};
-    for (int k = 0; k < EVP_NSTRESS; ++k)
-        if ((rc = upload_r8(h, sh[k], SL_S0 + k, p[P_S0 + k]))) return rc;
+    if (!(h->par.state_residency == 1 && h->stress_on_device))
+        for (int k = 0; k < EVP_NSTRESS; ++k)
+            if ((rc = upload_r8(h, sh[k], SL_S0 + k, p[P_S0 + k]))) return rc;
     if ((rc = upload_mask(h, st->iceumask, 0, h->mk[M_ICEUMASK]))) return rc;
     CU(cudaEventRecord(h->ev[1], h->st));
 
@@ -775,8 +777,10 @@ static int do_run(evp_b200_handle *h, const evp_b200_inputs *in, const double *s
     double *sh[EVP_NSTRESS] = {st->stressp_1, st->stressp_2, st->stressp_3, st->stressp_4,
                                st->stressm_1, st->stressm_2, st->stressm_3, st->stressm_4,
                                st->stress12_1, st->stress12_2, st->stress12_3, st->stress12_4};
-    for (int k = 0; k < EVP_NSTRESS; ++k)
-        if ((rc = download_r8(h, sh[k], SL_S0 + k, p[P_S0 + k], PACK_TNE_KEEP))) return rc;
+    if (h->par.state_residency != 1)
+        for (int k = 0; k < EVP_NSTRESS; ++k)
+            if ((rc = download_r8(h, sh[k], SL_S0 + k, p[P_S0 + k], PACK_TNE_KEEP))) return rc;
+    h->stress_on_device = true;
     if ((rc = download_mask(h, st->iceumask, 0, h->mk[M_ICEUMASK], PACK_INT_KEEP))) return rc;
     if (out) {
         struct { double *dst; int id; int policy; } outs[] = {
@@ -857,6 +861,30 @@ int evp_b200_principal_stress(evp_b200_handle *h, const double *sp1, const doubl
     CU(cudaMemcpyAsync(sig1, s + 4 * n, bytes, cudaMemcpyDeviceToHost, h->st));
     CU(cudaMemcpyAsync(sig2, s + 5 * n, bytes, cudaMemcpyDeviceToHost, h->st));
     CU(cudaStreamSynchronize(h->st));
+    return 0;
+}
+
+int evp_b200_download_state(evp_b200_handle *h, evp_b200_state *st) {
+    if (!h || !st) return fail(EVP_B200_ERR_ARG, "NULL argument");
+    if (!h->stress_on_device) return fail(EVP_B200_ERR_STATE, "no device state yet: call evp_b200_step/run first");
+    CU(cudaSetDevice(h->device));
+    double **p = h->pl;
+    int rc = 0;
+    if ((rc = download_r8(h, st->uvel, SL_U, p[P_U0], PACK_FULL))) return rc;
+    if ((rc = download_r8(h, st->vvel, SL_V, p[P_V0], PACK_FULL))) return rc;
+    double *sh[EVP_NSTRESS] = {st->stressp_1, st->stressp_2, st->stressp_3, st->stressp_4,
+                               st->stressm_1, st->stressm_2, st->stressm_3, st->stressm_4,
+                               st->stress12_1, st->stress12_2, st->stress12_3, st->stress12_4};
+    for (int k = 0; k < EVP_NSTRESS; ++k)
+        if ((rc = download_r8(h, sh[k], SL_S0 + k, p[P_S0 + k], PACK_TNE_KEEP))) return rc;
+    if ((rc = download_mask(h, st->iceumask, 0, h->mk[M_ICEUMASK], PACK_INT_KEEP))) return rc;
+    CU(cudaStreamSynchronize(h->st));
+    return 0;
+}
+
+int evp_b200_invalidate_device_state(evp_b200_handle *h) {
+    if (!h) return fail(EVP_B200_ERR_ARG, "NULL argument");
+    h->stress_on_device = false;
     return 0;
 }
 

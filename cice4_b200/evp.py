@@ -33,8 +33,8 @@ BND = {"open": 0, "closed": 1, "cyclic": 2, "tripole": 3}
 EXPORTS = [
     "evp_b200_abi_version", "evp_b200_last_error", "evp_b200_default_params", "evp_b200_init",
     "evp_b200_prep", "evp_b200_run", "evp_b200_step", "evp_b200_subcycle_resident",
-    "evp_b200_principal_stress", "evp_b200_get_timings", "evp_b200_comm_unique_id",
-    "evp_b200_comm_init", "evp_b200_finalize",
+    "evp_b200_principal_stress", "evp_b200_get_timings", "evp_b200_download_state",
+    "evp_b200_invalidate_device_state", "evp_b200_comm_unique_id", "evp_b200_comm_init", "evp_b200_finalize",
 ]
 
 
@@ -60,7 +60,7 @@ class Params(C.Structure):
                 ("ncat", C.c_int32), ("mu_rdg", C.c_double),
                 ("math_mode", C.c_int32), ("pin_host", C.c_int32), ("use_graph", C.c_int32),
                 ("tile_threads", C.c_int32), ("tile_rows", C.c_int32), ("kernel_variant", C.c_int32),
-                ("exchange_mode", C.c_int32)]
+                ("state_residency", C.c_int32), ("exchange_mode", C.c_int32)]
 
 
 STATIC_D = ["dxt", "dyt", "dxhy", "dyhx", "cxp", "cyp", "cxm", "cym",
@@ -125,6 +125,8 @@ def load_library(path: str = LIB_PATH) -> C.CDLL:
     L.evp_b200_subcycle_resident.argtypes = [H, C.c_int32, C.POINTER(C.c_float)]
     L.evp_b200_principal_stress.argtypes = [H, c_dp, c_dp, c_dp, c_dp, c_dp, c_dp]
     L.evp_b200_get_timings.argtypes = [H, C.POINTER(Timings)]
+    L.evp_b200_download_state.argtypes = [H, C.POINTER(State)]
+    L.evp_b200_invalidate_device_state.argtypes = [H]
     L.evp_b200_comm_unique_id.argtypes = [C.POINTER(C.c_uint8)]
     L.evp_b200_comm_init.argtypes = [H, C.POINTER(C.c_uint8)]
     L.evp_b200_finalize.argtypes = [H]
@@ -383,6 +385,23 @@ class IceDynEvp:
             _check(L.evp_b200_step(self._h, C.byref(inp), sp, C.byref(st), C.byref(out)))
         self.flux.update(res)
         return res
+
+    def _state_struct(self) -> State:
+        st = State()
+        for n in STATE_D:
+            setattr(st, n, _dptr(self.state[n]))
+        st.iceumask = _iptr(self.state["iceumask"])
+        return st
+
+    def download_state(self) -> None:
+        """state_residency = 1: bring the device-resident stresses back into `self.state` (what the
+        shim calls before dumpfile / ice_write_hist)."""
+        st = self._state_struct()
+        _check(load_library().evp_b200_download_state(self._h, C.byref(st)))
+
+    def invalidate_device_state(self) -> None:
+        """The host arrays of `self.state` were changed by the caller (restartfile): upload them again."""
+        _check(load_library().evp_b200_invalidate_device_state(self._h))
 
     def principal_stress(self, stressp_1, stressm_1, stress12_1, prs_sig):
         """source/ice_dyn_evp.F90:1558-1609 -> (sig1, sig2)."""

@@ -63,7 +63,8 @@
          integer(c_int32_t) :: coupled_tilt, use_ocnslope, hemisphere_turning, wind_from_strax
          integer(c_int32_t) :: kstrength, krdg_partic, krdg_redist, ncat
          real(c_double) :: mu_rdg
-         integer(c_int32_t) :: math_mode, pin_host, use_graph, tile_threads, tile_rows, kernel_variant, exchange_mode
+         integer(c_int32_t) :: math_mode, pin_host, use_graph, tile_threads, tile_rows, kernel_variant
+         integer(c_int32_t) :: state_residency, exchange_mode
       end type
 
       type, bind(C) :: evp_b200_static_fields
@@ -246,7 +247,8 @@
       p%kstrength = kstrength; p%krdg_partic = krdg_partic; p%krdg_redist = krdg_redist
       p%ncat = ncat; p%mu_rdg = mu_rdg
       p%math_mode = 0; p%pin_host = 1; p%use_graph = 1
-      p%tile_threads = 0; p%tile_rows = 0; p%kernel_variant = 0; p%exchange_mode = 0
+      p%tile_threads = 0; p%tile_rows = 0; p%kernel_variant = 0
+      p%state_residency = 0; p%exchange_mode = 0
 
       g%dxt = c_loc(dxt); g%dyt = c_loc(dyt); g%dxhy = c_loc(dxhy); g%dyhx = c_loc(dyhx)
       g%cxp = c_loc(cxp); g%cyp = c_loc(cyp); g%cxm = c_loc(cxm); g%cym = c_loc(cym)

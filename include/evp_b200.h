@@ -95,6 +95,11 @@ typedef struct {
     int32_t tile_rows;      /* 0 = default; U rows marched per CTA */
     int32_t kernel_variant; /* 0 = default; bit 2 (4): tripole fold as a separate kernel; bit 4 (16): 2-plane
                                metric path (needs HTE/HTN) */
+    int32_t state_residency; /* 0 = the whole state is uploaded and downloaded by every call (host arrays always
+                               current: restart-exact drop-in); 1 = the 12 stress arrays stay on the device
+                               between calls: uploaded by the first call after init or after
+                               evp_b200_invalidate_device_state, brought back only by evp_b200_download_state
+                               (before dumpfile / ice_write_hist); uvel, vvel, iceumask still round-trip */
     int32_t exchange_mode;  /* multi-rank velocity halo inside the ndte loop: 0 = peer-to-peer stores from the
                                subcycle kernel into the neighbour's ghost rows (CUDA IPC over NVLink, flags for
                                ordering), 1 = NCCL send/recv after every subcycle */
@@ -190,6 +195,12 @@ int evp_b200_principal_stress(evp_b200_handle *h, const double *stressp_1, const
                               double *sig1, double *sig2);
 
 int evp_b200_get_timings(const evp_b200_handle *h, evp_b200_timings *t);
+
+/* state_residency = 1: copy the device-resident stresses (and uvel, vvel, iceumask) into the caller's
+ * arrays -- what dumpfile (source/ice_restart.F90:197-246) and ice_write_hist need; and tell the library
+ * that the caller changed the host arrays (restartfile, :427-487) so the next call uploads them again. */
+int evp_b200_download_state(evp_b200_handle *h, evp_b200_state *st);
+int evp_b200_invalidate_device_state(evp_b200_handle *h);
 
 /* multi-GPU: one handle per rank (y-slab).  id is the 128-byte ncclUniqueId made by rank 0
  * (evp_b200_comm_unique_id) and broadcast by the host (MPI_Bcast in the Fortran world,

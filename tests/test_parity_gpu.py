@@ -246,3 +246,28 @@ def test_two_plane_metric_path_and_fallback(oracle, evp_lib):
     assert dyn2.timings()["reserved"] == rows_on - 1
     _compare_exact(dyn2, out2, st2, f2, lay)
     assert not np.array_equal(st2["uvel"], st["uvel"])
+
+
+def test_stress_residency(oracle, evp_lib):
+    """state_residency = 1: stresses stay on the device between calls, the host
+    arrays are refreshed only by download_state; invalidate_device_state re-uploads them."""
+    case = synth.make_case("om1deg", nx=64, ny=48, realistic=True)
+    lay = E.BlockLayout.cartesian(64, 48, 32, 24)
+    st, f, strengths, _ = oracle_steps(oracle, case, nsteps=3)
+    dyn, out = cuda_steps(case, nsteps=3, strengths=strengths, layout=lay, state_residency=1)
+    assert np.all(dyn.state["stressp_1"] == 0.0)          # never downloaded so far
+    for n in ("uvel", "vvel", "iceumask"):                 # these still round-trip
+        assert np.array_equal(_merge(dyn.state[n], lay), st[n]), n
+    dyn.download_state()
+    _compare_exact(dyn, out, st, f, lay)
+    # the caller overwrites its arrays (restartfile): the next call must use them
+    for n in STATE[2:14]:
+        dyn.state[n][...] *= 0.5
+    st_h = {n: _merge(dyn.state[n], lay).copy(order="F") for n in STATE}
+    dyn.invalidate_device_state()
+    p = oracle.make_params()
+    f2, _ = oracle.run_evp(case.grid, case.inputs, st_h, p)
+    inputs = {k: E.split_blocks(v, lay, "cyclic", "tripole") for k, v in case.inputs.items()}
+    out2 = dyn.evp(3600.0, inputs, strength=E.split_blocks(f2["strength"], lay, "cyclic", "tripole"))
+    dyn.download_state()
+    _compare_exact(dyn, out2, st_h, f2, lay)
