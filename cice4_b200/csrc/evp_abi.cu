@@ -254,13 +254,13 @@ void fill_subargs(evp_b200_handle *h, SubArgs &a, int cur) {
         if (h->north >= 0) { // north neighbour's south ghost row = its row 0
             a.peer_n_u = h->peer_pool[0] + (size_t)pu * h->peer_cells[0];
             a.peer_n_v = h->peer_pool[0] + (size_t)pv * h->peer_cells[0];
-            a.peer_n_flag = h->peer_sync[0] + 3;
+            a.peer_n_flag = h->peer_sync[0] + EVP_SYNC_FS;
         }
         if (h->south >= 0) { // south neighbour's north ghost row = its row nyl+1
             const size_t off = (size_t)(h->peer_nyl[1] + 1) * h->pg.pitch;
             a.peer_s_u = h->peer_pool[1] + (size_t)pu * h->peer_cells[1] + off;
             a.peer_s_v = h->peer_pool[1] + (size_t)pv * h->peer_cells[1] + off;
-            a.peer_s_flag = h->peer_sync[1] + 2;
+            a.peer_s_flag = h->peer_sync[1] + EVP_SYNC_FN;
         }
     }
 }
@@ -321,7 +321,7 @@ int run_subcycle_loop(evp_b200_handle *h) {
     CU(cudaGetLastError());
     // peer-to-peer halo: the ghost rows of the final copy are complete once both neighbours have
     // published the epoch of their last subcycle kernel
-    if (h->p2p) aux_wait_peers(h->sync, h->north >= 0, h->south >= 0, h->st);
+    if (h->p2p) aux_wait_peers(h->sync, h->north >= 0, h->south >= 0, h->grid_x, h->st);
     if (h->cur != 0) { // odd ndte: bring the result back to copy 0 so the next loop starts there
         const size_t bytes = h->pg.cells * sizeof(double);
         CU(cudaMemcpyAsync(h->pl[P_U0], h->pl[P_U1], bytes, cudaMemcpyDeviceToDevice, h->st));
@@ -340,7 +340,9 @@ int choose_tiling(evp_b200_handle *h) {
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device);
     const int nx = h->pg.nx, nyl = h->pg.nyl;
     // default: 128 threads per CTA; short slabs (multi-GPU) run better with one 256-thread CTA per SM
-    int nt = h->par.tile_threads > 0 ? h->par.tile_threads : (nyl <= 300 ? 256 : 128);
+    // (decided from the mean slab height so that all ranks of a chain use the same strips)
+    const int nyl_mean = h->dims.ny_global / h->dims.nranks;
+    int nt = h->par.tile_threads > 0 ? h->par.tile_threads : (nyl_mean <= 300 ? 256 : 128);
     if (nt != 64 && nt != 128 && nt != 256) nt = 128;
     // balanced strips: ncx strips of strip_w U columns, strip_w + 1 <= nt threads hold T columns
     const int ncx = (nx + (nt - 1) - 1) / (nt - 1);
@@ -558,8 +560,8 @@ int evp_b200_init(const evp_b200_dims *d, const evp_b200_params *p, const evp_b2
     CU(cudaMemsetAsync(h->stage, 0, sizeof(double) * h->blocked_elems * h->n_stage, h->st));
     CU(cudaMemsetAsync(h->stage_i, 0, sizeof(int32_t) * h->blocked_elems * 2, h->st));
     CU(cudaMalloc(&h->fold_scratch, sizeof(double) * 2 * pg.pitch));
-    CU(cudaMalloc(&h->sync, sizeof(int) * 64));
-    CU(cudaMemsetAsync(h->sync, 0, sizeof(int) * 64, h->st));
+    CU(cudaMalloc(&h->sync, sizeof(int) * EVP_SYNC_INTS));
+    CU(cudaMemsetAsync(h->sync, 0, sizeof(int) * EVP_SYNC_INTS, h->st));
     CU(cudaMalloc(&h->d_blk_tab, sizeof(int) * h->blk_tab.size()));
     CU(cudaMemcpyAsync(h->d_blk_tab, h->blk_tab.data(), sizeof(int) * h->blk_tab.size(), cudaMemcpyHostToDevice, h->st));
     h->bg.nx_block = d->nx_block;
@@ -982,6 +984,7 @@ int evp_b200_comm_init(evp_b200_handle *h, const uint8_t id[128]) {
                 h->peer_cells[k] = (size_t)theirs[k].cells;
             }
         cudaGetLastError();
+        if (h->grid_x > EVP_SYNC_MAXCX) ok = false;
         h->p2p = ok;   // on failure the NCCL exchange stays in use (evp_b200_get_timings reports the mode)
     }
     return 0;

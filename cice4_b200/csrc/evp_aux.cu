@@ -436,12 +436,14 @@ __global__ void k_check_metrics(PlaneGeom pg, MetricCheckArgs a) {
     if (threadIdx.x == 0) a.row_ht[j] = bad ? 0 : 1;
 }
 
-__global__ void k_wait_peers(int *sync, int has_north, int has_south) {
+__global__ void k_wait_peers(int *sync, int has_north, int has_south, int ncx) {
     const int e = *(volatile int *)(sync + 1);
-    if (has_north)
-        while (*(volatile int *)(sync + 2) < e) __nanosleep(50);
-    if (has_south)
-        while (*(volatile int *)(sync + 3) < e) __nanosleep(50);
+    for (int x = threadIdx.x; x < ncx; x += blockDim.x) {
+        if (has_north)
+            while (*(volatile int *)(sync + EVP_SYNC_FN + x) < e) __nanosleep(50);
+        if (has_south)
+            while (*(volatile int *)(sync + EVP_SYNC_FS + x) < e) __nanosleep(50);
+    }
     __threadfence_system();
 }
 
@@ -520,8 +522,8 @@ void aux_ice_strength(const PlaneGeom &pg, const StrengthArgs &a, cudaStream_t s
     dim3 grid(nblk(pg.nx + 2), pg.nyl + 2);
     k_ice_strength<<<grid, TPB, 0, s>>>(pg, a);
 }
-void aux_wait_peers(int *sync, int has_north, int has_south, cudaStream_t s) {
-    k_wait_peers<<<1, 1, 0, s>>>(sync, has_north, has_south);
+void aux_wait_peers(int *sync, int has_north, int has_south, int ncx, cudaStream_t s) {
+    k_wait_peers<<<1, 128, 0, s>>>(sync, has_north, has_south, ncx);
 }
 void aux_check_metrics(const PlaneGeom &pg, const MetricCheckArgs &a, cudaStream_t s) {
     k_check_metrics<<<pg.nyl + 2, 256, 0, s>>>(pg, a);

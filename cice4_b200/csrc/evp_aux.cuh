@@ -92,7 +92,7 @@ struct StrengthArgs {
 void aux_ice_strength(const PlaneGeom &pg, const StrengthArgs &a, cudaStream_t s); // ice_mechred.F90:1869-2036
 
 // spin until both neighbours have published at least this rank's epoch (see SubArgs::sync)
-void aux_wait_peers(int *sync, int has_north, int has_south, cudaStream_t s);
+void aux_wait_peers(int *sync, int has_north, int has_south, int ncx, cudaStream_t s);
 
 // row_ht[j] = 1 iff on every ocean T cell (tmask) of row j, columns 1..nx+1, the eight metric planes
 // equal the init_grid2 formulas applied to HTE/HTN bit for bit (rows 1..nyl+1; others 0)

@@ -12,6 +12,10 @@
 #include <cstdint>
 
 #define EVP_NSTRESS 12
+#define EVP_SYNC_MAXCX 128
+#define EVP_SYNC_FN 32
+#define EVP_SYNC_FS (EVP_SYNC_FN + EVP_SYNC_MAXCX)
+#define EVP_SYNC_INTS (EVP_SYNC_FS + EVP_SYNC_MAXCX)
 
 // argument block of the fused stress+stepu subcycle kernel
 struct SubArgs {
@@ -44,10 +48,14 @@ struct SubArgs {
     // ghost rows of the neighbours' u_new/v_new planes, mapped through CUDA IPC:
     // peer_n_* = row 0 of the north neighbour, peer_s_* = row nyl+1 of the south neighbour
     double *peer_n_u, *peer_n_v, *peer_s_u, *peer_s_v;
-    // sync block in local memory: [0] CTAs finished (counter), [1] subcycle kernels completed on this
-    // rank (epoch), [2] epoch published by the north neighbour, [3] by the south neighbour
+    // sync block in local memory (EVP_SYNC_INTS ints): [0] CTAs finished (counter), [1] subcycle
+    // kernels completed on this rank (epoch), [4] fold counter, then two arrays of per-strip epochs
+    // written by the neighbours' boundary CTAs through their mapping of this block:
+    //   [EVP_SYNC_FN + x] = epochs finished by strip x of the NORTH neighbour's southernmost chunk,
+    //   [EVP_SYNC_FS + x] = epochs finished by strip x of the SOUTH neighbour's northernmost chunk.
     int *sync;
-    int *peer_n_flag, *peer_s_flag; // where this rank publishes its epoch: north's sync[3], south's sync[2]
+    // where this rank's boundary CTAs publish: the north neighbour's FS array, the south neighbour's FN array
+    int *peer_n_flag, *peer_s_flag;
     int p2p;                         // 1 = the above are in use
     // ---- tripole u-fold of u_new/v_new inside the kernel (top slab only) ------------------------
     int fold;              // 1 = the last CTA of the northernmost chunk to finish applies the fold

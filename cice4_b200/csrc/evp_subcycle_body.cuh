@@ -355,7 +355,17 @@ __device__ __forceinline__ void stepu_cell(const SubArgs &a, const URow &u, doub
 // End of a subcycle kernel: tripole fold by the last CTA of the northernmost chunk (top slab), then
 // publication of this rank's epoch to the neighbours (peer-to-peer halo).
 template <int NT>
-__device__ __forceinline__ void k_subcycle_epilogue(const SubArgs &a, int tid, bool top) {
+__device__ __forceinline__ void k_subcycle_epilogue(const SubArgs &a, int tid, bool top, bool bot, int epoch) {
+    if (a.p2p && ((top && a.peer_n_flag) || (bot && a.peer_s_flag))) {
+        // boundary CTA done: its stores into the neighbour's ghost row are made visible system-wide,
+        // then its per-strip epoch is published in the neighbour's sync block
+        __syncthreads();
+        if (tid == 0) {
+            __threadfence_system();
+            if (top && a.peer_n_flag) *(volatile int *)(a.peer_n_flag + blockIdx.x) = epoch + 1;
+            if (bot && a.peer_s_flag) *(volatile int *)(a.peer_s_flag + blockIdx.x) = epoch + 1;
+        }
+    }
     if (a.fold && top) {
         // Tripole u-fold (north-south part of the halo update on the top slab): the CTAs of the
         // northernmost chunk hold rows nyl-1 and nyl; the last of them to finish symmetrises the
@@ -427,20 +437,15 @@ __device__ __forceinline__ void k_subcycle_epilogue(const SubArgs &a, int tid, b
         }
     }
     if (a.p2p) {
-        // Publish completion: every CTA makes its (peer) stores visible system-wide, the last one to
-        // finish bumps this rank's epoch and writes it into both neighbours' sync blocks.
+        // the last CTA of the grid to finish advances this rank's count of completed kernels
         __syncthreads();
         if (tid == 0) {
-            __threadfence_system();
+            __threadfence();
             const unsigned total = gridDim.x * gridDim.y;
             const unsigned prev = atomicAdd((unsigned *)a.sync, 1u);
             if (prev == total - 1) {
                 a.sync[0] = 0;
-                const int e = a.sync[1] + 1;
-                a.sync[1] = e;
-                __threadfence_system();
-                if (a.peer_n_flag) *(volatile int *)a.peer_n_flag = e;
-                if (a.peer_s_flag) *(volatile int *)a.peer_s_flag = e;
+                a.sync[1] = a.sync[1] + 1;
             }
         }
     }
@@ -458,21 +463,27 @@ __global__ void __launch_bounds__(NT) k_subcycle(const __grid_constant__ SubArgs
     const int j0 = __ldg(a.chunks + 2 * blockIdx.y);
     const int nrows = __ldg(a.chunks + 2 * blockIdx.y + 1);
     const bool top = (j0 + nrows - 1 == a.nyl), bot = (j0 == 1);
-    if (a.p2p) {
-        // Before reading the ghost rows the neighbours stored during their previous subcycle kernel,
-        // and before storing into their ghost rows of the buffer they read during that kernel, wait
-        // until they have published at least as many completed subcycles as this rank has.
-        if ((top && a.peer_n_flag) || (bot && a.peer_s_flag)) {
-            if (tid == 0) {
-                const int e = *(volatile int *)(a.sync + 1);
-                if (top && a.peer_n_flag)
-                    while (*(volatile int *)(a.sync + 2) < e) __nanosleep(20);
-                if (bot && a.peer_s_flag)
-                    while (*(volatile int *)(a.sync + 3) < e) __nanosleep(20);
-                __threadfence_system();
-            }
-            __syncthreads();
+    int epoch = 0;
+    if (a.p2p && ((top && a.peer_n_flag) || (bot && a.peer_s_flag))) {
+        // A boundary CTA reads ghost-row columns that strips x-1, x, x+1 of the neighbour's adjacent
+        // chunk stored during that rank's previous subcycle kernel, and stores into ghost-row columns
+        // those strips read during it.  Both are safe once these three strips have published at
+        // least as many finished kernels as this rank has completed (per-strip epochs: the
+        // neighbour's boundary CTAs run first and are short, so normally nothing waits).
+        __shared__ int s_epoch;
+        if (tid < 3) {
+            const int e = *(volatile int *)(a.sync + 1);
+            const int ncx = (int)gridDim.x;
+            const int x = ((int)blockIdx.x + tid - 1 + ncx) % ncx;
+            if (top && a.peer_n_flag)
+                while (*(volatile int *)(a.sync + EVP_SYNC_FN + x) < e) __nanosleep(20);
+            if (bot && a.peer_s_flag)
+                while (*(volatile int *)(a.sync + EVP_SYNC_FS + x) < e) __nanosleep(20);
+            __threadfence_system();
+            if (tid == 0) s_epoch = e;
         }
+        __syncthreads();
+        epoch = s_epoch;
     }
     const int jlast = min(j0 + nrows, a.nyl + 1); // last T row of this CTA
     const bool colT = (tid <= a.strip_w) && (i <= a.nx + 1);
@@ -552,7 +563,7 @@ __global__ void __launch_bounds__(NT) k_subcycle(const __grid_constant__ SubArgs
         tm_raw = tm_raw2;
         um_raw = um_raw1;
     }
-    k_subcycle_epilogue<NT>(a, tid, top);
+    k_subcycle_epilogue<NT>(a, tid, top, bot, epoch);
 }
 
 // HT (2-plane metric path) is chosen by a.row_ht
