@@ -271,3 +271,69 @@ def test_stress_residency(oracle, evp_lib):
     out2 = dyn.evp(3600.0, inputs, strength=E.split_blocks(f2["strength"], lay, "cyclic", "tripole"))
     dyn.download_state()
     _compare_exact(dyn, out2, st_h, f2, lay)
+
+
+def test_edge_no_ice_and_all_land(oracle, evp_lib):
+    """Empty inputs: an ice-free ocean and an all-land domain give all-zero dynamics, and the state
+    left by a previous call is cleared exactly as evp_prep2 does (:827-840, :886-894)."""
+    case = synth.make_case("om1deg", nx=48, ny=36)
+    lay = E.BlockLayout.single_block(48, 36)
+    # previous step with ice, then the ice disappears
+    st, f, strengths, _ = oracle_steps(oracle, case, nsteps=1)
+    for k in ("aice", "vice", "vsno", "aicen", "vicen", "strairxT", "strairyT"):
+        case.inputs[k][...] = 0.0
+    case.inputs["aice0"][...] = 1.0
+    p = oracle.make_params()
+    f2, _ = oracle.run_evp(case.grid, case.inputs, st, p)
+    assert np.all(st["uvel"] == 0.0) and np.all(st["stressp_1"] == 0.0) and np.all(st["iceumask"] == 0)
+    case_ice = synth.make_case("om1deg", nx=48, ny=36)
+    dyn, _ = cuda_steps(case_ice, nsteps=1, strengths=strengths)
+    inputs = {k: E.split_blocks(v, lay, "cyclic", "tripole") for k, v in case.inputs.items()}
+    out = dyn.evp(3600.0, inputs, strength=E.split_blocks(f2["strength"], lay, "cyclic", "tripole"))
+    _compare_exact(dyn, out, st, f2, lay)
+    # all land
+    case2 = synth.make_case("gx3", nx=20, ny=16, ew="cyclic", ns="open")
+    case2.grid.f["tmask"][...] = 0
+    case2.grid.f["umask"][...] = 0
+    st3, f3, s3, _ = oracle_steps(oracle, case2, nsteps=1)
+    dyn3, out3 = cuda_steps(case2, nsteps=1, strengths=s3)
+    _compare_exact(dyn3, out3, st3, f3, E.BlockLayout.single_block(20, 16))
+    assert np.all(dyn3.state["uvel"] == 0.0)
+
+
+@pytest.mark.parametrize("nx,ny,ew,ns", [(8, 6, "cyclic", "tripole"), (5, 4, "open", "open"), (6, 3, "cyclic", "open"),
+                                         (257, 3, "cyclic", "tripole"), (129, 47, "cyclic", "cyclic")])
+def test_edge_small_and_ragged_sizes(oracle, evp_lib, nx, ny, ew, ns):
+    """Minimum and ragged sizes: fewer columns than one strip, strips that do not divide nx, slabs of
+    2-3 rows, a fold row shorter than a warp."""
+    case = synth.make_case("x", nx=nx, ny=ny, ew=ew, ns=ns)
+    st, f, strengths, _ = oracle_steps(oracle, case, nsteps=2, ndte=24)
+    lay = E.BlockLayout.single_block(nx, ny)
+    dyn, out = cuda_steps(case, nsteps=2, strengths=strengths, ndte=24)
+    _compare_exact(dyn, out, st, f, lay)
+
+
+def test_restart_like_state(oracle, evp_lib):
+    """Non-zero incoming state incl. ghost cells (what restartfile leaves: scattered velocities,
+    N/E ghost stresses filled, W/S ghost stresses zeroed, source/ice_restart.F90:427-539)."""
+    case = synth.make_case("om1deg", nx=64, ny=48, realistic=True)
+    lay = E.BlockLayout.cartesian(64, 48, 16, 24)
+    rng = np.random.default_rng(11)
+    st0 = synth.zero_state(66, 50)
+    for n in STATE[:2]:
+        st0[n][...] = 0.05 * rng.standard_normal(st0[n].shape)
+    for n in STATE[2:14]:
+        st0[n][...] = 1.0e3 * rng.standard_normal(st0[n].shape)
+        st0[n][0, :] = 0.0
+        st0[n][:, 0] = 0.0
+    st0["iceumask"][1:-1, 1:-1] = (rng.random((64, 48)) > 0.5).astype(np.int32)
+    st_o = {k: v.copy(order="F") for k, v in st0.items()}
+    p = oracle.make_params()
+    f, _ = oracle.run_evp(case.grid, case.inputs, st_o, p)
+    dyn = E.IceDynEvp(lay, "cyclic", "tripole")
+    dyn.init_evp(3600.0, E.grid_fields_in_blocks(case.grid, lay, "cyclic", "tripole"))
+    for k in STATE:
+        dyn.state[k][...] = E.split_blocks(st0[k], lay, "cyclic", "tripole")
+    inputs = {k: E.split_blocks(v, lay, "cyclic", "tripole") for k, v in case.inputs.items()}
+    out = dyn.evp(3600.0, inputs, strength=E.split_blocks(f["strength"], lay, "cyclic", "tripole"))
+    _compare_exact(dyn, out, st_o, f, lay)
