@@ -31,6 +31,16 @@ BYTES_T = 34 * 8   # per active T cell and subcycle: 12+12 stresses, strength, 9
 BYTES_U = 14 * 8   # per active U cell and subcycle: u,v read+write, 10 U fields
 
 
+def measured_traffic():
+    """DRAM bytes per launch of the dominant kernel from the committed ncu --set full capture."""
+    p = os.path.join(ROOT, "profiles", "traffic.json")
+    try:
+        d = json.load(open(p))
+        return int(d["dram_bytes_read_per_launch"]) + int(d["dram_bytes_write_per_launch"]), d["source"]
+    except Exception:
+        return None, None
+
+
 def measured_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -234,6 +244,9 @@ def run_b200(args):
     value = nx * ny * ndte / (ms_loop * 1e-3)
     kernel_s = ms_loop * 1e-3 / ndte
     peak, peak_src = measured_peaks()
+    traffic, traffic_src = measured_traffic()
+    if world != 1 or args.workload != "om025" or args.realistic:
+        traffic, traffic_src = None, None            # the capture is of the 1-GPU om025 dense launch
     achieved = bytes_per_sub / kernel_s / 1e9        # whole job, all GPUs
 
     # ---- end to end through the public call, host buffers ----------------------------------------
@@ -297,7 +310,8 @@ def run_b200(args):
                    "parallelism": f"{world} y-slab(s), one process per GPU"
                                   + (", NCCL row exchange every subcycle" if world > 1 else "")},
         "roofline": {"bound": "hbm", "achieved": achieved / world, "peak": peak, "unit": "GB/s",
-                     "frac": achieved / world / peak, "traffic": None, "peak_source": peak_src,
+                     "frac": achieved / world / peak, "traffic": traffic, "traffic_source": traffic_src,
+                     "peak_source": peak_src,
                      "per": "GPU", "kernel": "k_subcycle (fused stress+stepu)", "kernel_us": kernel_s * 1e6,
                      "algorithmic_bytes_per_launch": bytes_per_sub / world,
                      "frac_of_nominal_8TBs": achieved / world / 8000.0},
