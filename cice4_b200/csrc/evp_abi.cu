@@ -97,6 +97,9 @@ struct evp_b200_handle {
     std::unordered_map<const void *, size_t> pinned;
     int grid_x = 0, grid_y = 0, threads = 128, strip_w = 0, rows = 0;
     int *d_chunks = nullptr;          // row-chunk table of the subcycle kernel (2 ints per chunk)
+    int *d_rowcnt = nullptr;          // active T cells per row (load balance of the chunks)
+    bool balance = false;             // rebuild the chunk table from icetmask every call
+    float w_bot = 1.f, w_top = 1.f;   // relative cost targets of the boundary chunks
     int sub_launches_per_loop = 0;
     // y-slab chain: neighbour ranks (-1 = none) and the NCCL communicator (dlopen()ed entry points)
     int north = -1, south = -1;
@@ -403,7 +406,13 @@ int choose_tiling(evp_b200_handle *h) {
     for (int k = 0; k < ncy; ++k)
         if (tab[2 * k] + tab[2 * k + 1] - 1 == nyl) top_rows = tab[2 * k + 1];
     h->fold_in_kernel = fold_wanted && top_rows >= 2;
+    h->w_bot = (float)w_bot;
+    h->w_top = (float)w_top;
+    // with the default tiling the chunk table is re-balanced by active cells on the device each call
+    h->balance = h->par.tile_rows <= 0 && ncy >= 3 && (h->par.kernel_variant & 32) == 0;
     if (h->d_chunks) cudaFree(h->d_chunks);
+    if (h->d_rowcnt) cudaFree(h->d_rowcnt);
+    CU(cudaMalloc(&h->d_rowcnt, sizeof(int) * (nyl + 2)));
     CU(cudaMalloc(&h->d_chunks, sizeof(int) * tab.size()));
     CU(cudaMemcpy(h->d_chunks, tab.data(), sizeof(int) * tab.size(), cudaMemcpyHostToDevice));
     return 0;
@@ -440,37 +449,9 @@ void evp_b200_default_params(evp_b200_params *p) {
     p->use_graph = 1;
 }
 
-int evp_b200_init(const evp_b200_dims *d, const evp_b200_params *p, const evp_b200_static_fields *g,
-                  evp_b200_handle **out) {
-    if (!d || !p || !g || !out) return fail(EVP_B200_ERR_ARG, "NULL argument");
-    *out = nullptr;
-    if (d->nblocks < 1 || d->nblocks > d->max_blocks) return fail(EVP_B200_ERR_ARG, "bad nblocks");
-    if (d->nx_block < 3 || d->ny_block < 3) return fail(EVP_B200_ERR_ARG, "bad block size");
-    if (!d->ilo || !d->ihi || !d->jlo || !d->jhi || !d->iglob_lo || !d->jglob_lo)
-        return fail(EVP_B200_ERR_ARG, "block index arrays are NULL");
-    if (d->ns_boundary > EVP_B200_BND_TRIPOLE || d->ew_boundary > EVP_B200_BND_CYCLIC || d->ew_boundary < 0 ||
-        d->ns_boundary < 0)
-        return fail(EVP_B200_ERR_UNSUPPORTED, "boundary type not supported (tripoleT is not implemented)");
-    if (d->nranks < 1 || d->rank < 0 || d->rank >= d->nranks) return fail(EVP_B200_ERR_ARG, "bad rank/nranks");
-    if (d->slab_jlo < 1 || d->slab_jhi > d->ny_global || d->slab_jhi - d->slab_jlo + 1 < 2)
-        return fail(EVP_B200_ERR_ARG, "bad slab rows (each slab needs at least 2 rows)");
-    if (d->nranks == 1 && (d->slab_jlo != 1 || d->slab_jhi != d->ny_global))
-        return fail(EVP_B200_ERR_ARG, "slab must span the domain when nranks == 1");
-    if (d->nranks > 1 && d->ns_boundary == EVP_B200_BND_CYCLIC)
-        return fail(EVP_B200_ERR_UNSUPPORTED, "north-south cyclic domains are single-slab only");
-    if (d->nranks > 1 && ((d->rank == 0) != (d->slab_jlo == 1) || (d->rank == d->nranks - 1) != (d->slab_jhi == d->ny_global)))
-        return fail(EVP_B200_ERR_ARG, "slabs must be ordered south to north by rank");
-    if (p->ndte < 1 || !(p->dt > 0.0)) return fail(EVP_B200_ERR_ARG, "bad dt/ndte");
-    if (p->ncat < 1 || p->ncat > 16) return fail(EVP_B200_ERR_ARG, "ncat out of range");
-    if (d->ns_boundary == EVP_B200_BND_TRIPOLE && d->nx_global + 2 > 8 * 1024)
-        return fail(EVP_B200_ERR_UNSUPPORTED, "tripole fold kernel supports nx_global <= 8190");
-
-    int ndev = 0;
-    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev < 1) {
-        cudaGetLastError();
-        return fail(EVP_B200_ERR_CUDA, "no CUDA device: libevp_b200 has no CPU fallback");
-    }
-    evp_b200_handle *h = new evp_b200_handle();
+// everything of evp_b200_init that can fail after the handle exists; the caller finalizes on error
+static int init_handle(evp_b200_handle *h, const evp_b200_dims *d, const evp_b200_params *p,
+                       const evp_b200_static_fields *g) {
     h->dims = *d;
     h->par = *p;
     if (d->device >= 0) {
@@ -486,7 +467,6 @@ int evp_b200_init(const evp_b200_dims *d, const evp_b200_params *p, const evp_b2
     for (int b = 0; b < d->nblocks; ++b) {
         if (d->ilo[b] < 2 || d->jlo[b] < 2 || d->ihi[b] > d->nx_block - 1 || d->jhi[b] > d->ny_block - 1 ||
             d->ihi[b] < d->ilo[b] || d->jhi[b] < d->jlo[b]) {
-            delete h;
             return fail(EVP_B200_ERR_ARG, "block %d: bad ilo/ihi/jlo/jhi (nghost must be 1)", b);
         }
         h->blk_tab[b * 6 + 0] = d->ilo[b];
@@ -498,13 +478,11 @@ int evp_b200_init(const evp_b200_dims *d, const evp_b200_params *p, const evp_b2
         const int ig1 = d->iglob_lo[b] + (d->ihi[b] - d->ilo[b]);
         const int jg1 = d->jglob_lo[b] + (d->jhi[b] - d->jlo[b]);
         if (d->iglob_lo[b] < 1 || ig1 > d->nx_global || d->jglob_lo[b] < d->slab_jlo || jg1 > d->slab_jhi) {
-            delete h;
             return fail(EVP_B200_ERR_ARG, "block %d lies outside the slab", b);
         }
         covered += (long)(d->ihi[b] - d->ilo[b] + 1) * (d->jhi[b] - d->jlo[b] + 1);
     }
     if (covered != (long)d->nx_global * nyl) {
-        delete h;
         return fail(EVP_B200_ERR_ARG, "blocks cover %ld cells, slab has %ld (land-block elimination is not supported)",
                     covered, (long)d->nx_global * nyl);
     }
@@ -577,7 +555,7 @@ int evp_b200_init(const evp_b200_dims *d, const evp_b200_params *p, const evp_b2
     int slot = 0;
     for (auto &s : statics) {
         int rc = upload_r8(h, s.src, slot++, h->pl[s.id]);
-        if (rc) { evp_b200_finalize(h); return rc; }
+        if (rc) return rc;
     }
     int rc = upload_mask(h, g->tmask, 0, h->mk[M_TMASK]);
     if (!rc) rc = upload_mask(h, g->umask, 1, h->mk[M_UMASK]);
@@ -598,10 +576,51 @@ int evp_b200_init(const evp_b200_dims *d, const evp_b200_params *p, const evp_b2
             for (uint8_t f : flags) h->rows_ht += f ? 1 : 0;
         }
     }
-    if (rc) { evp_b200_finalize(h); return rc; }
+    if (rc) return rc;
     CU(cudaStreamSynchronize(h->st));
-    if (int trc = choose_tiling(h)) { evp_b200_finalize(h); return trc; }
+    if (int trc = choose_tiling(h)) return trc;
     memset(&h->tm, 0, sizeof(h->tm));
+    return EVP_B200_OK;
+}
+
+int evp_b200_init(const evp_b200_dims *d, const evp_b200_params *p, const evp_b200_static_fields *g,
+                  evp_b200_handle **out) {
+    if (!d || !p || !g || !out) return fail(EVP_B200_ERR_ARG, "NULL argument");
+    *out = nullptr;
+    if (d->nblocks < 1 || d->nblocks > d->max_blocks) return fail(EVP_B200_ERR_ARG, "bad nblocks");
+    if (d->nx_block < 3 || d->ny_block < 3) return fail(EVP_B200_ERR_ARG, "bad block size");
+    if (!d->ilo || !d->ihi || !d->jlo || !d->jhi || !d->iglob_lo || !d->jglob_lo)
+        return fail(EVP_B200_ERR_ARG, "block index arrays are NULL");
+    if (d->ns_boundary > EVP_B200_BND_TRIPOLE || d->ew_boundary > EVP_B200_BND_CYCLIC || d->ew_boundary < 0 ||
+        d->ns_boundary < 0)
+        return fail(EVP_B200_ERR_UNSUPPORTED, "boundary type not supported (tripoleT is not implemented)");
+    if (d->nranks < 1 || d->rank < 0 || d->rank >= d->nranks) return fail(EVP_B200_ERR_ARG, "bad rank/nranks");
+    if (d->slab_jlo < 1 || d->slab_jhi > d->ny_global || d->slab_jhi - d->slab_jlo + 1 < 2)
+        return fail(EVP_B200_ERR_ARG, "bad slab rows (each slab needs at least 2 rows)");
+    if (d->nranks == 1 && (d->slab_jlo != 1 || d->slab_jhi != d->ny_global))
+        return fail(EVP_B200_ERR_ARG, "slab must span the domain when nranks == 1");
+    if (d->nranks > 1 && d->ns_boundary == EVP_B200_BND_CYCLIC)
+        return fail(EVP_B200_ERR_UNSUPPORTED, "north-south cyclic domains are single-slab only");
+    if (d->nranks > 1 && ((d->rank == 0) != (d->slab_jlo == 1) || (d->rank == d->nranks - 1) != (d->slab_jhi == d->ny_global)))
+        return fail(EVP_B200_ERR_ARG, "slabs must be ordered south to north by rank");
+    if (p->ndte < 1 || !(p->dt > 0.0)) return fail(EVP_B200_ERR_ARG, "bad dt/ndte");
+    if (p->ncat < 1 || p->ncat > 16) return fail(EVP_B200_ERR_ARG, "ncat out of range");
+    if (d->ns_boundary == EVP_B200_BND_TRIPOLE && d->nx_global + 2 > 8 * 1024)
+        return fail(EVP_B200_ERR_UNSUPPORTED, "tripole fold kernel supports nx_global <= 8190");
+
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev < 1) {
+        cudaGetLastError();
+        return fail(EVP_B200_ERR_CUDA, "no CUDA device: libevp_b200 has no CPU fallback");
+    }
+    evp_b200_handle *h = new evp_b200_handle();
+    const int rc = init_handle(h, d, p, g);
+    if (rc) {
+        const std::string msg = g_err; // finalize must not lose the reason
+        evp_b200_finalize(h);
+        g_err = msg;
+        return rc;
+    }
     *out = h;
     return EVP_B200_OK;
 }
@@ -748,6 +767,9 @@ static int do_run(evp_b200_handle *h, const evp_b200_inputs *in, const double *s
         if ((rc = exchange_rows(h, pp, 2, sizeof(double)))) return rc;
     }
     h->cur = 0;
+    if (h->balance) // chunks of equal ACTIVE work; an inactive row inside a chunk still costs ~30 % of an active one
+        aux_balance_chunks(pg, h->mk[M_ICETMASK], h->mk[M_ICEUMASK], h->d_rowcnt, h->d_chunks, h->grid_y,
+                           h->w_bot, h->w_top, h->fold_in_kernel ? 2 : 1, 0.3f * (float)(pg.nx + 1), h->st);
     CU(cudaEventRecord(h->ev[3], h->st));
     // ---- :347-404 ------------------------------------------------------------------------------
     if ((rc = run_subcycle_loop(h))) return rc;
@@ -1002,6 +1024,7 @@ int evp_b200_finalize(evp_b200_handle *h) {
     cudaFree(h->sync);
     cudaFree(h->fold_scratch);
     cudaFree(h->d_chunks);
+    cudaFree(h->d_rowcnt);
     cudaFree(h->row_ht);
     if (h->comm && h->pCommDestroy) h->pCommDestroy(h->comm);
     if (h->graph_exec) cudaGraphExecDestroy(h->graph_exec);

@@ -436,6 +436,90 @@ __global__ void k_check_metrics(PlaneGeom pg, MetricCheckArgs a) {
     if (threadIdx.x == 0) a.row_ht[j] = bad ? 0 : 1;
 }
 
+__global__ void k_row_active(PlaneGeom pg, const uint8_t *__restrict__ icetmask,
+                             const uint8_t *__restrict__ iceumask, int *__restrict__ rowcnt) {
+    const int j = blockIdx.x; // 0..nyl+1
+    int c = 0;
+    for (int i = 1 + threadIdx.x; i <= pg.nx + 1; i += blockDim.x) {
+        const size_t idx = (size_t)j * pg.pitch + i;
+        c += (icetmask[idx] ? 1 : 0) + ((iceumask[idx] && !icetmask[idx]) ? 1 : 0); // rows with T or U work
+    }
+    __shared__ int tot;
+    if (threadIdx.x == 0) tot = 0;
+    __syncthreads();
+    for (int o = 16; o > 0; o >>= 1) c += __shfl_down_sync(0xffffffffu, c, o);
+    if ((threadIdx.x & 31) == 0) atomicAdd(&tot, c);
+    __syncthreads();
+    if (threadIdx.x == 0) rowcnt[j] = tot;
+}
+
+// single thread: a few thousand rows at most
+__global__ void k_balance_chunks(PlaneGeom pg, const int *__restrict__ rowcnt, int *__restrict__ chunks, int ncy,
+                                 float w_bot, float w_top, int min_top, float row_overhead) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    const int nyl = pg.nyl;
+    auto cost = [&](int j) { return row_overhead + (float)rowcnt[j]; };
+    if (ncy == 1) {
+        chunks[0] = 1; chunks[1] = nyl;
+        return;
+    }
+    float total = 0.f;
+    for (int j = 1; j <= nyl; ++j) total += cost(j);
+    const int n_int = ncy - 2;
+    const float unit = total / ((float)n_int + w_bot + w_top);
+    // north chunk: from the top down
+    int n_top = 0;
+    float acc = 0.f;
+    while (n_top < nyl - (ncy - 1) && (n_top < min_top || acc < w_top * unit)) {
+        acc += cost(nyl - n_top);
+        ++n_top;
+    }
+    if (n_top < 1) n_top = 1;
+    // south chunk: from the bottom up, leaving one row for each interior chunk
+    int n_bot = 0;
+    acc = 0.f;
+    while (n_bot < nyl - n_top - n_int && (n_bot < 1 || acc < w_bot * unit)) {
+        acc += cost(1 + n_bot);
+        ++n_bot;
+    }
+    chunks[0] = 1; chunks[1] = n_bot;
+    chunks[2] = nyl - n_top + 1; chunks[3] = n_top;
+    // interior: greedy with a running target so that rounding does not pile up on the last chunk
+    int j = 1 + n_bot;
+    const int jend = nyl - n_top; // last interior row
+    float rest = 0.f;
+    for (int r = j; r <= jend; ++r) rest += cost(r);
+    for (int k = 0; k < n_int; ++k) {
+        const int chunks_left = n_int - k;
+        const float target = rest / (float)chunks_left;
+        int n = 0;
+        acc = 0.f;
+        // every remaining chunk must keep at least one row
+        while (j + n <= jend - (chunks_left - 1) && (n < 1 || acc + 0.5f * cost(j + n) < target)) {
+            acc += cost(j + n);
+            ++n;
+        }
+        if (k == n_int - 1) { // last interior chunk takes what is left
+            while (j + n <= jend) { acc += cost(j + n); ++n; }
+        }
+        chunks[2 * (2 + k)] = j;
+        chunks[2 * (2 + k) + 1] = n;
+        j += n;
+        rest -= acc;
+    }
+    // Trim rows without any active T or U cell from both ends of the interior chunks: such rows
+    // belong to no chunk (nothing is computed there; velocities and stresses are 0 in both copies),
+    // and an all-inactive chunk becomes empty (its CTAs exit at once).  The boundary chunks keep
+    // their rows: they carry the fold and the peer-to-peer halo.
+    for (int k = 2; k < ncy; ++k) {
+        int j0 = chunks[2 * k], n = chunks[2 * k + 1];
+        while (n > 0 && rowcnt[j0] == 0) { ++j0; --n; }
+        while (n > 0 && rowcnt[j0 + n - 1] == 0) --n;
+        chunks[2 * k] = j0;
+        chunks[2 * k + 1] = n;
+    }
+}
+
 __global__ void k_wait_peers(int *sync, int has_north, int has_south, int ncx) {
     const int e = *(volatile int *)(sync + 1);
     for (int x = threadIdx.x; x < ncx; x += blockDim.x) {
@@ -527,4 +611,10 @@ void aux_wait_peers(int *sync, int has_north, int has_south, int ncx, cudaStream
 }
 void aux_check_metrics(const PlaneGeom &pg, const MetricCheckArgs &a, cudaStream_t s) {
     k_check_metrics<<<pg.nyl + 2, 256, 0, s>>>(pg, a);
+}
+void aux_balance_chunks(const PlaneGeom &pg, const uint8_t *icetmask, const uint8_t *iceumask, int *rowcnt,
+                        int *chunks, int ncy, float w_bot, float w_top, int min_top, float row_overhead,
+                        cudaStream_t s) {
+    k_row_active<<<pg.nyl + 2, 128, 0, s>>>(pg, icetmask, iceumask, rowcnt);
+    k_balance_chunks<<<1, 32, 0, s>>>(pg, rowcnt, chunks, ncy, w_bot, w_top, min_top, row_overhead);
 }

@@ -102,3 +102,14 @@ struct MetricCheckArgs {
     uint8_t *row_ht;
 };
 void aux_check_metrics(const PlaneGeom &pg, const MetricCheckArgs &a, cudaStream_t s);
+
+// Load balance of the subcycle kernel's row chunks by ACTIVE work (device-side replacement of the
+// reference's compressed index lists icellt/indxti, source/ice_dyn_evp.F90:850-859): rebuilds the
+// chunk table (j0, n) in launch order [south, north, interior south->north] so that every chunk
+// carries about the same cost, cost(row) = row_overhead + active T cells of the row; the boundary
+// chunks get w_bot / w_top of an interior chunk's cost.  ncy chunks, each >= 1 row (north >= min_top).
+// Rows without any active T or U cell are trimmed from the ends of the interior chunks (they belong to
+// no chunk); an all-inactive chunk becomes empty.
+void aux_balance_chunks(const PlaneGeom &pg, const uint8_t *icetmask, const uint8_t *iceumask, int *rowcnt,
+                        int *chunks, int ncy, float w_bot, float w_top, int min_top, float row_overhead,
+                        cudaStream_t s);

@@ -485,6 +485,7 @@ __global__ void __launch_bounds__(NT) k_subcycle(const __grid_constant__ SubArgs
         __syncthreads();
         epoch = s_epoch;
     }
+    if (nrows > 0) { // an empty chunk (all rows inactive, trimmed by the load balancer) has nothing to do
     const int jlast = min(j0 + nrows, a.nyl + 1); // last T row of this CTA
     const bool colT = (tid <= a.strip_w) && (i <= a.nx + 1);
     const bool colU = (tid < a.strip_w) && (i <= a.nx);
@@ -562,6 +563,7 @@ __global__ void __launch_bounds__(NT) k_subcycle(const __grid_constant__ SubArgs
         t = tn;
         tm_raw = tm_raw2;
         um_raw = um_raw1;
+    }
     }
     k_subcycle_epilogue<NT>(a, tid, top, bot, epoch);
 }
