@@ -538,7 +538,7 @@ static int init_handle(evp_b200_handle *h, const evp_b200_dims *d, const evp_b20
     CU(cudaMemsetAsync(h->stage, 0, sizeof(double) * h->blocked_elems * h->n_stage, h->st));
     CU(cudaMemsetAsync(h->stage_i, 0, sizeof(int32_t) * h->blocked_elems * 2, h->st));
     CU(cudaMalloc(&h->fold_scratch, sizeof(double) * 2 * pg.pitch));
-    CU(cudaMalloc(&h->sync, sizeof(int) * EVP_SYNC_INTS));
+    CU(cudaMalloc(&h->sync, sizeof(int) * EVP_SYNC_INTS + 4 * sizeof(double))); // + diagnostics scratch
     CU(cudaMemsetAsync(h->sync, 0, sizeof(int) * EVP_SYNC_INTS, h->st));
     CU(cudaMalloc(&h->d_blk_tab, sizeof(int) * h->blk_tab.size()));
     CU(cudaMemcpyAsync(h->d_blk_tab, h->blk_tab.data(), sizeof(int) * h->blk_tab.size(), cudaMemcpyHostToDevice, h->st));
@@ -884,6 +884,20 @@ int evp_b200_principal_stress(evp_b200_handle *h, const double *sp1, const doubl
     aux_principal_stress(n, s, s + n, s + 2 * n, s + 3 * n, h->par.puny, s + 4 * n, s + 5 * n, h->st);
     CU(cudaMemcpyAsync(sig1, s + 4 * n, bytes, cudaMemcpyDeviceToHost, h->st));
     CU(cudaMemcpyAsync(sig2, s + 5 * n, bytes, cudaMemcpyDeviceToHost, h->st));
+    CU(cudaStreamSynchronize(h->st));
+    return 0;
+}
+
+int evp_b200_diagnostics(evp_b200_handle *h, double out[4]) {
+    if (!h || !out) return fail(EVP_B200_ERR_ARG, "NULL argument");
+    if (!h->resident) return fail(EVP_B200_ERR_STATE, "no device-resident result: call evp_b200_step/run first");
+    CU(cudaSetDevice(h->device));
+    double *d = (double *)(h->sync + EVP_SYNC_INTS); // 4 doubles behind the sync block
+    CU(cudaMemsetAsync(d, 0, 4 * sizeof(double), h->st));
+    // lmask_s: ULAT < -puny  <=>  fcor = 2*omega*sin(ULAT) < 2*omega*sin(-puny)
+    const double fcor_south = 2.0 * 7.292e-5 * sin(-h->par.puny);
+    aux_diagnostics(h->pg, h->pl[P_U0], h->pl[P_V0], h->pl[P_STRENGTH], h->pl[P_FCOR], fcor_south, d, h->st);
+    CU(cudaMemcpyAsync(out, d, 4 * sizeof(double), cudaMemcpyDeviceToHost, h->st));
     CU(cudaStreamSynchronize(h->st));
     return 0;
 }

@@ -520,6 +520,36 @@ __global__ void k_balance_chunks(PlaneGeom pg, const int *__restrict__ rowcnt, i
     }
 }
 
+// non-negative doubles order like their bit patterns
+__device__ __forceinline__ void atomic_max_nonneg(double *addr, double v) {
+    atomicMax((unsigned long long *)addr, (unsigned long long)__double_as_longlong(v));
+}
+
+__global__ void k_diagnostics(PlaneGeom pg, const double *__restrict__ u, const double *__restrict__ v,
+                              const double *__restrict__ strength, const double *__restrict__ fcor,
+                              double fcor_south, double *out4) {
+    const int i = 1 + blockIdx.x * blockDim.x + threadIdx.x;
+    const int j = 1 + blockIdx.y;
+    double sp[2] = {0.0, 0.0}, pm[2] = {0.0, 0.0};
+    if (i <= pg.nx && j <= pg.nyl) {
+        const size_t idx = (size_t)j * pg.pitch + i;
+        const int south = fcor[idx] < fcor_south ? 1 : 0; // lmask_s: ULAT < -puny
+        sp[south] = sqrt(u[idx] * u[idx] + v[idx] * v[idx]);
+        pm[south] = fmax(strength[idx], 0.0) / 1000.0;
+    }
+    for (int o = 16; o > 0; o >>= 1)
+        for (int k = 0; k < 2; ++k) {
+            sp[k] = fmax(sp[k], __shfl_down_sync(0xffffffffu, sp[k], o));
+            pm[k] = fmax(pm[k], __shfl_down_sync(0xffffffffu, pm[k], o));
+        }
+    if ((threadIdx.x & 31) == 0) {
+        if (sp[0] > 0.0) atomic_max_nonneg(out4 + 0, sp[0]);
+        if (sp[1] > 0.0) atomic_max_nonneg(out4 + 1, sp[1]);
+        if (pm[0] > 0.0) atomic_max_nonneg(out4 + 2, pm[0]);
+        if (pm[1] > 0.0) atomic_max_nonneg(out4 + 3, pm[1]);
+    }
+}
+
 __global__ void k_wait_peers(int *sync, int has_north, int has_south, int ncx) {
     const int e = *(volatile int *)(sync + 1);
     for (int x = threadIdx.x; x < ncx; x += blockDim.x) {
@@ -617,4 +647,9 @@ void aux_balance_chunks(const PlaneGeom &pg, const uint8_t *icetmask, const uint
                         cudaStream_t s) {
     k_row_active<<<pg.nyl + 2, 128, 0, s>>>(pg, icetmask, iceumask, rowcnt);
     k_balance_chunks<<<1, 32, 0, s>>>(pg, rowcnt, chunks, ncy, w_bot, w_top, min_top, row_overhead);
+}
+void aux_diagnostics(const PlaneGeom &pg, const double *u, const double *v, const double *strength,
+                     const double *fcor, double fcor_south, double *out4, cudaStream_t s) {
+    dim3 grid(nblk(pg.nx), pg.nyl);
+    k_diagnostics<<<grid, TPB, 0, s>>>(pg, u, v, strength, fcor, fcor_south, out4);
 }

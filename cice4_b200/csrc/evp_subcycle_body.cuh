@@ -454,6 +454,10 @@ __device__ __forceinline__ void k_subcycle_epilogue(const SubArgs &a, int tid, b
 template <int NT, bool LAST, bool HT>
 __global__ void __launch_bounds__(NT) k_subcycle(const __grid_constant__ SubArgs a) {
     __shared__ double xch[2][4][NT];
+    // programmatic dependent launch: let the next subcycle kernel be scheduled as SMs drain, and
+    // wait here until the previous grid has completed and flushed (no-ops without the attribute)
+    asm volatile("griddepcontrol.launch_dependents;");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
     const int tid = threadIdx.x;
     const int i = 1 + blockIdx.x * a.strip_w + tid;
     // Row chunks come from a table in launch order: the southernmost and northernmost chunk first
@@ -568,16 +572,34 @@ __global__ void __launch_bounds__(NT) k_subcycle(const __grid_constant__ SubArgs
     k_subcycle_epilogue<NT>(a, tid, top, bot, epoch);
 }
 
+// Launch with programmatic dependent launch (PDL): the next subcycle kernel may be scheduled while
+// this one drains; its CTAs block in griddepcontrol.wait at their first instruction until this grid
+// has completed and its stores are visible, so only launch latency and ramp-up overlap.
+template <typename K>
+static void launch_k(K kernel, const SubArgs &a, dim3 grid, dim3 block, bool pdl, cudaStream_t s) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = 0;
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl ? 1 : 0;
+    cudaLaunchKernelEx(&cfg, kernel, a);
+}
+
 // HT (2-plane metric path) is chosen by a.row_ht
 template <int NT>
-static void launch_nt(const SubArgs &a, bool last, unsigned gx, unsigned gy, cudaStream_t s) {
+static void launch_nt(const SubArgs &a, bool last, bool pdl, unsigned gx, unsigned gy, cudaStream_t s) {
     dim3 grid(gx, gy), block(NT);
     if (a.row_ht) {
-        if (last) k_subcycle<NT, true, true><<<grid, block, 0, s>>>(a);
-        else k_subcycle<NT, false, true><<<grid, block, 0, s>>>(a);
+        if (last) launch_k(k_subcycle<NT, true, true>, a, grid, block, pdl, s);
+        else launch_k(k_subcycle<NT, false, true>, a, grid, block, pdl, s);
     } else {
-        if (last) k_subcycle<NT, true, false><<<grid, block, 0, s>>>(a);
-        else k_subcycle<NT, false, false><<<grid, block, 0, s>>>(a);
+        if (last) launch_k(k_subcycle<NT, true, false>, a, grid, block, pdl, s);
+        else launch_k(k_subcycle<NT, false, false>, a, grid, block, pdl, s);
     }
 }
 
@@ -585,11 +607,11 @@ static void launch_nt(const SubArgs &a, bool last, unsigned gx, unsigned gy, cud
 
 void EVP_SUB_LAUNCH(const SubArgs &a, bool last, int variant, int threads, unsigned grid_x,
                     unsigned grid_y, void *stream) {
-    (void)variant;
+    const bool pdl = (variant & 64) != 0;
     cudaStream_t s = (cudaStream_t)stream;
     switch (threads) {
-    case 64: EVP_SUB_NS::launch_nt<64>(a, last, grid_x, grid_y, s); break;
-    case 256: EVP_SUB_NS::launch_nt<256>(a, last, grid_x, grid_y, s); break;
-    default: EVP_SUB_NS::launch_nt<128>(a, last, grid_x, grid_y, s); break;
+    case 64: EVP_SUB_NS::launch_nt<64>(a, last, pdl, grid_x, grid_y, s); break;
+    case 256: EVP_SUB_NS::launch_nt<256>(a, last, pdl, grid_x, grid_y, s); break;
+    default: EVP_SUB_NS::launch_nt<128>(a, last, pdl, grid_x, grid_y, s); break;
     }
 }

@@ -33,7 +33,7 @@ BND = {"open": 0, "closed": 1, "cyclic": 2, "tripole": 3}
 EXPORTS = [
     "evp_b200_abi_version", "evp_b200_last_error", "evp_b200_default_params", "evp_b200_init",
     "evp_b200_prep", "evp_b200_run", "evp_b200_step", "evp_b200_subcycle_resident",
-    "evp_b200_principal_stress", "evp_b200_get_timings", "evp_b200_download_state",
+    "evp_b200_principal_stress", "evp_b200_get_timings", "evp_b200_diagnostics", "evp_b200_download_state",
     "evp_b200_invalidate_device_state", "evp_b200_comm_unique_id", "evp_b200_comm_init", "evp_b200_finalize",
 ]
 
@@ -125,6 +125,7 @@ def load_library(path: str = LIB_PATH) -> C.CDLL:
     L.evp_b200_subcycle_resident.argtypes = [H, C.c_int32, C.POINTER(C.c_float)]
     L.evp_b200_principal_stress.argtypes = [H, c_dp, c_dp, c_dp, c_dp, c_dp, c_dp]
     L.evp_b200_get_timings.argtypes = [H, C.POINTER(Timings)]
+    L.evp_b200_diagnostics.argtypes = [H, c_dp]
     L.evp_b200_download_state.argtypes = [H, C.POINTER(State)]
     L.evp_b200_invalidate_device_state.argtypes = [H]
     L.evp_b200_comm_unique_id.argtypes = [C.POINTER(C.c_uint8)]
@@ -424,6 +425,13 @@ class IceDynEvp:
         t = Timings()
         _check(load_library().evp_b200_get_timings(self._h, C.byref(t)))
         return {n: getattr(t, n) for n, _ in Timings._fields_}
+
+    def diagnostics(self) -> Dict[str, float]:
+        """max ice speed / max strength per hemisphere of this slab, as runtime_diags prints them
+        (/root/reference/source/ice_diagnostics.F90:294-346)."""
+        out = (C.c_double * 4)()
+        _check(load_library().evp_b200_diagnostics(self._h, out))
+        return dict(umaxn=out[0], umaxs=out[1], pmaxn=out[2], pmaxs=out[3])
 
     def finalize(self) -> None:
         if self._h:

@@ -196,6 +196,12 @@ int evp_b200_principal_stress(evp_b200_handle *h, const double *stressp_1, const
 
 int evp_b200_get_timings(const evp_b200_handle *h, evp_b200_timings *t);
 
+/* Velocity / strength diagnostics of runtime_diags (source/ice_diagnostics.F90:294-346) from the
+ * device-resident result of the last call, this slab only (the caller combines slabs with
+ * global_maxval): out[0] = max ice speed (m/s), northern hemisphere (lmask_n: ULAT >= -puny),
+ * out[1] = southern; out[2] = max strength (kN/m) north, out[3] = south.  Interior cells only. */
+int evp_b200_diagnostics(evp_b200_handle *h, double out[4]);
+
 /* state_residency = 1: copy the device-resident stresses (and uvel, vvel, iceumask) into the caller's
  * arrays -- what dumpfile (source/ice_restart.F90:197-246) and ice_write_hist need; and tell the library
  * that the caller changed the host arrays (restartfile, :427-487) so the next call uploads them again. */

@@ -78,7 +78,7 @@ def test_fma_mode_within_tolerance(oracle, evp_lib, label, kw):
 
 
 @pytest.mark.parametrize("threads,rows,variant", [(64, 5, 0), (128, 7, 4), (256, 0, 0), (128, 1000, 0),
-                                                  (128, 0, 16), (64, 9, 16 + 4)])
+                                                  (128, 0, 16), (64, 9, 16 + 4), (128, 0, 64), (256, 11, 64)])
 def test_tiling_invariance(oracle, evp_lib, threads, rows, variant):
     """Strip width, rows per CTA and the prefetch variant must not change a single bit."""
     case = synth.make_case("om1deg", nx=300, ny=90)
@@ -337,3 +337,20 @@ def test_restart_like_state(oracle, evp_lib):
     inputs = {k: E.split_blocks(v, lay, "cyclic", "tripole") for k, v in case.inputs.items()}
     out = dyn.evp(3600.0, inputs, strength=E.split_blocks(f["strength"], lay, "cyclic", "tripole"))
     _compare_exact(dyn, out, st_o, f, lay)
+
+
+def test_device_diagnostics(oracle, evp_lib):
+    """max ice speed / max strength per hemisphere (runtime_diags, ice_diagnostics.F90:294-346)
+    reduced on the device; maxima are order-independent, so the comparison is exact."""
+    case = synth.make_case("om1deg", nx=64, ny=48)
+    st, f, strengths, _ = oracle_steps(oracle, case, nsteps=1)
+    lay = E.BlockLayout.single_block(64, 48)
+    dyn, out = cuda_steps(case, strengths=strengths)
+    d = dyn.diagnostics()
+    I = (slice(1, 65), slice(1, 49))
+    speed = np.sqrt(st["uvel"][I] ** 2 + st["vvel"][I] ** 2)
+    north = case.grid.f["ULAT"][I] >= -1e-11
+    assert d["umaxn"] == speed[north].max() and d["umaxs"] == speed[~north].max()
+    assert d["pmaxn"] == (f["strength"][I][north] / 1000.0).max()
+    assert d["pmaxs"] == (f["strength"][I][~north] / 1000.0).max()
+    assert 0.01 < d["umaxn"] < 2.0
