@@ -453,10 +453,14 @@ __global__ void k_row_active(PlaneGeom pg, const uint8_t *__restrict__ icetmask,
     if (threadIdx.x == 0) rowcnt[j] = tot;
 }
 
-// single thread: a few thousand rows at most
-__global__ void k_balance_chunks(PlaneGeom pg, const int *__restrict__ rowcnt, int *__restrict__ chunks, int ncy,
+// one CTA: the row costs are staged in shared memory by all threads, then thread 0 walks them (a few
+// thousand rows at most; the serial pass over global memory took 110 us at 1080 rows)
+__global__ void k_balance_chunks(PlaneGeom pg, const int *__restrict__ rowcnt_g, int *__restrict__ chunks, int ncy,
                                  float w_bot, float w_top, int min_top, float row_overhead) {
-    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    extern __shared__ int rowcnt[]; // nyl + 2 entries
+    for (int j = threadIdx.x; j <= pg.nyl + 1; j += blockDim.x) rowcnt[j] = rowcnt_g[j];
+    __syncthreads();
+    if (threadIdx.x != 0) return;
     const int nyl = pg.nyl;
     auto cost = [&](int j) { return row_overhead + (float)rowcnt[j]; };
     if (ncy == 1) {
@@ -646,7 +650,8 @@ void aux_balance_chunks(const PlaneGeom &pg, const uint8_t *icetmask, const uint
                         int *chunks, int ncy, float w_bot, float w_top, int min_top, float row_overhead,
                         cudaStream_t s) {
     k_row_active<<<pg.nyl + 2, 128, 0, s>>>(pg, icetmask, iceumask, rowcnt);
-    k_balance_chunks<<<1, 32, 0, s>>>(pg, rowcnt, chunks, ncy, w_bot, w_top, min_top, row_overhead);
+    k_balance_chunks<<<1, 256, sizeof(int) * (pg.nyl + 2), s>>>(pg, rowcnt, chunks, ncy, w_bot, w_top, min_top,
+                                                                 row_overhead);
 }
 void aux_diagnostics(const PlaneGeom &pg, const double *u, const double *v, const double *strength,
                      const double *fcor, double fcor_south, double *out4, cudaStream_t s) {
