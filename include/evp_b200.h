@@ -94,7 +94,8 @@ typedef struct {
     int32_t tile_threads;   /* 0 = default; threads per CTA of the subcycle kernel */
     int32_t tile_rows;      /* 0 = default; U rows marched per CTA */
     int32_t kernel_variant; /* 0 = default; bit 2 (4): tripole fold as a separate kernel; bit 4 (16): 2-plane
-                               metric path (needs HTE/HTN) */
+                               metric path (needs HTE/HTN); bit 5 (32): uniform row chunks instead of the
+                               per-call active-work balance; bit 6 (64): programmatic dependent launch */
     int32_t state_residency; /* 0 = the whole state is uploaded and downloaded by every call (host arrays always
                                current: restart-exact drop-in); 1 = the 12 stress arrays stay on the device
                                between calls: uploaded by the first call after init or after
