@@ -77,6 +77,8 @@ struct evp_b200_handle {
     double dtei, ecci, dte2T, denom1, denom2, rcon, dragw;
     int device = 0;
     cudaStream_t st = nullptr;
+    cudaStream_t st2 = nullptr;       // early download of outputs that are final before the ndte loop
+    cudaEvent_t ev_early = nullptr, ev_early_done = nullptr;
     double *pool = nullptr;
     double *pl[P_COUNT];
     double *cat = nullptr; // aicen, vicen planes (2*ncat), allocated on first device ice_strength
@@ -159,13 +161,15 @@ int upload_mask(evp_b200_handle *h, const int32_t *host, int slot, uint8_t *plan
 
 // fresh = the staging slot does not hold the caller's current values: fill it from the host
 // first for KEEP policies (not needed for state fields, whose slot was uploaded this call)
-int download_r8(evp_b200_handle *h, double *host, int slot, const double *plane, int policy) {
+int download_r8(evp_b200_handle *h, double *host, int slot, const double *plane, int policy,
+                cudaStream_t s = nullptr) {
     if (!host) return 0;
+    if (!s) s = h->st;
     double *stg = h->stage + (size_t)slot * h->blocked_elems;
     const size_t bytes = h->blocked_elems * sizeof(double);
     pin(h, host, bytes);
-    aux_block_r8(h->bg, h->pg, plane, h->mk[M_ICETMASK], stg, policy, h->st);
-    CU(cudaMemcpyAsync(host, stg, bytes, cudaMemcpyDeviceToHost, h->st));
+    aux_block_r8(h->bg, h->pg, plane, h->mk[M_ICETMASK], stg, policy, s);
+    CU(cudaMemcpyAsync(host, stg, bytes, cudaMemcpyDeviceToHost, s));
     return 0;
 }
 
@@ -524,6 +528,9 @@ static int init_handle(evp_b200_handle *h, const evp_b200_dims *d, const evp_b20
     h->blocked_elems = (size_t)d->nx_block * d->ny_block * d->max_blocks;
 
     CU(cudaStreamCreateWithFlags(&h->st, cudaStreamNonBlocking));
+    CU(cudaStreamCreateWithFlags(&h->st2, cudaStreamNonBlocking));
+    CU(cudaEventCreateWithFlags(&h->ev_early, cudaEventDisableTiming));
+    CU(cudaEventCreateWithFlags(&h->ev_early_done, cudaEventDisableTiming));
     for (auto &e : h->ev) CU(cudaEventCreate(&e));
     CU(cudaMalloc(&h->pool, sizeof(double) * pg.cells * P_COUNT));
     CU(cudaMemsetAsync(h->pool, 0, sizeof(double) * pg.cells * P_COUNT, h->st));
@@ -771,6 +778,22 @@ static int do_run(evp_b200_handle *h, const evp_b200_inputs *in, const double *s
         aux_balance_chunks(pg, h->mk[M_ICETMASK], h->mk[M_ICEUMASK], h->d_rowcnt, h->d_chunks, h->grid_y,
                            h->w_bot, h->w_top, h->fold_in_kernel ? 2 : 1, 0.3f * (float)(pg.nx + 1), h->st);
     CU(cudaEventRecord(h->ev[3], h->st));
+    // Outputs that are final before the subcycle loop travel to the host on a second stream while
+    // the loop runs (copy engine and SMs overlap): strairx/y, strtltx/y, fm, strength, sicemass.
+    struct EarlyOut { double *dst; int id; int policy; int slot; };
+    const EarlyOut early[] = {
+        {out ? out->strairx : nullptr, P_STRAIRX, PACK_INT_ZERO, SL_OUT0 + 0},
+        {out ? out->strairy : nullptr, P_STRAIRY, PACK_INT_ZERO, SL_OUT0 + 1},
+        {out ? out->strtltx : nullptr, P_STRTLTX, PACK_INT_ZERO, SL_OUT0 + 2},
+        {out ? out->strtlty : nullptr, P_STRTLTY, PACK_INT_ZERO, SL_OUT0 + 3},
+        {out ? out->fm : nullptr, P_FM, PACK_INT_ZERO, SL_OUT0 + 10},
+        {out ? out->strength : nullptr, P_STRENGTH, PACK_FULL, SL_OUT0 + 16},
+        {out ? out->sicemass : nullptr, P_TMASS, PACK_FULL, SL_OUT0 + 17}};
+    CU(cudaEventRecord(h->ev_early, h->st));
+    CU(cudaStreamWaitEvent(h->st2, h->ev_early, 0));
+    for (const EarlyOut &e : early)
+        if ((rc = download_r8(h, e.dst, e.slot, p[e.id], e.policy, h->st2))) return rc;
+    CU(cudaEventRecord(h->ev_early_done, h->st2));
     // ---- :347-404 ------------------------------------------------------------------------------
     if ((rc = run_subcycle_loop(h))) return rc;
     CU(cudaEventRecord(h->ev[4], h->st));
@@ -820,10 +843,13 @@ static int do_run(evp_b200_handle *h, const evp_b200_inputs *in, const double *s
             {out->sig1, P_SIG1, PACK_FULL}, {out->sig2, P_SIG2, PACK_FULL}};
         int slot = SL_OUT0;
         for (auto &o : outs) {
-            if ((rc = download_r8(h, o.dst, slot, p[o.id], o.policy))) return rc;
+            const bool was_early = o.id == P_STRAIRX || o.id == P_STRAIRY || o.id == P_STRTLTX || o.id == P_STRTLTY ||
+                                   o.id == P_FM || o.id == P_STRENGTH || o.id == P_TMASS;
+            if (!was_early && (rc = download_r8(h, o.dst, slot, p[o.id], o.policy))) return rc;
             ++slot;
         }
     }
+    CU(cudaStreamWaitEvent(h->st, h->ev_early_done, 0));
     CU(cudaEventRecord(h->ev[6], h->st));
     CU(cudaStreamSynchronize(h->st));
     CU(cudaEventElapsedTime(&h->tm.upload_ms, h->ev[0], h->ev[1]));
@@ -1052,6 +1078,9 @@ int evp_b200_finalize(evp_b200_handle *h) {
     cudaFree(h->d_blk_tab);
     for (auto &e : h->ev)
         if (e) cudaEventDestroy(e);
+    if (h->ev_early) cudaEventDestroy(h->ev_early);
+    if (h->ev_early_done) cudaEventDestroy(h->ev_early_done);
+    if (h->st2) cudaStreamDestroy(h->st2);
     if (h->st) cudaStreamDestroy(h->st);
     cudaGetLastError();
     delete h;
