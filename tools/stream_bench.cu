@@ -27,8 +27,8 @@ __global__ void kB(P p, size_t n2) {
     for (int k = 0; k < NW; ++k) ((double2 *)p.w[k])[i] = make_double2(s.x + k, s.y + k);
 }
 template <int NT>
-__global__ void __launch_bounds__(NT) kC(P p, int nx, int ny, int pitch, int strip, int rows) {
-    int i = 1 + blockIdx.x * strip + threadIdx.x;
+__global__ void __launch_bounds__(NT) kC(P p, int nx, int ny, int pitch, int strip, int rows, int ibase = 1) {
+    int i = ibase + blockIdx.x * strip + threadIdx.x;
     int j0 = 1 + blockIdx.y * rows, j1 = min(j0 + rows, ny + 1);
     if (threadIdx.x >= strip || i > nx) return;
     double v[NR];
@@ -81,6 +81,9 @@ int main() {
     time("C march 128 thr, strip 120, rows 23", [&] { kC<128><<<dim3(12, 47), 128>>>(p, nx, ny, pitch, 120, 23); }, bc);
     time("C march 256 thr, strip 240, rows 45", [&] { kC<256><<<dim3(6, 24), 256>>>(p, nx, ny, pitch, 240, 45); }, bc);
     time("C march 64 thr, strip 60, rows 45", [&] { kC<64><<<dim3(24, 24), 64>>>(p, nx, ny, pitch, 60, 45); }, bc);
+    time("C march 128 thr, strip 128 ALIGNED (i0 = 0), rows 45", [&] { kC<128><<<dim3(12, 24), 128>>>(p, nx, ny, pitch, 128, 45, 0); }, bc * 1456.0 / 1440.0);
+    time("C march 128 thr, strip 128 aligned+1 (i0 = 1), rows 45", [&] { kC<128><<<dim3(12, 24), 128>>>(p, nx, ny, pitch, 128, 45, 1); }, bc * 1456.0 / 1440.0);
+    time("C march 128 thr, strip 112 aligned (i0 = 16), rows 45", [&] { kC<128><<<dim3(13, 24), 128>>>(p, nx, ny, pitch, 112, 45, 16); }, bc * 1456.0 / 1440.0);
     time("C march 128 thr, strip 120, rows 12", [&] { kC<128><<<dim3(12, 90), 128>>>(p, nx, ny, pitch, 120, 12); }, bc);
     return 0;
 }
