@@ -1,0 +1,112 @@
+#!/usr/bin/env python3
+"""build_ref.py -- TEST INFRASTRUCTURE ONLY.
+
+Builds `oracle/_ref/libevp_ref_<variant>.so`: the reference's own EVP path, machine-translated from
+the Fortran under /root/reference (oracle/f90_to_c.py) and hosted by oracle/ref_glue.c.  One library
+per CPP variant the reference is built with:
+
+    cice4   no defines                     (drivers/cice4)
+    auscom  -DAusCOM -Dcoupled             (drivers/access-om, bld/Macros.nci:56-57)
+    access  -DAusCOM -Dcoupled -DACCESS    (drivers/access-cm)
+    coupled -Dcoupled                      (slope tilt without the AusCOM changes)
+
+Needs /root/reference (this container only).  Generated C and the libraries stay under oracle/_ref/
+(git-ignored): no reference source is ever committed.  Run:  python oracle/build_ref.py
+"""
+import os
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, HERE)
+import f90_to_c as T  # noqa: E402
+
+REF = os.environ.get("CICE4_REFERENCE", "/root/reference")
+OUT = os.path.join(HERE, "_ref")
+
+# variant -> (cpp defines, driver directory whose ice_constants.F90 the build uses)
+VARIANTS = {
+    "cice4": ((), "cice4"),
+    "coupled": (("coupled",), "cice4"),
+    "auscom": (("AusCOM", "coupled"), "access-om"),
+    "access": (("AusCOM", "coupled", "ACCESS"), "access-cm"),
+}
+
+BLOCK3 = ["nx_block", "ny_block", "max_blocks"]
+
+
+def available():
+    return os.path.isfile(os.path.join(REF, "source", "ice_dyn_evp.F90"))
+
+
+def translate(defines, driver):
+    tr = T.Translator(defines)
+    src = os.path.join(REF, "source")
+    # modules whose variables the path uses -- the few that are not plain declarations are listed
+    # by hand: ice_blocks / ice_domain_size make these compile-time parameters of the executable
+    for n in ("nx_block", "ny_block", "max_blocks", "ncat", "nblocks", "halo_info", "timer_dynamics",
+              "timer_bound"):
+        tr.add_global(T.Decl(n, "integer"))
+    tr.add_global(T.Decl("blocks_ice", "integer", ["max_blocks"]))                 # source/ice_domain.F90
+    tr.add_global(T.Decl("work1", "real", BLOCK3))                                 # source/ice_work.F90
+    if "AusCOM" in defines:
+        tr.add_global(T.Decl("use_ocnslope", "logical"))                           # drivers/access-om/cpl_parameters.F90:40
+        tr.add_global(T.Decl("sicemass", "real", BLOCK3))                          # drivers/access-om/cpl_interface.F90:418
+    tr.module_decls(os.path.join(REF, "drivers", driver, "ice_constants.F90"))
+    tr.module_decls(os.path.join(src, "ice_dyn_evp.F90"), dims_override={"fcor_blk": BLOCK3})
+    tr.module_decls(os.path.join(src, "ice_mechred.F90"))
+    tr.module_decls(os.path.join(src, "ice_state.F90"),
+                    only={"aice", "vice", "vsno", "aice0", "aicen", "vicen", "uvel", "vvel", "strength", "divu",
+                          "shear"})
+    tr.module_decls(os.path.join(src, "ice_flux.F90"),
+                    only={"strairxt", "strairyt", "strax", "stray", "uocn", "vocn", "ss_tltx", "ss_tlty",
+                          "stressp_1", "stressp_2", "stressp_3", "stressp_4", "stressm_1", "stressm_2",
+                          "stressm_3", "stressm_4", "stress12_1", "stress12_2", "stress12_3", "stress12_4",
+                          "iceumask", "strairx", "strairy", "strtltx", "strtlty", "strintx", "strinty",
+                          "strocnx", "strocny", "strocnxt", "strocnyt", "fm", "prs_sig", "rdg_conv", "rdg_shear"})
+    tr.module_decls(os.path.join(src, "ice_grid.F90"),
+                    only={"dxt", "dyt", "dxhy", "dyhx", "cxp", "cyp", "cxm", "cym", "tarea", "tarear", "tinyarea",
+                          "uarea", "uarear", "tmask", "umask"})
+    missing = set()
+    for path, subs in (
+        (os.path.join(src, "ice_mechred.F90"), ["asum_ridging", "ridge_itd", "ice_strength"]),
+        (os.path.join(src, "ice_grid.F90"), ["to_ugrid", "to_tgrid", "t2ugrid_vector", "u2tgrid_vector"]),
+        (os.path.join(src, "ice_dyn_evp.F90"), ["set_evp_parameters", "evp_prep1", "evp_prep2", "stress", "stepu",
+                                                "evp_finish", "principal_stress", "evp"]),
+    ):
+        for s in subs:
+            missing.update(tr.subroutine(path, s))
+    missing -= set(tr.subs) | {"get_block", "ice_haloupdate", "ice_timer_start", "ice_timer_stop"}
+    if missing:
+        raise T.TranslateError("unresolved names: " + ", ".join(sorted(missing)))
+    return tr.emit_file()
+
+
+def build(verbose=False):
+    if not available():
+        raise RuntimeError("reference sources not found under " + REF)
+    os.makedirs(OUT, exist_ok=True)
+    cc = "/usr/bin/gcc" if os.access("/usr/bin/gcc", os.X_OK) else "gcc"
+    for name, (defines, driver) in VARIANTS.items():
+        gen = os.path.join(OUT, "evp_ref_%s.c" % name)
+        with open(gen, "w") as fh:
+            fh.write(translate(defines, driver))
+        # strict: the parity authority (no FMA contraction).  fast (cice4 only): the reference's
+        # production optimisation level (bld/Macros.nci:26 is -O3 -xHost), timed by bench.py
+        builds = [("", ["-O2", "-ffp-contract=off", "-fno-fast-math"])]
+        if name == "cice4":
+            builds.append(("_fast", ["-O3", "-march=x86-64-v3"]))
+        for suffix, opt in builds:
+            cmd = [cc, "-std=gnu11"] + opt + ["-fPIC", "-shared", "-Wall", "-Wno-unused", "-Wno-parentheses",
+                                              "-Wno-maybe-uninitialized", '-DREF_GEN="%s"' % gen, "-I", HERE]
+            if "AusCOM" in defines:
+                cmd.append("-DREF_AUSCOM")
+            cmd += ["-o", os.path.join(OUT, "libevp_ref_%s%s.so" % (name, suffix)),
+                    os.path.join(HERE, "ref_glue.c"), os.path.join(HERE, "evp_oracle.c"), "-lm"]
+            if verbose:
+                print(" ".join(cmd))
+            subprocess.check_call(cmd)
+
+
+if __name__ == "__main__":
+    build(verbose=True)

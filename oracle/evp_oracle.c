@@ -7,8 +7,8 @@
  * evaluation, same parenthesisation).  Build with -ffp-contract=off so the
  * compiler does not fuse multiply-adds.
  *
- * PARITY UNPINNED for evp() outputs (no reference golden vectors, no Fortran
- * compiler here) -- see the header.
+ * Pinned bit for bit against the machine-translated reference (oracle/_ref)
+ * -- see the header.
  */
 #include "evp_oracle.h"
 

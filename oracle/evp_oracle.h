@@ -6,13 +6,17 @@
  * the "port" CPU baseline in bench.py.  Nothing in the product
  * (cice4_b200/, include/) may call, link or import anything in oracle/.
  *
- * PARITY UNPINNED for the EVP results themselves: the reference ships no
- * golden vectors for evp() and no Fortran compiler exists in this image, so
- * this restatement cannot be checked against the reference's own output.  It
- * follows the Fortran statement by statement (file:line cited per function)
- * and is pinned only where the reference offers known answers: grid decoding
- * and set_evp_parameters (ice.log.Linux.LANL.coyote:101-119,181-183) and the
- * ITD bounds (:185-190).  See tests/test_oracle_golden.py.
+ * PARITY PINNED against the reference itself.  The reference is Fortran and this image has no
+ * Fortran compiler, so the reference's own source text of `evp` and everything it calls is
+ * machine-translated to C at build time (oracle/f90_to_c.py, oracle/build_ref.py ->
+ * oracle/_ref/libevp_ref_<variant>.so, git-ignored) and this restatement is required to agree with it
+ * BIT FOR BIT: directly where /root/reference exists (tests/test_oracle_vs_ref.py: 7 domain types x
+ * 5 CPP variants, namelist options, dt/ndte sweeps) and everywhere through the committed outputs of
+ * that library (tests/golden/ref_evp_*.npz, tests/test_oracle_golden.py).  Hand-written in the
+ * translated reference are only get_block and the index copying of ice_HaloUpdate (oracle/ref_glue.c,
+ * which reuses orc_halo_* below; cross-checked against an independent numpy restatement).  The
+ * reference's known answers are pinned too: grid decoding and set_evp_parameters
+ * (ice.log.Linux.LANL.coyote:101-119,181-183) and the ITD bounds (:185-190).
  *
  * Build: -O2 -ffp-contract=off (strict: no FMA contraction) for parity;
  *        -O3 -march=native -fopenmp for the timed CPU baseline.

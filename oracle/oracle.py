@@ -1,7 +1,8 @@
 """TEST INFRASTRUCTURE ONLY: ctypes loader for the CPU oracle (oracle/evp_oracle.c).
 
 Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference
-legs may import this module.  PARITY UNPINNED for evp() outputs (see evp_oracle.h).
+legs may import this module.  The oracle is pinned bit for bit against the machine-translated
+reference (oracle/_ref, loaded by ref_lib() below; see evp_oracle.h).
 """
 from __future__ import annotations
 
@@ -174,6 +175,68 @@ def run_evp(grid, inputs, state, params: Optional[OrcParams] = None, strength_in
     if rc != 0:
         raise RuntimeError("orc_evp failed")
     return f, sec.value
+
+
+# ---------------------------------------------------------------------------------------------
+# oracle/_ref: the reference's own Fortran, machine-translated and compiled (oracle/build_ref.py)
+# ---------------------------------------------------------------------------------------------
+REF_DIR = os.path.join(HERE, "_ref")
+_ref_libs: Dict[str, C.CDLL] = {}
+
+
+def ref_variant(p: OrcParams) -> str:
+    """CPP variant of the reference build that the run-time flags of `p` stand for."""
+    if p.auscom:
+        if not p.coupled:
+            raise ValueError("the reference builds AusCOM only together with coupled")
+        return "access" if p.access_wind else "auscom"
+    if p.access_wind:
+        raise ValueError("the reference builds ACCESS only together with AusCOM")
+    return "coupled" if p.coupled else "cice4"
+
+
+def ref_available() -> bool:
+    return all(os.path.exists(os.path.join(REF_DIR, f"libevp_ref_{v}.so"))
+               for v in ("cice4", "coupled", "auscom", "access"))
+
+
+def ref_lib(variant: str) -> C.CDLL:
+    if variant not in _ref_libs:
+        L = C.CDLL(os.path.join(REF_DIR, f"libevp_ref_{variant}.so"))
+        L.ref_evp.restype = C.c_int
+        L.ref_evp.argtypes = [C.POINTER(OrcGrid), C.POINTER(OrcParams), C.POINTER(OrcFields), C.c_double]
+        L.ref_set_evp_parameters.restype = None
+        L.ref_set_evp_parameters.argtypes = [C.POINTER(OrcParams), C.c_double, c_dp]
+        L.ref_subcycle_only.restype = C.c_int
+        L.ref_subcycle_only.argtypes = [C.POINTER(OrcGrid), C.POINTER(OrcParams), C.POINTER(OrcFields),
+                                        C.c_double, C.c_int, c_dp]
+        L.ref_principal_stress.restype = None
+        L.ref_principal_stress.argtypes = [C.POINTER(OrcParams), C.c_int32, C.c_int32] + [c_dp] * 6
+        _ref_libs[variant] = L
+    return _ref_libs[variant]
+
+
+def run_evp_ref(grid, inputs, state, params: OrcParams, dt: float):
+    """One `evp(dt)` call of the translated reference (same contract as run_evp; the locals of the
+    reference's `evp` -- icetmask, tmass, umass, aiu, ... -- are not exported)."""
+    f = Fields(grid.f, inputs, state, None)
+    g = make_grid(grid.nx_block, grid.ny_block, grid.ew, grid.ns)
+    rc = ref_lib(ref_variant(params)).ref_evp(C.byref(g), C.byref(params), C.byref(f.c), dt)
+    if rc != 0:
+        raise RuntimeError("ref_evp failed")
+    return f
+
+
+def time_subcycles_ref(grid, fields: Fields, params: OrcParams, dt: float, nsub: int) -> float:
+    """Seconds for `nsub` subcycles of the translated reference's own stress + stepu (+ 2 halo updates),
+    -O3 serial build, on fields prepared by run_evp."""
+    g = make_grid(grid.nx_block, grid.ny_block, grid.ew, grid.ns)
+    sec = C.c_double(0.0)
+    rc = ref_lib("cice4_fast").ref_subcycle_only(C.byref(g), C.byref(params), C.byref(fields.c), dt, nsub,
+                                                 C.byref(sec))
+    if rc != 0:
+        raise RuntimeError("ref_subcycle_only failed")
+    return sec.value
 
 
 def time_subcycles(grid, fields: Fields, params: OrcParams, nsub: int, lib_kind: str = "fast") -> float:

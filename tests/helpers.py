@@ -54,3 +54,42 @@ def maxabs(a, b):
 def relerr(a, b):
     scale = float(np.max(np.abs(b)))
     return maxabs(a, b) / scale if scale > 0 else maxabs(a, b)
+
+
+# ------------------------------------------------------------------------------------------------
+# committed outputs of the reference itself (tests/golden/make_ref_golden.py)
+# ------------------------------------------------------------------------------------------------
+import glob
+import os
+from types import SimpleNamespace
+
+from cice4_b200 import grid as G
+
+GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+REF_GOLDEN = sorted(glob.glob(os.path.join(GOLDEN_DIR, "ref_evp_*.npz")))
+
+
+def load_ref_golden(path):
+    """-> namespace(grid, inputs, over, dt, ndte, nsteps, ref_state, ref_out)"""
+    z = np.load(path)
+    grid = G.Grid(int(z["meta_nx"]), int(z["meta_ny"]), int(z["meta_ew"]), int(z["meta_ns"]))
+    inputs, over, ref_state, ref_out = {}, {}, {}, {}
+    for k in z.files:
+        a = z[k]
+        if k.startswith("grid_"):
+            grid.f[k[5:]] = np.asfortranarray(a)
+        elif k.startswith("in_"):
+            inputs[k[3:]] = np.asfortranarray(a)
+        elif k.startswith("param_"):
+            over[k[6:]] = a.item()
+        elif k.startswith("ref_strength_"):
+            pass
+        elif k.startswith("ref_state_"):
+            ref_state[k[10:]] = a
+        elif k.startswith("ref_out_"):
+            ref_out[k[8:]] = a
+    return SimpleNamespace(grid=grid, inputs=inputs, over=over, dt=float(z["meta_dt"]), ndte=int(z["meta_ndte"]),
+                           nsteps=int(z["meta_nsteps"]), ref_state=ref_state, ref_out=ref_out,
+                           ref_strengths=[np.asfortranarray(z["ref_strength_%d" % k])
+                                          for k in range(int(z["meta_nsteps"]))],
+                           label=os.path.basename(path)[8:-4])

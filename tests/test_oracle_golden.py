@@ -3,7 +3,11 @@ reference offers for this path, and check the invariants the reference guarantee
 
 Known answers: /root/reference/ice.log.Linux.LANL.coyote
   :101-119 grid record min/max, :181-183 dte / tdamp, :185-190 hin_max.
-The EVP outputs themselves have no golden vectors in the reference (parity unpinned).
+The reference ships no golden vectors for the EVP outputs themselves; those are pinned by the
+committed OUTPUTS OF THE REFERENCE ITSELF (tests/golden/ref_evp_*.npz, made by
+tests/golden/make_ref_golden.py from the reference's own Fortran text, machine-translated to C at
+build time because the image has no Fortran compiler) and, in the build container, by direct
+comparison with that translated reference (tests/test_oracle_vs_ref.py).
 """
 import numpy as np
 import pytest
@@ -11,6 +15,28 @@ import pytest
 from cice4_b200 import grid as G
 from cice4_b200 import synth
 from conftest import GX3_FIXTURE
+from helpers import REF_GOLDEN, load_ref_golden
+
+
+@pytest.mark.parametrize("path", REF_GOLDEN, ids=[p.split("ref_evp_")[-1][:-4] for p in REF_GOLDEN])
+def test_oracle_matches_reference_golden(oracle, path):
+    """oracle/evp_oracle.c reproduces the reference's own evp() outputs BIT FOR BIT (state after
+    `nsteps` calls + every output field), all CPP variants and boundary types of the fixtures."""
+    c = load_ref_golden(path)
+    p = oracle.make_params(dt=c.dt, ndte=c.ndte, **c.over)
+    st = synth.zero_state(c.grid.nx_block, c.grid.ny_block)
+    f = None
+    for _ in range(c.nsteps):
+        f, _sec = oracle.run_evp(c.grid, c.inputs, st, p)
+    bad = [n for n, a in c.ref_state.items() if not np.array_equal(st[n], a)]
+    bad += [n for n, a in c.ref_out.items() if not np.array_equal(f[n], a)]
+    assert not bad, f"oracle differs from the reference in {bad}"
+    assert len(c.ref_state) == 15 and len(c.ref_out) >= 17
+    assert np.abs(c.ref_state["uvel"]).max() > 1e-2
+
+
+def test_reference_golden_fixtures_present():
+    assert len(REF_GOLDEN) >= 4
 
 
 def test_set_evp_parameters_known_answers(oracle):

@@ -1,0 +1,117 @@
+"""CPU tests (build container): the hand-written oracle against THE REFERENCE ITSELF.
+
+oracle/_ref/libevp_ref_<variant>.so is the reference's own Fortran source of `evp` and everything it
+calls, translated statement by statement to C by oracle/f90_to_c.py at build time (the image has no
+Fortran compiler) and compiled with gcc -O2 -ffp-contract=off -- see oracle/build_ref.py and
+oracle/ref_glue.c.  It exists only where /root/reference does (this container, built by
+__graft_entry__.build()); elsewhere these tests skip and the committed outputs of the same library
+(tests/golden/ref_evp_*.npz, checked by tests/test_oracle_golden.py) stand in.
+
+Every comparison is bit-exact: state after consecutive calls and every output field.
+"""
+import numpy as np
+import pytest
+
+from cice4_b200 import synth
+from conftest import GX3_FIXTURE
+from oracle import oracle as O
+
+pytestmark = pytest.mark.skipif(not O.ref_available(), reason="oracle/_ref not built (needs /root/reference)")
+
+DOMAINS = [
+    ("gx3-real-grid", dict(name="gx3", realistic=True, gx3_fixture=GX3_FIXTURE)),
+    ("gx3-dense", dict(name="gx3", realistic=False, gx3_fixture=GX3_FIXTURE)),
+    ("tripole-64x48-realistic", dict(name="om1deg", nx=64, ny=48, realistic=True)),
+    ("tripole-91x37", dict(name="om1deg", nx=91, ny=37)),
+    ("cyclic-cyclic-40x33", dict(name="x", nx=40, ny=33, ew="cyclic", ns="cyclic")),
+    ("open-open-37x29", dict(name="x", nx=37, ny=29, ew="open", ns="open")),
+    ("closed-closed-30x31", dict(name="x", nx=30, ny=31, ew="closed", ns="closed")),
+]
+TURN = dict(cosw=0.9063077870366499, sinw=0.42261826174069944)
+VARIANTS = [
+    ("cice4", dict()),
+    ("coupled", dict(coupled=1)),
+    ("auscom-geostrophic-tilt", dict(auscom=1, coupled=1, use_ocnslope=0, **TURN)),
+    ("auscom-ocnslope", dict(auscom=1, coupled=1, use_ocnslope=1, **TURN)),
+    ("access", dict(auscom=1, coupled=1, use_ocnslope=1, access_wind=1)),
+]
+
+
+def _inputs(case, over, seed=11):
+    inp = dict(case.inputs)
+    g = case.grid
+    rng = np.random.default_rng(seed)
+    inp["strax"] = np.asfortranarray(0.9 * inp["strairxT"] + 0.001)
+    inp["stray"] = np.asfortranarray(1.1 * inp["strairyT"] - 0.002)
+    inp["ss_tltx"] = np.asfortranarray(1e-6 * rng.standard_normal((g.nx_block, g.ny_block)))
+    inp["ss_tlty"] = np.asfortranarray(1e-6 * rng.standard_normal((g.nx_block, g.ny_block)))
+    return inp
+
+
+def _both(case, over, dt=3600.0, ndte=120, nsteps=2):
+    g = case.grid
+    inp = _inputs(case, over)
+    p = O.make_params(dt=dt, ndte=ndte, **over)
+    st_o = synth.zero_state(g.nx_block, g.ny_block)
+    st_r = synth.zero_state(g.nx_block, g.ny_block)
+    for _ in range(nsteps):
+        f_o, _sec = O.run_evp(g, inp, st_o, p)
+        f_r = O.run_evp_ref(g, inp, st_r, p, dt)
+    bad = [n for n in O.STATE_D + ["iceumask"] if not np.array_equal(st_o[n], st_r[n])]
+    outs = [n for n in O.OUT_D if n != "sicemass" or over.get("auscom")]
+    bad += [n for n in outs if not np.array_equal(f_o[n], f_r[n])]
+    return bad, st_r
+
+
+@pytest.mark.parametrize("dom", DOMAINS, ids=[d[0] for d in DOMAINS])
+@pytest.mark.parametrize("var", VARIANTS, ids=[v[0] for v in VARIANTS])
+def test_oracle_bit_exact_vs_reference(dom, var):
+    """cold start + warm second call, ndte = 120, every domain type x every CPP variant"""
+    case = synth.make_case(**dom[1])
+    bad, st = _both(case, var[1])
+    assert not bad, f"oracle differs from the reference in {bad}"
+    assert np.abs(st["uvel"]).max() > 1e-2
+
+
+@pytest.mark.parametrize("over", [
+    dict(evp_damping=1), dict(kstrength=0), dict(krdg_partic=0), dict(krdg_redist=0),
+    dict(krdg_partic=0, krdg_redist=0), dict(mu_rdg=3.0), dict(evp_damping=1, auscom=1, coupled=1, **TURN),
+], ids=["evp_damping", "hibler79", "partic0", "redist0", "partic0-redist0", "mu_rdg3", "damping-auscom"])
+def test_namelist_options_bit_exact_vs_reference(over):
+    case = synth.make_case("om1deg", nx=48, ny=40, realistic=True)
+    bad, _ = _both(case, over)
+    assert not bad, f"oracle differs from the reference in {bad}"
+
+
+@pytest.mark.parametrize("dt,ndte", [(3600.0, 120), (1800.0, 120), (600.0, 240), (3600.0, 7), (900.0, 1)])
+def test_time_step_and_ndte_bit_exact_vs_reference(dt, ndte):
+    case = synth.make_case("x", nx=33, ny=26, ew="cyclic", ns="open")
+    bad, _ = _both(case, dict(), dt=dt, ndte=ndte, nsteps=3)
+    assert not bad, f"oracle differs from the reference in {bad}"
+
+
+@pytest.mark.parametrize("dt,ndte", [(3600.0, 120), (1800.0, 120), (600.0, 240), (7200.0, 77)])
+def test_set_evp_parameters_vs_reference(dt, ndte):
+    """source/ice_dyn_evp.F90:535-577 as the reference computes it"""
+    import ctypes as C
+    p = O.make_params(dt=dt, ndte=ndte)
+    out = (C.c_double * 6)()
+    O.ref_lib("cice4").ref_set_evp_parameters(C.byref(p), dt, out)
+    assert list(out) == [p.dtei, p.ecci, p.dte2T, p.denom1, p.denom2, p.rcon]
+
+
+def test_principal_stress_vs_reference():
+    """source/ice_dyn_evp.F90:1558-1609"""
+    import ctypes as C
+    case = synth.make_case("om1deg", nx=48, ny=40, realistic=True)
+    g = case.grid
+    p = O.make_params()
+    st = synth.zero_state(g.nx_block, g.ny_block)
+    f, _ = O.run_evp(g, case.inputs, st, p)
+    s1, s2 = O.principal_stress(st["stressp_1"], st["stressm_1"], st["stress12_1"], f["prs_sig"])
+    r1, r2 = np.zeros_like(s1, order="F"), np.zeros_like(s1, order="F")
+    O.ref_lib("cice4").ref_principal_stress(C.byref(p), g.nx_block, g.ny_block, O._ptr(st["stressp_1"]),
+                                            O._ptr(st["stressm_1"]), O._ptr(st["stress12_1"]),
+                                            O._ptr(f["prs_sig"]), O._ptr(r1), O._ptr(r2))
+    assert np.array_equal(s1, r1) and np.array_equal(s2, r2)
+    assert (r1 < 1e29).any() and (r1 == 1e30).any()

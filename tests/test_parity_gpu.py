@@ -12,7 +12,7 @@ import pytest
 from cice4_b200 import evp as E
 from cice4_b200 import synth
 from conftest import GX3_FIXTURE
-from helpers import OUT_CMP, STATE, cuda_steps, maxabs, oracle_steps, relerr
+from helpers import OUT_CMP, REF_GOLDEN, STATE, cuda_steps, load_ref_golden, maxabs, oracle_steps, relerr
 
 pytestmark = pytest.mark.gpu
 
@@ -55,6 +55,43 @@ CASES = [
     ("cyclic-cyclic-40x33", dict(name="x", nx=40, ny=33, ew="cyclic", ns="cyclic")),
     ("open-open-37x29", dict(name="x", nx=37, ny=29, ew="open", ns="open")),
 ]
+
+
+@pytest.mark.parametrize("path", REF_GOLDEN, ids=[p.split("ref_evp_")[-1][:-4] for p in REF_GOLDEN])
+def test_cuda_matches_reference_golden(evp_lib, path):
+    """The CUDA path against the committed OUTPUTS OF THE REFERENCE ITSELF
+    (tests/golden/make_ref_golden.py): unfused math is bit-exact for the state and every output,
+    FMA mode within the north_star tolerance.  No oracle involved."""
+    from types import SimpleNamespace
+    c = load_ref_golden(path)
+    inputs = dict(c.inputs)
+    cpar = {}
+    for k, v in c.over.items():
+        cpar[{"auscom": "hemisphere_turning", "coupled": "coupled_tilt", "access_wind": "wind_from_strax"}.get(k, k)] = v
+    if c.over.get("access_wind"):  # the ABI takes strax/stray through the strairxT/yT pointers
+        inputs["strairxT"], inputs["strairyT"] = inputs.pop("strax"), inputs.pop("stray")
+    inputs = {k: v for k, v in inputs.items() if k in E.INPUT_D}
+    case = SimpleNamespace(grid=c.grid, inputs=inputs)
+    lay = E.BlockLayout.single_block(c.grid.nx, c.grid.ny)
+    want = [n for n in c.ref_out if n != "strength"]
+    # (1) the reference's ice_strength of every call supplied by the host, as the Fortran shim does in
+    #     its two-phase mode: unfused math must reproduce the reference bit for bit
+    dyn, out = cuda_steps(case, nsteps=c.nsteps, strengths=c.ref_strengths, want=want, dt=c.dt, ndte=c.ndte,
+                          math_mode=0, **cpar)
+    bad = [n for n in STATE if not np.array_equal(_merge(dyn.state[n], lay), c.ref_state[n])]
+    bad += [n for n in want if not np.array_equal(_merge(out[n], lay), c.ref_out[n])]
+    assert not bad, f"CUDA path differs from the reference in {bad}"
+    dyn.finalize()
+    # (2) FMA-contracted math and (3) ice_strength on the device (device exp): within the tolerance
+    for par in (dict(strengths=c.ref_strengths, math_mode=1), dict(strengths=None, math_mode=0)):
+        dyn, out = cuda_steps(case, nsteps=c.nsteps, want=want + ["strength"], dt=c.dt, ndte=c.ndte, **par, **cpar)
+        for n in ("uvel", "vvel"):
+            assert maxabs(_merge(dyn.state[n], lay), c.ref_state[n]) <= TOL_U, n
+        for n in STATE[2:14]:
+            assert relerr(_merge(dyn.state[n], lay), c.ref_state[n]) <= TOL_S, n
+        assert np.array_equal(_merge(dyn.state["iceumask"], lay), c.ref_state["iceumask"])
+        assert relerr(_merge(out["strength"], lay), c.ref_out["strength"]) <= 1e-12
+        dyn.finalize()
 
 
 @pytest.mark.parametrize("label,kw", CASES, ids=[c[0] for c in CASES])
