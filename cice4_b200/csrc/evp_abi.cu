@@ -55,7 +55,8 @@ enum PlaneId {
     P_STROCNXT, P_STROCNYT, P_FM, P_PRS_SIG, P_DIVU, P_SHEAR, P_RDG_CONV, P_RDG_SHEAR, P_STRENGTH,
     P_SIG1, P_SIG2,
     // ping-pong state: u, v, 12 stresses, two copies each
-    P_U0, P_U1, P_V0, P_V1, P_S0, P_S1 = P_S0 + EVP_NSTRESS, P_COUNT = P_S1 + EVP_NSTRESS
+    // state copy 0 (u, v, 12 stresses) and, EVP_STATE_PLANES planes behind each, copy 1 (SubArgs::copy_stride)
+    P_U0, P_V0, P_S0, P_U1 = P_S0 + EVP_NSTRESS, P_V1, P_S1, P_COUNT = P_S1 + EVP_NSTRESS
 };
 enum MaskId { M_TMASK, M_UMASK, M_TMPHM, M_ICETMASK, M_ICEUMASK, M_COUNT };
 
@@ -99,6 +100,9 @@ struct evp_b200_handle {
     std::unordered_map<const void *, size_t> pinned;
     int grid_x = 0, grid_y = 0, threads = 128, strip_w = 0, rows = 0;
     int *d_chunks = nullptr;          // row-chunk table of the subcycle kernel (2 ints per chunk)
+    int *d_cta_epoch = nullptr;       // persistent kernel: subcycles finished per CTA (grid_x * grid_y ints)
+    bool persistent = false;          // run the ndte loop as one cooperative launch (k_persist)
+    int epoch_count = 0;              // subcycles completed on this rank since init (== sync[1] with p2p)
     int *d_rowcnt = nullptr;          // active T cells per row (load balance of the chunks)
     bool balance = false;             // rebuild the chunk table from icetmask every call
     float w_bot = 1.f, w_top = 1.f;   // relative cost targets of the boundary chunks
@@ -231,12 +235,15 @@ void fill_subargs(evp_b200_handle *h, SubArgs &a, int cur) {
     a.forcex = p[P_FORCEX]; a.forcey = p[P_FORCEY]; a.umassdtei = p[P_UMASSDTEI]; a.fm = p[P_FM];
     a.uarear = p[P_UAREAR];
     a.icetmask = h->mk[M_ICETMASK]; a.iceumask = h->mk[M_ICEUMASK];
-    a.u_old = p[cur ? P_U1 : P_U0]; a.v_old = p[cur ? P_V1 : P_V0];
-    a.u_new = p[cur ? P_U0 : P_U1]; a.v_new = p[cur ? P_V0 : P_V1];
-    for (int k = 0; k < EVP_NSTRESS; ++k) {
-        a.s_old[k] = p[(cur ? P_S1 : P_S0) + k];
-        a.s_new[k] = p[(cur ? P_S0 : P_S1) + k];
-    }
+    static_assert(P_U1 - P_U0 == P_V1 - P_V0 && P_U1 - P_U0 == P_S1 - P_S0, "state copies must be equidistant");
+    a.u = p[P_U0];
+    a.v = p[P_V0];
+    for (int k = 0; k < EVP_NSTRESS; ++k) a.s[k] = p[P_S0 + k];
+    a.copy_stride = (long long)(P_U1 - P_U0) * (long long)h->pg.cells;
+    a.flip = cur ? 1 : 0; // copy that is read; copy flip ^ 1 is written
+    a.nsub = 1;
+    a.cta_epoch = h->d_cta_epoch;
+    a.epoch0 = h->epoch_count;
     a.divu = p[P_DIVU]; a.shear = p[P_SHEAR]; a.rdg_conv = p[P_RDG_CONV]; a.rdg_shear = p[P_RDG_SHEAR];
     a.prs_sig = p[P_PRS_SIG]; a.strintx = p[P_STRINTX]; a.strinty = p[P_STRINTY];
     a.strocnx = p[P_STROCNX]; a.strocny = p[P_STROCNY];
@@ -253,20 +260,23 @@ void fill_subargs(evp_b200_handle *h, SubArgs &a, int cur) {
     a.fold = h->fold_in_kernel ? 1 : 0;
     a.fold_scratch = h->fold_scratch;
     a.peer_n_u = a.peer_n_v = a.peer_s_u = a.peer_s_v = nullptr;
+    a.peer_n_stride = a.peer_s_stride = 0;
     a.peer_n_flag = a.peer_s_flag = nullptr;
     a.sync = h->sync;
     a.p2p = h->p2p ? 1 : 0;
     if (h->p2p) {
-        const int pu = cur ? P_U0 : P_U1, pv = cur ? P_V0 : P_V1; // the neighbours' `new` copies
+        // the neighbours' pools are laid out like ours (same plane ids, their own plane size)
         if (h->north >= 0) { // north neighbour's south ghost row = its row 0
-            a.peer_n_u = h->peer_pool[0] + (size_t)pu * h->peer_cells[0];
-            a.peer_n_v = h->peer_pool[0] + (size_t)pv * h->peer_cells[0];
+            a.peer_n_u = h->peer_pool[0] + (size_t)P_U0 * h->peer_cells[0];
+            a.peer_n_v = h->peer_pool[0] + (size_t)P_V0 * h->peer_cells[0];
+            a.peer_n_stride = (long long)(P_U1 - P_U0) * (long long)h->peer_cells[0];
             a.peer_n_flag = h->peer_sync[0] + EVP_SYNC_FS;
         }
         if (h->south >= 0) { // south neighbour's north ghost row = its row nyl+1
             const size_t off = (size_t)(h->peer_nyl[1] + 1) * h->pg.pitch;
-            a.peer_s_u = h->peer_pool[1] + (size_t)pu * h->peer_cells[1] + off;
-            a.peer_s_v = h->peer_pool[1] + (size_t)pv * h->peer_cells[1] + off;
+            a.peer_s_u = h->peer_pool[1] + (size_t)P_U0 * h->peer_cells[1] + off;
+            a.peer_s_v = h->peer_pool[1] + (size_t)P_V0 * h->peer_cells[1] + off;
+            a.peer_s_stride = (long long)(P_U1 - P_U0) * (long long)h->peer_cells[1];
             a.peer_s_flag = h->peer_sync[1] + EVP_SYNC_FN;
         }
     }
@@ -282,9 +292,10 @@ int launch_subcycle(evp_b200_handle *h, int cur, bool last) {
     int n = 1;
     if (h->pg.ns_cyclic) n += 2;
     if (h->pg.tripole && !h->fold_in_kernel) n += 1;
-    if (!h->fold_in_kernel) aux_halo_uv_ns(h->pg, a.u_new, a.v_new, h->st);
+    double *u_new = a.flip ? a.u : a.u + a.copy_stride, *v_new = a.flip ? a.v : a.v + a.copy_stride;
+    if (!h->fold_in_kernel) aux_halo_uv_ns(h->pg, u_new, v_new, h->st);
     if (h->dims.nranks > 1 && !h->p2p) {
-        void *pp[2] = {a.u_new, a.v_new};
+        void *pp[2] = {u_new, v_new};
         if (exchange_rows(h, pp, 2, sizeof(double))) return -1;
         n += 1;
     }
@@ -297,7 +308,19 @@ int run_subcycle_loop(evp_b200_handle *h) {
     // NCCL send/recv inside a captured graph dead-locked on 2 x B200 (NCCL 2.28.9): with the NCCL
     // exchange the loop is launched on the stream; the peer-to-peer exchange has no host calls
     const bool graph_ok = h->par.use_graph && (h->dims.nranks == 1 || h->p2p);
-    if (graph_ok) {
+    if (h->persistent) {
+        // all ndte subcycles in one cooperative launch (k_persist): CTAs synchronise with their
+        // neighbours only, through per-CTA epochs that count from zero in every launch
+        SubArgs a;
+        fill_subargs(h, a, 0);
+        a.nsub = ndte;
+        CU(cudaMemsetAsync(h->d_cta_epoch, 0, sizeof(int) * (size_t)h->grid_x * h->grid_y, h->st));
+        persist_launch_fn fn = h->par.math_mode == 1 ? evp_persist_launch_fast : evp_persist_launch_strict;
+        const int e = fn(a, h->threads, (unsigned)h->grid_x, (unsigned)h->grid_y, (void *)h->st, nullptr);
+        if (e != 0) return fail(EVP_B200_ERR_CUDA, "persistent subcycle kernel: %s", cudaGetErrorString((cudaError_t)e));
+        h->sub_launches_per_loop = 1;
+        h->cur = ndte & 1;
+    } else if (graph_ok) {
         if (!h->graph_exec) {
             CU(cudaStreamBeginCapture(h->st, cudaStreamCaptureModeThreadLocal));
             int cur = 0, n = 0;
@@ -326,6 +349,7 @@ int run_subcycle_loop(evp_b200_handle *h) {
         h->sub_launches_per_loop = n;
     }
     CU(cudaGetLastError());
+    h->epoch_count += ndte;
     // peer-to-peer halo: the ghost rows of the final copy are complete once both neighbours have
     // published the epoch of their last subcycle kernel
     if (h->p2p) aux_wait_peers(h->sync, h->north >= 0, h->south >= 0, h->grid_x, h->st);
@@ -338,6 +362,27 @@ int run_subcycle_loop(evp_b200_handle *h) {
         h->cur = 0;
     }
     return 0;
+}
+
+// Whether the ndte loop runs as ONE cooperative launch (k_persist) instead of one launch per subcycle:
+// opt-in through kernel_variant bit 7 (128), where it is possible.  Measured on B200 it is bit-identical
+// but not faster: the neighbour waits cost ~3 us per subcycle against a ~2 us launch gap
+// inside a CUDA graph, so the graph of k_subcycle launches stays the default.
+void decide_persistent(evp_b200_handle *h) {
+    h->persistent = false;
+    if ((h->par.kernel_variant & 128) == 0) return;
+    if (h->pg.ns_cyclic) return;                          // the north-south wrap runs between the kernels
+    if (h->pg.tripole && !h->fold_in_kernel) return;      // so does the separate tripole fold
+    if (h->dims.nranks > 1 && !h->p2p) return;            // and the NCCL row exchange
+    if (h->par.ndte < 2) return;
+    int sms = 148, per_sm = 0;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device);
+    SubArgs a;
+    fill_subargs(h, a, 0);
+    persist_launch_fn fn = h->par.math_mode == 1 ? evp_persist_launch_fast : evp_persist_launch_strict;
+    if (fn(a, h->threads, 0, 0, nullptr, &per_sm) != 0) { cudaGetLastError(); return; }
+    if ((long)h->grid_x * h->grid_y > (long)per_sm * sms) return; // every CTA must be resident
+    h->persistent = true;
 }
 
 // Tiling of the subcycle kernel: balanced strips in x, one wave of CTAs in total, row chunks in
@@ -416,8 +461,10 @@ int choose_tiling(evp_b200_handle *h) {
     h->balance = h->par.tile_rows <= 0 && ncy >= 3 && (h->par.kernel_variant & 32) == 0;
     if (h->d_chunks) cudaFree(h->d_chunks);
     if (h->d_rowcnt) cudaFree(h->d_rowcnt);
+    if (h->d_cta_epoch) cudaFree(h->d_cta_epoch);
     CU(cudaMalloc(&h->d_rowcnt, sizeof(int) * (nyl + 2)));
     CU(cudaMalloc(&h->d_chunks, sizeof(int) * tab.size()));
+    CU(cudaMalloc(&h->d_cta_epoch, sizeof(int) * (size_t)ncx * ncy));
     CU(cudaMemcpy(h->d_chunks, tab.data(), sizeof(int) * tab.size(), cudaMemcpyHostToDevice));
     return 0;
 }
@@ -586,6 +633,7 @@ static int init_handle(evp_b200_handle *h, const evp_b200_dims *d, const evp_b20
     if (rc) return rc;
     CU(cudaStreamSynchronize(h->st));
     if (int trc = choose_tiling(h)) return trc;
+    decide_persistent(h); // multi-rank: decided again once the peer-to-peer halo is set up (comm_init)
     memset(&h->tm, 0, sizeof(h->tm));
     return EVP_B200_OK;
 }
@@ -851,7 +899,11 @@ static int do_run(evp_b200_handle *h, const evp_b200_inputs *in, const double *s
     }
     CU(cudaStreamWaitEvent(h->st, h->ev_early_done, 0));
     CU(cudaEventRecord(h->ev[6], h->st));
+    int wait_gave_up = 0; // sync[6]: a bounded flag wait inside the subcycle kernels timed out
+    CU(cudaMemcpyAsync(&wait_gave_up, h->sync + 6, sizeof(int), cudaMemcpyDeviceToHost, h->st));
     CU(cudaStreamSynchronize(h->st));
+    if (wait_gave_up)
+        return fail(EVP_B200_ERR_STATE, "subcycle kernel: a wait for a neighbouring CTA / GPU timed out (results invalid)");
     CU(cudaEventElapsedTime(&h->tm.upload_ms, h->ev[0], h->ev[1]));
     CU(cudaEventElapsedTime(&h->tm.prep_ms, h->ev[1], h->ev[3]));
     CU(cudaEventElapsedTime(&h->tm.subcycle_ms, h->ev[3], h->ev[4]));
@@ -1048,6 +1100,7 @@ int evp_b200_comm_init(evp_b200_handle *h, const uint8_t id[128]) {
         cudaGetLastError();
         if (h->grid_x > EVP_SYNC_MAXCX) ok = false;
         h->p2p = ok;   // on failure the NCCL exchange stays in use (evp_b200_get_timings reports the mode)
+        decide_persistent(h);
     }
     return 0;
 }
@@ -1065,6 +1118,7 @@ int evp_b200_finalize(evp_b200_handle *h) {
     cudaFree(h->fold_scratch);
     cudaFree(h->d_chunks);
     cudaFree(h->d_rowcnt);
+    cudaFree(h->d_cta_epoch);
     cudaFree(h->row_ht);
     if (h->comm && h->pCommDestroy) h->pCommDestroy(h->comm);
     if (h->graph_exec) cudaGraphExecDestroy(h->graph_exec);

@@ -24,11 +24,14 @@ struct SubArgs {
     // U-cell statics (:1339-1349)
     const double *aiu, *uocn, *vocn, *waterx, *watery, *forcex, *forcey, *umassdtei, *fm, *uarear;
     const uint8_t *icetmask, *iceumask;
-    // ping-pong state
-    const double *u_old, *v_old;
-    double *u_new, *v_new;
-    const double *s_old[EVP_NSTRESS]; // stressp_1..4, stressm_1..4, stress12_1..4
-    double *s_new[EVP_NSTRESS];
+    // ping-pong state: two copies of u, v and of the 12 stresses (stressp_1..4, stressm_1..4,
+    // stress12_1..4).  The pointers are copy 0; copy 1 of every plane lies copy_stride doubles behind
+    // it.  A one-subcycle launch reads copy `flip` and writes copy `flip ^ 1`; the persistent kernel
+    // alternates by itself starting from `flip`.
+    double *u, *v;
+    double *s[EVP_NSTRESS];
+    long long copy_stride;
+    int flip;
     // written on the last subcycle only (ksub == ndte, :1103-1115; :1415-1418,:1434-1435)
     double *divu, *shear, *rdg_conv, *rdg_shear, *prs_sig, *strintx, *strinty, *strocnx, *strocny;
     int nx, nyl, pitch;
@@ -38,6 +41,13 @@ struct SubArgs {
     // row chunks in launch order (blockIdx.y): chunks[2k] = first U row, chunks[2k+1] = number of U
     // rows.  Boundary chunks come first and are shorter (see choose_tiling in evp_abi.cu).
     const int *chunks;
+    // persistent kernel (all ndte subcycles in one cooperative launch): subcycles to run; one epoch
+    // per CTA (cta_epoch[blockIdx.y * gridDim.x + blockIdx.x] = subcycles of THIS launch the CTA has
+    // finished; zeroed by the host before the launch); subcycles this rank had completed before the
+    // launch (== sync[1] at launch; the peer-to-peer flags and the fold epoch count from there)
+    int nsub;
+    int *cta_epoch;
+    int epoch0;
     int evp_damping, hemisphere_turning;
     // 2-plane metric path: on rows where row_ht[j] != 0 the eight metrics are re-derived from the
     // primary cell widths with the (unfused) init_grid2 formulas instead of being loaded
@@ -45,11 +55,14 @@ struct SubArgs {
     const uint8_t *row_ht;
     double ecci, dte2T, denom1, denom2, rcon, dragw, cosw, sinw;
     // ---- multi-rank peer-to-peer velocity halo (exchange_mode 0); all null/0 on one rank -------
-    // ghost rows of the neighbours' u_new/v_new planes, mapped through CUDA IPC:
-    // peer_n_* = row 0 of the north neighbour, peer_s_* = row nyl+1 of the south neighbour
+    // ghost rows of the neighbours' u/v planes (copy 0; copy 1 lies peer_*_stride doubles behind),
+    // mapped through CUDA IPC: peer_n_* = row 0 of the north neighbour, peer_s_* = row nyl+1 of the
+    // south neighbour
     double *peer_n_u, *peer_n_v, *peer_s_u, *peer_s_v;
-    // sync block in local memory (EVP_SYNC_INTS ints): [0] CTAs finished (counter), [1] subcycle
-    // kernels completed on this rank (epoch), [4] fold counter, then two arrays of per-strip epochs
+    long long peer_n_stride, peer_s_stride;
+    // sync block in local memory (EVP_SYNC_INTS ints): [0] CTAs finished (counter), [1] subcycles
+    // completed on this rank (epoch), [4] fold counter, [5] subcycles whose tripole fold is complete
+    // (persistent kernel), [6] error flag (a bounded wait gave up), then two arrays of per-strip epochs
     // written by the neighbours' boundary CTAs through their mapping of this block:
     //   [EVP_SYNC_FN + x] = epochs finished by strip x of the NORTH neighbour's southernmost chunk,
     //   [EVP_SYNC_FS + x] = epochs finished by strip x of the SOUTH neighbour's northernmost chunk.
@@ -92,4 +105,13 @@ void evp_subcycle_launch_strict(const SubArgs &a, bool last, int variant, int th
                                 unsigned grid_x, unsigned grid_y, void *stream);
 void evp_subcycle_launch_fast(const SubArgs &a, bool last, int variant, int threads,
                               unsigned grid_x, unsigned grid_y, void *stream);
+// persistent kernel: a.nsub subcycles in one cooperative launch (ctas_per_sm == nullptr), or, with
+// ctas_per_sm != nullptr, only the occupancy query (resident CTAs per SM; the grid must fit in one
+// wave).  Returns a cudaError_t value.
+typedef int (*persist_launch_fn)(const SubArgs &a, int threads, unsigned grid_x, unsigned grid_y, void *stream,
+                                 int *ctas_per_sm);
+int evp_persist_launch_strict(const SubArgs &a, int threads, unsigned grid_x, unsigned grid_y, void *stream,
+                              int *ctas_per_sm);
+int evp_persist_launch_fast(const SubArgs &a, int threads, unsigned grid_x, unsigned grid_y, void *stream,
+                            int *ctas_per_sm);
 int evp_subcycle_max_threads(void);

@@ -2,7 +2,8 @@
 //
 // Included by evp_subcycle_strict.cu (nvcc -fmad=false: unfused IEEE arithmetic, bit-identical to
 // the unfused CPU oracle) and evp_subcycle_fast.cu (-fmad=true: nvcc contracts a*b+c into DFMA).
-// EVP_SUB_LAUNCH names the exported launcher.
+// EVP_SUB_LAUNCH / EVP_PERSIST_LAUNCH name the exported launchers: k_subcycle runs one subcycle per
+// launch, k_persist (end of this file) all ndte subcycles in one cooperative launch.
 //
 // What it replaces: `stress` (source/ice_dyn_evp.F90:947-1293) and `stepu` (:1302-1443) for one
 // ksub, plus the east-west part of the two ice_HaloUpdate calls (:397-402).  The reference writes
@@ -38,6 +39,13 @@
 
 namespace EVP_SUB_NS {
 
+// State that other CTAs rewrite while the persistent kernel runs must not be served by the
+// (non-coherent) L1: COH selects ld.global.cg; the one-subcycle kernel keeps the read-only path.
+template <bool COH>
+__device__ __forceinline__ double ld_state(const double *p) {
+    return COH ? __ldcg(p) : __ldg(p);
+}
+
 struct TRow {
     double s[EVP_NSTRESS];
     double strength, dxt, dyt, dxhy, dyhx, cxp, cyp, cxm, cym, tiny, tarear;
@@ -70,22 +78,26 @@ struct URow {
 
 // `act` comes from a mask byte that was loaded one iteration earlier, so the data loads below
 // are issued without waiting on a dependent mask load.
-template <bool LAST, bool HT>
-__device__ __forceinline__ void load_T(const SubArgs &a, TRow &t, int i, int j, bool colT, bool act) {
-    const size_t idx = (size_t)j * a.pitch + i;
+// `so` / `sn`: offset (in doubles) of the state copy that is read / written; copy 1 of every state plane
+// lies a.copy_stride behind copy 0, so one register selects the copy for all 14 planes and the plane
+// pointers themselves stay constant-bank operands.
+template <bool LAST, bool HT, bool COH>
+__device__ __forceinline__ void load_T(const SubArgs &a, size_t so, TRow &t, int i, int j, bool colT, bool act) {
+    size_t idx = (size_t)j * a.pitch + i + so;
     t.act = act;
     if (colT) {
-        t.u = __ldg(a.u_old + idx);
-        t.v = __ldg(a.v_old + idx);
-        t.uw = __ldg(a.u_old + idx - 1);
-        t.vw = __ldg(a.v_old + idx - 1);
+        t.u = ld_state<COH>(a.u + idx);
+        t.v = ld_state<COH>(a.v + idx);
+        t.uw = ld_state<COH>(a.u + idx - 1);
+        t.vw = ld_state<COH>(a.v + idx - 1);
     } else {
         t.u = t.v = t.uw = t.vw = 0.0;
     }
     t.ht = false;
     if (t.act) {
 #pragma unroll
-        for (int k = 0; k < EVP_NSTRESS; ++k) t.s[k] = __ldg(a.s_old[k] + idx);
+        for (int k = 0; k < EVP_NSTRESS; ++k) t.s[k] = ld_state<COH>(a.s[k] + idx);
+        idx -= so;
         t.strength = __ldg(a.strength + idx);
         if (HT && __ldg(a.row_ht + j)) { // uniform per row
             t.ht = true;
@@ -146,7 +158,7 @@ __device__ __forceinline__ void div4(double n, double d1, double d2, double d3, 
 // source/ice_dyn_evp.F90:1056-1291 for one T cell.  (un,vn)=(i,j) (uw,vw)=(i-1,j) (us,vs)=(i,j-1)
 // (usw,vsw)=(i-1,j-1).  Operation order is the Fortran's.
 template <bool LAST>
-__device__ __forceinline__ void stress_cell(const SubArgs &a, const TRow &t, double us, double vs,
+__device__ __forceinline__ void stress_cell(const SubArgs &a, size_t sn, const TRow &t, double us, double vs,
                                             double usw, double vsw, size_t idx, bool store,
                                             double (&str)[8]) {
     const double p5 = 0.5, p25 = 0.25, c4 = 4.0;
@@ -234,9 +246,10 @@ __device__ __forceinline__ void stress_cell(const SubArgs &a, const TRow &t, dou
     const double s124 = (t.s[11] + c1se * shearse * p5) * a.denom2;
 
     if (store) {
-        a.s_new[0][idx] = sp1; a.s_new[1][idx] = sp2; a.s_new[2][idx] = sp3; a.s_new[3][idx] = sp4;
-        a.s_new[4][idx] = sm1; a.s_new[5][idx] = sm2; a.s_new[6][idx] = sm3; a.s_new[7][idx] = sm4;
-        a.s_new[8][idx] = s121; a.s_new[9][idx] = s122; a.s_new[10][idx] = s123; a.s_new[11][idx] = s124;
+        const size_t idn = idx + sn;
+        a.s[0][idn] = sp1; a.s[1][idn] = sp2; a.s[2][idn] = sp3; a.s[3][idn] = sp4;
+        a.s[4][idn] = sm1; a.s[5][idn] = sm2; a.s[6][idn] = sm3; a.s[7][idn] = sm4;
+        a.s[8][idn] = s121; a.s[9][idn] = s122; a.s[10][idn] = s123; a.s[11][idn] = s124;
     }
 
     // :1196-1215
@@ -286,8 +299,9 @@ __device__ __forceinline__ void stress_cell(const SubArgs &a, const TRow &t, dou
 
 // source/ice_dyn_evp.F90:1386-1441 for one U cell; sx, sy are the two str sums of :1415-1418
 template <bool LAST>
-__device__ __forceinline__ void stepu_cell(const SubArgs &a, const URow &u, double uold, double vold,
+__device__ __forceinline__ void stepu_cell(const SubArgs &a, size_t sn, const URow &u, double uold, double vold,
                                            double sx, double sy, int i, int j, size_t idx) {
+    double *const u_new = a.u + sn, *const v_new = a.v + sn;
     const double du = u.uocn - uold, dv = u.vocn - vold;
     const double vrel = u.aiu * a.dragw * sqrt(du * du + dv * dv); // :1394
     const double taux = vrel * u.waterx;                            // :1397-1398
@@ -313,30 +327,35 @@ __device__ __forceinline__ void stepu_cell(const SubArgs &a, const URow &u, doub
         unew = nu / ab2;
         vnew = nv / ab2;
     }
-    a.u_new[idx] = unew;
-    a.v_new[idx] = vnew;
+    u_new[idx] = unew;
+    v_new[idx] = vnew;
     if (a.ew_cyclic) { // east-west part of ice_HaloUpdate(uvel/vvel), serial/ice_boundary.F90:3629-3668
         if (i == a.nx) {
-            a.u_new[idx - a.nx] = unew;
-            a.v_new[idx - a.nx] = vnew;
+            u_new[idx - a.nx] = unew;
+            v_new[idx - a.nx] = vnew;
         }
         if (i == 1) {
-            a.u_new[idx + a.nx] = unew;
-            a.v_new[idx + a.nx] = vnew;
+            u_new[idx + a.nx] = unew;
+            v_new[idx + a.nx] = vnew;
         }
     }
     if (a.p2p) {
         // slab-to-slab part of the halo update: the top / bottom physical row goes straight into the
         // neighbour GPU's ghost row over NVLink (whole padded row: the wrap columns travel with it)
         double *pu = nullptr, *pv = nullptr;
-        if (j == a.nyl && a.peer_n_u) { pu = a.peer_n_u; pv = a.peer_n_v; }
-        if (j == 1 && a.peer_s_u) {
+        const bool second = sn != 0; // the neighbours' copies are laid out like ours
+        if (j == a.nyl && a.peer_n_flag) {
+            pu = a.peer_n_u + (second ? a.peer_n_stride : 0);
+            pv = a.peer_n_v + (second ? a.peer_n_stride : 0);
+        }
+        if (j == 1 && a.peer_s_flag) {
             if (pu) { // one-row slab: both neighbours
                 pu[i] = unew; pv[i] = vnew;
                 if (a.ew_cyclic && i == a.nx) { pu[0] = unew; pv[0] = vnew; }
                 if (a.ew_cyclic && i == 1) { pu[a.nx + 1] = unew; pv[a.nx + 1] = vnew; }
             }
-            pu = a.peer_s_u; pv = a.peer_s_v;
+            pu = a.peer_s_u + (second ? a.peer_s_stride : 0);
+            pv = a.peer_s_v + (second ? a.peer_s_stride : 0);
         }
         if (pu) {
             pu[i] = unew; pv[i] = vnew;
@@ -352,10 +371,48 @@ __device__ __forceinline__ void stepu_cell(const SubArgs &a, const URow &u, doub
     }
 }
 
-// End of a subcycle kernel: tripole fold by the last CTA of the northernmost chunk (top slab), then
-// publication of this rank's epoch to the neighbours (peer-to-peer halo).
-template <int NT>
-__device__ __forceinline__ void k_subcycle_epilogue(const SubArgs &a, int tid, bool top, bool bot, int epoch) {
+// Bounded spin on a flag that another CTA (or another GPU) advances: a protocol bug or a dead peer must
+// not hang the device.  After ~2^26 polls the error flag sync[6] is raised and the wait gives up; the
+// host reports EVP_B200_ERR_STATE after the loop.
+__device__ __forceinline__ int ld_acquire(const int *p) {
+    int v;
+    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void wait_flag_ge(const int *flag, int want, int *sync) {
+    unsigned spins = 0;
+    while (ld_acquire(flag) < want) {
+        if (++spins > (1u << 26)) {
+            *(volatile int *)(sync + 6) = 1;
+            break;
+        }
+    }
+}
+
+// Start of a subcycle on a boundary CTA of a multi-rank run (peer-to-peer halo): wait until strips
+// x-1, x, x+1 of the neighbour's adjacent chunk have published `e` finished subcycles.
+// A boundary CTA reads ghost-row columns that those strips stored during that rank's previous
+// subcycle, and stores into ghost-row columns those strips read during it.  Both are safe once they
+// have published at least as many finished subcycles as this rank has completed (per-strip epochs:
+// the neighbour's boundary CTAs run first and are short, so normally nothing waits).
+__device__ __forceinline__ void p2p_wait(const SubArgs &a, int tid, bool top, bool bot, int e) {
+    if (tid < 3) {
+        const int ncx = (int)gridDim.x;
+        const int x = ((int)blockIdx.x + tid - 1 + ncx) % ncx;
+        if (top && a.peer_n_flag) wait_flag_ge(a.sync + EVP_SYNC_FN + x, e, a.sync);
+        if (bot && a.peer_s_flag) wait_flag_ge(a.sync + EVP_SYNC_FS + x, e, a.sync);
+        __threadfence_system();
+    }
+    __syncthreads();
+}
+
+// End of a subcycle: publication of this rank's epoch to the neighbours (peer-to-peer halo), then the
+// tripole fold by the last CTA of the northernmost chunk (top slab).  `sn` = offset of the copy just written.
+// PERSIST: the fold's completion is published in sync[5] (the top chunk waits for it before the next
+// subcycle) and the rank-level counter is left to the end of the persistent kernel.
+template <int NT, bool PERSIST>
+__device__ __forceinline__ void subcycle_epilogue(const SubArgs &a, size_t sn, int tid, bool top, bool bot, int epoch) {
+    double *const u_new = a.u + sn, *const v_new = a.v + sn;
     if (a.p2p && ((top && a.peer_n_flag) || (bot && a.peer_s_flag))) {
         // boundary CTA done: its stores into the neighbour's ghost row are made visible system-wide,
         // then its per-strip epoch is published in the neighbour's sync block
@@ -390,7 +447,7 @@ __device__ __forceinline__ void k_subcycle_epilogue(const SubArgs &a, int tid, b
                     const int c = c0 + q * NT + tid;
                     if (c < 2 * ncol) {
                         const int f = c >= ncol, cc = f ? c - ncol : c;
-                        val[q] = __ldcg((f ? a.v_new : a.u_new) + rtop + cc);
+                        val[q] = __ldcg((f ? v_new : u_new) + rtop + cc);
                     }
                 }
 #pragma unroll
@@ -410,7 +467,7 @@ __device__ __forceinline__ void k_subcycle_epilogue(const SubArgs &a, int tid, b
                     const int c = c0 + q * NT + tid;
                     if (c < 2 * ncol) {
                         const int f = c >= ncol, cc = f ? c - ncol : c;
-                        const double *fld = f ? a.v_new : a.u_new;
+                        const double *fld = f ? v_new : u_new;
                         int ig = cc;
                         if (cc == 0) ig = a.ew_cyclic ? a.nx : 1;
                         if (cc == a.nx + 1) ig = a.ew_cyclic ? 1 : a.nx;
@@ -427,16 +484,25 @@ __device__ __forceinline__ void k_subcycle_epilogue(const SubArgs &a, int tid, b
                     const int c = c0 + q * NT + tid;
                     if (c < 2 * ncol) {
                         const int f = c >= ncol, cc = f ? c - ncol : c;
-                        double *fld = f ? a.v_new : a.u_new;
+                        double *fld = f ? v_new : u_new;
                         fld[rtop + cc] = vt[q];
                         fld[rtop + a.pitch + cc] = vg[q];
                     }
                 }
             }
-            if (tid == 0) a.sync[4] = 0;
+            if (PERSIST) {
+                __syncthreads();
+                if (tid == 0) {
+                    a.sync[4] = 0;
+                    __threadfence();
+                    *(volatile int *)(a.sync + 5) = epoch + 1;
+                }
+            } else if (tid == 0) {
+                a.sync[4] = 0;
+            }
         }
     }
-    if (a.p2p) {
+    if (!PERSIST && a.p2p) {
         // the last CTA of the grid to finish advances this rank's count of completed kernels
         __syncthreads();
         if (tid == 0) {
@@ -451,9 +517,95 @@ __device__ __forceinline__ void k_subcycle_epilogue(const SubArgs &a, int tid, b
     }
 }
 
+// One subcycle of one CTA: march north over the U rows j0 .. j0+nrows-1 of strip blockIdx.x, reading
+// the state copy at offset `so` and writing the one at offset `sn`.  COH: state loads bypass the
+// non-coherent L1 (persistent kernel).
+template <int NT, bool LAST, bool HT, bool COH>
+__device__ __forceinline__ void march(const SubArgs &a, size_t so, size_t sn, int tid, int i, int j0, int nrows) {
+    extern __shared__ double evp_xch[]; // [2][4][NT]: str(2,4,7,8) handed to the west neighbour thread
+    const int jlast = min(j0 + nrows, a.nyl + 1); // last T row of this CTA
+    const bool colT = (tid <= a.strip_w) && (i <= a.nx + 1);
+    const bool colU = (tid < a.strip_w) && (i <= a.nx);
+    const bool ownT = colT && (tid < a.strip_w || i == a.nx + 1);
+
+    double us = 0.0, vs = 0.0, usw = 0.0, vsw = 0.0;
+    if (colT) {
+        const size_t idx = (size_t)(j0 - 1) * a.pitch + i + so;
+        us = ld_state<COH>(a.u + idx);
+        vs = ld_state<COH>(a.v + idx);
+        usw = ld_state<COH>(a.u + idx - 1);
+        vsw = ld_state<COH>(a.v + idx - 1);
+    }
+    double px = 0.0, s5c = 0.0, s7c = 0.0;
+    // Mask bytes run two rows (T) / one row (U) ahead of the data they gate and are kept RAW in a
+    // register: the compare that consumes a byte sits one iteration after its load, so no data load
+    // ever waits on a mask load.
+    const uint8_t *tmk = a.icetmask + (size_t)j0 * a.pitch + i;
+    const uint8_t *umk = a.iceumask + (size_t)j0 * a.pitch + i;
+    unsigned tm_raw = (colT && j0 + 1 <= jlast) ? __ldg(tmk + a.pitch) : 0u; // T row j+1
+    unsigned um_raw = 0u;                                                     // U row j-1
+    TRow t;
+    load_T<LAST, HT, COH>(a, so, t, i, j0, colT, colT && (__ldg(tmk) != 0));
+    int par = 0;
+
+    for (int j = j0; j <= jlast; ++j) {
+        TRow tn;
+        URow uc;
+        const bool tm_next = tm_raw != 0u;
+        const bool um_cur = um_raw != 0u;
+        const unsigned tm_raw2 = (colT && j + 2 <= jlast) ? __ldg(tmk + 2 * (size_t)a.pitch) : 0u;
+        const unsigned um_raw1 = (colU && j + 1 <= jlast) ? __ldg(umk) : 0u; // U row j
+        tmk += a.pitch;
+        umk += a.pitch;
+        if (j < jlast) load_T<LAST, HT, COH>(a, so, tn, i, j + 1, colT, tm_next); // software prefetch of the next row
+        uc.act = false;
+        if (j > j0) load_U(a, uc, i, j - 1, um_cur);
+
+        const size_t idx = (size_t)j * a.pitch + i;
+        double str[8];
+        if (t.act) {
+            derive_metrics<HT>(t);
+            const bool store = ownT && (j < j0 + nrows || j == a.nyl + 1);
+            stress_cell<LAST>(a, sn, t, us, vs, usw, vsw, idx, store, str);
+        } else {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) str[k] = 0.0; // str(:,:,:) = c0, :1051
+        }
+        double *const xl = evp_xch + par * 4 * NT + tid;
+        xl[0 * NT] = str[1];
+        xl[1 * NT] = str[3];
+        xl[2 * NT] = str[6];
+        xl[3 * NT] = str[7];
+        __syncthreads();
+        double s2r = 0.0, s4r = 0.0, s7r = 0.0, s8r = 0.0;
+        if (tid < NT - 1) {
+            s2r = xl[0 * NT + 1];
+            s4r = xl[1 * NT + 1];
+            s7r = xl[2 * NT + 1];
+            s8r = xl[3 * NT + 1];
+        }
+        par ^= 1;
+
+        if (uc.act) {
+            const double sx = px + str[2] + s4r;          // ((s1 + s2) + s3) + s4
+            const double sy = s5c + str[5] + s7c + s8r;    // ((s5 + s6) + s7) + s8
+            stepu_cell<LAST>(a, sn, uc, us, vs, sx, sy, i, j - 1, idx - a.pitch);
+        }
+        px = str[0] + s2r;
+        s5c = str[4];
+        s7c = s7r;
+        us = t.u;
+        vs = t.v;
+        usw = t.uw;
+        vsw = t.vw;
+        t = tn;
+        tm_raw = tm_raw2;
+        um_raw = um_raw1;
+    }
+}
+
 template <int NT, bool LAST, bool HT>
 __global__ void __launch_bounds__(NT) k_subcycle(const __grid_constant__ SubArgs a) {
-    __shared__ double xch[2][4][NT];
     // programmatic dependent launch: let the next subcycle kernel be scheduled as SMs drain, and
     // wait here until the previous grid has completed and flushed (no-ops without the attribute)
     asm volatile("griddepcontrol.launch_dependents;");
@@ -469,107 +621,99 @@ __global__ void __launch_bounds__(NT) k_subcycle(const __grid_constant__ SubArgs
     const bool top = (j0 + nrows - 1 == a.nyl), bot = (j0 == 1);
     int epoch = 0;
     if (a.p2p && ((top && a.peer_n_flag) || (bot && a.peer_s_flag))) {
-        // A boundary CTA reads ghost-row columns that strips x-1, x, x+1 of the neighbour's adjacent
-        // chunk stored during that rank's previous subcycle kernel, and stores into ghost-row columns
-        // those strips read during it.  Both are safe once these three strips have published at
-        // least as many finished kernels as this rank has completed (per-strip epochs: the
-        // neighbour's boundary CTAs run first and are short, so normally nothing waits).
-        __shared__ int s_epoch;
-        if (tid < 3) {
-            const int e = *(volatile int *)(a.sync + 1);
-            const int ncx = (int)gridDim.x;
-            const int x = ((int)blockIdx.x + tid - 1 + ncx) % ncx;
-            if (top && a.peer_n_flag)
-                while (*(volatile int *)(a.sync + EVP_SYNC_FN + x) < e) __nanosleep(20);
-            if (bot && a.peer_s_flag)
-                while (*(volatile int *)(a.sync + EVP_SYNC_FS + x) < e) __nanosleep(20);
-            __threadfence_system();
-            if (tid == 0) s_epoch = e;
-        }
+        epoch = *(volatile int *)(a.sync + 1); // subcycle kernels completed on this rank
+        p2p_wait(a, tid, top, bot, epoch);
+    }
+    // an empty chunk (all rows inactive, trimmed by the load balancer) has nothing to do
+    const size_t so = a.flip ? (size_t)a.copy_stride : 0, sn = a.flip ? 0 : (size_t)a.copy_stride;
+    if (nrows > 0) march<NT, LAST, HT, false>(a, so, sn, tid, i, j0, nrows);
+    subcycle_epilogue<NT, false>(a, sn, tid, top, bot, epoch);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Persistent kernel: all a.nsub subcycles of one evp call in ONE cooperative launch (every CTA is
+// resident; the grid is the same one-wave grid as k_subcycle's and each CTA keeps its strip and row
+// chunk for the whole loop).  There is no grid-wide barrier: because u, v and the stresses are
+// ping-ponged, a CTA may start subcycle k as soon as its (up to eight) neighbouring CTAs have
+// finished subcycle k-1 -- that single condition covers the read-after-write of the neighbours' new
+// values and the write-after-read of the copy they were still reading.  Each CTA publishes the number
+// of subcycles it has finished in cta_epoch[] (zeroed by the host before the launch) after a
+// __threadfence; state loads use ld.global.cg, because the L1 is not coherent with the other SMs'
+// stores.  What this removes per subcycle: the kernel launch gap, the ramp-up and tail of a grid, and
+// the wait of every CTA for the slowest one.
+// ------------------------------------------------------------------------------------------------
+// one subcycle of the persistent loop on one CTA
+template <int NT, bool LAST, bool HT>
+__device__ __forceinline__ void persist_step(const SubArgs &a, int k, const int *s_nb, int *my_epoch, int tid, int i,
+                                             int j0, int nrows, bool top, bool bot, bool p2p_cta) {
+    const bool odd = ((a.flip + k) & 1) != 0;
+    const size_t so = odd ? (size_t)a.copy_stride : 0, sn = odd ? 0 : (size_t)a.copy_stride;
+    if (k > 0) {
+        if (tid < 8 && s_nb[tid] >= 0) wait_flag_ge(a.cta_epoch + s_nb[tid], k, a.sync);
+        if (tid == 8 && a.fold && top) wait_flag_ge(a.sync + 5, a.epoch0 + k, a.sync);
         __syncthreads();
-        epoch = s_epoch;
     }
-    if (nrows > 0) { // an empty chunk (all rows inactive, trimmed by the load balancer) has nothing to do
-    const int jlast = min(j0 + nrows, a.nyl + 1); // last T row of this CTA
-    const bool colT = (tid <= a.strip_w) && (i <= a.nx + 1);
-    const bool colU = (tid < a.strip_w) && (i <= a.nx);
-    const bool ownT = colT && (tid < a.strip_w || i == a.nx + 1);
-
-    double us = 0.0, vs = 0.0, usw = 0.0, vsw = 0.0;
-    if (colT) {
-        const size_t idx = (size_t)(j0 - 1) * a.pitch + i;
-        us = __ldg(a.u_old + idx);
-        vs = __ldg(a.v_old + idx);
-        usw = __ldg(a.u_old + idx - 1);
-        vsw = __ldg(a.v_old + idx - 1);
+    if (p2p_cta) p2p_wait(a, tid, top, bot, a.epoch0 + k);
+    march<NT, LAST, HT, true>(a, so, sn, tid, i, j0, nrows);
+    subcycle_epilogue<NT, true>(a, sn, tid, top, bot, a.epoch0 + k);
+    __syncthreads();
+    if (tid == 0) {
+        __threadfence();
+        *(volatile int *)my_epoch = k + 1;
     }
-    double px = 0.0, s5c = 0.0, s7c = 0.0;
-    // Mask bytes run two rows (T) / one row (U) ahead of the data they gate and are kept RAW in a
-    // register: the compare that consumes a byte sits one iteration after its load, so no data load
-    // ever waits on a mask load.
-    const uint8_t *tmk = a.icetmask + (size_t)j0 * a.pitch + i;
-    const uint8_t *umk = a.iceumask + (size_t)j0 * a.pitch + i;
-    unsigned tm_raw = (colT && j0 + 1 <= jlast) ? __ldg(tmk + a.pitch) : 0u; // T row j+1
-    unsigned um_raw = 0u;                                                     // U row j-1
-    TRow t;
-    load_T<LAST, HT>(a, t, i, j0, colT, colT && (__ldg(tmk) != 0));
-    int par = 0;
+}
 
-    for (int j = j0; j <= jlast; ++j) {
-        TRow tn;
-        URow uc;
-        const bool tm_next = tm_raw != 0u;
-        const bool um_cur = um_raw != 0u;
-        const unsigned tm_raw2 = (colT && j + 2 <= jlast) ? __ldg(tmk + 2 * (size_t)a.pitch) : 0u;
-        const unsigned um_raw1 = (colU && j + 1 <= jlast) ? __ldg(umk) : 0u; // U row j
-        tmk += a.pitch;
-        umk += a.pitch;
-        if (j < jlast) load_T<LAST, HT>(a, tn, i, j + 1, colT, tm_next); // software prefetch of the next row
-        uc.act = false;
-        if (j > j0) load_U(a, uc, i, j - 1, um_cur);
-
-        const size_t idx = (size_t)j * a.pitch + i;
-        double str[8];
-        if (t.act) {
-            derive_metrics<HT>(t);
-            const bool store = ownT && (j < j0 + nrows || j == a.nyl + 1);
-            stress_cell<LAST>(a, t, us, vs, usw, vsw, idx, store, str);
-        } else {
-#pragma unroll
-            for (int k = 0; k < 8; ++k) str[k] = 0.0; // str(:,:,:) = c0, :1051
+template <int NT, bool HT>
+__global__ void __launch_bounds__(NT) k_persist(const __grid_constant__ SubArgs a) {
+    __shared__ int s_nb[8];
+    const int tid = threadIdx.x;
+    const int i = 1 + blockIdx.x * a.strip_w + tid;
+    const int ncx = (int)gridDim.x, ncy = (int)gridDim.y;
+    const int j0 = __ldg(a.chunks + 2 * blockIdx.y);
+    const int nrows = __ldg(a.chunks + 2 * blockIdx.y + 1);
+    const bool top = (j0 + nrows - 1 == a.nyl), bot = (j0 == 1);
+    int *const my_epoch = a.cta_epoch + blockIdx.y * ncx + blockIdx.x;
+    if (nrows <= 0) { // empty chunk: nobody depends on it
+        if (tid == 0) *(volatile int *)my_epoch = 0x7fffffff;
+        return;
+    }
+    // the CTAs whose cells this one reads / whose reads it overwrites: strips x-1, x, x+1 of this chunk
+    // and of the chunks that own the rows just south and just north of it (rows without active cells
+    // belong to no chunk: nothing is read or written there)
+    if (tid < 8) {
+        int ys = -1, yn = -1;
+        for (int c = 0; c < ncy; ++c) {
+            const int cj = __ldg(a.chunks + 2 * c), cn = __ldg(a.chunks + 2 * c + 1);
+            if (cn <= 0) continue;
+            if (cj + cn == j0) ys = c;
+            if (cj == j0 + nrows) yn = c;
         }
-        xch[par][0][tid] = str[1];
-        xch[par][1][tid] = str[3];
-        xch[par][2][tid] = str[6];
-        xch[par][3][tid] = str[7];
-        __syncthreads();
-        double s2r = 0.0, s4r = 0.0, s7r = 0.0, s8r = 0.0;
-        if (tid < NT - 1) {
-            s2r = xch[par][0][tid + 1];
-            s4r = xch[par][1][tid + 1];
-            s7r = xch[par][2][tid + 1];
-            s8r = xch[par][3][tid + 1];
-        }
-        par ^= 1;
-
-        if (uc.act) {
-            const double sx = px + str[2] + s4r;          // ((s1 + s2) + s3) + s4
-            const double sy = s5c + str[5] + s7c + s8r;    // ((s5 + s6) + s7) + s8
-            stepu_cell<LAST>(a, uc, us, vs, sx, sy, i, j - 1, idx - a.pitch);
-        }
-        px = str[0] + s2r;
-        s5c = str[4];
-        s7c = s7r;
-        us = t.u;
-        vs = t.v;
-        usw = t.uw;
-        vsw = t.vw;
-        t = tn;
-        tm_raw = tm_raw2;
-        um_raw = um_raw1;
+        const int bx = (int)blockIdx.x;
+        int xw = bx - 1, xe = bx + 1;
+        if (xw < 0) xw = a.ew_cyclic ? ncx - 1 : -1;
+        if (xe >= ncx) xe = a.ew_cyclic ? 0 : -1;
+        // tid: 0 W, 1 E, 2 S, 3 SW, 4 SE, 5 N, 6 NW, 7 NE
+        const int y = tid < 2 ? (int)blockIdx.y : (tid < 5 ? ys : yn);
+        const int x = (tid == 2 || tid == 5) ? bx : ((tid == 0 || tid == 3 || tid == 6) ? xw : xe);
+        int nb = (x >= 0 && y >= 0) ? y * ncx + x : -1;
+        if (nb == (int)(blockIdx.y * ncx + blockIdx.x)) nb = -1; // a single strip wraps onto itself
+        s_nb[tid] = nb;
     }
+    __syncthreads();
+    const bool p2p_cta = a.p2p && ((top && a.peer_n_flag) || (bot && a.peer_s_flag));
+    // only the last subcycle's diagnostics are observable: it runs the LAST instance of the march
+    for (int k = 0; k < a.nsub - 1; ++k)
+        persist_step<NT, false, HT>(a, k, s_nb, my_epoch, tid, i, j0, nrows, top, bot, p2p_cta);
+    persist_step<NT, true, HT>(a, a.nsub - 1, s_nb, my_epoch, tid, i, j0, nrows, top, bot, p2p_cta);
+    if (a.p2p && tid == 0) { // rank-level count of completed subcycles (read by k_wait_peers and k_subcycle)
+        int live = 0; // empty chunks returned at once and are not counted
+        for (int c = 0; c < ncy; ++c) live += __ldg(a.chunks + 2 * c + 1) > 0 ? 1 : 0;
+        const unsigned prev = atomicAdd((unsigned *)a.sync, 1u);
+        if (prev == (unsigned)(live * ncx) - 1u) {
+            a.sync[0] = 0;
+            a.sync[1] = a.epoch0 + a.nsub;
+        }
     }
-    k_subcycle_epilogue<NT>(a, tid, top, bot, epoch);
 }
 
 // Launch with programmatic dependent launch (PDL): the next subcycle kernel may be scheduled while
@@ -580,7 +724,7 @@ static void launch_k(K kernel, const SubArgs &a, dim3 grid, dim3 block, bool pdl
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = grid;
     cfg.blockDim = block;
-    cfg.dynamicSmemBytes = 0;
+    cfg.dynamicSmemBytes = 2 * 4 * block.x * sizeof(double); // evp_xch
     cfg.stream = s;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
@@ -603,6 +747,21 @@ static void launch_nt(const SubArgs &a, bool last, bool pdl, unsigned gx, unsign
     }
 }
 
+template <int NT>
+static int persist_nt(const SubArgs &a, unsigned gx, unsigned gy, cudaStream_t s, int *ctas_per_sm) {
+    auto kern = a.row_ht ? k_persist<NT, true> : k_persist<NT, false>;
+    const size_t smem = 2 * 4 * NT * sizeof(double); // evp_xch
+    if (ctas_per_sm) {
+        int n = 0;
+        const cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kern, NT, smem);
+        *ctas_per_sm = n;
+        return (int)e;
+    }
+    SubArgs arg = a;
+    void *params[1] = {(void *)&arg};
+    return (int)cudaLaunchCooperativeKernel((const void *)kern, dim3(gx, gy), dim3(NT), params, smem, s);
+}
+
 } // namespace EVP_SUB_NS
 
 void EVP_SUB_LAUNCH(const SubArgs &a, bool last, int variant, int threads, unsigned grid_x,
@@ -613,5 +772,16 @@ void EVP_SUB_LAUNCH(const SubArgs &a, bool last, int variant, int threads, unsig
     case 64: EVP_SUB_NS::launch_nt<64>(a, last, pdl, grid_x, grid_y, s); break;
     case 256: EVP_SUB_NS::launch_nt<256>(a, last, pdl, grid_x, grid_y, s); break;
     default: EVP_SUB_NS::launch_nt<128>(a, last, pdl, grid_x, grid_y, s); break;
+    }
+}
+
+// persistent kernel: launch (ctas_per_sm == nullptr) or occupancy query; returns a cudaError_t value
+int EVP_PERSIST_LAUNCH(const SubArgs &a, int threads, unsigned grid_x, unsigned grid_y, void *stream,
+                       int *ctas_per_sm) {
+    cudaStream_t s = (cudaStream_t)stream;
+    switch (threads) {
+    case 64: return EVP_SUB_NS::persist_nt<64>(a, grid_x, grid_y, s, ctas_per_sm);
+    case 256: return EVP_SUB_NS::persist_nt<256>(a, grid_x, grid_y, s, ctas_per_sm);
+    default: return EVP_SUB_NS::persist_nt<128>(a, grid_x, grid_y, s, ctas_per_sm);
     }
 }

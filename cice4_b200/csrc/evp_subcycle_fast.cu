@@ -2,4 +2,5 @@
 // unfused build are rounding-level only (DESIGN.md states the measured bound).
 #define EVP_SUB_NS evp_sub_fast
 #define EVP_SUB_LAUNCH evp_subcycle_launch_fast
+#define EVP_PERSIST_LAUNCH evp_persist_launch_fast
 #include "evp_subcycle_body.cuh"

@@ -95,7 +95,10 @@ typedef struct {
     int32_t tile_rows;      /* 0 = default; U rows marched per CTA */
     int32_t kernel_variant; /* 0 = default; bit 2 (4): tripole fold as a separate kernel; bit 4 (16): 2-plane
                                metric path (needs HTE/HTN); bit 5 (32): uniform row chunks instead of the
-                               per-call active-work balance; bit 6 (64): programmatic dependent launch */
+                               per-call active-work balance; bit 6 (64): programmatic dependent launch;
+                               bit 7 (128): run the ndte loop as one persistent cooperative launch whose CTAs
+                               synchronise with their neighbours only (bit-identical; measured slower than
+                               the default graph of per-subcycle launches) */
     int32_t state_residency; /* 0 = the whole state is uploaded and downloaded by every call (host arrays always
                                current: restart-exact drop-in); 1 = the 12 stress arrays stay on the device
                                between calls: uploaded by the first call after init or after

@@ -126,6 +126,33 @@ def test_tiling_invariance(oracle, evp_lib, threads, rows, variant):
     _compare_exact(dyn, out, st, f, lay)
 
 
+PERSIST_CASES = [
+    ("gx3-real-grid", dict(name="gx3", realistic=True, gx3_fixture=GX3_FIXTURE), dict()),
+    ("tripole-130x70-realistic", dict(name="om1deg", nx=130, ny=70, realistic=True), dict()),
+    ("tripole-300x90-t64", dict(name="om1deg", nx=300, ny=90), dict(tile_threads=64)),
+    ("tripole-300x200-t128-2plane", dict(name="om1deg", nx=300, ny=200), dict(tile_threads=128, kernel_variant=128 + 16)),
+    ("open-open-37x29", dict(name="x", nx=37, ny=29, ew="open", ns="open"), dict()),
+    ("cyclic-open-50x40-odd-ndte", dict(name="gx3", nx=50, ny=40, ew="cyclic", ns="open"), dict(ndte=7)),
+    ("closed-closed-31x30", dict(name="x", nx=31, ny=30, ew="closed", ns="closed"), dict(ndte=2)),
+]
+
+
+@pytest.mark.parametrize("label,kw,par", PERSIST_CASES, ids=[c[0] for c in PERSIST_CASES])
+def test_persistent_kernel_bit_exact(oracle, evp_lib, label, kw, par):
+    """kernel_variant bit 7: the whole ndte loop as ONE cooperative launch whose CTAs synchronise with
+    their neighbours only (per-CTA epochs, no grid barrier).  Two consecutive calls, bit-exact."""
+    case = synth.make_case(**kw)
+    par = dict(par)
+    ndte = par.pop("ndte", 120)
+    variant = par.pop("kernel_variant", 128)
+    st, f, strengths, _ = oracle_steps(oracle, case, nsteps=2, ndte=ndte)
+    lay = E.BlockLayout.single_block(case.grid.nx, case.grid.ny)
+    dyn, out = cuda_steps(case, nsteps=2, strengths=strengths, math_mode=0, ndte=ndte, kernel_variant=variant, **par)
+    assert dyn.timings()["subcycle_launches"] == 1, "the persistent kernel was not used"
+    _compare_exact(dyn, out, st, f, lay)
+    dyn.finalize()
+
+
 def test_graph_and_stream_launch_agree(oracle, evp_lib):
     case = synth.make_case("om1deg", nx=64, ny=48)
     st, f, strengths, _ = oracle_steps(oracle, case, nsteps=1, ndte=30)
@@ -257,8 +284,9 @@ def test_two_gpus_bit_exact_vs_oracle(evp_lib):
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
            "--master-addr", "127.0.0.1", "--master-port", "29533", os.path.join(root, "tests", "multigpu_parity.py"),
            "--realistic"]
-    r = subprocess.run(cmd, capture_output=True, text=True, timeout=240)
-    assert r.returncode == 0 and "BIT-EXACT" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
+    for extra in ([], ["--kernel-variant", "128"]):   # graph of per-subcycle launches; persistent kernel
+        r = subprocess.run(cmd + extra, capture_output=True, text=True, timeout=240)
+        assert r.returncode == 0 and "BIT-EXACT" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
 
 
 def test_two_plane_metric_path_and_fallback(oracle, evp_lib):
