@@ -563,6 +563,9 @@ static int init_handle(evp_b200_handle *h, const evp_b200_dims *d, const evp_b20
     h->north = (d->rank < d->nranks - 1) ? d->rank + 1 : -1;
     h->south = (d->rank > 0) ? d->rank - 1 : -1;
     pg.cells = (size_t)pg.pitch * (pg.nyl + 2);
+    // the subcycle kernel addresses a plane and its second copy with 32-bit element offsets
+    if ((unsigned long long)(P_U1 - P_U0 + 1) * pg.cells >= (1ull << 31))
+        return fail(EVP_B200_ERR_ARG, "slab too large for 32-bit plane offsets (%zu cells): use more ranks", pg.cells);
     // Plane spacing: consecutive planes are streamed concurrently by the subcycle kernel (~40 of
     // them); a spacing that is a multiple of 4 KiB puts all streams on the same L2 slice / HBM
     // channel phase.  Skew the spacing by an odd number of 256-byte segments.

@@ -39,6 +39,9 @@
 
 namespace EVP_SUB_NS {
 
+// element offsets inside the plane pool fit 32 bits (checked at init): one IMAD.WIDE per address
+typedef int idx_t;
+
 // State that other CTAs rewrite while the persistent kernel runs must not be served by the
 // (non-coherent) L1: COH selects ld.global.cg; the one-subcycle kernel keeps the read-only path.
 template <bool COH>
@@ -82,8 +85,8 @@ struct URow {
 // lies a.copy_stride behind copy 0, so one register selects the copy for all 14 planes and the plane
 // pointers themselves stay constant-bank operands.
 template <bool LAST, bool HT, bool COH>
-__device__ __forceinline__ void load_T(const SubArgs &a, size_t so, TRow &t, int i, int j, bool colT, bool act) {
-    size_t idx = (size_t)j * a.pitch + i + so;
+__device__ __forceinline__ void load_T(const SubArgs &a, idx_t so, TRow &t, int i, int j, bool colT, bool act) {
+    idx_t idx = j * a.pitch + i + so;
     t.act = act;
     if (colT) {
         t.u = ld_state<COH>(a.u + idx);
@@ -121,7 +124,7 @@ __device__ __forceinline__ void load_T(const SubArgs &a, size_t so, TRow &t, int
 }
 
 __device__ __forceinline__ void load_U(const SubArgs &a, URow &u, int i, int j, bool act) {
-    const size_t idx = (size_t)j * a.pitch + i;
+    const idx_t idx = j * a.pitch + i;
     u.act = act;
     if (u.act) {
         u.aiu = __ldg(a.aiu + idx);
@@ -158,8 +161,8 @@ __device__ __forceinline__ void div4(double n, double d1, double d2, double d3, 
 // source/ice_dyn_evp.F90:1056-1291 for one T cell.  (un,vn)=(i,j) (uw,vw)=(i-1,j) (us,vs)=(i,j-1)
 // (usw,vsw)=(i-1,j-1).  Operation order is the Fortran's.
 template <bool LAST>
-__device__ __forceinline__ void stress_cell(const SubArgs &a, size_t sn, const TRow &t, double us, double vs,
-                                            double usw, double vsw, size_t idx, bool store,
+__device__ __forceinline__ void stress_cell(const SubArgs &a, idx_t sn, const TRow &t, double us, double vs,
+                                            double usw, double vsw, idx_t idx, bool store,
                                             double (&str)[8]) {
     const double p5 = 0.5, p25 = 0.25, c4 = 4.0;
     const double p166 = 1.0 / 6.0, p333 = 1.0 / 3.0, p111 = 1.0 / 9.0;
@@ -246,7 +249,7 @@ __device__ __forceinline__ void stress_cell(const SubArgs &a, size_t sn, const T
     const double s124 = (t.s[11] + c1se * shearse * p5) * a.denom2;
 
     if (store) {
-        const size_t idn = idx + sn;
+        const idx_t idn = idx + sn;
         a.s[0][idn] = sp1; a.s[1][idn] = sp2; a.s[2][idn] = sp3; a.s[3][idn] = sp4;
         a.s[4][idn] = sm1; a.s[5][idn] = sm2; a.s[6][idn] = sm3; a.s[7][idn] = sm4;
         a.s[8][idn] = s121; a.s[9][idn] = s122; a.s[10][idn] = s123; a.s[11][idn] = s124;
@@ -299,8 +302,8 @@ __device__ __forceinline__ void stress_cell(const SubArgs &a, size_t sn, const T
 
 // source/ice_dyn_evp.F90:1386-1441 for one U cell; sx, sy are the two str sums of :1415-1418
 template <bool LAST>
-__device__ __forceinline__ void stepu_cell(const SubArgs &a, size_t sn, const URow &u, double uold, double vold,
-                                           double sx, double sy, int i, int j, size_t idx) {
+__device__ __forceinline__ void stepu_cell(const SubArgs &a, idx_t sn, const URow &u, double uold, double vold,
+                                           double sx, double sy, int i, int j, idx_t idx) {
     double *const u_new = a.u + sn, *const v_new = a.v + sn;
     const double du = u.uocn - uold, dv = u.vocn - vold;
     const double vrel = u.aiu * a.dragw * sqrt(du * du + dv * dv); // :1394
@@ -411,7 +414,7 @@ __device__ __forceinline__ void p2p_wait(const SubArgs &a, int tid, bool top, bo
 // PERSIST: the fold's completion is published in sync[5] (the top chunk waits for it before the next
 // subcycle) and the rank-level counter is left to the end of the persistent kernel.
 template <int NT, bool PERSIST>
-__device__ __forceinline__ void subcycle_epilogue(const SubArgs &a, size_t sn, int tid, bool top, bool bot, int epoch) {
+__device__ __forceinline__ void subcycle_epilogue(const SubArgs &a, idx_t sn, int tid, bool top, bool bot, int epoch) {
     double *const u_new = a.u + sn, *const v_new = a.v + sn;
     if (a.p2p && ((top && a.peer_n_flag) || (bot && a.peer_s_flag))) {
         // boundary CTA done: its stores into the neighbour's ghost row are made visible system-wide,
@@ -521,7 +524,7 @@ __device__ __forceinline__ void subcycle_epilogue(const SubArgs &a, size_t sn, i
 // the state copy at offset `so` and writing the one at offset `sn`.  COH: state loads bypass the
 // non-coherent L1 (persistent kernel).
 template <int NT, bool LAST, bool HT, bool COH>
-__device__ __forceinline__ void march(const SubArgs &a, size_t so, size_t sn, int tid, int i, int j0, int nrows) {
+__device__ __forceinline__ void march(const SubArgs &a, idx_t so, idx_t sn, int tid, int i, int j0, int nrows) {
     extern __shared__ double evp_xch[]; // [2][4][NT]: str(2,4,7,8) handed to the west neighbour thread
     const int jlast = min(j0 + nrows, a.nyl + 1); // last T row of this CTA
     const bool colT = (tid <= a.strip_w) && (i <= a.nx + 1);
@@ -530,7 +533,7 @@ __device__ __forceinline__ void march(const SubArgs &a, size_t so, size_t sn, in
 
     double us = 0.0, vs = 0.0, usw = 0.0, vsw = 0.0;
     if (colT) {
-        const size_t idx = (size_t)(j0 - 1) * a.pitch + i + so;
+        const idx_t idx = (j0 - 1) * a.pitch + i + so;
         us = ld_state<COH>(a.u + idx);
         vs = ld_state<COH>(a.v + idx);
         usw = ld_state<COH>(a.u + idx - 1);
@@ -561,7 +564,7 @@ __device__ __forceinline__ void march(const SubArgs &a, size_t so, size_t sn, in
         uc.act = false;
         if (j > j0) load_U(a, uc, i, j - 1, um_cur);
 
-        const size_t idx = (size_t)j * a.pitch + i;
+        const idx_t idx = j * a.pitch + i;
         double str[8];
         if (t.act) {
             derive_metrics<HT>(t);
@@ -604,6 +607,8 @@ __device__ __forceinline__ void march(const SubArgs &a, size_t so, size_t sn, in
     }
 }
 
+// At ~210 registers per thread every scheduler (16384 registers) holds two warps: 8 warps per SM
+// whatever the CTA shape (96 x 3 or 160 x 2 would need <= 168 registers and spill).
 template <int NT, bool LAST, bool HT>
 __global__ void __launch_bounds__(NT) k_subcycle(const __grid_constant__ SubArgs a) {
     // programmatic dependent launch: let the next subcycle kernel be scheduled as SMs drain, and
@@ -625,7 +630,7 @@ __global__ void __launch_bounds__(NT) k_subcycle(const __grid_constant__ SubArgs
         p2p_wait(a, tid, top, bot, epoch);
     }
     // an empty chunk (all rows inactive, trimmed by the load balancer) has nothing to do
-    const size_t so = a.flip ? (size_t)a.copy_stride : 0, sn = a.flip ? 0 : (size_t)a.copy_stride;
+    const idx_t so = a.flip ? (idx_t)a.copy_stride : 0, sn = a.flip ? 0 : (idx_t)a.copy_stride;
     if (nrows > 0) march<NT, LAST, HT, false>(a, so, sn, tid, i, j0, nrows);
     subcycle_epilogue<NT, false>(a, sn, tid, top, bot, epoch);
 }
@@ -647,7 +652,7 @@ template <int NT, bool LAST, bool HT>
 __device__ __forceinline__ void persist_step(const SubArgs &a, int k, const int *s_nb, int *my_epoch, int tid, int i,
                                              int j0, int nrows, bool top, bool bot, bool p2p_cta) {
     const bool odd = ((a.flip + k) & 1) != 0;
-    const size_t so = odd ? (size_t)a.copy_stride : 0, sn = odd ? 0 : (size_t)a.copy_stride;
+    const idx_t so = odd ? (idx_t)a.copy_stride : 0, sn = odd ? 0 : (idx_t)a.copy_stride;
     if (k > 0) {
         if (tid < 8 && s_nb[tid] >= 0) wait_flag_ge(a.cta_epoch + s_nb[tid], k, a.sync);
         if (tid == 8 && a.fold && top) wait_flag_ge(a.sync + 5, a.epoch0 + k, a.sync);
