@@ -240,6 +240,12 @@ void fill_subargs(evp_b200_handle *h, SubArgs &a, int cur) {
     a.v = p[P_V0];
     for (int k = 0; k < EVP_NSTRESS; ++k) a.s[k] = p[P_S0 + k];
     a.copy_stride = (long long)(P_U1 - P_U0) * (long long)h->pg.cells;
+    {
+        const double *tp[25] = {a.u, a.v, a.s[0], a.s[1], a.s[2], a.s[3], a.s[4], a.s[5], a.s[6], a.s[7], a.s[8],
+                                a.s[9], a.s[10], a.s[11], a.strength, a.dxt, a.dyt, a.dxhy, a.dyhx, a.cxp, a.cyp,
+                                a.cxm, a.cym, a.tinyarea, a.tarear};
+        for (int k = 0; k < 25; ++k) a.tplane[k] = tp[k];
+    }
     a.flip = cur ? 1 : 0; // copy that is read; copy flip ^ 1 is written
     a.nsub = 1;
     a.cta_epoch = h->d_cta_epoch;
@@ -396,11 +402,22 @@ int choose_tiling(evp_b200_handle *h) {
     const int nyl_mean = h->dims.ny_global / h->dims.nranks;
     int nt = h->par.tile_threads > 0 ? h->par.tile_threads : (nyl_mean <= 300 ? 256 : 128);
     if (nt != 64 && nt != 128 && nt != 256) nt = 128;
+    // TMA-staged kernel (kernel_variant bits 8 / 9): 128 threads, even strips of at most nt - 2 columns
+    // (16-byte aligned row segments), 2 or 3 CTAs per SM
+    const bool tma = (h->par.kernel_variant & (256 | 512)) != 0;
+    if (tma) {
+        nt = 128;
+        const int e = h->par.math_mode == 1 ? evp_subcycle_configure_fast() : evp_subcycle_configure_strict();
+        if (e != 0) return fail(EVP_B200_ERR_CUDA, "TMA-staged subcycle kernel: %s", cudaGetErrorString((cudaError_t)e));
+    }
     // balanced strips: ncx strips of strip_w U columns, strip_w + 1 <= nt threads hold T columns
-    const int ncx = (nx + (nt - 1) - 1) / (nt - 1);
-    const int strip_w = (nx + ncx - 1) / ncx;
+    const int wmax = tma ? nt - 2 : nt - 1;
+    const int ncx = (nx + wmax - 1) / wmax;
+    int strip_w = (nx + ncx - 1) / ncx;
+    if (tma && (strip_w & 1)) ++strip_w;
     // resident CTAs per SM at ~210 registers per thread: 256 threads
-    const int per_sm = (nt == 256) ? 1 : (nt == 128 ? 2 : 4);
+    int per_sm = (nt == 256) ? 1 : (nt == 128 ? 2 : 4);
+    if (tma && (h->par.kernel_variant & 256) == 0) per_sm = 3;
     int ncy = (per_sm * sms) / ncx; // one wave
     if (ncy < 1) ncy = 1;
     if (ncy > nyl) ncy = nyl;
@@ -582,7 +599,9 @@ static int init_handle(evp_b200_handle *h, const evp_b200_dims *d, const evp_b20
     CU(cudaEventCreateWithFlags(&h->ev_early, cudaEventDisableTiming));
     CU(cudaEventCreateWithFlags(&h->ev_early_done, cudaEventDisableTiming));
     for (auto &e : h->ev) CU(cudaEventCreate(&e));
-    CU(cudaMalloc(&h->pool, sizeof(double) * pg.cells * P_COUNT));
+    // + one row: the TMA-staged kernel copies whole 16-byte aligned row segments and may read past the
+    // last column of a row (into the next row; past the pool only for the last row of the last plane)
+    CU(cudaMalloc(&h->pool, sizeof(double) * (pg.cells * P_COUNT + pg.pitch)));
     CU(cudaMemsetAsync(h->pool, 0, sizeof(double) * pg.cells * P_COUNT, h->st));
     for (int k = 0; k < P_COUNT; ++k) h->pl[k] = h->pool + (size_t)k * pg.cells;
     CU(cudaMalloc(&h->mpool, pg.cells * M_COUNT));

@@ -24,6 +24,9 @@ struct SubArgs {
     // U-cell statics (:1339-1349)
     const double *aiu, *uocn, *vocn, *waterx, *watery, *forcex, *forcey, *umassdtei, *fm, *uarear;
     const uint8_t *icetmask, *iceumask;
+    // the planes a T row needs, in the order the TMA-staged kernel lays them out in shared memory:
+    // u, v, 12 stresses (copy 0), strength, dxt, dyt, dxhy, dyhx, cxp, cyp, cxm, cym, tinyarea, tarear
+    const double *tplane[25];
     // ping-pong state: two copies of u, v and of the 12 stresses (stressp_1..4, stressm_1..4,
     // stress12_1..4).  The pointers are copy 0; copy 1 of every plane lies copy_stride doubles behind
     // it.  A one-subcycle launch reads copy `flip` and writes copy `flip ^ 1`; the persistent kernel
@@ -114,4 +117,6 @@ int evp_persist_launch_strict(const SubArgs &a, int threads, unsigned grid_x, un
                               int *ctas_per_sm);
 int evp_persist_launch_fast(const SubArgs &a, int threads, unsigned grid_x, unsigned grid_y, void *stream,
                             int *ctas_per_sm);
+int evp_subcycle_configure_strict(void);
+int evp_subcycle_configure_fast(void);
 int evp_subcycle_max_threads(void);

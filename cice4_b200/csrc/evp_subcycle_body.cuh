@@ -636,6 +636,216 @@ __global__ void __launch_bounds__(NT) k_subcycle(const __grid_constant__ SubArgs
 }
 
 // ------------------------------------------------------------------------------------------------
+// TMA-staged variant of the one-subcycle kernel (kernel_variant bits 8/9).  The 24 (LAST: 25) planes a
+// T row needs -- u, v, 12 stresses, strength, 9 metrics (+ tarear) -- are brought into shared memory
+// by one thread per CTA with 1-D bulk copies (cp.async.bulk, one 16-byte-aligned row segment of
+// strip_w + 2 columns per plane) that complete on an mbarrier, S rows deep, instead of being
+// prefetched one row ahead in registers by every thread.  That frees ~54 registers per thread (three
+// warps per scheduler fit) and lengthens the prefetch distance from one row to S - 1.  Whole row
+// segments are copied whether or not their cells are active; the U-point fields, the masks and all
+// stores stay as in march().  The arithmetic is the same code (stress_cell / stepu_cell): results are
+// bit-identical.
+// ------------------------------------------------------------------------------------------------
+template <bool LAST> struct TmaPlanes { static constexpr int N = LAST ? 25 : 24; };
+
+__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+
+// Warp 0 issues one row: lane 0 arms the stage's mbarrier with the byte count, then lanes 0 .. NP-1 issue
+// one bulk copy each (plane `lane` of SubArgs::tplane; the first 14 are state planes and take the copy
+// offset).  Issued by a single thread the copies cost ~250 serial instructions per row and made warp 0
+// the straggler of every row barrier.
+template <bool LAST, int W>
+__device__ __forceinline__ void tma_issue_row(const SubArgs &a, int lane, idx_t so, idx_t goff, unsigned bytes,
+                                              double *stage, unsigned bar) {
+    constexpr int NP = TmaPlanes<LAST>::N;
+    if (lane == 0)
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes * (unsigned)NP)
+                     : "memory");
+    __syncwarp();
+    if (lane < NP) {
+        const double *src = a.tplane[lane] + (lane < 2 + EVP_NSTRESS ? so : 0) + goff;
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                         smem_u32(stage + lane * W)),
+                     "l"(src), "r"(bytes), "r"(bar)
+                     : "memory");
+    }
+}
+
+template <int NT, bool LAST, int S>
+__device__ __forceinline__ void march_tma(const SubArgs &a, idx_t so, idx_t sn, int tid, int i, int j0, int nrows) {
+    constexpr int W = NT + 2;                 // doubles per staged plane row (16-byte multiple)
+    constexpr int NP = TmaPlanes<LAST>::N;
+    extern __shared__ double evp_xch[];       // [2][4][NT] exchange line, then S stages of NP x W, then S mbarriers
+    double *const stages = evp_xch + 2 * 4 * NT;
+    unsigned long long *const bars = (unsigned long long *)(stages + S * NP * W);
+    const int jlast = min(j0 + nrows, a.nyl + 1); // last T row of this CTA
+    const int nT = jlast - j0 + 1;
+    const bool colT = (tid <= a.strip_w) && (i <= a.nx + 1);
+    const bool colU = (tid < a.strip_w) && (i <= a.nx);
+    const bool ownT = colT && (tid < a.strip_w || i == a.nx + 1);
+    // staged segment: plane columns c0 .. c0 + strip_w + 1, c0 = i0 - 1 (even: strip_w is even)
+    const int c0 = blockIdx.x * a.strip_w;
+    const unsigned bytes = (unsigned)(a.strip_w + 2) * 8u;
+
+    if (tid == 0) {
+#pragma unroll
+        for (int q = 0; q < S; ++q)
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(bars + q)) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (tid < 32) {
+#pragma unroll
+        for (int q = 0; q < S; ++q)
+            if (q < nT)
+                tma_issue_row<LAST, W>(a, tid, so, (idx_t)(j0 + q) * a.pitch + c0, bytes, stages + q * NP * W,
+                                       smem_u32(bars + q));
+    }
+
+    double us = 0.0, vs = 0.0, usw = 0.0, vsw = 0.0;
+    if (colT) {
+        const idx_t idx = (j0 - 1) * a.pitch + i + so;
+        us = __ldcg(a.u + idx);
+        vs = __ldcg(a.v + idx);
+        usw = __ldcg(a.u + idx - 1);
+        vsw = __ldcg(a.v + idx - 1);
+    }
+    double px = 0.0, s5c = 0.0, s7c = 0.0;
+    const uint8_t *tmk = a.icetmask + (size_t)j0 * a.pitch + i;
+    const uint8_t *umk = a.iceumask + (size_t)j0 * a.pitch + i;
+    unsigned tm_raw = colT ? __ldg(tmk) : 0u; // T row j (one row ahead of its use is enough here)
+    unsigned um_raw = 0u;                     // U row j-1
+    int par = 0, st = 0;
+    unsigned phase = 0;
+
+    for (int r = 0; r < nT; ++r) {
+        const int j = j0 + r;
+        URow uc;
+        const bool tact = tm_raw != 0u;
+        const bool um_cur = um_raw != 0u;
+        const unsigned tm_raw1 = (colT && j + 1 <= jlast) ? __ldg(tmk + a.pitch) : 0u; // T row j+1
+        const unsigned um_raw1 = (colU && j + 1 <= jlast) ? __ldg(umk) : 0u;           // U row j
+        tmk += a.pitch;
+        umk += a.pitch;
+        uc.act = false;
+        if (j > j0) load_U(a, uc, i, j - 1, um_cur);
+
+        // wait for the row's bulk copies (bounded: a protocol bug must not hang the device)
+        {
+            const unsigned bar = smem_u32(bars + st);
+            unsigned done = 0, spins = 0;
+            while (!done) {
+                asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                             : "=r"(done)
+                             : "r"(bar), "r"(phase)
+                             : "memory");
+                if (!done && ++spins > (1u << 22)) {
+                    *(volatile int *)(a.sync + 6) = 1;
+                    break;
+                }
+            }
+        }
+        const double *sg = stages + st * NP * W + tid;
+        TRow t;
+        t.act = tact;
+        t.ht = false;
+        if (colT) {
+            t.uw = sg[0 * W];
+            t.u = sg[0 * W + 1];
+            t.vw = sg[1 * W];
+            t.v = sg[1 * W + 1];
+        } else {
+            t.u = t.v = t.uw = t.vw = 0.0;
+        }
+        const idx_t idx = j * a.pitch + i;
+        double str[8];
+        if (t.act) {
+#pragma unroll
+            for (int k = 0; k < EVP_NSTRESS; ++k) t.s[k] = sg[(2 + k) * W + 1];
+            t.strength = sg[14 * W + 1];
+            t.dxt = sg[15 * W + 1];
+            t.dyt = sg[16 * W + 1];
+            t.dxhy = sg[17 * W + 1];
+            t.dyhx = sg[18 * W + 1];
+            t.cxp = sg[19 * W + 1];
+            t.cyp = sg[20 * W + 1];
+            t.cxm = sg[21 * W + 1];
+            t.cym = sg[22 * W + 1];
+            t.tiny = sg[23 * W + 1];
+            if (LAST) t.tarear = sg[(NP - 1) * W + 1];
+            const bool store = ownT && (j < j0 + nrows || j == a.nyl + 1);
+            stress_cell<LAST>(a, sn, t, us, vs, usw, vsw, idx, store, str);
+        } else {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) str[k] = 0.0; // str(:,:,:) = c0, :1051
+        }
+        double *const xl = evp_xch + par * 4 * NT + tid;
+        xl[0 * NT] = str[1];
+        xl[1 * NT] = str[3];
+        xl[2 * NT] = str[6];
+        xl[3 * NT] = str[7];
+        __syncthreads();
+        // every thread has read stage `st` (its values went into str before the barrier): refill it
+        if (tid < 32 && r + S < nT) {
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            tma_issue_row<LAST, W>(a, tid, so, (idx_t)(j + S) * a.pitch + c0, bytes, stages + st * NP * W,
+                                   smem_u32(bars + st));
+        }
+        double s2r = 0.0, s4r = 0.0, s7r = 0.0, s8r = 0.0;
+        if (tid < NT - 1) {
+            s2r = xl[0 * NT + 1];
+            s4r = xl[1 * NT + 1];
+            s7r = xl[2 * NT + 1];
+            s8r = xl[3 * NT + 1];
+        }
+        par ^= 1;
+
+        if (uc.act) {
+            const double sx = px + str[2] + s4r;          // ((s1 + s2) + s3) + s4
+            const double sy = s5c + str[5] + s7c + s8r;    // ((s5 + s6) + s7) + s8
+            stepu_cell<LAST>(a, sn, uc, us, vs, sx, sy, i, j - 1, idx - a.pitch);
+        }
+        px = str[0] + s2r;
+        s5c = str[4];
+        s7c = s7r;
+        us = t.u;
+        vs = t.v;
+        usw = t.uw;
+        vsw = t.vw;
+        tm_raw = tm_raw1;
+        um_raw = um_raw1;
+        if (++st == S) {
+            st = 0;
+            phase ^= 1u;
+        }
+    }
+}
+
+template <int NT, bool LAST, int S, int MINB>
+__global__ void __launch_bounds__(NT, MINB) k_subcycle_tma(const __grid_constant__ SubArgs a) {
+    asm volatile("griddepcontrol.launch_dependents;");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    const int tid = threadIdx.x;
+    const int i = 1 + blockIdx.x * a.strip_w + tid;
+    const int j0 = __ldg(a.chunks + 2 * blockIdx.y);
+    const int nrows = __ldg(a.chunks + 2 * blockIdx.y + 1);
+    const bool top = (j0 + nrows - 1 == a.nyl), bot = (j0 == 1);
+    int epoch = 0;
+    if (a.p2p && ((top && a.peer_n_flag) || (bot && a.peer_s_flag))) {
+        epoch = *(volatile int *)(a.sync + 1);
+        p2p_wait(a, tid, top, bot, epoch);
+    }
+    const idx_t so = a.flip ? (idx_t)a.copy_stride : 0, sn = a.flip ? 0 : (idx_t)a.copy_stride;
+    if (nrows > 0) march_tma<NT, LAST, S>(a, so, sn, tid, i, j0, nrows);
+    subcycle_epilogue<NT, false>(a, sn, tid, top, bot, epoch);
+}
+
+template <int NT, int S>
+static constexpr size_t tma_smem_bytes() {
+    return (size_t)(2 * 4 * NT + S * 25 * (NT + 2)) * sizeof(double) + S * sizeof(unsigned long long);
+}
+
+// ------------------------------------------------------------------------------------------------
 // Persistent kernel: all a.nsub subcycles of one evp call in ONE cooperative launch (every CTA is
 // resident; the grid is the same one-wave grid as k_subcycle's and each CTA keeps its strip and row
 // chunk for the whole loop).  There is no grid-wide barrier: because u, v and the stresses are
@@ -739,10 +949,28 @@ static void launch_k(K kernel, const SubArgs &a, dim3 grid, dim3 block, bool pdl
     cudaLaunchKernelEx(&cfg, kernel, a);
 }
 
-// HT (2-plane metric path) is chosen by a.row_ht
+template <typename K>
+static void launch_tma(K kernel, size_t smem, const SubArgs &a, dim3 grid, dim3 block, cudaStream_t s) {
+    kernel<<<grid, block, smem, s>>>(a);
+}
+
+// HT (2-plane metric path) is chosen by a.row_ht; variant bit 8 (256): TMA staging, 3 rows deep, 2 CTAs
+// per SM; bit 9 (512): TMA staging, 2 rows deep, 3 CTAs per SM (<= 168 registers) -- 128 threads only
 template <int NT>
-static void launch_nt(const SubArgs &a, bool last, bool pdl, unsigned gx, unsigned gy, cudaStream_t s) {
+static void launch_nt(const SubArgs &a, bool last, bool pdl, int variant, unsigned gx, unsigned gy, cudaStream_t s) {
     dim3 grid(gx, gy), block(NT);
+    if constexpr (NT == 128) {
+        if (variant & 256) {
+            if (last) launch_tma(k_subcycle_tma<NT, true, 3, 2>, tma_smem_bytes<NT, 3>(), a, grid, block, s);
+            else launch_tma(k_subcycle_tma<NT, false, 3, 2>, tma_smem_bytes<NT, 3>(), a, grid, block, s);
+            return;
+        }
+        if (variant & 512) {
+            if (last) launch_tma(k_subcycle_tma<NT, true, 2, 3>, tma_smem_bytes<NT, 2>(), a, grid, block, s);
+            else launch_tma(k_subcycle_tma<NT, false, 2, 3>, tma_smem_bytes<NT, 2>(), a, grid, block, s);
+            return;
+        }
+    }
     if (a.row_ht) {
         if (last) launch_k(k_subcycle<NT, true, true>, a, grid, block, pdl, s);
         else launch_k(k_subcycle<NT, false, true>, a, grid, block, pdl, s);
@@ -774,10 +1002,26 @@ void EVP_SUB_LAUNCH(const SubArgs &a, bool last, int variant, int threads, unsig
     const bool pdl = (variant & 64) != 0;
     cudaStream_t s = (cudaStream_t)stream;
     switch (threads) {
-    case 64: EVP_SUB_NS::launch_nt<64>(a, last, pdl, grid_x, grid_y, s); break;
-    case 256: EVP_SUB_NS::launch_nt<256>(a, last, pdl, grid_x, grid_y, s); break;
-    default: EVP_SUB_NS::launch_nt<128>(a, last, pdl, grid_x, grid_y, s); break;
+    case 64: EVP_SUB_NS::launch_nt<64>(a, last, pdl, variant, grid_x, grid_y, s); break;
+    case 256: EVP_SUB_NS::launch_nt<256>(a, last, pdl, variant, grid_x, grid_y, s); break;
+    default: EVP_SUB_NS::launch_nt<128>(a, last, pdl, variant, grid_x, grid_y, s); break;
     }
+}
+
+// opt in to more than 48 KB of dynamic shared memory for the TMA-staged kernels (once per device, outside
+// any stream capture); returns a cudaError_t value
+int EVP_SUB_CONFIGURE(void) {
+    using namespace EVP_SUB_NS;
+    cudaError_t e = cudaSuccess;
+    auto set = [&](auto kernel, size_t smem) {
+        const cudaError_t r = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e == cudaSuccess) e = r;
+    };
+    set(k_subcycle_tma<128, false, 3, 2>, tma_smem_bytes<128, 3>());
+    set(k_subcycle_tma<128, true, 3, 2>, tma_smem_bytes<128, 3>());
+    set(k_subcycle_tma<128, false, 2, 3>, tma_smem_bytes<128, 2>());
+    set(k_subcycle_tma<128, true, 2, 3>, tma_smem_bytes<128, 2>());
+    return (int)e;
 }
 
 // persistent kernel: launch (ctas_per_sm == nullptr) or occupancy query; returns a cudaError_t value

@@ -3,6 +3,7 @@
 #define EVP_SUB_NS evp_sub_strict
 #define EVP_SUB_LAUNCH evp_subcycle_launch_strict
 #define EVP_PERSIST_LAUNCH evp_persist_launch_strict
+#define EVP_SUB_CONFIGURE evp_subcycle_configure_strict
 #include "evp_subcycle_body.cuh"
 
 int evp_subcycle_max_threads(void) { return 256; }

@@ -153,6 +153,20 @@ def test_persistent_kernel_bit_exact(oracle, evp_lib, label, kw, par):
     dyn.finalize()
 
 
+@pytest.mark.parametrize("variant", [256, 512], ids=["3-rows-deep-2-ctas", "2-rows-deep-3-ctas"])
+@pytest.mark.parametrize("label,kw", [CASES[0], CASES[3], CASES[5], ("tripole-300x200", dict(name="om1deg", nx=300, ny=200))],
+                         ids=["gx3-real-grid", "tripole-130x70-realistic", "open-open-37x29", "tripole-300x200"])
+def test_tma_staged_kernel_bit_exact(oracle, evp_lib, label, kw, variant):
+    """kernel_variant bits 8 / 9: the T-row planes reach the SM through TMA bulk copies into shared
+    memory (mbarrier pipeline) instead of per-thread register prefetch.  Same arithmetic: bit-exact."""
+    case = synth.make_case(**kw)
+    st, f, strengths, _ = oracle_steps(oracle, case, nsteps=2)
+    lay = E.BlockLayout.single_block(case.grid.nx, case.grid.ny)
+    dyn, out = cuda_steps(case, nsteps=2, strengths=strengths, math_mode=0, kernel_variant=variant)
+    _compare_exact(dyn, out, st, f, lay)
+    dyn.finalize()
+
+
 def test_graph_and_stream_launch_agree(oracle, evp_lib):
     case = synth.make_case("om1deg", nx=64, ny=48)
     st, f, strengths, _ = oracle_steps(oracle, case, nsteps=1, ndte=30)
