@@ -2,6 +2,8 @@
 // the subcycle kernel allow, without its arithmetic?  NR planes read, NW planes written, fp64.
 //   A: flat 1-D, 8-byte accesses      B: flat 1-D, 16-byte accesses
 //   C: marching strips (one column per thread, rows in a loop, next-row prefetch), 8-byte accesses
+//   D: like C, but on a strip-tiled layout [strip][row][plane][column]: all planes of a strip row are
+//      contiguous and a CTA walks one contiguous region (what an AoSoA plane pool would give)
 // nvcc -O3 -gencode arch=compute_100a,code=sm_100a tools/stream_bench.cu -o gpurun_out/stream_bench
 #include <cuda_runtime.h>
 #include <cstdio>
@@ -52,6 +54,32 @@ __global__ void __launch_bounds__(NT) kC(P p, int nx, int ny, int pitch, int str
         for (int k = 0; k < NR; ++k) v[k] = nv[k];
     }
 }
+template <int NT>
+__global__ void __launch_bounds__(NT) kD(const double *rd, double *wr, int strip, int rows_total, int rows) {
+    // CTA (x, y): strip x, rows y*rows .. ; read region [x][row][NR][strip], write region [x][row][NW][strip]
+    const int t = threadIdx.x;
+    if (t >= strip) return;
+    const int j0 = blockIdx.y * rows, j1 = min(j0 + rows, rows_total);
+    const double *r0 = rd + (size_t)blockIdx.x * rows_total * NR * strip;
+    double *w0 = wr + (size_t)blockIdx.x * rows_total * NW * strip;
+    double v[NR];
+#pragma unroll
+    for (int k = 0; k < NR; ++k) v[k] = __ldg(r0 + ((size_t)j0 * NR + k) * strip + t);
+    for (int j = j0; j < j1; ++j) {
+        double nv[NR];
+        if (j + 1 < j1) {
+#pragma unroll
+            for (int k = 0; k < NR; ++k) nv[k] = __ldg(r0 + ((size_t)(j + 1) * NR + k) * strip + t);
+        }
+        double s = 0;
+#pragma unroll
+        for (int k = 0; k < NR; ++k) s += v[k];
+#pragma unroll
+        for (int k = 0; k < NW; ++k) w0[((size_t)j * NW + k) * strip + t] = s + k;
+#pragma unroll
+        for (int k = 0; k < NR; ++k) v[k] = nv[k];
+    }
+}
 int main() {
     const int nx = 1440, ny = 1080, pitch = 1456;
     const size_t cells = (size_t)pitch * (ny + 2);
@@ -85,5 +113,13 @@ int main() {
     time("C march 128 thr, strip 128 aligned+1 (i0 = 1), rows 45", [&] { kC<128><<<dim3(12, 24), 128>>>(p, nx, ny, pitch, 128, 45, 1); }, bc * 1456.0 / 1440.0);
     time("C march 128 thr, strip 112 aligned (i0 = 16), rows 45", [&] { kC<128><<<dim3(13, 24), 128>>>(p, nx, ny, pitch, 112, 45, 16); }, bc * 1456.0 / 1440.0);
     time("C march 128 thr, strip 120, rows 12", [&] { kC<128><<<dim3(12, 90), 128>>>(p, nx, ny, pitch, 120, 12); }, bc);
+    // D: the same 12 x 24 CTAs and bytes as the first C line, strip-tiled layout (pool reused: 12 strips x
+    // 1080 rows x (37 + 14) planes x 120 columns <= the pool)
+    time("D tiled layout, 128 thr, strip 120, rows 45", [&] {
+        kD<128><<<dim3(12, 24), 128>>>(pool, pool + (size_t)12 * 1080 * NR * 120, 120, 1080, 45); }, bc);
+    time("D tiled layout, 128 thr, strip 128, rows 45", [&] {
+        kD<128><<<dim3(11, 24), 128>>>(pool, pool + (size_t)11 * 1080 * NR * 128, 128, 1080, 45); }, bc * (11.0 * 128) / 1440.0);
+    time("D tiled layout, 256 thr, strip 240, rows 45", [&] {
+        kD<256><<<dim3(6, 24), 256>>>(pool, pool + (size_t)6 * 1080 * NR * 240, 240, 1080, 45); }, bc);
     return 0;
 }
