@@ -1075,6 +1075,11 @@ int evp_b200_comm_init(evp_b200_handle *h, const uint8_t id[128]) {
         h->comm = nullptr;
         return fail(EVP_B200_ERR_COMM, "ncclCommInitRank failed: %s", h->pGetErrorString(r));
     }
+    // the epochs of the peer-to-peer halo count from here on every rank (calls made before the
+    // communicator existed did not advance sync[1]); the neighbours cannot write into this block before
+    // they have received its handle below, which is ordered after this memset on the stream
+    h->epoch_count = 0;
+    CU(cudaMemsetAsync(h->sync, 0, sizeof(int) * EVP_SYNC_INTS, h->st));
     if (h->par.exchange_mode == 0) {
         // Peer-to-peer halo: swap CUDA IPC handles of the plane pool and the sync block with both
         // neighbours (through the communicator just made), map them, and let the subcycle kernel
@@ -1091,8 +1096,12 @@ int evp_b200_comm_init(evp_b200_handle *h, const uint8_t id[128]) {
         mine.nyl = h->pg.nyl;
         mine.pitch = h->pg.pitch;
         mine.cells = h->pg.cells;
+        auto allReduce = (ncclResult_t(*)(const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t,
+                                          cudaStream_t))dlsym(h->nccl_lib, "ncclAllReduce");
+        if (!allReduce) return fail(EVP_B200_ERR_COMM, "libnccl lacks ncclAllReduce");
         char *d = nullptr;
-        CU(cudaMalloc(&d, 3 * sizeof(PeerInfo)));
+        CU(cudaMalloc(&d, 3 * sizeof(PeerInfo) + sizeof(int)));
+        struct Free { char *p; ~Free() { cudaFree(p); } } free_d{d}; // also on the error returns below
         CU(cudaMemcpyAsync(d, &mine, sizeof(PeerInfo), cudaMemcpyHostToDevice, h->st));
         ncclResult_t q = h->pGroupStart();
         const int nb[2] = {h->north, h->south};
@@ -1106,7 +1115,6 @@ int evp_b200_comm_init(evp_b200_handle *h, const uint8_t id[128]) {
         if (q != ncclSuccess) return fail(EVP_B200_ERR_COMM, "IPC handle exchange failed: %s", h->pGetErrorString(q));
         CU(cudaMemcpyAsync(theirs, d + sizeof(PeerInfo), 2 * sizeof(PeerInfo), cudaMemcpyDeviceToHost, h->st));
         CU(cudaStreamSynchronize(h->st));
-        cudaFree(d);
         bool ok = true;
         for (int k = 0; k < 2 && ok; ++k)
             if (nb[k] >= 0) {
@@ -1121,7 +1129,15 @@ int evp_b200_comm_init(evp_b200_handle *h, const uint8_t id[128]) {
             }
         cudaGetLastError();
         if (h->grid_x > EVP_SYNC_MAXCX) ok = false;
-        h->p2p = ok;   // on failure the NCCL exchange stays in use (evp_b200_get_timings reports the mode)
+        // every rank must use the same exchange inside the loop: peer-to-peer only if ALL ranks can
+        int mine_ok = ok ? 1 : 0, all_ok = 0;
+        int *d_ok = (int *)(d + 3 * sizeof(PeerInfo));
+        CU(cudaMemcpyAsync(d_ok, &mine_ok, sizeof(int), cudaMemcpyHostToDevice, h->st));
+        q = allReduce(d_ok, d_ok, 1, ncclInt, ncclMin, h->comm, h->st);
+        if (q != ncclSuccess) return fail(EVP_B200_ERR_COMM, "ncclAllReduce failed: %s", h->pGetErrorString(q));
+        CU(cudaMemcpyAsync(&all_ok, d_ok, sizeof(int), cudaMemcpyDeviceToHost, h->st));
+        CU(cudaStreamSynchronize(h->st));
+        h->p2p = all_ok != 0; // otherwise the NCCL exchange stays in use (evp_b200_get_timings reports the mode)
         decide_persistent(h);
     }
     return 0;
