@@ -18,8 +18,11 @@ import subprocess
 import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-sys.path.insert(0, HERE)
-import f90_to_c as T  # noqa: E402
+if __package__:
+    from . import f90_to_c as T
+else:  # run as a script: import the sibling module without putting oracle/ itself on sys.path
+    sys.path.insert(0, os.path.dirname(HERE))
+    from oracle import f90_to_c as T  # noqa: E402
 
 REF = os.environ.get("CICE4_REFERENCE", "/root/reference")
 OUT = os.path.join(HERE, "_ref")

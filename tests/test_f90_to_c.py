@@ -7,14 +7,11 @@ TranslateError -- the translator never guesses.
 import ctypes as C
 import os
 import subprocess
-import sys
 
 import numpy as np
 import pytest
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-sys.path.insert(0, os.path.join(ROOT, "oracle"))
-import f90_to_c as T  # noqa: E402
+from oracle import f90_to_c as T
 
 MODULE = """
       module demo_mod
