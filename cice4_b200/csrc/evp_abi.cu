@@ -397,10 +397,11 @@ int choose_tiling(evp_b200_handle *h) {
     int sms = 148;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device);
     const int nx = h->pg.nx, nyl = h->pg.nyl;
-    // default: 128 threads per CTA; short slabs (multi-GPU) run better with one 256-thread CTA per SM
+    // default: 128 threads per CTA; short slabs (multi-GPU: 19.5 vs 23.0 us at 135 rows) run better with one
+    // 256-thread CTA per SM, 300 rows and more with two 128-thread CTAs (1 degree: 12.7 vs 13.6 us)
     // (decided from the mean slab height so that all ranks of a chain use the same strips)
     const int nyl_mean = h->dims.ny_global / h->dims.nranks;
-    int nt = h->par.tile_threads > 0 ? h->par.tile_threads : (nyl_mean <= 300 ? 256 : 128);
+    int nt = h->par.tile_threads > 0 ? h->par.tile_threads : (nyl_mean < 300 ? 256 : 128);
     if (nt != 64 && nt != 128 && nt != 256) nt = 128;
     // TMA-staged kernel (kernel_variant bits 8 / 9): 128 threads, even strips of at most nt - 2 columns
     // (16-byte aligned row segments), 2 or 3 CTAs per SM
