@@ -52,6 +52,34 @@ def read_pop_grid(grid_path: str, kmt_path: str, nx: int, ny: int) -> Dict[str, 
     return out
 
 
+def read_pop_grid_nc(grid_path: str, kmt_path: str, auscom: bool = False) -> Dict[str, np.ndarray]:
+    """popgrid_nc (ice_grid.F90:617-839): NetCDF-3 grid file with the variables `ulat, ulon, htn, hte,
+    angle` (radians / cm, dimensions (ny, nx)) and a kmt file with `kmt`; the AusCOM build also reads
+    `tlat, tlon, angleT, tarea, uarea` from the grid file (:790-818) and, if present, `kmu` from the kmt
+    file (:713-731).  Returned arrays use Fortran (i, j) indexing like read_pop_grid."""
+    from scipy.io import netcdf_file
+
+    def var(nc, name):
+        if name not in nc.variables:
+            raise ValueError(f"variable {name!r} missing")
+        a = np.array(nc.variables[name][:], dtype=np.float64)
+        a = a.reshape(a.shape[-2:])          # a leading time / record dimension of length 1 is dropped
+        return np.ascontiguousarray(a.T)
+
+    out: Dict[str, np.ndarray] = {}
+    with netcdf_file(grid_path, "r", mmap=False) as g:
+        for name in ["ulat", "ulon", "htn", "hte", "angle"] + (["tlat", "tlon", "angleT", "tarea", "uarea"] if auscom else []):
+            out[name.upper() if name != "angleT" else "ANGLET"] = var(g, name)
+    with netcdf_file(kmt_path, "r", mmap=False) as k:
+        out["KMT"] = var(k, "kmt").astype(np.int32)
+        if auscom and "kmu" in k.variables:
+            out["KMU"] = var(k, "kmu").astype(np.int32)
+    for a in ("ANGLE", "ANGLET"):                # :766-767, :806-807
+        if a in out:
+            out[a] = np.clip(out[a], -np.pi, np.pi)
+    return out
+
+
 def write_rda8(path: str, records: List[np.ndarray]) -> None:
     with open(path, "wb") as f:
         for a in records:

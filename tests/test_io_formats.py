@@ -58,3 +58,37 @@ def test_gx3_reader_matches_fixture():
     z = np.load(GX3_FIXTURE)
     for k in ("ULAT", "ULON", "HTN", "HTE", "KMT"):
         np.testing.assert_array_equal(g[k], z[k])
+
+
+def test_netcdf_grid_reader(tmp_path):
+    """popgrid_nc layout (ice_grid.F90:617-839): NetCDF-3 files with (ny, nx) variables."""
+    from scipy.io import netcdf_file
+    rng = np.random.default_rng(4)
+    nx, ny = 12, 9
+    fields = {n: rng.standard_normal((nx, ny)) for n in
+              ["ulat", "ulon", "htn", "hte", "angle", "tlat", "tlon", "angleT", "tarea", "uarea"]}
+    fields["angle"][0, 0] = 4.0                      # clipped to pi like the reference does
+    gp, kp = str(tmp_path / "grid.nc"), str(tmp_path / "kmt.nc")
+    with netcdf_file(gp, "w") as f:
+        f.createDimension("ny", ny)
+        f.createDimension("nx", nx)
+        for n, a in fields.items():
+            v = f.createVariable(n, "d", ("ny", "nx"))
+            v[:] = a.T
+    kmt = rng.integers(0, 2, size=(nx, ny))
+    with netcdf_file(kp, "w") as f:
+        f.createDimension("time", 1)
+        f.createDimension("ny", ny)
+        f.createDimension("nx", nx)
+        v = f.createVariable("kmt", "d", ("time", "ny", "nx"))
+        v[0] = kmt.T
+    g = IO.read_pop_grid_nc(gp, kp)
+    assert set(g) == {"ULAT", "ULON", "HTN", "HTE", "ANGLE", "KMT"}
+    np.testing.assert_array_equal(g["HTN"], fields["htn"])
+    np.testing.assert_array_equal(g["KMT"], kmt)
+    assert g["ANGLE"][0, 0] == np.pi
+    ga = IO.read_pop_grid_nc(gp, kp, auscom=True)
+    np.testing.assert_array_equal(ga["TAREA"], fields["tarea"])
+    assert "ANGLET" in ga and "KMU" not in ga
+    with pytest.raises(ValueError):
+        IO.read_pop_grid_nc(kp, kp)
