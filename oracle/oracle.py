@@ -141,8 +141,9 @@ class Fields:
 
     def __init__(self, grid_fields: Dict[str, np.ndarray], inputs: Dict[str, np.ndarray],
                  state: Dict[str, np.ndarray], strength_in: Optional[np.ndarray] = None):
-        nxb, nyb = grid_fields["dxt"].shape
-        self.shape = (nxb, nyb)
+        shape = grid_fields["dxt"].shape      # (nx_block, ny_block) or (nx_block, ny_block, nblocks)
+        nxb, nyb = shape[:2]
+        self.shape = shape
         self.arr: Dict[str, Optional[np.ndarray]] = {}
         for n in _D_STATIC + _I_STATIC:
             self.arr[n] = grid_fields[n]
@@ -152,8 +153,8 @@ class Fields:
         for n in STATE_D + _I_STATE:
             self.arr[n] = state[n]
         for n in OUT_D + SCRATCH_D:
-            self.arr[n] = np.zeros((nxb, nyb), order="F")
-        self.arr["icetmask"] = np.zeros((nxb, nyb), dtype=np.int32, order="F")
+            self.arr[n] = np.zeros(shape, order="F")
+        self.arr["icetmask"] = np.zeros(shape, dtype=np.int32, order="F")
         self.c = OrcFields()
         for n, _t in OrcFields._fields_:
             a = self.arr[n]
@@ -224,6 +225,32 @@ def run_evp_ref(grid, inputs, state, params: OrcParams, dt: float):
     rc = ref_lib(ref_variant(params)).ref_evp(C.byref(g), C.byref(params), C.byref(f.c), dt)
     if rc != 0:
         raise RuntimeError("ref_evp failed")
+    return f
+
+
+class RefLayout(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in ("nblocks", "nx_global", "ny_global")] + \
+               [(n, c_ip) for n in ("ilo", "ihi", "jlo", "jhi", "iglob_lo", "jglob_lo")]
+
+
+def run_evp_ref_blocks(layout, ew: int, ns: int, grid_fields_blk, inputs_blk, state_blk, params: OrcParams,
+                       dt: float):
+    """One `evp(dt)` call of the translated reference on a create_blocks decomposition.  `layout` is a
+    cice4_b200.evp.BlockLayout; every array is in block layout (nx_block, ny_block[, ncat], nblocks) with
+    the ghost cells a multi-block run would hold (cice4_b200.evp.split_blocks); state arrays are updated
+    in place."""
+    L = ref_lib(ref_variant(params))
+    L.ref_evp_blocks.restype = C.c_int
+    L.ref_evp_blocks.argtypes = [C.POINTER(OrcGrid), C.POINTER(RefLayout), C.POINTER(OrcParams),
+                                 C.POINTER(OrcFields), C.c_double]
+    f = Fields(grid_fields_blk, inputs_blk, state_blk, None)
+    g = OrcGrid(layout.nx_block, layout.ny_block, 2, layout.nx_block - 1, 2, layout.ny_block - 1, ew, ns)
+    lay = RefLayout(layout.nblocks, layout.nx_global, layout.ny_global,
+                    *[a.ctypes.data_as(c_ip) for a in (layout.ilo, layout.ihi, layout.jlo, layout.jhi,
+                                                      layout.iglob_lo, layout.jglob_lo)])
+    rc = L.ref_evp_blocks(C.byref(g), C.byref(lay), C.byref(params), C.byref(f.c), dt)
+    if rc != 0:
+        raise RuntimeError("ref_evp_blocks failed")
     return f
 
 

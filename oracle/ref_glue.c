@@ -15,8 +15,9 @@
  *                    in tests/test_oracle_golden.py)
  *   ice_timer_start/stop -> no-ops
  *
- * ref_evp() binds the module variables of ice_state / ice_flux / ice_grid / ice_dyn_evp to the
- * caller's arrays (one block, max_blocks = 1) and calls the translated `evp(dt)`.
+ * ref_evp() / ref_evp_blocks() bind the module variables of ice_state / ice_flux / ice_grid /
+ * ice_dyn_evp to the caller's arrays (one block, or a create_blocks decomposition) and call the
+ * translated `evp(dt)`.
  */
 #include <stdint.h>
 #include <stdlib.h>
@@ -36,14 +37,54 @@ static void v_ice_timer_stop(int32_t *t) { (void)t; }
 
 #include REF_GEN
 
-static orc_grid g_grid;
+/* Domain of the current call.  One block: g_grid describes the block itself.  Several blocks
+ * (ref_evp_blocks): g_grid carries nx_block/ny_block of a block and the boundary types, g_lay the
+ * decomposition (source/ice_blocks.F90:196-222: per block the physical index range inside the block and
+ * the global index of its first physical cell), g_glob the whole domain as one padded block. */
+typedef struct {
+    int32_t nblocks, nx_global, ny_global;
+    const int32_t *ilo, *ihi, *jlo, *jhi, *iglob_lo, *jglob_lo;
+} ref_layout;
+
+static orc_grid g_grid, g_glob;
+static ref_layout g_lay;
+static int32_t *g_block_ids;
 
 static struct f_block v_get_block(int32_t block_id, int32_t local_id) {
     struct f_block b = {g_grid.ilo, g_grid.ihi, g_grid.jlo, g_grid.jhi};
     (void)block_id;
-    (void)local_id;
+    if (g_lay.nblocks > 0) {
+        const int k = local_id - 1;
+        b.v_ilo = g_lay.ilo[k]; b.v_ihi = g_lay.ihi[k]; b.v_jlo = g_lay.jlo[k]; b.v_jhi = g_lay.jhi[k];
+    }
     return b;
 }
+
+/* ice_HaloUpdate over several blocks: what the reference's message/copy lists achieve is that every
+ * ghost cell holds the value of the neighbouring block's physical cell, or the boundary condition of
+ * the domain.  Done here by assembling the domain as one padded block, applying the one-block halo
+ * update (orc_halo_*) and handing every block its ring [ilo-1, ihi+1] x [jlo-1, jhi+1] back (the
+ * physical cells too: the tripole fold also symmetrises the top physical row). */
+#define HALO_BLOCKS(T, HALO, FILL)                                                                          \
+    static void halo_blocks_##T(T *a, int loc, int kind) {                                                    \
+        const int nxb = g_grid.nx_block, nyb = g_grid.ny_block, nxg = g_glob.nx_block, nyg = g_glob.ny_block; \
+        T *glob = (T *)calloc((size_t)nxg * nyg, sizeof(T));                                                  \
+        if (!glob) abort();                                                                                   \
+        for (int b = 0; b < g_lay.nblocks; ++b)                                                               \
+            for (int j = g_lay.jlo[b]; j <= g_lay.jhi[b]; ++j)                                                \
+                for (int i = g_lay.ilo[b]; i <= g_lay.ihi[b]; ++i)                                            \
+                    glob[(size_t)(g_lay.jglob_lo[b] + j - g_lay.jlo[b]) * nxg + (g_lay.iglob_lo[b] + i - g_lay.ilo[b])] = \
+                        a[((size_t)b * nyb + (j - 1)) * nxb + (i - 1)];                                       \
+        HALO(glob, &g_glob, loc, kind, FILL);                                                                 \
+        for (int b = 0; b < g_lay.nblocks; ++b)                                                               \
+            for (int j = g_lay.jlo[b] - 1; j <= g_lay.jhi[b] + 1; ++j)                                        \
+                for (int i = g_lay.ilo[b] - 1; i <= g_lay.ihi[b] + 1; ++i)                                    \
+                    a[((size_t)b * nyb + (j - 1)) * nxb + (i - 1)] =                                          \
+                        glob[(size_t)(g_lay.jglob_lo[b] + j - g_lay.jlo[b]) * nxg + (g_lay.iglob_lo[b] + i - g_lay.ilo[b])]; \
+        free(glob);                                                                                           \
+    }
+HALO_BLOCKS(double, orc_halo_r8, 0.0)
+HALO_BLOCKS(int32_t, orc_halo_i4, 0)
 
 /* field_loc_* / field_type_* of drivers/cice4/ice_constants.F90 arrive as the translated parameter
  * values; map them by value onto the oracle's enums */
@@ -62,23 +103,39 @@ static int map_kind(int32_t kind) {
 }
 static void shim_halo_r8(double *a, int32_t *halo, int32_t *loc, int32_t *kind) {
     (void)halo;
-    orc_halo_r8(a, &g_grid, map_loc(*loc), map_kind(*kind), 0.0);
+    if (g_lay.nblocks > 0) halo_blocks_double(a, map_loc(*loc), map_kind(*kind));
+    else orc_halo_r8(a, &g_grid, map_loc(*loc), map_kind(*kind), 0.0);
 }
 static void shim_halo_i4(int32_t *a, int32_t *halo, int32_t *loc, int32_t *kind) {
     (void)halo;
-    orc_halo_i4(a, &g_grid, map_loc(*loc), map_kind(*kind), 0);
+    if (g_lay.nblocks > 0) halo_blocks_int32_t(a, map_loc(*loc), map_kind(*kind));
+    else orc_halo_i4(a, &g_grid, map_loc(*loc), map_kind(*kind), 0);
 }
 
 static int32_t one_block[1] = {1};
 
-static void bind_domain(const orc_grid *g, const orc_params *p) {
+/* lay == NULL: one block spanning the domain */
+static void bind_domain(const orc_grid *g, const orc_params *p, const ref_layout *lay) {
     g_grid = *g;
+    memset(&g_lay, 0, sizeof(g_lay));
     v_nx_block = g->nx_block;
     v_ny_block = g->ny_block;
     v_max_blocks = 1;
     v_nblocks = 1;
-    v_ncat = p->ncat;
     v_blocks_ice_ = one_block;
+    if (lay) {
+        g_lay = *lay;
+        g_glob = *g;
+        g_glob.nx_block = lay->nx_global + 2; g_glob.ny_block = lay->ny_global + 2;
+        g_glob.ilo = 2; g_glob.ihi = lay->nx_global + 1; g_glob.jlo = 2; g_glob.jhi = lay->ny_global + 1;
+        v_max_blocks = v_nblocks = lay->nblocks;
+        free(g_block_ids);
+        g_block_ids = (int32_t *)malloc(sizeof(int32_t) * lay->nblocks);
+        if (!g_block_ids) abort();
+        for (int b = 0; b < lay->nblocks; ++b) g_block_ids[b] = b + 1;
+        v_blocks_ice_ = g_block_ids;
+    }
+    v_ncat = p->ncat;
     ref_init_parameters();
 }
 
@@ -101,18 +158,19 @@ static void bind_scalars(const orc_params *p) {
 /* set_evp_parameters as the reference computes it: returns the six derived module scalars */
 void ref_set_evp_parameters(const orc_params *p, double dt, double *out6) {
     orc_grid g = {3, 3, 2, 2, 2, 2, 0, 0};
-    bind_domain(&g, p);
+    bind_domain(&g, p, NULL);
     bind_scalars(p);
     v_set_evp_parameters(&dt);
     out6[0] = v_dtei; out6[1] = v_ecci; out6[2] = v_dte2t;
     out6[3] = v_denom1; out6[4] = v_denom2; out6[5] = v_rcon;
 }
 
-/* the reference's evp(dt) on one block; same argument structs as orc_evp.  f->strength_in is
- * ignored (the reference always calls ice_strength). */
-int ref_evp(const orc_grid *g, const orc_params *p, const orc_fields *f, double dt) {
-    const size_t plane = (size_t)g->nx_block * g->ny_block;
-    bind_domain(g, p);
+/* the reference's evp(dt); same argument structs as orc_evp, every array (nx_block, ny_block, nblocks)
+ * (aicen / vicen: (nx_block, ny_block, ncat, nblocks)).  f->strength_in is ignored (the reference
+ * always calls ice_strength). */
+static int ref_evp_impl(const orc_grid *g, const ref_layout *lay, const orc_params *p, const orc_fields *f, double dt) {
+    const size_t plane = (size_t)g->nx_block * g->ny_block * (lay ? lay->nblocks : 1);
+    bind_domain(g, p, lay);
     bind_scalars(p);
     v_set_evp_parameters(&dt); /* init_evp, source/ice_dyn_evp.F90:476 */
 
@@ -152,6 +210,17 @@ int ref_evp(const orc_grid *g, const orc_params *p, const orc_fields *f, double 
     return 0;
 }
 
+/* one block spanning the domain */
+int ref_evp(const orc_grid *g, const orc_params *p, const orc_fields *f, double dt) {
+    return ref_evp_impl(g, NULL, p, f, dt);
+}
+
+/* the domain decomposed into blocks (create_blocks, source/ice_blocks.F90:196-222): g holds nx_block,
+ * ny_block of a block and the domain's boundary types */
+int ref_evp_blocks(const orc_grid *g, const ref_layout *lay, const orc_params *p, const orc_fields *f, double dt) {
+    return ref_evp_impl(g, lay, p, f, dt);
+}
+
 /* Timing helper (bench.py cpu_baseline kind "reference"): nsub subcycles of the reference's own
  * stress + stepu + the two velocity halo updates (source/ice_dyn_evp.F90:347-404) on fields that a
  * previous orc_evp / ref_evp call has prepared (icetmask, iceumask, aiu, waterx, ... valid in f).
@@ -166,7 +235,7 @@ int ref_subcycle_only(const orc_grid *g, const orc_params *p, const orc_fields *
     struct timespec t0, t1;
     if (!ix || !str) return -1;
     int32_t *indxti = ix, *indxtj = ix + plane, *indxui = ix + 2 * plane, *indxuj = ix + 3 * plane;
-    bind_domain(g, p);
+    bind_domain(g, p, NULL);
     bind_scalars(p);
     v_set_evp_parameters(&dt);
     for (int j = g->jlo; j <= g->jhi + 1; ++j) /* the lists evp_prep2 builds, :850-859, :867-880 */
@@ -201,6 +270,6 @@ int ref_subcycle_only(const orc_grid *g, const orc_params *p, const orc_fields *
 void ref_principal_stress(const orc_params *p, int32_t nx_block, int32_t ny_block, double *stressp_1,
                           double *stressm_1, double *stress12_1, double *prs_sig, double *sig1, double *sig2) {
     orc_grid g = {nx_block, ny_block, 2, nx_block - 1, 2, ny_block - 1, 0, 0};
-    bind_domain(&g, p);
+    bind_domain(&g, p, NULL);
     v_principal_stress(&nx_block, &ny_block, stressp_1, stressm_1, stress12_1, prs_sig, sig1, sig2);
 }

@@ -57,8 +57,47 @@ def add_variant_inputs(case, over):
     return inp
 
 
+# block decompositions of one of the problems above: (label of the problem, bx, by)
+BLOCK_CASES = [("cice4_tripole_28x22", 10, 8)]
+
+
+def blocks_golden():
+    """The reference run on a create_blocks decomposition: its state and outputs in BLOCK layout (the
+    problem itself is the fixture of the same label)."""
+    from cice4_b200 import evp as E
+    for label, bx, by in BLOCK_CASES:
+        kw, over, dt, ndte, nsteps = CASES[label]
+        case = synth.make_case(**kw)
+        g = case.grid
+        inp = add_variant_inputs(case, over)
+        p = O.make_params(dt=dt, ndte=ndte, **over)
+        ew = {v: k for k, v in E.BND.items()}[g.ew]
+        ns = {v: k for k, v in E.BND.items()}[g.ns]
+        lay = E.BlockLayout.cartesian(g.nx, g.ny, bx, by)
+        gfb = {k: np.asfortranarray(v) for k, v in E.grid_fields_in_blocks(g, lay, ew, ns).items() if v is not None}
+        inb = {k: np.asfortranarray(E.split_blocks(v, lay, ew, ns)) for k, v in inp.items()}
+        stb = {k: np.zeros(lay.shape, dtype=v.dtype, order="F") for k, v in synth.zero_state(3, 3).items()}
+        strengths = []
+        for _ in range(nsteps):
+            fb = O.run_evp_ref_blocks(lay, g.ew, g.ns, gfb, inb, stb, p, dt)
+            strengths.append(fb["strength"].copy(order="F"))
+        out = {"meta_bx": bx, "meta_by": by}
+        for k, a in enumerate(strengths):
+            out["ref_strength_%d" % k] = a
+        for k in O.STATE_D + ["iceumask"]:
+            out["ref_state_" + k] = stb[k]
+        for k in O.OUT_D:
+            if k == "sicemass" and not over.get("auscom"):
+                continue
+            out["ref_out_" + k] = fb[k]
+        path = os.path.join(HERE, "refblocks_%s_b%dx%d.npz" % (label, bx, by))
+        np.savez_compressed(path, **out)
+        print("%-36s %d blocks of %dx%d  %6.1f KB" % (label, lay.nblocks, bx, by, os.path.getsize(path) / 1024))
+
+
 def main():
     build_ref.build()
+    blocks_golden()
     for label, (kw, over, dt, ndte, nsteps) in CASES.items():
         case = synth.make_case(**kw)
         g = case.grid

@@ -93,3 +93,25 @@ def load_ref_golden(path):
                            ref_strengths=[np.asfortranarray(z["ref_strength_%d" % k])
                                           for k in range(int(z["meta_nsteps"]))],
                            label=os.path.basename(path)[8:-4])
+
+
+# which cells of a block `evp` defines, per field (the CUDA marshalling policies PACK_FULL / PACK_TNE_* /
+# PACK_INT_* of csrc/evp_abi.cu): lo / hi = how far the region extends below ilo / beyond ihi
+BLOCK_REGION = {"uvel": (1, 1), "vvel": (1, 1), "iceumask": (0, 0)}
+BLOCK_REGION.update({n: (0, 1) for n in E.STATE_D[2:]})                                  # stresses: + N/E ghosts
+BLOCK_REGION.update({n: (0, 1) for n in ("prs_sig", "divu", "shear", "rdg_conv", "rdg_shear")})
+BLOCK_REGION.update({n: (0, 0) for n in ("strairx", "strairy", "strtltx", "strtlty", "strintx", "strinty",
+                                         "strocnx", "strocny", "strocnxT", "strocnyT", "fm")})
+BLOCK_REGION.update({"strength": (1, 1), "sicemass": (1, 1)})
+
+
+def block_region_mismatches(name, got_blk, want_blk, layout):
+    """blocks in which `got_blk` differs from `want_blk` on the cells evp defines for field `name`"""
+    lo, hi = BLOCK_REGION[name]
+    bad = []
+    for b in range(layout.nblocks):
+        i0, i1 = layout.ilo[b] - 1 - lo, layout.ihi[b] + hi
+        j0, j1 = layout.jlo[b] - 1 - lo, layout.jhi[b] + hi
+        if not np.array_equal(got_blk[i0:i1, j0:j1, b], want_blk[i0:i1, j0:j1, b]):
+            bad.append(b)
+    return bad

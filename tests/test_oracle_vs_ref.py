@@ -90,6 +90,43 @@ def test_time_step_and_ndte_bit_exact_vs_reference(dt, ndte):
     assert not bad, f"oracle differs from the reference in {bad}"
 
 
+@pytest.mark.parametrize("bx,by", [(10, 8), (7, 11), (14, 5), (28, 22), (9, 22)])
+@pytest.mark.parametrize("var", [VARIANTS[0], VARIANTS[4]], ids=["cice4", "access"])
+def test_reference_on_block_decompositions(bx, by, var):
+    """The translated reference itself run on create_blocks decompositions (padded edge blocks included;
+    several blocks exercise the block loops of `evp`, the per-block index lists and get_block): on the
+    cells evp defines in each block it must equal the single-block oracle -- the reference's own
+    decomposition invariance (doc/cicedoc.pdf 4.6), and the cell sets the CUDA marshalling reproduces."""
+    from cice4_b200 import evp as E
+    from helpers import BLOCK_REGION, block_region_mismatches
+    case = synth.make_case("om1deg", nx=28, ny=22, realistic=True)
+    g = case.grid
+    over = var[1]
+    inp = _inputs(case, over)
+    p = O.make_params(dt=3600.0, ndte=120, **over)
+    ew = {v: k for k, v in E.BND.items()}[g.ew]
+    ns = {v: k for k, v in E.BND.items()}[g.ns]
+    st = synth.zero_state(g.nx_block, g.ny_block)
+    for _ in range(2):
+        f, _sec = O.run_evp(g, inp, st, p)
+    lay = E.BlockLayout.cartesian(g.nx, g.ny, bx, by)
+    gfb = {k: np.asfortranarray(v) for k, v in E.grid_fields_in_blocks(g, lay, ew, ns).items() if v is not None}
+    inb = {k: np.asfortranarray(E.split_blocks(v, lay, ew, ns)) for k, v in inp.items()}
+    stb = {k: np.zeros(lay.shape, dtype=v.dtype, order="F") for k, v in st.items()}
+    for _ in range(2):
+        fb = O.run_evp_ref_blocks(lay, g.ew, g.ns, gfb, inb, stb, p, 3600.0)
+    bad = {}
+    for n in BLOCK_REGION:
+        if n == "sicemass" and not over.get("auscom"):
+            continue
+        got = stb[n] if n in stb else fb[n]
+        want = E.split_blocks(st[n] if n in st else f[n], lay, ew, ns)
+        b = block_region_mismatches(n, got, want, lay)
+        if b:
+            bad[n] = b
+    assert not bad, f"blocks that differ from the single-block result: {bad}"
+
+
 @pytest.mark.parametrize("dt,ndte", [(3600.0, 120), (1800.0, 120), (600.0, 240), (7200.0, 77)])
 def test_set_evp_parameters_vs_reference(dt, ndte):
     """source/ice_dyn_evp.F90:535-577 as the reference computes it"""

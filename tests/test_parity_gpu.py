@@ -94,6 +94,38 @@ def test_cuda_matches_reference_golden(evp_lib, path):
         dyn.finalize()
 
 
+def test_cuda_block_layout_matches_reference_blocks(evp_lib):
+    """The caller's block layout against THE REFERENCE RUN ON THE SAME BLOCKS (committed outputs of the
+    translated reference on a 10 x 8 create_blocks decomposition of the 28 x 22 tripole problem, padded
+    edge blocks included): on the cells evp defines in every block -- velocities with their ghost ring,
+    stresses and T-point diagnostics with their north/east ghost cells, U-point outputs on the physical
+    cells -- the CUDA path returns the reference's block arrays bit for bit."""
+    import os
+    from types import SimpleNamespace
+    from helpers import BLOCK_REGION, GOLDEN_DIR, block_region_mismatches
+    base = [p for p in REF_GOLDEN if p.endswith("ref_evp_cice4_tripole_28x22.npz")][0]
+    c = load_ref_golden(base)
+    z = np.load(os.path.join(GOLDEN_DIR, "refblocks_cice4_tripole_28x22_b10x8.npz"))
+    lay = E.BlockLayout.cartesian(c.grid.nx, c.grid.ny, int(z["meta_bx"]), int(z["meta_by"]))
+    assert lay.nblocks == 9
+    case = SimpleNamespace(grid=c.grid, inputs={k: v for k, v in c.inputs.items() if k in E.INPUT_D})
+    want = [n for n in BLOCK_REGION if "ref_out_" + n in z.files]
+    dyn, out = cuda_steps(case, nsteps=c.nsteps, strengths=c.ref_strengths, layout=lay, want=want, dt=c.dt,
+                          ndte=c.ndte, math_mode=0, **c.over)
+    bad = {}
+    for n in BLOCK_REGION:
+        if "ref_state_" + n in z.files:
+            b = block_region_mismatches(n, dyn.state[n], z["ref_state_" + n], lay)
+        elif "ref_out_" + n in z.files:
+            b = block_region_mismatches(n, out[n], z["ref_out_" + n], lay)
+        else:
+            continue
+        if b:
+            bad[n] = b
+    assert not bad, f"blocks that differ from the reference's: {bad}"
+    dyn.finalize()
+
+
 @pytest.mark.parametrize("label,kw", CASES, ids=[c[0] for c in CASES])
 def test_bit_exact_vs_oracle_two_steps(oracle, evp_lib, label, kw):
     """Cold start + warm second call (the timed configuration), unfused math: bit-exact."""
