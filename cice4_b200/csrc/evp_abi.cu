@@ -103,6 +103,7 @@ struct evp_b200_handle {
     int *d_cta_epoch = nullptr;       // persistent kernel: subcycles finished per CTA (grid_x * grid_y ints)
     bool persistent = false;          // run the ndte loop as one cooperative launch (k_persist)
     int epoch_count = 0;              // subcycles completed on this rank since init (== sync[1] with p2p)
+    long eliminated_cells = 0;        // cells of the slab without a block (eliminated land blocks)
     int *d_rowcnt = nullptr;          // active T cells per row (load balance of the chunks)
     bool balance = false;             // rebuild the chunk table from icetmask every call
     float w_bot = 1.f, w_top = 1.f;   // relative cost targets of the boundary chunks
@@ -533,6 +534,11 @@ static int init_handle(evp_b200_handle *h, const evp_b200_dims *d, const evp_b20
     const int nyl = d->slab_jhi - d->slab_jlo + 1;
     h->blk_tab.resize((size_t)d->nblocks * 6);
     long covered = 0;
+    // cells of the slab not covered by any block are the land blocks the reference's distribution has
+    // eliminated (source/ice_distribution.F90: blocks without ocean points get no task): they stay land
+    // with zero fields in the planes, which is what the halo update's zero fill gives their neighbours'
+    // ghost cells in the reference (mpi|serial/ice_boundary.F90, "fill out halo region")
+    std::vector<uint8_t> cover((size_t)d->nx_global * nyl, 0);
     for (int b = 0; b < d->nblocks; ++b) {
         if (d->ilo[b] < 2 || d->jlo[b] < 2 || d->ihi[b] > d->nx_block - 1 || d->jhi[b] > d->ny_block - 1 ||
             d->ihi[b] < d->ilo[b] || d->jhi[b] < d->jlo[b]) {
@@ -549,12 +555,15 @@ static int init_handle(evp_b200_handle *h, const evp_b200_dims *d, const evp_b20
         if (d->iglob_lo[b] < 1 || ig1 > d->nx_global || d->jglob_lo[b] < d->slab_jlo || jg1 > d->slab_jhi) {
             return fail(EVP_B200_ERR_ARG, "block %d lies outside the slab", b);
         }
+        for (int jg = d->jglob_lo[b]; jg <= jg1; ++jg)
+            for (int ig = d->iglob_lo[b]; ig <= ig1; ++ig) {
+                uint8_t &c = cover[(size_t)(jg - d->slab_jlo) * d->nx_global + (ig - 1)];
+                if (c) return fail(EVP_B200_ERR_ARG, "block %d overlaps another block at global cell (%d, %d)", b, ig, jg);
+                c = 1;
+            }
         covered += (long)(d->ihi[b] - d->ilo[b] + 1) * (d->jhi[b] - d->jlo[b] + 1);
     }
-    if (covered != (long)d->nx_global * nyl) {
-        return fail(EVP_B200_ERR_ARG, "blocks cover %ld cells, slab has %ld (land-block elimination is not supported)",
-                    covered, (long)d->nx_global * nyl);
-    }
+    h->eliminated_cells = (long)d->nx_global * nyl - covered;
 
     // set_evp_parameters, source/ice_dyn_evp.F90:563-575
     {

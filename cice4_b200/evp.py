@@ -212,6 +212,25 @@ class BlockLayout:
                 jg.append(js)
         return cls(nx, ny, bx + 2, by + 2, ilo, ihi, jlo, jhi, ig, jg)
 
+    def without(self, blocks: Sequence[int]) -> "BlockLayout":
+        """The layout with the listed blocks removed: land-block elimination of the reference's
+        distribution (/root/reference/source/ice_distribution.F90: blocks without ocean points are
+        assigned to no task).  The library treats cells that no block covers as land."""
+        keep = [b for b in range(self.nblocks) if b not in set(blocks)]
+        pick = lambda v: [int(v[b]) for b in keep]
+        return BlockLayout(self.nx_global, self.ny_global, self.nx_block, self.ny_block, pick(self.ilo),
+                           pick(self.ihi), pick(self.jlo), pick(self.jhi), pick(self.iglob_lo), pick(self.jglob_lo))
+
+    def land_blocks(self, tmask_padded: np.ndarray) -> list:
+        """Indices of the blocks without a single ocean T cell (tmask: padded single-block array)."""
+        out = []
+        for b in range(self.nblocks):
+            i0, j0 = self.iglob_lo[b], self.jglob_lo[b]
+            ni, nj = self.ihi[b] - self.ilo[b] + 1, self.jhi[b] - self.jlo[b] + 1
+            if not tmask_padded[i0:i0 + ni, j0:j0 + nj].any():
+                out.append(b)
+        return out
+
     @property
     def shape(self):
         return (self.nx_block, self.ny_block, self.max_blocks)

@@ -127,6 +127,41 @@ def test_reference_on_block_decompositions(bx, by, var):
     assert not bad, f"blocks that differ from the single-block result: {bad}"
 
 
+def test_reference_with_land_blocks_eliminated():
+    """Land-block elimination (source/ice_distribution.F90): the translated reference run WITHOUT the
+    blocks that hold no ocean cell (their neighbours' ghost cells are zero-filled by the halo update)
+    gives the single-block result on every remaining block -- the property the CUDA path relies on when
+    it treats cells that no block covers as land."""
+    from cice4_b200 import evp as E
+    from helpers import BLOCK_REGION, block_region_mismatches
+    case = synth.make_case("om1deg", nx=96, ny=64, realistic=True)
+    g = case.grid
+    p = O.make_params(dt=3600.0, ndte=120)
+    ew = {v: k for k, v in E.BND.items()}[g.ew]
+    ns = {v: k for k, v in E.BND.items()}[g.ns]
+    st = synth.zero_state(g.nx_block, g.ny_block)
+    for _ in range(2):
+        f, _sec = O.run_evp(g, case.inputs, st, p)
+    full = E.BlockLayout.cartesian(g.nx, g.ny, 8, 8)
+    land = full.land_blocks(g.f["tmask"])
+    assert len(land) >= 5
+    lay = full.without(land)
+    gfb = {k: np.asfortranarray(v) for k, v in E.grid_fields_in_blocks(g, lay, ew, ns).items() if v is not None}
+    inb = {k: np.asfortranarray(E.split_blocks(v, lay, ew, ns)) for k, v in case.inputs.items()}
+    stb = {k: np.zeros(lay.shape, dtype=v.dtype, order="F") for k, v in st.items()}
+    for _ in range(2):
+        fb = O.run_evp_ref_blocks(lay, g.ew, g.ns, gfb, inb, stb, p, 3600.0)
+    bad = {}
+    for n in BLOCK_REGION:
+        if n == "sicemass":
+            continue
+        got = stb[n] if n in stb else fb[n]
+        b = block_region_mismatches(n, got, E.split_blocks(st[n] if n in st else f[n], lay, ew, ns), lay)
+        if b:
+            bad[n] = b
+    assert not bad, bad
+
+
 @pytest.mark.parametrize("dt,ndte", [(3600.0, 120), (1800.0, 120), (600.0, 240), (7200.0, 77)])
 def test_set_evp_parameters_vs_reference(dt, ndte):
     """source/ice_dyn_evp.F90:535-577 as the reference computes it"""

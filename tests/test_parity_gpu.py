@@ -233,6 +233,30 @@ def test_block_decomposition_invariance(oracle, evp_lib, bx, by):
         np.testing.assert_array_equal(ublk[:ni, :nj, b], want[:ni, :nj, b])
 
 
+def test_land_block_elimination(oracle, evp_lib):
+    """Blocks without ocean cells left out of the caller's layout (the reference's distribution assigns
+    them to no task): the cells no block covers are land to the library, and every remaining block gets
+    the single-block result bit for bit (tests/test_oracle_vs_ref.py shows the reference does too)."""
+    from helpers import BLOCK_REGION, block_region_mismatches
+    case = synth.make_case("om1deg", nx=96, ny=64, realistic=True)
+    g = case.grid
+    st, f, strengths, _ = oracle_steps(oracle, case, nsteps=2)
+    full = E.BlockLayout.cartesian(g.nx, g.ny, 8, 8)
+    land = full.land_blocks(g.f["tmask"])
+    assert len(land) >= 5
+    lay = full.without(land)
+    names = [n for n in BLOCK_REGION if n != "sicemass"]
+    dyn, out = cuda_steps(case, nsteps=2, strengths=strengths, layout=lay, want=[n for n in names if n not in STATE])
+    bad = {}
+    for n in names:
+        got = dyn.state[n] if n in dyn.state else out[n]
+        b = block_region_mismatches(n, got, E.split_blocks(st[n] if n in st else f[n], lay, "cyclic", "tripole"), lay)
+        if b:
+            bad[n] = b
+    assert not bad, bad
+    dyn.finalize()
+
+
 def test_two_phase_prep_run(oracle, evp_lib):
     """evp_b200_prep + evp_b200_run (host ice_strength in between, as the Fortran shim does)."""
     case = synth.make_case("om1deg", nx=64, ny=48, realistic=True)
