@@ -62,8 +62,9 @@ typedef struct {
      * global index of the first physical cell, this_block%i_glob(ilo), %j_glob(jlo) */
     const int32_t *ilo, *ihi, *jlo, *jhi;
     const int32_t *iglob_lo, *jglob_lo;
-    /* rows of the global domain owned by this handle (1-based, inclusive); the local
-     * blocks must tile [1..nx_global] x [slab_jlo..slab_jhi] exactly */
+    /* rows of the global domain owned by this handle (1-based, inclusive); the local blocks
+     * lie inside [1..nx_global] x [slab_jlo..slab_jhi] and do not overlap; cells that no
+     * block covers are land (the reference's land-block elimination, ice_distribution.F90) */
     int32_t slab_jlo, slab_jhi;
     int32_t rank, nranks;       /* position in the south->north chain of y-slabs */
     int32_t device;             /* CUDA device ordinal, -1 = current */
