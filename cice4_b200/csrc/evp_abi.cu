@@ -420,6 +420,7 @@ int choose_tiling(evp_b200_handle *h) {
     // resident CTAs per SM at ~210 registers per thread: 256 threads
     int per_sm = (nt == 256) ? 1 : (nt == 128 ? 2 : 4);
     if (tma && (h->par.kernel_variant & 256) == 0) per_sm = 3;
+    if (!tma && nt == 128 && (h->par.kernel_variant & 1024)) per_sm = 3; // late-load kernel: 3 CTAs per SM
     int ncy = (per_sm * sms) / ncx; // one wave
     if (ncy < 1) ncy = 1;
     if (ncy > nyl) ncy = nyl;

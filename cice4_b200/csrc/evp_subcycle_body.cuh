@@ -523,7 +523,10 @@ __device__ __forceinline__ void subcycle_epilogue(const SubArgs &a, idx_t sn, in
 // One subcycle of one CTA: march north over the U rows j0 .. j0+nrows-1 of strip blockIdx.x, reading
 // the state copy at offset `so` and writing the one at offset `sn`.  COH: state loads bypass the
 // non-coherent L1 (persistent kernel).
-template <int NT, bool LAST, bool HT, bool COH>
+// LATE: the loads of T row j+1 are issued after the arithmetic of row j instead of before it: nothing is
+// prefetched across the stress computation, which frees ~50 registers (three warps per scheduler fit)
+// at the price of an exposed load latency per row that the third warp has to hide.
+template <int NT, bool LAST, bool HT, bool COH, bool LATE = false>
 __device__ __forceinline__ void march(const SubArgs &a, idx_t so, idx_t sn, int tid, int i, int j0, int nrows) {
     extern __shared__ double evp_xch[]; // [2][4][NT]: str(2,4,7,8) handed to the west neighbour thread
     const int jlast = min(j0 + nrows, a.nyl + 1); // last T row of this CTA
@@ -560,7 +563,7 @@ __device__ __forceinline__ void march(const SubArgs &a, idx_t so, idx_t sn, int 
         const unsigned um_raw1 = (colU && j + 1 <= jlast) ? __ldg(umk) : 0u; // U row j
         tmk += a.pitch;
         umk += a.pitch;
-        if (j < jlast) load_T<LAST, HT, COH>(a, so, tn, i, j + 1, colT, tm_next); // software prefetch of the next row
+        if (!LATE && j < jlast) load_T<LAST, HT, COH>(a, so, tn, i, j + 1, colT, tm_next); // software prefetch of the next row
         uc.act = false;
         if (j > j0) load_U(a, uc, i, j - 1, um_cur);
 
@@ -601,6 +604,7 @@ __device__ __forceinline__ void march(const SubArgs &a, idx_t so, idx_t sn, int 
         vs = t.v;
         usw = t.uw;
         vsw = t.vw;
+        if (LATE && j < jlast) load_T<LAST, HT, COH>(a, so, tn, i, j + 1, colT, tm_next);
         t = tn;
         tm_raw = tm_raw2;
         um_raw = um_raw1;
@@ -609,8 +613,8 @@ __device__ __forceinline__ void march(const SubArgs &a, idx_t so, idx_t sn, int 
 
 // At ~210 registers per thread every scheduler (16384 registers) holds two warps: 8 warps per SM
 // whatever the CTA shape (96 x 3 or 160 x 2 would need <= 168 registers and spill).
-template <int NT, bool LAST, bool HT>
-__global__ void __launch_bounds__(NT) k_subcycle(const __grid_constant__ SubArgs a) {
+template <int NT, bool LAST, bool HT, bool LATE = false, int MINB = 1>
+__global__ void __launch_bounds__(NT, MINB) k_subcycle(const __grid_constant__ SubArgs a) {
     // programmatic dependent launch: let the next subcycle kernel be scheduled as SMs drain, and
     // wait here until the previous grid has completed and flushed (no-ops without the attribute)
     asm volatile("griddepcontrol.launch_dependents;");
@@ -631,7 +635,7 @@ __global__ void __launch_bounds__(NT) k_subcycle(const __grid_constant__ SubArgs
     }
     // an empty chunk (all rows inactive, trimmed by the load balancer) has nothing to do
     const idx_t so = a.flip ? (idx_t)a.copy_stride : 0, sn = a.flip ? 0 : (idx_t)a.copy_stride;
-    if (nrows > 0) march<NT, LAST, HT, false>(a, so, sn, tid, i, j0, nrows);
+    if (nrows > 0) march<NT, LAST, HT, false, LATE>(a, so, sn, tid, i, j0, nrows);
     subcycle_epilogue<NT, false>(a, sn, tid, top, bot, epoch);
 }
 
@@ -960,6 +964,11 @@ template <int NT>
 static void launch_nt(const SubArgs &a, bool last, bool pdl, int variant, unsigned gx, unsigned gy, cudaStream_t s) {
     dim3 grid(gx, gy), block(NT);
     if constexpr (NT == 128) {
+        if (variant & 1024) { // no prefetch across the arithmetic, 3 CTAs per SM (<= 168 registers)
+            if (last) launch_k(k_subcycle<NT, true, false, true, 3>, a, grid, block, pdl, s);
+            else launch_k(k_subcycle<NT, false, false, true, 3>, a, grid, block, pdl, s);
+            return;
+        }
         if (variant & 256) {
             if (last) launch_tma(k_subcycle_tma<NT, true, 3, 2>, tma_smem_bytes<NT, 3>(), a, grid, block, s);
             else launch_tma(k_subcycle_tma<NT, false, 3, 2>, tma_smem_bytes<NT, 3>(), a, grid, block, s);

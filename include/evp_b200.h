@@ -101,7 +101,8 @@ typedef struct {
                                synchronise with their neighbours only (bit-identical; measured slower than
                                the default graph of per-subcycle launches); bit 8 (256) / bit 9
                                (512): T-row planes staged through shared memory by TMA bulk copies, 3 rows
-                               deep with 2 CTAs per SM / 2 rows deep with 3 CTAs per SM */
+                               deep with 2 CTAs per SM / 2 rows deep with 3 CTAs per SM; bit 10 (1024): no
+                               register prefetch across the arithmetic (<= 168 registers, 3 CTAs per SM) */
     int32_t state_residency; /* 0 = the whole state is uploaded and downloaded by every call (host arrays always
                                current: restart-exact drop-in); 1 = the 12 stress arrays stay on the device
                                between calls: uploaded by the first call after init or after

@@ -147,7 +147,7 @@ def test_fma_mode_within_tolerance(oracle, evp_lib, label, kw):
 
 
 @pytest.mark.parametrize("threads,rows,variant", [(64, 5, 0), (128, 7, 4), (256, 0, 0), (128, 1000, 0),
-                                                  (128, 0, 16), (64, 9, 16 + 4), (128, 0, 64), (256, 11, 64)])
+                                                  (128, 0, 16), (64, 9, 16 + 4), (128, 0, 64), (256, 11, 64), (128, 0, 1024)])
 def test_tiling_invariance(oracle, evp_lib, threads, rows, variant):
     """Strip width, rows per CTA and the prefetch variant must not change a single bit."""
     case = synth.make_case("om1deg", nx=300, ny=90)
