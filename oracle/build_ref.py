@@ -10,12 +10,16 @@ per CPP variant the reference is built with:
     access  -DAusCOM -Dcoupled -DACCESS    (drivers/access-cm)
     coupled -Dcoupled                      (slope tilt without the AusCOM changes)
 
-Needs /root/reference (this container only).  Generated C and the libraries stay under oracle/_ref/
-(git-ignored): no reference source is ever committed.  Run:  python oracle/build_ref.py
+Needs /root/reference (this container only).  The generated C lives in a temporary directory for the
+duration of the build (EVP_REF_KEEP_C=1 keeps it for inspection); only the libraries are written to
+oracle/_ref/ (git-ignored): no reference source, translated or not, enters the repository tree.
+Run:  python oracle/build_ref.py
 """
 import os
+import shutil
 import subprocess
 import sys
+import tempfile
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 if __package__:
@@ -89,9 +93,13 @@ def build(verbose=False):
     if not available():
         raise RuntimeError("reference sources not found under " + REF)
     os.makedirs(OUT, exist_ok=True)
+    for stale in os.listdir(OUT):      # generated C of earlier builds: only libraries stay in oracle/_ref
+        if stale.endswith(".c"):
+            os.remove(os.path.join(OUT, stale))
     cc = "/usr/bin/gcc" if os.access("/usr/bin/gcc", os.X_OK) else "gcc"
+    tmp = tempfile.mkdtemp(prefix="evp_ref_")   # the translated text never enters the repository tree
     for name, (defines, driver) in VARIANTS.items():
-        gen = os.path.join(OUT, "evp_ref_%s.c" % name)
+        gen = os.path.join(tmp, "evp_ref_%s.c" % name)
         with open(gen, "w") as fh:
             fh.write(translate(defines, driver))
         # strict: the parity authority (no FMA contraction).  fast (cice4 only): the reference's
@@ -109,6 +117,10 @@ def build(verbose=False):
             if verbose:
                 print(" ".join(cmd))
             subprocess.check_call(cmd)
+    if os.environ.get("EVP_REF_KEEP_C"):
+        print("generated C kept in", tmp)
+    else:
+        shutil.rmtree(tmp, ignore_errors=True)
 
 
 if __name__ == "__main__":

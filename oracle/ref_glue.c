@@ -5,8 +5,8 @@
  * reference's own `evp`, `set_evp_parameters`, `evp_prep1/2`, `stress`, `stepu`, `evp_finish`,
  * `principal_stress` (source/ice_dyn_evp.F90), `to_ugrid`, `to_tgrid`, `t2ugrid_vector`,
  * `u2tgrid_vector` (source/ice_grid.F90) and `ice_strength`, `asum_ridging`, `ridge_itd`
- * (source/ice_mechred.F90) are translated statement by statement into REF_GEN (a generated file
- * under oracle/_ref/, never committed) and #included below.  What the translated code calls but the
+ * (source/ice_mechred.F90) are translated statement by statement into REF_GEN (a generated file in a
+ * temporary build directory, never committed) and #included below.  What the translated code calls but the
  * translator does not cover is supplied here by hand:
  *
  *   get_block        (source/ice_blocks.F90:349-378)  -> the single block of the test domain
