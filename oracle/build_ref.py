@@ -46,7 +46,7 @@ def available():
     return os.path.isfile(os.path.join(REF, "source", "ice_dyn_evp.F90"))
 
 
-def translate(defines, driver):
+def translate(defines, driver, omp=False):
     tr = T.Translator(defines)
     src = os.path.join(REF, "source")
     # modules whose variables the path uses -- the few that are not plain declarations are listed
@@ -82,7 +82,9 @@ def translate(defines, driver):
                                                 "evp_finish", "principal_stress", "evp"]),
     ):
         for s in subs:
-            missing.update(tr.subroutine(path, s))
+            # timing build: the cell loops of stress / stepu (independent iterations over the index lists,
+            # as the OpenMP directives of later CICE versions assume) run on all host threads
+            missing.update(tr.subroutine(path, s, omp={"ij"} if omp and s in ("stress", "stepu") else None))
     missing -= set(tr.subs) | {"get_block", "ice_haloupdate", "ice_timer_start", "ice_timer_stop"}
     if missing:
         raise T.TranslateError("unresolved names: " + ", ".join(sorted(missing)))
@@ -103,13 +105,17 @@ def build(verbose=False):
         with open(gen, "w") as fh:
             fh.write(translate(defines, driver))
         # strict: the parity authority (no FMA contraction).  fast (cice4 only): the reference's
-        # production optimisation level (bld/Macros.nci:26 is -O3 -xHost), timed by bench.py
-        builds = [("", ["-O2", "-ffp-contract=off", "-fno-fast-math"])]
+        # production optimisation level (bld/Macros.nci:26 is -O3 -xHost) with the cell loops of stress
+        # and stepu on all host threads, timed by bench.py
+        builds = [("", ["-O2", "-ffp-contract=off", "-fno-fast-math"], gen)]
         if name == "cice4":
-            builds.append(("_fast", ["-O3", "-march=x86-64-v3"]))
-        for suffix, opt in builds:
+            gen_omp = os.path.join(tmp, "evp_ref_%s_omp.c" % name)
+            with open(gen_omp, "w") as fh:
+                fh.write(translate(defines, driver, omp=True))
+            builds.append(("_fast", ["-O3", "-march=x86-64-v3", "-fopenmp"], gen_omp))
+        for suffix, opt, src in builds:
             cmd = [cc, "-std=gnu11"] + opt + ["-fPIC", "-shared", "-Wall", "-Wno-unused", "-Wno-parentheses",
-                                              "-Wno-maybe-uninitialized", '-DREF_GEN="%s"' % gen, "-I", HERE]
+                                              "-Wno-maybe-uninitialized", '-DREF_GEN="%s"' % src, "-I", HERE]
             if "AusCOM" in defines:
                 cmd.append("-DREF_AUSCOM")
             cmd += ["-o", os.path.join(OUT, "libevp_ref_%s%s.so" % (name, suffix)),

@@ -254,13 +254,22 @@ def run_evp_ref_blocks(layout, ew: int, ns: int, grid_fields_blk, inputs_blk, st
     return f
 
 
-def time_subcycles_ref(grid, fields: Fields, params: OrcParams, dt: float, nsub: int) -> float:
-    """Seconds for `nsub` subcycles of the translated reference's own stress + stepu (+ 2 halo updates),
-    -O3 serial build, on fields prepared by run_evp."""
+def omp_set_num_threads(n: int) -> None:
+    """Thread count of the OpenMP regions of the libraries loaded in this process (libgomp)."""
+    C.CDLL("libgomp.so.1").omp_set_num_threads(int(n))
+
+
+def time_subcycles_ref(grid, fields: Fields, params: OrcParams, dt: float, nsub: int,
+                       threads: Optional[int] = None) -> float:
+    """Seconds for `nsub` subcycles of the translated reference's own stress + stepu (+ 2 halo updates)
+    on fields prepared by run_evp: the -O3 build whose cell loops run on `threads` OpenMP threads
+    (None = the current setting; 1 = the reference's serial build)."""
     g = make_grid(grid.nx_block, grid.ny_block, grid.ew, grid.ns)
     sec = C.c_double(0.0)
-    rc = ref_lib("cice4_fast").ref_subcycle_only(C.byref(g), C.byref(params), C.byref(fields.c), dt, nsub,
-                                                 C.byref(sec))
+    L = ref_lib("cice4_fast")
+    if threads is not None:
+        omp_set_num_threads(threads)
+    rc = L.ref_subcycle_only(C.byref(g), C.byref(params), C.byref(fields.c), dt, nsub, C.byref(sec))
     if rc != 0:
         raise RuntimeError("ref_subcycle_only failed")
     return sec.value

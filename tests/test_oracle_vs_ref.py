@@ -214,3 +214,27 @@ def test_reference_fma_build_within_tolerance():
     for n in O.STATE_D[2:]:
         assert np.abs(a[n] - b[n]).max() <= 1e-10 * np.abs(a[n]).max(), n
     assert any(not np.array_equal(a[n], b[n]) for n in O.STATE_D)   # the builds do differ
+
+
+def test_reference_timing_build_is_thread_invariant():
+    """The timing build of the translated reference runs the cell loops of stress / stepu on OpenMP threads
+    (independent iterations over the index lists): one thread and many give the same bits."""
+    import ctypes as C
+    import os
+    if not os.path.exists(os.path.join(O.REF_DIR, "libevp_ref_cice4_fast.so")):
+        pytest.skip("fast build of the translated reference not present")
+    case = synth.make_case("x", nx=70, ny=55, ew="cyclic", ns="open")
+    g = case.grid
+    p = O.make_params(dt=3600.0, ndte=40)
+    res = []
+    for threads in (1, 4):
+        O.omp_set_num_threads(threads)
+        st = synth.zero_state(g.nx_block, g.ny_block)
+        gg = O.make_grid(g.nx_block, g.ny_block, g.ew, g.ns)
+        f = O.Fields(g.f, case.inputs, st, None)
+        assert O.ref_lib("cice4_fast").ref_evp(C.byref(gg), C.byref(p), C.byref(f.c), 3600.0) == 0
+        res.append((st, f))
+    for n in O.STATE_D:
+        assert np.array_equal(res[0][0][n], res[1][0][n]), n
+    for n in ("divu", "strintx", "strocnxT", "prs_sig"):
+        assert np.array_equal(res[0][1][n], res[1][1][n]), n
