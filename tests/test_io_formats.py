@@ -92,3 +92,26 @@ def test_netcdf_grid_reader(tmp_path):
     assert "ANGLET" in ga and "KMU" not in ga
     with pytest.raises(ValueError):
         IO.read_pop_grid_nc(kp, kp)
+
+
+def test_block_layout_land_block_helpers():
+    """BlockLayout.land_blocks / .without (land-block elimination of the caller's layout)"""
+    from cice4_b200 import evp as E
+    nx, ny = 20, 12
+    lay = E.BlockLayout.cartesian(nx, ny, 8, 5)          # 3 x 3 blocks, padded east / north edge
+    assert lay.nblocks == 9 and lay.shape == (10, 7, 9)
+    tmask = np.ones((nx + 2, ny + 2), dtype=np.int32)
+    tmask[1:9, 1:6] = 0                                  # block 0 entirely land
+    tmask[17:21, 11:13] = 0                              # the small north-east corner block entirely land
+    tmask[9:17, 6:11] = 0
+    tmask[12, 8] = 1                                     # block 4: one ocean cell left
+    land = lay.land_blocks(tmask)
+    assert land == [0, 8]
+    sub = lay.without(land)
+    assert sub.nblocks == 7 and sub.nx_block == lay.nx_block
+    assert list(sub.iglob_lo) == [int(lay.iglob_lo[b]) for b in range(9) if b not in land]
+    # split / merge on the reduced layout: covered cells round-trip, uncovered cells stay zero
+    a = np.asfortranarray(np.arange((nx + 2) * (ny + 2), dtype=np.float64).reshape(nx + 2, ny + 2))
+    back = E.merge_blocks(E.split_blocks(a, sub, "cyclic", "open"), sub)
+    assert np.array_equal(back[9:17, 1:6], a[9:17, 1:6])
+    assert not back[1:9, 1:6].any()
