@@ -221,6 +221,22 @@ int exchange_rows(evp_b200_handle *h, void *const *planes, int n, size_t elem) {
     return 0;
 }
 
+// sync[6]: a bounded flag wait inside the subcycle kernels (or k_wait_peers) gave up.  Reported once and
+// cleared, so that one time-out does not poison every later call; the epochs of a multi-rank chain are
+// undefined after it, so the caller has to re-initialise all ranks.  Synchronises the stream.
+int check_wait_flag(evp_b200_handle *h) {
+    int gave_up = 0;
+    CU(cudaMemcpyAsync(&gave_up, h->sync + 6, sizeof(int), cudaMemcpyDeviceToHost, h->st));
+    CU(cudaStreamSynchronize(h->st));
+    if (gave_up) {
+        CU(cudaMemsetAsync(h->sync + 6, 0, sizeof(int), h->st));
+        CU(cudaStreamSynchronize(h->st));
+        return fail(EVP_B200_ERR_STATE, "subcycle kernel: a wait for a neighbouring CTA / GPU timed out (results invalid%s)",
+                    h->dims.nranks > 1 ? "; re-initialise every rank of the chain" : "");
+    }
+    return 0;
+}
+
 int halo_r8(evp_b200_handle *h, double *plane, int loc, int isign) {
     aux_halo_r8(h->pg, plane, loc, isign, h->st);
     void *pp[1] = {plane};
@@ -295,7 +311,11 @@ int launch_subcycle(evp_b200_handle *h, int cur, bool last) {
     SubArgs a;
     fill_subargs(h, a, cur);
     subcycle_launch_fn fn = h->par.math_mode == 1 ? evp_subcycle_launch_fast : evp_subcycle_launch_strict;
-    fn(a, last, h->par.kernel_variant, h->threads, (unsigned)h->grid_x, (unsigned)h->grid_y, (void *)h->st);
+    const int e = fn(a, last, h->par.kernel_variant, h->threads, (unsigned)h->grid_x, (unsigned)h->grid_y, (void *)h->st);
+    if (e != 0) {
+        fail(EVP_B200_ERR_CUDA, "subcycle kernel launch: %s", cudaGetErrorString((cudaError_t)e));
+        return -1;
+    }
     int n = 1;
     if (h->pg.ns_cyclic) n += 2;
     if (h->pg.tripole && !h->fold_in_kernel) n += 1;
@@ -334,13 +354,20 @@ int run_subcycle_loop(evp_b200_handle *h) {
             bool bad = false;
             for (int k = 1; k <= ndte; ++k) {
                 const int m = launch_subcycle(h, cur, k == ndte);
-                if (m < 0) bad = true;
+                if (m < 0) { bad = true; break; }
                 n += m;
                 cur ^= 1;
             }
             h->sub_launches_per_loop = n;
+            const std::string why = g_err;
             CU(cudaStreamEndCapture(h->st, &h->graph));
-            if (bad) return EVP_B200_ERR_COMM;
+            if (bad) {
+                cudaGraphDestroy(h->graph);
+                h->graph = nullptr;
+                cudaGetLastError();
+                g_err = why;
+                return EVP_B200_ERR_CUDA;
+            }
             CU(cudaGraphInstantiate(&h->graph_exec, h->graph, 0));
         }
         CU(cudaGraphLaunch(h->graph_exec, h->st));
@@ -349,7 +376,7 @@ int run_subcycle_loop(evp_b200_handle *h) {
         int n = 0;
         for (int k = 1; k <= ndte; ++k) {
             const int m = launch_subcycle(h, h->cur, k == ndte);
-            if (m < 0) return EVP_B200_ERR_COMM;
+            if (m < 0) return EVP_B200_ERR_CUDA;
             n += m;
             h->cur ^= 1;
         }
@@ -362,8 +389,25 @@ int run_subcycle_loop(evp_b200_handle *h) {
     if (h->p2p) aux_wait_peers(h->sync, h->north >= 0, h->south >= 0, h->grid_x, h->st);
     if (h->cur != 0) { // odd ndte: bring the result back to copy 0 so the next loop starts there
         const size_t bytes = h->pg.cells * sizeof(double);
-        CU(cudaMemcpyAsync(h->pl[P_U0], h->pl[P_U1], bytes, cudaMemcpyDeviceToDevice, h->st));
-        CU(cudaMemcpyAsync(h->pl[P_V0], h->pl[P_V1], bytes, cudaMemcpyDeviceToDevice, h->st));
+        if (h->p2p) {
+            // The neighbours have seen this rank's last epoch and may already run their next loop, whose
+            // first kernel stores into THIS rank's copy-1 ghost rows: copy the rows this rank owns only,
+            // and fetch the ghost rows of copy 0 from the neighbours' copy 0 (two-sided, so it is also
+            // ordered after their copy-back).
+            const size_t off = (size_t)h->pg.pitch, rows = (size_t)h->pg.pitch * h->pg.nyl * sizeof(double);
+            CU(cudaMemcpyAsync(h->pl[P_U0] + off, h->pl[P_U1] + off, rows, cudaMemcpyDeviceToDevice, h->st));
+            CU(cudaMemcpyAsync(h->pl[P_V0] + off, h->pl[P_V1] + off, rows, cudaMemcpyDeviceToDevice, h->st));
+            if (h->pg.tripole) { // the fold's ghost row belongs to this rank
+                const size_t g = (size_t)h->pg.pitch * (h->pg.nyl + 1), gb = (size_t)h->pg.pitch * sizeof(double);
+                CU(cudaMemcpyAsync(h->pl[P_U0] + g, h->pl[P_U1] + g, gb, cudaMemcpyDeviceToDevice, h->st));
+                CU(cudaMemcpyAsync(h->pl[P_V0] + g, h->pl[P_V1] + g, gb, cudaMemcpyDeviceToDevice, h->st));
+            }
+            void *pp[2] = {h->pl[P_U0], h->pl[P_V0]};
+            if (int rc = exchange_rows(h, pp, 2, sizeof(double))) return rc;
+        } else {
+            CU(cudaMemcpyAsync(h->pl[P_U0], h->pl[P_U1], bytes, cudaMemcpyDeviceToDevice, h->st));
+            CU(cudaMemcpyAsync(h->pl[P_V0], h->pl[P_V1], bytes, cudaMemcpyDeviceToDevice, h->st));
+        }
         for (int k = 0; k < EVP_NSTRESS; ++k)
             CU(cudaMemcpyAsync(h->pl[P_S0 + k], h->pl[P_S1 + k], bytes, cudaMemcpyDeviceToDevice, h->st));
         h->cur = 0;
@@ -591,9 +635,6 @@ static int init_handle(evp_b200_handle *h, const evp_b200_dims *d, const evp_b20
     h->north = (d->rank < d->nranks - 1) ? d->rank + 1 : -1;
     h->south = (d->rank > 0) ? d->rank - 1 : -1;
     pg.cells = (size_t)pg.pitch * (pg.nyl + 2);
-    // the subcycle kernel addresses a plane and its second copy with 32-bit element offsets
-    if ((unsigned long long)(P_U1 - P_U0 + 1) * pg.cells >= (1ull << 31))
-        return fail(EVP_B200_ERR_ARG, "slab too large for 32-bit plane offsets (%zu cells): use more ranks", pg.cells);
     // Plane spacing: consecutive planes are streamed concurrently by the subcycle kernel (~40 of
     // them); a spacing that is a multiple of 4 KiB puts all streams on the same L2 slice / HBM
     // channel phase.  Skew the spacing by an odd number of 256-byte segments.
@@ -601,8 +642,14 @@ static int init_handle(evp_b200_handle *h, const evp_b200_dims *d, const evp_b20
         long skew = 1 * 32 + 0; // doubles
         if (const char *e = getenv("EVP_B200_PLANE_SKEW")) skew = atol(e);
         if (skew < 0) skew = 0;
+        if (skew > 4096) skew = 4096;
         pg.cells += (size_t)skew;
     }
+    // the subcycle kernel addresses a plane and its second copy with 32-bit element offsets: the largest
+    // one is copy_stride (P_U1 - P_U0 planes) plus an index inside the last plane
+    if ((unsigned long long)(P_U1 - P_U0 + 1) * pg.cells + (unsigned long long)pg.pitch >= (1ull << 31))
+        return fail(EVP_B200_ERR_ARG, "slab too large for 32-bit plane offsets (%zu cells per plane): use more ranks",
+                    pg.cells);
     h->blocked_elems = (size_t)d->nx_block * d->ny_block * d->max_blocks;
 
     CU(cudaStreamCreateWithFlags(&h->st, cudaStreamNonBlocking));
@@ -713,7 +760,20 @@ int evp_b200_init(const evp_b200_dims *d, const evp_b200_params *p, const evp_b2
     return EVP_B200_OK;
 }
 
-static int do_prep(evp_b200_handle *h, const evp_b200_inputs *in, evp_b200_state *st, int32_t *icetmask_out) {
+// On every error return the streams are drained before control goes back to the caller: asynchronous
+// downloads into the caller's arrays must not still be in flight when the caller frees or reuses them.
+static int drain_on_error(evp_b200_handle *h, int rc) {
+    if (rc && h) {
+        const std::string why = g_err;
+        if (h->st) cudaStreamSynchronize(h->st);
+        if (h->st2) cudaStreamSynchronize(h->st2);
+        cudaGetLastError();
+        g_err = why;
+    }
+    return rc;
+}
+
+static int do_prep_impl(evp_b200_handle *h, const evp_b200_inputs *in, evp_b200_state *st, int32_t *icetmask_out) {
     if (!h || !in || !st) return fail(EVP_B200_ERR_ARG, "NULL argument");
     CU(cudaSetDevice(h->device));
     const PlaneGeom &pg = h->pg;
@@ -796,8 +856,12 @@ static int do_prep(evp_b200_handle *h, const evp_b200_inputs *in, evp_b200_state
     return 0;
 }
 
-static int do_run(evp_b200_handle *h, const evp_b200_inputs *in, const double *strength, evp_b200_state *st,
-                  evp_b200_outputs *out) {
+static int do_prep(evp_b200_handle *h, const evp_b200_inputs *in, evp_b200_state *st, int32_t *icetmask_out) {
+    return drain_on_error(h, do_prep_impl(h, in, st, icetmask_out));
+}
+
+static int do_run_impl(evp_b200_handle *h, const evp_b200_inputs *in, const double *strength, evp_b200_state *st,
+                       evp_b200_outputs *out) {
     if (!h || !st) return fail(EVP_B200_ERR_ARG, "NULL argument");
     if (!h->prepared) return fail(EVP_B200_ERR_STATE, "evp_b200_run called before evp_b200_prep");
     CU(cudaSetDevice(h->device));
@@ -932,11 +996,7 @@ static int do_run(evp_b200_handle *h, const evp_b200_inputs *in, const double *s
     }
     CU(cudaStreamWaitEvent(h->st, h->ev_early_done, 0));
     CU(cudaEventRecord(h->ev[6], h->st));
-    int wait_gave_up = 0; // sync[6]: a bounded flag wait inside the subcycle kernels timed out
-    CU(cudaMemcpyAsync(&wait_gave_up, h->sync + 6, sizeof(int), cudaMemcpyDeviceToHost, h->st));
-    CU(cudaStreamSynchronize(h->st));
-    if (wait_gave_up)
-        return fail(EVP_B200_ERR_STATE, "subcycle kernel: a wait for a neighbouring CTA / GPU timed out (results invalid)");
+    if ((rc = check_wait_flag(h))) return rc;
     CU(cudaEventElapsedTime(&h->tm.upload_ms, h->ev[0], h->ev[1]));
     CU(cudaEventElapsedTime(&h->tm.prep_ms, h->ev[1], h->ev[3]));
     CU(cudaEventElapsedTime(&h->tm.subcycle_ms, h->ev[3], h->ev[4]));
@@ -948,6 +1008,11 @@ static int do_run(evp_b200_handle *h, const evp_b200_inputs *in, const double *s
     h->tm.reserved = h->rows_ht; // rows on the 2-plane metric path
     h->prepared = false;
     return 0;
+}
+
+static int do_run(evp_b200_handle *h, const evp_b200_inputs *in, const double *strength, evp_b200_state *st,
+                  evp_b200_outputs *out) {
+    return drain_on_error(h, do_run_impl(h, in, strength, st, out));
 }
 
 int evp_b200_prep(evp_b200_handle *h, const evp_b200_inputs *in, evp_b200_state *st, int32_t *icetmask_out) {
@@ -976,7 +1041,7 @@ int evp_b200_subcycle_resident(evp_b200_handle *h, int32_t repeats, float *ms_pe
         if (rc) return rc;
     }
     CU(cudaEventRecord(h->ev[4], h->st));
-    CU(cudaStreamSynchronize(h->st));
+    if (int rc = check_wait_flag(h)) return rc; // a timing of an invalid loop is not reported
     float ms = 0.f;
     CU(cudaEventElapsedTime(&ms, h->ev[3], h->ev[4]));
     if (ms_per_loop) *ms_per_loop = ms / (float)repeats;
@@ -1034,6 +1099,33 @@ int evp_b200_download_state(evp_b200_handle *h, evp_b200_state *st) {
 int evp_b200_invalidate_device_state(evp_b200_handle *h) {
     if (!h) return fail(EVP_B200_ERR_ARG, "NULL argument");
     h->stress_on_device = false;
+    return 0;
+}
+
+int evp_b200_selftest_ieee(int64_t n, uint64_t seed, uint64_t out[6]) {
+    if (n < 1 || !out) return fail(EVP_B200_ERR_ARG, "bad argument");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev < 1) {
+        cudaGetLastError();
+        return fail(EVP_B200_ERR_CUDA, "no CUDA device: libevp_b200 has no CPU fallback");
+    }
+    unsigned long long o[6] = {0, 0, 0, 0, 0, 0};
+    const int e = aux_selftest_ieee((long long)n, (unsigned long long)seed, o);
+    if (e != 0) return fail(EVP_B200_ERR_CUDA, "selftest kernel: %s", cudaGetErrorString((cudaError_t)e));
+    for (int k = 0; k < 6; ++k) out[k] = o[k];
+    return 0;
+}
+
+int evp_b200_unpin(evp_b200_handle *h, const void *host_ptr) {
+    if (!h) return fail(EVP_B200_ERR_ARG, "NULL argument");
+    auto it = h->pinned.find(host_ptr);
+    if (it == h->pinned.end()) return 0;
+    CU(cudaSetDevice(h->device));
+    CU(cudaStreamSynchronize(h->st));
+    CU(cudaStreamSynchronize(h->st2));
+    cudaHostUnregister(const_cast<void *>(host_ptr));
+    cudaGetLastError();
+    h->pinned.erase(it);
     return 0;
 }
 

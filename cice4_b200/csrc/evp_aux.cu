@@ -8,6 +8,8 @@
 
 #include <cmath>
 
+#include "evp_ieee.cuh"
+
 namespace {
 
 constexpr int TPB = 256;
@@ -554,18 +556,123 @@ __global__ void k_diagnostics(PlaneGeom pg, const double *__restrict__ u, const 
     }
 }
 
+// Bounded like the in-kernel waits (wait_flag_ge in evp_subcycle_body.cuh): a neighbour that returned
+// early on an error, crashed or timed out must not hang this GPU.  After ~2^24 polls (seconds) the error
+// flag sync[6] is raised and the host reports EVP_B200_ERR_STATE.
+__device__ __forceinline__ int ld_acquire_sys(const int *p) {
+    int v;
+    asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void wait_peer_flag(const int *flag, int want, int *sync) {
+    unsigned spins = 0;
+    while (ld_acquire_sys(flag) < want) {
+        __nanosleep(64);
+        if (++spins > (1u << 24)) {
+            *(volatile int *)(sync + 6) = 1;
+            break;
+        }
+    }
+}
 __global__ void k_wait_peers(int *sync, int has_north, int has_south, int ncx) {
     const int e = *(volatile int *)(sync + 1);
     for (int x = threadIdx.x; x < ncx; x += blockDim.x) {
-        if (has_north)
-            while (*(volatile int *)(sync + EVP_SYNC_FN + x) < e) __nanosleep(50);
-        if (has_south)
-            while (*(volatile int *)(sync + EVP_SYNC_FS + x) < e) __nanosleep(50);
+        if (has_north) wait_peer_flag(sync + EVP_SYNC_FN + x, e, sync);
+        if (has_south) wait_peer_flag(sync + EVP_SYNC_FS + x, e, sync);
     }
     __threadfence_system();
 }
 
+// ---------------------------------------------------------------------------------------------
+// self-test of evp_ieee.cuh against the compiler's own IEEE sqrt() and operator/
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned long long splitmix64(unsigned long long &x) {
+    unsigned long long z = (x += 0x9e3779b97f4a7c15ull);
+    z = (z ^ (z >> 30)) * 0xbf58476d1ce4e5b9ull;
+    z = (z ^ (z >> 27)) * 0x94d049bb133111ebull;
+    return z ^ (z >> 31);
+}
+// a double with the given 11-bit exponent field and random sign / mantissa
+__device__ __forceinline__ double with_exponent(unsigned long long r, int e) {
+    e = e < 0 ? 0 : (e > 2047 ? 2047 : e);
+    return __longlong_as_double((long long)((r & 0x800fffffffffffffull) | ((unsigned long long)e << 52)));
+}
+__device__ __forceinline__ bool same_bits(double a, double b) {
+    return __double_as_longlong(a) == __double_as_longlong(b) || (a != a && b != b);
+}
+// out[0] sqrt mismatches (ok but different bits), out[1] sqrt fast-path count, out[2] div mismatches,
+// out[3] div fast-path count, out[4] shared-reciprocal (two quotients, one rcp_refined) mismatches,
+// out[5] operands tested per function
+__global__ void k_selftest_ieee(long long n, unsigned long long seed, unsigned long long *out) {
+    unsigned long long c[5] = {0, 0, 0, 0, 0};
+    for (long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += (long long)gridDim.x * blockDim.x) {
+        unsigned long long st = seed + 0x632be59bd9b4e019ull * (unsigned long long)(k + 1);
+        const unsigned long long r1 = splitmix64(st), r2 = splitmix64(st), r3 = splitmix64(st), r4 = splitmix64(st);
+        double a, num, den;
+        switch ((int)(k & 7)) {
+        case 0: // any bit pattern: all exponents, subnormals, infinities, NaNs, both signs
+            a = __longlong_as_double((long long)r1); num = __longlong_as_double((long long)r2);
+            den = __longlong_as_double((long long)r3);
+            break;
+        case 1: // the magnitudes EVP works with (1e-30 .. 1e+30)
+        case 2:
+            a = with_exponent(r1, 1023 - 100 + (int)(r4 % 200)) ; a = fabs(a);
+            num = with_exponent(r2, 1023 - 100 + (int)((r4 >> 8) % 200));
+            den = with_exponent(r3, 1023 - 100 + (int)((r4 >> 16) % 200));
+            break;
+        case 3: // sqrt: around the lower range check (high word 0x03500000) and the upper one (0x7ff00000)
+            a = fabs(with_exponent(r1, ((r4 & 1) ? 0x035 : 0x7ff) - 2 + (int)((r4 >> 1) % 5)));
+            // division: numerator around the |n| range check (exponent field 0x036)
+            num = with_exponent(r2, 0x036 - 2 + (int)((r4 >> 8) % 5));
+            den = with_exponent(r3, 1023 - 8 + (int)((r4 >> 16) % 16));
+            break;
+        case 4: // division: quotient around the tiny-result check (exponent field of q near 1)
+            a = fabs(with_exponent(r1, (int)(r4 % 4)));                     // subnormal / smallest normals
+            num = with_exponent(r2, 1023 - 400 + (int)((r4 >> 8) % 16));
+            den = with_exponent(r3, 1023 + 620 - 8 + (int)((r4 >> 16) % 16));  // q ~ 2^-1020
+            break;
+        case 5: // huge quotients / overflow, zero and signed-zero operands
+            a = (r4 & 3) == 0 ? 0.0 : fabs(with_exponent(r1, 2046 - (int)(r4 % 3)));
+            num = (r4 & 12) == 0 ? 0.0 : with_exponent(r2, 2046 - (int)((r4 >> 8) % 40));
+            den = (r4 & 48) == 0 ? -0.0 : with_exponent(r3, 1 + (int)((r4 >> 16) % 40));
+            break;
+        case 6: // perfect squares and exactly representable quotients (ties / exact cases)
+            { const double m = (double)(r1 & 0x3ffffff); a = m * m; den = (double)((r3 & 0xfffff) + 1); num = den * (double)(r2 & 0xfffff); }
+            break;
+        default: // operands one ulp around powers of two
+            a = fabs(with_exponent(((r4 & 1) ? 0ull : 0x000fffffffffffffull) ^ (r1 & 3), 1023 - 60 + (int)(r4 % 120)));
+            num = with_exponent(((r4 & 2) ? 0ull : 0x000fffffffffffffull) ^ (r2 & 3), 1023 - 60 + (int)((r4 >> 8) % 120));
+            den = with_exponent(((r4 & 4) ? 0ull : 0x000fffffffffffffull) ^ (r3 & 3), 1023 - 60 + (int)((r4 >> 16) % 120));
+            break;
+        }
+        bool ok;
+        const double sf = evp_ieee::sqrt_fast(a, ok);
+        if (ok) { ++c[1]; if (!same_bits(sf, sqrt(a))) ++c[0]; }
+        const double r = evp_ieee::rcp_refined(den);
+        const double qf = evp_ieee::div_fast(num, den, r, ok);
+        if (ok) { ++c[3]; if (!same_bits(qf, num / den)) ++c[2]; }
+        // two numerators over one denominator share the refined reciprocal (stepu, :1426-1427)
+        bool ok2;
+        const double q2 = evp_ieee::div_fast(a, den, r, ok2);
+        if (ok2 && !same_bits(q2, a / den)) ++c[4];
+    }
+    for (int q = 0; q < 5; ++q)
+        if (c[q]) atomicAdd(out + q, c[q]);
+}
+
 } // namespace
+
+int aux_selftest_ieee(long long n, unsigned long long seed, unsigned long long out[6]) {
+    unsigned long long *d = nullptr;
+    cudaError_t e = cudaMalloc(&d, 6 * sizeof(unsigned long long));
+    if (e != cudaSuccess) return (int)e;
+    cudaMemset(d, 0, 6 * sizeof(unsigned long long));
+    k_selftest_ieee<<<148 * 8, 256>>>(n, seed, d);
+    e = cudaMemcpy(out, d, 6 * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
+    cudaFree(d);
+    out[5] = (unsigned long long)n;
+    return (int)e;
+}
 
 // ---------------------------------------------------------------------------------------------
 // launchers

@@ -117,3 +117,7 @@ void aux_balance_chunks(const PlaneGeom &pg, const uint8_t *icetmask, const uint
 // max ice speed / max strength per hemisphere (source/ice_diagnostics.F90:294-346); out4 must be zeroed
 void aux_diagnostics(const PlaneGeom &pg, const double *u, const double *v, const double *strength,
                      const double *fcor, double fcor_south, double *out4, cudaStream_t s);
+
+// evp_ieee.cuh (the straight-line IEEE sqrt / division of the subcycle kernel) against sqrt() and operator/
+// on n generated operands; see k_selftest_ieee for out[0..5].  Returns a cudaError_t value.
+int aux_selftest_ieee(long long n, unsigned long long seed, unsigned long long out[6]);

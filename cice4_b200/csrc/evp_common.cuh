@@ -100,14 +100,15 @@ __host__ __device__ inline void evp_fold_necorner(const double *top, const doubl
     vghost = isign * below[k]; // j=2: row jhi+1 <- isign*buf(iSrc, 1)
 }
 
-typedef void (*subcycle_launch_fn)(const SubArgs &a, bool last, int variant, int threads,
-                                   unsigned grid_x, unsigned grid_y, void *stream);
+// returns a cudaError_t value (the launch status)
+typedef int (*subcycle_launch_fn)(const SubArgs &a, bool last, int variant, int threads,
+                                  unsigned grid_x, unsigned grid_y, void *stream);
 
 // defined in evp_subcycle_strict.cu (-fmad=false) and evp_subcycle_fast.cu (-fmad=true)
-void evp_subcycle_launch_strict(const SubArgs &a, bool last, int variant, int threads,
-                                unsigned grid_x, unsigned grid_y, void *stream);
-void evp_subcycle_launch_fast(const SubArgs &a, bool last, int variant, int threads,
-                              unsigned grid_x, unsigned grid_y, void *stream);
+int evp_subcycle_launch_strict(const SubArgs &a, bool last, int variant, int threads,
+                               unsigned grid_x, unsigned grid_y, void *stream);
+int evp_subcycle_launch_fast(const SubArgs &a, bool last, int variant, int threads,
+                             unsigned grid_x, unsigned grid_y, void *stream);
 // persistent kernel: a.nsub subcycles in one cooperative launch (ctas_per_sm == nullptr), or, with
 // ctas_per_sm != nullptr, only the occupancy query (resident CTAs per SM; the grid must fit in one
 // wave).  Returns a cudaError_t value.

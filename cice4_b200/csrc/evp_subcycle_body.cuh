@@ -42,8 +42,9 @@ namespace EVP_SUB_NS {
 // element offsets inside the plane pool fit 32 bits (checked at init): one IMAD.WIDE per address
 typedef int idx_t;
 
-// State that other CTAs rewrite while the persistent kernel runs must not be served by the
-// (non-coherent) L1: COH selects ld.global.cg; the one-subcycle kernel keeps the read-only path.
+// State that other CTAs (persistent kernel) or the neighbour GPUs (peer-to-peer halo) rewrite while
+// the kernel runs must not be served by the non-coherent path: COH selects ld.global.cg; the
+// one-subcycle kernel on a single rank keeps the read-only path (ld.global.nc).
 template <bool COH>
 __device__ __forceinline__ double ld_state(const double *p) {
     return COH ? __ldcg(p) : __ldg(p);
@@ -613,7 +614,11 @@ __device__ __forceinline__ void march(const SubArgs &a, idx_t so, idx_t sn, int 
 
 // At ~210 registers per thread every scheduler (16384 registers) holds two warps: 8 warps per SM
 // whatever the CTA shape (96 x 3 or 160 x 2 would need <= 168 registers and spill).
-template <int NT, bool LAST, bool HT, bool LATE = false, int MINB = 1>
+// COH: u, v and the stresses are read with ld.global.cg instead of the read-only (non-coherent) path.
+// Needed with the peer-to-peer halo: the neighbour GPU stores into this slab's ghost rows while this
+// kernel may already be running (the boundary CTAs only wait on the flag before READING those rows), and
+// ld.global.nc requires the data to be read-only for the whole kernel.
+template <int NT, bool LAST, bool HT, bool LATE = false, int MINB = 1, bool COH = false>
 __global__ void __launch_bounds__(NT, MINB) k_subcycle(const __grid_constant__ SubArgs a) {
     // programmatic dependent launch: let the next subcycle kernel be scheduled as SMs drain, and
     // wait here until the previous grid has completed and flushed (no-ops without the attribute)
@@ -635,7 +640,7 @@ __global__ void __launch_bounds__(NT, MINB) k_subcycle(const __grid_constant__ S
     }
     // an empty chunk (all rows inactive, trimmed by the load balancer) has nothing to do
     const idx_t so = a.flip ? (idx_t)a.copy_stride : 0, sn = a.flip ? 0 : (idx_t)a.copy_stride;
-    if (nrows > 0) march<NT, LAST, HT, false, LATE>(a, so, sn, tid, i, j0, nrows);
+    if (nrows > 0) march<NT, LAST, HT, COH, LATE>(a, so, sn, tid, i, j0, nrows);
     subcycle_epilogue<NT, false>(a, sn, tid, top, bot, epoch);
 }
 
@@ -939,7 +944,7 @@ __global__ void __launch_bounds__(NT) k_persist(const __grid_constant__ SubArgs 
 // this one drains; its CTAs block in griddepcontrol.wait at their first instruction until this grid
 // has completed and its stores are visible, so only launch latency and ramp-up overlap.
 template <typename K>
-static void launch_k(K kernel, const SubArgs &a, dim3 grid, dim3 block, bool pdl, cudaStream_t s) {
+static int launch_k(K kernel, const SubArgs &a, dim3 grid, dim3 block, bool pdl, cudaStream_t s) {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = grid;
     cfg.blockDim = block;
@@ -950,43 +955,52 @@ static void launch_k(K kernel, const SubArgs &a, dim3 grid, dim3 block, bool pdl
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
     cfg.numAttrs = pdl ? 1 : 0;
-    cudaLaunchKernelEx(&cfg, kernel, a);
+    return (int)cudaLaunchKernelEx(&cfg, kernel, a);
 }
 
 template <typename K>
-static void launch_tma(K kernel, size_t smem, const SubArgs &a, dim3 grid, dim3 block, cudaStream_t s) {
+static int launch_tma(K kernel, size_t smem, const SubArgs &a, dim3 grid, dim3 block, cudaStream_t s) {
     kernel<<<grid, block, smem, s>>>(a);
+    return (int)cudaPeekAtLastError();
 }
 
 // HT (2-plane metric path) is chosen by a.row_ht; variant bit 8 (256): TMA staging, 3 rows deep, 2 CTAs
 // per SM; bit 9 (512): TMA staging, 2 rows deep, 3 CTAs per SM (<= 168 registers) -- 128 threads only
 template <int NT>
-static void launch_nt(const SubArgs &a, bool last, bool pdl, int variant, unsigned gx, unsigned gy, cudaStream_t s) {
+static int launch_nt(const SubArgs &a, bool last, bool pdl, int variant, unsigned gx, unsigned gy, cudaStream_t s) {
     dim3 grid(gx, gy), block(NT);
     if constexpr (NT == 128) {
         if (variant & 1024) { // no prefetch across the arithmetic, 3 CTAs per SM (<= 168 registers)
-            if (last) launch_k(k_subcycle<NT, true, false, true, 3>, a, grid, block, pdl, s);
-            else launch_k(k_subcycle<NT, false, false, true, 3>, a, grid, block, pdl, s);
-            return;
+            if (a.p2p) {
+                if (last) return launch_k(k_subcycle<NT, true, false, true, 3, true>, a, grid, block, pdl, s);
+                return launch_k(k_subcycle<NT, false, false, true, 3, true>, a, grid, block, pdl, s);
+            }
+            if (last) return launch_k(k_subcycle<NT, true, false, true, 3>, a, grid, block, pdl, s);
+            return launch_k(k_subcycle<NT, false, false, true, 3>, a, grid, block, pdl, s);
         }
         if (variant & 256) {
-            if (last) launch_tma(k_subcycle_tma<NT, true, 3, 2>, tma_smem_bytes<NT, 3>(), a, grid, block, s);
-            else launch_tma(k_subcycle_tma<NT, false, 3, 2>, tma_smem_bytes<NT, 3>(), a, grid, block, s);
-            return;
+            if (last) return launch_tma(k_subcycle_tma<NT, true, 3, 2>, tma_smem_bytes<NT, 3>(), a, grid, block, s);
+            return launch_tma(k_subcycle_tma<NT, false, 3, 2>, tma_smem_bytes<NT, 3>(), a, grid, block, s);
         }
         if (variant & 512) {
-            if (last) launch_tma(k_subcycle_tma<NT, true, 2, 3>, tma_smem_bytes<NT, 2>(), a, grid, block, s);
-            else launch_tma(k_subcycle_tma<NT, false, 2, 3>, tma_smem_bytes<NT, 2>(), a, grid, block, s);
-            return;
+            if (last) return launch_tma(k_subcycle_tma<NT, true, 2, 3>, tma_smem_bytes<NT, 2>(), a, grid, block, s);
+            return launch_tma(k_subcycle_tma<NT, false, 2, 3>, tma_smem_bytes<NT, 2>(), a, grid, block, s);
         }
     }
-    if (a.row_ht) {
-        if (last) launch_k(k_subcycle<NT, true, true>, a, grid, block, pdl, s);
-        else launch_k(k_subcycle<NT, false, true>, a, grid, block, pdl, s);
-    } else {
-        if (last) launch_k(k_subcycle<NT, true, false>, a, grid, block, pdl, s);
-        else launch_k(k_subcycle<NT, false, false>, a, grid, block, pdl, s);
+    if (a.p2p) { // the neighbours write this slab's ghost rows during the kernel: coherent state loads
+        if (a.row_ht) {
+            if (last) return launch_k(k_subcycle<NT, true, true, false, 1, true>, a, grid, block, pdl, s);
+            return launch_k(k_subcycle<NT, false, true, false, 1, true>, a, grid, block, pdl, s);
+        }
+        if (last) return launch_k(k_subcycle<NT, true, false, false, 1, true>, a, grid, block, pdl, s);
+        return launch_k(k_subcycle<NT, false, false, false, 1, true>, a, grid, block, pdl, s);
     }
+    if (a.row_ht) {
+        if (last) return launch_k(k_subcycle<NT, true, true>, a, grid, block, pdl, s);
+        return launch_k(k_subcycle<NT, false, true>, a, grid, block, pdl, s);
+    }
+    if (last) return launch_k(k_subcycle<NT, true, false>, a, grid, block, pdl, s);
+    return launch_k(k_subcycle<NT, false, false>, a, grid, block, pdl, s);
 }
 
 template <int NT>
@@ -1006,14 +1020,15 @@ static int persist_nt(const SubArgs &a, unsigned gx, unsigned gy, cudaStream_t s
 
 } // namespace EVP_SUB_NS
 
-void EVP_SUB_LAUNCH(const SubArgs &a, bool last, int variant, int threads, unsigned grid_x,
-                    unsigned grid_y, void *stream) {
+// returns a cudaError_t value (the launch status)
+int EVP_SUB_LAUNCH(const SubArgs &a, bool last, int variant, int threads, unsigned grid_x,
+                   unsigned grid_y, void *stream) {
     const bool pdl = (variant & 64) != 0;
     cudaStream_t s = (cudaStream_t)stream;
     switch (threads) {
-    case 64: EVP_SUB_NS::launch_nt<64>(a, last, pdl, variant, grid_x, grid_y, s); break;
-    case 256: EVP_SUB_NS::launch_nt<256>(a, last, pdl, variant, grid_x, grid_y, s); break;
-    default: EVP_SUB_NS::launch_nt<128>(a, last, pdl, variant, grid_x, grid_y, s); break;
+    case 64: return EVP_SUB_NS::launch_nt<64>(a, last, pdl, variant, grid_x, grid_y, s);
+    case 256: return EVP_SUB_NS::launch_nt<256>(a, last, pdl, variant, grid_x, grid_y, s);
+    default: return EVP_SUB_NS::launch_nt<128>(a, last, pdl, variant, grid_x, grid_y, s);
     }
 }
 

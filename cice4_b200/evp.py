@@ -35,6 +35,7 @@ EXPORTS = [
     "evp_b200_prep", "evp_b200_run", "evp_b200_step", "evp_b200_subcycle_resident",
     "evp_b200_principal_stress", "evp_b200_get_timings", "evp_b200_diagnostics", "evp_b200_download_state",
     "evp_b200_invalidate_device_state", "evp_b200_comm_unique_id", "evp_b200_comm_init", "evp_b200_finalize",
+    "evp_b200_unpin", "evp_b200_selftest_ieee",
 ]
 
 
@@ -131,6 +132,8 @@ def load_library(path: str = LIB_PATH) -> C.CDLL:
     L.evp_b200_comm_unique_id.argtypes = [C.POINTER(C.c_uint8)]
     L.evp_b200_comm_init.argtypes = [H, C.POINTER(C.c_uint8)]
     L.evp_b200_finalize.argtypes = [H]
+    L.evp_b200_unpin.argtypes = [H, C.c_void_p]
+    L.evp_b200_selftest_ieee.argtypes = [C.c_int64, C.c_uint64, C.POINTER(C.c_uint64)]
     for n in EXPORTS:
         if n not in ("evp_b200_last_error", "evp_b200_default_params"):
             getattr(L, n).restype = C.c_int
@@ -338,13 +341,25 @@ class IceDynEvp:
         buf = (C.c_uint8 * 128).from_buffer_copy(uid)
         _check(load_library().evp_b200_comm_init(self._h, buf))
 
-    def _as_block(self, a: np.ndarray, dtype) -> np.ndarray:
+    def _as_block(self, a: np.ndarray, dtype, temps: Optional[list] = None) -> np.ndarray:
+        """`a` in the block layout; a copy is made only when `a` does not conform, and such per-call
+        temporaries are collected in `temps` so that the library forgets them before Python frees them."""
         sh = self.layout.shape
+        orig = a
         if a.ndim == 2:
             a = a.reshape(a.shape[0], a.shape[1], 1, order="F")
         if a.shape != sh:
             raise EvpB200Error(f"array shape {a.shape} does not match the block layout {sh}")
-        return np.asfortranarray(a, dtype=dtype)
+        a = np.asfortranarray(a, dtype=dtype)
+        if temps is not None and not np.shares_memory(a, orig):
+            temps.append(a)
+        return a
+
+    def _unpin(self, temps) -> None:
+        if self.params is not None and self.params.pin_host and self._h:
+            L = load_library()
+            for a in temps:
+                L.evp_b200_unpin(self._h, C.c_void_p(a.ctypes.data))
 
     # --- evp ------------------------------------------------------------------------------
     def evp(self, dt: float, inputs: Dict[str, np.ndarray], strength: Optional[np.ndarray] = None,
@@ -361,16 +376,20 @@ class IceDynEvp:
         sh = self.layout.shape
         inp = Inputs()
         keep = []
+        temps = []   # arrays made for this call only (non-conforming inputs): unpinned before they are freed
         for n in INPUT_D:
             a = inputs.get(n)
             if a is None or (strength is not None and n in ("aice0", "aicen", "vicen")):
                 continue   # the category arrays feed only the device ice_strength
             if n in ("aicen", "vicen"):
+                orig = a
                 if a.ndim == 3:
                     a = a.reshape(a.shape[0], a.shape[1], a.shape[2], 1, order="F")
                 a = np.asfortranarray(a, dtype=np.float64)
+                if not np.shares_memory(a, orig):
+                    temps.append(a)
             else:
-                a = self._as_block(a, np.float64)
+                a = self._as_block(a, np.float64, temps)
             keep.append(a)
             setattr(inp, n, _dptr(a))
         st = State()
@@ -391,18 +410,23 @@ class IceDynEvp:
             setattr(out, n, _dptr(a))
         sp = None
         if strength is not None:
-            sarr = self._as_block(strength, np.float64)
+            sarr = self._as_block(strength, np.float64, temps)
             keep.append(sarr)
             sp = _dptr(sarr)
-        if two_phase:
-            if sp is None:
-                raise EvpB200Error("two_phase needs a host strength array")
-            icet = np.zeros(sh, dtype=np.int32, order="F")
-            _check(L.evp_b200_prep(self._h, C.byref(inp), C.byref(st), _iptr(icet)))
-            _check(L.evp_b200_run(self._h, sp, C.byref(st), C.byref(out)))
-            res["icetmask"] = icet
-        else:
-            _check(L.evp_b200_step(self._h, C.byref(inp), sp, C.byref(st), C.byref(out)))
+        try:
+            if two_phase:
+                if sp is None:
+                    raise EvpB200Error("two_phase needs a host strength array")
+                icet = self.flux.get("icetmask")
+                if icet is None or icet.shape != sh:
+                    icet = np.zeros(sh, dtype=np.int32, order="F")
+                _check(L.evp_b200_prep(self._h, C.byref(inp), C.byref(st), _iptr(icet)))
+                _check(L.evp_b200_run(self._h, sp, C.byref(st), C.byref(out)))
+                res["icetmask"] = icet
+            else:
+                _check(L.evp_b200_step(self._h, C.byref(inp), sp, C.byref(st), C.byref(out)))
+        finally:
+            self._unpin(temps)
         self.flux.update(res)
         return res
 
@@ -451,6 +475,15 @@ class IceDynEvp:
         out = (C.c_double * 4)()
         _check(load_library().evp_b200_diagnostics(self._h, out))
         return dict(umaxn=out[0], umaxs=out[1], pmaxn=out[2], pmaxs=out[3])
+
+    @staticmethod
+    def selftest_ieee(n: int = 1 << 27, seed: int = 1) -> Dict[str, int]:
+        """evp_b200_selftest_ieee: the straight-line IEEE sqrt / division of the subcycle kernel against
+        sqrt() and operator/ on `n` generated operands (on the current CUDA device)."""
+        out = (C.c_uint64 * 6)()
+        _check(load_library().evp_b200_selftest_ieee(n, seed, out))
+        return dict(sqrt_mismatch=out[0], sqrt_fast=out[1], div_mismatch=out[2], div_fast=out[3],
+                    div_shared_rcp_mismatch=out[4], n=out[5])
 
     def finalize(self) -> None:
         if self._h:

@@ -90,7 +90,10 @@ typedef struct {
     double mu_rdg;
     /* library knobs */
     int32_t math_mode;      /* 0 = unfused IEEE (bit-exact vs the unfused CPU oracle); 1 = FMA-contracted */
-    int32_t pin_host;       /* 1 = cudaHostRegister caller arrays on first use */
+    int32_t pin_host;       /* 1 = cudaHostRegister caller arrays on first use (keyed by address).  The caller
+                               promises that a pinned array stays allocated until evp_b200_finalize, or tells the
+                               library with evp_b200_unpin before freeing it (the Fortran module arrays live for
+                               the whole run; the Python mirror unpins its per-call temporaries) */
     int32_t use_graph;      /* 1 = replay the ndte loop as one CUDA graph */
     int32_t tile_threads;   /* 0 = default; threads per CTA of the subcycle kernel */
     int32_t tile_rows;      /* 0 = default; U rows marched per CTA */
@@ -204,6 +207,10 @@ int evp_b200_principal_stress(evp_b200_handle *h, const double *stressp_1, const
 
 int evp_b200_get_timings(const evp_b200_handle *h, evp_b200_timings *t);
 
+/* pin_host = 1: forget (cudaHostUnregister) a caller array before the caller frees it; unknown pointers
+ * are ignored.  Waits for the handle's streams first. */
+int evp_b200_unpin(evp_b200_handle *h, const void *host_ptr);
+
 /* Velocity / strength diagnostics of runtime_diags (source/ice_diagnostics.F90:294-346) from the
  * device-resident result of the last call, this slab only (the caller combines slabs with
  * global_maxval): out[0] = max ice speed (m/s), northern hemisphere (lmask_n: ULAT >= -puny),
@@ -222,6 +229,15 @@ int evp_b200_invalidate_device_state(evp_b200_handle *h);
  * mpi/ice_boundary.F90:1028-1417 between tasks. */
 int evp_b200_comm_unique_id(uint8_t id[128]);
 int evp_b200_comm_init(evp_b200_handle *h, const uint8_t id[128]);
+
+/* Self-test of the straight-line IEEE sqrt / division sequences the subcycle kernel uses
+ * (csrc/evp_ieee.cuh) against the compiler's sqrt() and operator/ on n generated operands (random bit
+ * patterns, EVP magnitudes, operands around every range check, subnormal / huge / zero / exact cases),
+ * on the current device.  out[0] = sqrt results that took the fast path and differ in any bit, out[1] =
+ * sqrt operands on the fast path, out[2] / out[3] the same for n/d, out[4] = mismatches of a second
+ * quotient sharing the refined reciprocal, out[5] = n.  Bit-exactness of the kernel against
+ * source/ice_dyn_evp.F90:1095-1098,1131-1134,1426-1427 rests on out[0] = out[2] = out[4] = 0. */
+int evp_b200_selftest_ieee(int64_t n, uint64_t seed, uint64_t out[6]);
 
 int evp_b200_finalize(evp_b200_handle *h);
 

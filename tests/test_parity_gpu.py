@@ -313,6 +313,50 @@ def test_principal_stress(oracle, evp_lib):
     np.testing.assert_array_equal(_merge(g2, lay), s2)
 
 
+FULL_SIZE = [
+    # BASELINE.json configs at their full size, with the dt the bench uses (synth.CONFIG_DT)
+    ("gx1-320x384", dict(name="gx1"), 3600.0),
+    ("om1deg-360x300-tripole", dict(name="om1deg"), 3600.0),
+    ("om025-1440x1080-tripole", dict(name="om025"), 1800.0),
+]
+
+
+@pytest.mark.parametrize("label,kw,dt", FULL_SIZE, ids=[c[0] for c in FULL_SIZE])
+def test_full_size_vs_oracle(oracle, evp_lib, label, kw, dt):
+    """The benchmarked configurations themselves (gx1, access-om 1 deg, access-om 0.25 deg at full size,
+    dense mask as in bench.py): cold start + warm second call through the C ABI against the strict
+    serial oracle (source/ice_dyn_evp.F90:347-404 for the loop).  math_mode 0: every state and output
+    field BIT-EXACT; math_mode 1 (FMA-contracted): max |du|,|dv| <= 1e-10 m/s, relative stress error
+    <= 1e-10 (BASELINE north_star tolerance)."""
+    case = synth.make_case(**kw)
+    assert synth.CONFIG_DT[kw["name"]] == dt
+    st, f, strengths, _ = oracle_steps(oracle, case, nsteps=2, dt=dt)
+    lay = E.BlockLayout.single_block(case.grid.nx, case.grid.ny)
+    dyn, out = cuda_steps(case, nsteps=2, strengths=strengths, math_mode=0, dt=dt)
+    _compare_exact(dyn, out, st, f, lay)
+    assert np.abs(st["uvel"]).max() > 1e-3
+    dyn.finalize()
+    dyn, out = cuda_steps(case, nsteps=2, strengths=strengths, math_mode=1, dt=dt)
+    _compare_tol(dyn, out, st, f, lay)
+    dyn.finalize()
+
+
+def test_ieee_sequences_match_sqrt_and_division(evp_lib):
+    """csrc/evp_ieee.cuh (sqrt_fast / rcp_refined / div_fast, the interleaved straight-line expansions the
+    subcycle kernel uses for :1095-1098, :1131-1134, :1426-1427) against sqrt() and operator/ on 2^27
+    (1.3e8) generated operands: random bit patterns, EVP magnitudes, operands around each range check
+    (high word 0x03500000 / 0x7ff00000 for sqrt, |n| ~ 2^-969 and tiny quotients for the division),
+    subnormal, huge, zero, exact and one-ulp-around-powers-of-two cases.  Whenever the fast path accepts
+    an operand its result must equal the IEEE result in every bit."""
+    r = E.IceDynEvp.selftest_ieee(1 << 27, seed=20260101)
+    assert r["n"] == 1 << 27
+    assert r["sqrt_mismatch"] == 0 and r["div_mismatch"] == 0 and r["div_shared_rcp_mismatch"] == 0, r
+    # the fast path must actually be exercised (and rejected for the special operands)
+    assert 0.3 * r["n"] < r["sqrt_fast"] < r["n"] and 0.25 * r["n"] < r["div_fast"] < r["n"], r
+    r2 = E.IceDynEvp.selftest_ieee(1 << 22, seed=7)
+    assert r2["sqrt_mismatch"] == 0 and r2["div_mismatch"] == 0 and r2["div_shared_rcp_mismatch"] == 0, r2
+
+
 def test_full_size_properties_om025(evp_lib):
     """BASELINE metric size (1440 x 1080, tripole): size-independent properties instead of the
     (slow) oracle: tripole symmetry, masked cells stay zero, unfused vs FMA within tolerance,
