@@ -487,7 +487,8 @@ def run_b200(args):
             x = measure(ctx, c, args, nd, max(2, min(args.steps, 5)), warmup, full=False)
             table.append({"workload": workload_string(c, nd, False), "n_gpus": world, "value": x["value"], "unit": UNIT,
                           "us_per_subcycle": x["kernel_us"], "roofline_frac_per_gpu": x["frac"],
-                          "l2_resident": x["l2_resident"], "e2e_value": c.grid.nx * c.grid.ny * nd / x["e2e_s"],
+                          "l2_resident": x["l2_resident"], "active_T_cells": x["icellt"], "active_U_cells": x["icellu"],
+                          "e2e_value": c.grid.nx * c.grid.ny * nd / x["e2e_s"],
                           "e2e_ms_per_call": x["e2e_s"] * 1e3,
                           "scaling": "weak (3600 x 338 rows per GPU)" if wl == "p01w" else "strong",
                           "exchange_mode_used": int(x["tm"]["exchange_mode_used"]),

@@ -25,7 +25,7 @@ UNITS = [
     ("evp_aux.cu", ["-fmad=false"]),
     ("evp_abi.cu", ["-fmad=false"]),
 ]
-DEPS = ["evp_common.cuh", "evp_aux.cuh", "evp_subcycle_body.cuh", "evp_ieee.cuh", os.path.join("..", "..", "include", "evp_b200.h")]
+DEPS = ["evp_common.cuh", "evp_aux.cuh", "evp_subcycle_body.cuh", "evp_ieee.cuh", "evp_tiled.cuh", os.path.join("..", "..", "include", "evp_b200.h")]
 
 
 def _nvcc() -> str:

@@ -91,8 +91,15 @@ struct evp_b200_handle {
     int32_t *stage_i = nullptr; // 2 slots of blocked_elems int32
     double *stage_cat = nullptr;
     cudaEvent_t ev[8];
-    cudaGraph_t graph = nullptr;
-    cudaGraphExec_t graph_exec = nullptr;
+    cudaGraph_t graph[2] = {nullptr, nullptr};            // ndte loop starting from state copy 0 / 1
+    cudaGraphExec_t graph_exec[2] = {nullptr, nullptr};
+    // strip-tiled layout of the subcycle loop (evp_tiled.cuh) and the TMA-fed kernel that runs on it
+    bool tiled = false;               // the ndte loop runs k_subcycle_tiled on `tiles`
+    int tiled_stages = 2;             // pipeline depth per warp: 2 (3 CTAs per SM) or 3 (2 CTAs per SM)
+    TileGeom tg = {nullptr, 0, 0};
+    bool tiles_static = false;        // static part of the loop-invariant block packed
+    bool planes_stale = false;        // the current state lives in the tiles only (after evp_b200_subcycle_resident)
+    double *peer_tiles[2] = {nullptr, nullptr};
     int cur = 0; // which ping-pong copy holds the current state
     bool prepared = false, resident = false;
     bool stress_on_device = false;    // state_residency = 1: copy 0 of the stress planes is current
@@ -287,6 +294,15 @@ void fill_subargs(evp_b200_handle *h, SubArgs &a, int cur) {
     a.peer_n_flag = a.peer_s_flag = nullptr;
     a.sync = h->sync;
     a.p2p = h->p2p ? 1 : 0;
+    a.tiles = h->tiled ? h->tg.tiles : nullptr;
+    a.t_ns = h->tg.ns;
+    a.t_nr = h->tg.nr;
+    a.peer_n_tiles = a.peer_s_tiles = nullptr;
+    a.peer_n_nr = a.peer_s_nr = 0;
+    if (h->p2p && h->tiled) {
+        if (h->north >= 0) { a.peer_n_tiles = h->peer_tiles[0]; a.peer_n_nr = h->peer_nyl[0] + 2; }
+        if (h->south >= 0) { a.peer_s_tiles = h->peer_tiles[1]; a.peer_s_nr = h->peer_nyl[1] + 2; }
+    }
     if (h->p2p) {
         // the neighbours' pools are laid out like ours (same plane ids, their own plane size)
         if (h->north >= 0) { // north neighbour's south ghost row = its row 0
@@ -310,13 +326,21 @@ void fill_subargs(evp_b200_handle *h, SubArgs &a, int cur) {
 int launch_subcycle(evp_b200_handle *h, int cur, bool last) {
     SubArgs a;
     fill_subargs(h, a, cur);
-    subcycle_launch_fn fn = h->par.math_mode == 1 ? evp_subcycle_launch_fast : evp_subcycle_launch_strict;
-    const int e = fn(a, last, h->par.kernel_variant, h->threads, (unsigned)h->grid_x, (unsigned)h->grid_y, (void *)h->st);
+    int e;
+    if (h->tiled) {
+        tiled_launch_fn fn = h->par.math_mode == 1 ? evp_tiled_launch_fast : evp_tiled_launch_strict;
+        e = fn(a, last, h->tiled_stages, (h->par.kernel_variant & 64) != 0, (unsigned)h->grid_x, (unsigned)h->grid_y,
+               (void *)h->st, nullptr);
+    } else {
+        subcycle_launch_fn fn = h->par.math_mode == 1 ? evp_subcycle_launch_fast : evp_subcycle_launch_strict;
+        e = fn(a, last, h->par.kernel_variant, h->threads, (unsigned)h->grid_x, (unsigned)h->grid_y, (void *)h->st);
+    }
     if (e != 0) {
         fail(EVP_B200_ERR_CUDA, "subcycle kernel launch: %s", cudaGetErrorString((cudaError_t)e));
         return -1;
     }
     int n = 1;
+    if (h->tiled) return n; // east-west wrap, tripole fold and slab-to-slab rows are all inside the kernel
     if (h->pg.ns_cyclic) n += 2;
     if (h->pg.tripole && !h->fold_in_kernel) n += 1;
     double *u_new = a.flip ? a.u : a.u + a.copy_stride, *v_new = a.flip ? a.v : a.v + a.copy_stride;
@@ -331,7 +355,10 @@ int launch_subcycle(evp_b200_handle *h, int cur, bool last) {
 
 int run_subcycle_loop(evp_b200_handle *h) {
     const int ndte = h->par.ndte;
-    if (h->cur != 0) return fail(EVP_B200_ERR_STATE, "subcycle loop must start from state copy 0");
+    // the plane kernels always start from state copy 0 (an odd ndte is copied back below); the tiled
+    // kernel starts from whichever copy is current
+    if (h->cur != 0 && !h->tiled) return fail(EVP_B200_ERR_STATE, "subcycle loop must start from state copy 0");
+    const int c0 = h->cur;
     // NCCL send/recv inside a captured graph dead-locked on 2 x B200 (NCCL 2.28.9): with the NCCL
     // exchange the loop is launched on the stream; the peer-to-peer exchange has no host calls
     const bool graph_ok = h->par.use_graph && (h->dims.nranks == 1 || h->p2p);
@@ -348,9 +375,9 @@ int run_subcycle_loop(evp_b200_handle *h) {
         h->sub_launches_per_loop = 1;
         h->cur = ndte & 1;
     } else if (graph_ok) {
-        if (!h->graph_exec) {
+        if (!h->graph_exec[c0]) {
             CU(cudaStreamBeginCapture(h->st, cudaStreamCaptureModeThreadLocal));
-            int cur = 0, n = 0;
+            int cur = c0, n = 0;
             bool bad = false;
             for (int k = 1; k <= ndte; ++k) {
                 const int m = launch_subcycle(h, cur, k == ndte);
@@ -360,18 +387,18 @@ int run_subcycle_loop(evp_b200_handle *h) {
             }
             h->sub_launches_per_loop = n;
             const std::string why = g_err;
-            CU(cudaStreamEndCapture(h->st, &h->graph));
+            CU(cudaStreamEndCapture(h->st, &h->graph[c0]));
             if (bad) {
-                cudaGraphDestroy(h->graph);
-                h->graph = nullptr;
+                cudaGraphDestroy(h->graph[c0]);
+                h->graph[c0] = nullptr;
                 cudaGetLastError();
                 g_err = why;
                 return EVP_B200_ERR_CUDA;
             }
-            CU(cudaGraphInstantiate(&h->graph_exec, h->graph, 0));
+            CU(cudaGraphInstantiate(&h->graph_exec[c0], h->graph[c0], 0));
         }
-        CU(cudaGraphLaunch(h->graph_exec, h->st));
-        h->cur = ndte & 1;
+        CU(cudaGraphLaunch(h->graph_exec[c0], h->st));
+        h->cur = c0 ^ (ndte & 1);
     } else {
         int n = 0;
         for (int k = 1; k <= ndte; ++k) {
@@ -386,7 +413,11 @@ int run_subcycle_loop(evp_b200_handle *h) {
     h->epoch_count += ndte;
     // peer-to-peer halo: the ghost rows of the final copy are complete once both neighbours have
     // published the epoch of their last subcycle kernel
-    if (h->p2p) aux_wait_peers(h->sync, h->north >= 0, h->south >= 0, h->grid_x, h->st);
+    if (h->p2p) aux_wait_peers(h->sync, h->north >= 0, h->south >= 0, h->tiled ? h->tg.ns : h->grid_x, h->st);
+    if (h->tiled) {
+        h->planes_stale = true; // the result is in tile copy h->cur
+        return 0;
+    }
     if (h->cur != 0) { // odd ndte: bring the result back to copy 0 so the next loop starts there
         const size_t bytes = h->pg.cells * sizeof(double);
         if (h->p2p) {
@@ -412,6 +443,42 @@ int run_subcycle_loop(evp_b200_handle *h) {
             CU(cudaMemcpyAsync(h->pl[P_S0 + k], h->pl[P_S1 + k], bytes, cudaMemcpyDeviceToDevice, h->st));
         h->cur = 0;
     }
+    return 0;
+}
+
+// tiled layout: bring the current state (tile copy h->cur) back into the planes U0, V0, S0
+int sync_planes(evp_b200_handle *h) {
+    if (!h->tiled || !h->planes_stale) return 0;
+    TileStateArgs ta;
+    ta.u = h->pl[P_U0];
+    ta.v = h->pl[P_V0];
+    for (int k = 0; k < EVP_NSTRESS; ++k) ta.s[k] = h->pl[P_S0 + k];
+    aux_tile_unpack_state(h->pg, h->tg, h->cur, ta, h->st);
+    CU(cudaGetLastError());
+    h->planes_stale = false;
+    return 0;
+}
+
+// tiled layout: planes U0, V0, S0 and the loop-invariant fields of this call -> tiles (state copy 0 current)
+int pack_tiles(evp_b200_handle *h) {
+    double **p = h->pl;
+    if (!h->tiles_static) {
+        TileStaticArgs sa = {p[P_DXT], p[P_DYT], p[P_DXHY], p[P_DYHX], p[P_CXP], p[P_CYP], p[P_CXM], p[P_CYM],
+                             p[P_TINYAREA], p[P_UAREAR]};
+        aux_tile_pack_static(h->pg, h->tg, sa, h->st);
+        h->tiles_static = true;
+    }
+    TileCallArgs ca;
+    ca.strength = p[P_STRENGTH]; ca.aiu = p[P_AIU]; ca.uocn = p[P_UOCN]; ca.vocn = p[P_VOCN];
+    ca.waterx = p[P_WATERX]; ca.watery = p[P_WATERY]; ca.forcex = p[P_FORCEX]; ca.forcey = p[P_FORCEY];
+    ca.umassdtei = p[P_UMASSDTEI]; ca.fm = p[P_FM];
+    ca.icetmask = h->mk[M_ICETMASK]; ca.iceumask = h->mk[M_ICEUMASK];
+    ca.u = p[P_U0]; ca.v = p[P_V0];
+    for (int k = 0; k < EVP_NSTRESS; ++k) ca.s[k] = p[P_S0 + k];
+    aux_tile_pack_call(h->pg, h->tg, ca, h->st);
+    CU(cudaGetLastError());
+    h->cur = 0;
+    h->planes_stale = false;
     return 0;
 }
 
@@ -442,29 +509,49 @@ int choose_tiling(evp_b200_handle *h) {
     int sms = 148;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device);
     const int nx = h->pg.nx, nyl = h->pg.nyl;
-    // default: 128 threads per CTA; short slabs (multi-GPU: 19.5 vs 23.0 us at 135 rows) run better with one
-    // 256-thread CTA per SM, 300 rows and more with two 128-thread CTAs (1 degree: 12.7 vs 13.6 us)
-    // (decided from the mean slab height so that all ranks of a chain use the same strips)
-    const int nyl_mean = h->dims.ny_global / h->dims.nranks;
-    int nt = h->par.tile_threads > 0 ? h->par.tile_threads : (nyl_mean < 300 ? 256 : 128);
-    if (nt != 64 && nt != 128 && nt != 256) nt = 128;
-    // TMA-staged kernel (kernel_variant bits 8 / 9): 128 threads, even strips of at most nt - 2 columns
-    // (16-byte aligned row segments), 2 or 3 CTAs per SM
-    const bool tma = (h->par.kernel_variant & (256 | 512)) != 0;
-    if (tma) {
+    int nt, ncx, strip_w, per_sm;
+    bool tma = false;
+    if (h->tiled) {
+        // strip-tiled TMA-fed kernel: one warp per strip of 31 U columns, 4 warps per CTA; resident CTAs per
+        // SM from the occupancy of the kernel itself (shared memory: 2 or 3 pipeline stages per warp)
+        h->tiled_stages = (h->par.kernel_variant & 4096) ? 3 : 2;
         nt = 128;
-        const int e = h->par.math_mode == 1 ? evp_subcycle_configure_fast() : evp_subcycle_configure_strict();
-        if (e != 0) return fail(EVP_B200_ERR_CUDA, "TMA-staged subcycle kernel: %s", cudaGetErrorString((cudaError_t)e));
+        strip_w = EVT_UW;
+        ncx = (evt_nstrips(nx) + 3) / 4;
+        SubArgs a;
+        fill_subargs(h, a, 0);
+        tiled_launch_fn fn = h->par.math_mode == 1 ? evp_tiled_launch_fast : evp_tiled_launch_strict;
+        per_sm = 0;
+        const int e = fn(a, false, h->tiled_stages, false, 0, 0, nullptr, &per_sm);
+        if (e != 0 || per_sm < 1) {
+            cudaGetLastError();
+            return fail(EVP_B200_ERR_CUDA, "tiled subcycle kernel cannot be configured: %s", cudaGetErrorString((cudaError_t)e));
+        }
+    } else {
+        // default: 128 threads per CTA; short slabs (multi-GPU: 19.5 vs 23.0 us at 135 rows) run better with one
+        // 256-thread CTA per SM, 300 rows and more with two 128-thread CTAs (1 degree: 12.7 vs 13.6 us)
+        // (decided from the mean slab height so that all ranks of a chain use the same strips)
+        const int nyl_mean = h->dims.ny_global / h->dims.nranks;
+        nt = h->par.tile_threads > 0 ? h->par.tile_threads : (nyl_mean < 300 ? 256 : 128);
+        if (nt != 64 && nt != 128 && nt != 256) nt = 128;
+        // TMA-staged kernel (kernel_variant bits 8 / 9): 128 threads, even strips of at most nt - 2 columns
+        // (16-byte aligned row segments), 2 or 3 CTAs per SM
+        tma = (h->par.kernel_variant & (256 | 512)) != 0;
+        if (tma) {
+            nt = 128;
+            const int e = h->par.math_mode == 1 ? evp_subcycle_configure_fast() : evp_subcycle_configure_strict();
+            if (e != 0) return fail(EVP_B200_ERR_CUDA, "TMA-staged subcycle kernel: %s", cudaGetErrorString((cudaError_t)e));
+        }
+        // balanced strips: ncx strips of strip_w U columns, strip_w + 1 <= nt threads hold T columns
+        const int wmax = tma ? nt - 2 : nt - 1;
+        ncx = (nx + wmax - 1) / wmax;
+        strip_w = (nx + ncx - 1) / ncx;
+        if (tma && (strip_w & 1)) ++strip_w;
+        // resident CTAs per SM at ~210 registers per thread: 256 threads
+        per_sm = (nt == 256) ? 1 : (nt == 128 ? 2 : 4);
+        if (tma && (h->par.kernel_variant & 256) == 0) per_sm = 3;
+        if (!tma && nt == 128 && (h->par.kernel_variant & 1024)) per_sm = 3; // late-load kernel: 3 CTAs per SM
     }
-    // balanced strips: ncx strips of strip_w U columns, strip_w + 1 <= nt threads hold T columns
-    const int wmax = tma ? nt - 2 : nt - 1;
-    const int ncx = (nx + wmax - 1) / wmax;
-    int strip_w = (nx + ncx - 1) / ncx;
-    if (tma && (strip_w & 1)) ++strip_w;
-    // resident CTAs per SM at ~210 registers per thread: 256 threads
-    int per_sm = (nt == 256) ? 1 : (nt == 128 ? 2 : 4);
-    if (tma && (h->par.kernel_variant & 256) == 0) per_sm = 3;
-    if (!tma && nt == 128 && (h->par.kernel_variant & 1024)) per_sm = 3; // late-load kernel: 3 CTAs per SM
     int ncy = (per_sm * sms) / ncx; // one wave
     if (ncy < 1) ncy = 1;
     if (ncy > nyl) ncy = nyl;
@@ -519,6 +606,11 @@ int choose_tiling(evp_b200_handle *h) {
     for (int k = 0; k < ncy; ++k)
         if (tab[2 * k] + tab[2 * k + 1] - 1 == nyl) top_rows = tab[2 * k + 1];
     h->fold_in_kernel = fold_wanted && top_rows >= 2;
+    if (h->tiled && h->pg.tripole && !h->fold_in_kernel) {
+        // the separate fold kernel works on planes: tiny slabs / variant bit 2 fall back to the plane kernels
+        h->tiled = false;
+        return choose_tiling(h);
+    }
     h->w_bot = (float)w_bot;
     h->w_top = (float)w_top;
     // with the default tiling the chunk table is re-balanced by active cells on the device each call
@@ -712,7 +804,22 @@ static int init_handle(evp_b200_handle *h, const evp_b200_dims *d, const evp_b20
     }
     if (rc) return rc;
     CU(cudaStreamSynchronize(h->st));
+    // The strip-tiled TMA-fed kernel (kernel_variant bit 11) needs everything of the per-subcycle halo update
+    // inside the kernel: no north-south cyclic wrap, no NCCL exchange in the loop, per-strip flags for all strips
+    h->tiled = (p->kernel_variant & 2048) != 0 && (p->kernel_variant & (16 | 128 | 256 | 512 | 1024)) == 0 &&
+               !pg.ns_cyclic && !(d->nranks > 1 && p->exchange_mode != 0) && evt_nstrips(pg.nx) <= EVP_SYNC_MAXCX;
+    if (h->tiled) {
+        h->tg.ns = evt_nstrips(pg.nx);
+        h->tg.nr = pg.nyl + 2;
+        const size_t tb = sizeof(double) * (size_t)h->tg.ns * h->tg.nr * EVT_ROW_D;
+        CU(cudaMalloc(&h->tg.tiles, tb));
+        CU(cudaMemsetAsync(h->tg.tiles, 0, tb, h->st));
+    }
     if (int trc = choose_tiling(h)) return trc;
+    if (!h->tiled && h->tg.tiles) {
+        cudaFree(h->tg.tiles);
+        h->tg.tiles = nullptr;
+    }
     decide_persistent(h); // multi-rank: decided again once the peer-to-peer halo is set up (comm_init)
     memset(&h->tm, 0, sizeof(h->tm));
     return EVP_B200_OK;
@@ -779,6 +886,7 @@ static int do_prep_impl(evp_b200_handle *h, const evp_b200_inputs *in, evp_b200_
     const PlaneGeom &pg = h->pg;
     double **p = h->pl;
     const size_t pbytes = pg.cells * sizeof(double);
+    if (int src = sync_planes(h)) return src; // resident stresses must be current in the planes
     CU(cudaEventRecord(h->ev[0], h->st));
     // ---- upload inputs and state --------------------------------------------------------------
     int rc = 0;
@@ -908,13 +1016,19 @@ static int do_run_impl(evp_b200_handle *h, const evp_b200_inputs *in, const doub
     if ((rc = halo_r8(h, p[P_STRENGTH], 1, 1))) return rc;
     if ((rc = halo_r8(h, p[P_U0], 2, -1))) return rc;
     if ((rc = halo_r8(h, p[P_V0], 2, -1))) return rc;
-    // second ping-pong copy: same ghost / masked-out values as copy 0; stresses outside the T list are 0
-    CU(cudaMemcpyAsync(p[P_U1], p[P_U0], pbytes, cudaMemcpyDeviceToDevice, h->st));
-    CU(cudaMemcpyAsync(p[P_V1], p[P_V0], pbytes, cudaMemcpyDeviceToDevice, h->st));
-    CU(cudaMemsetAsync(p[P_S1], 0, pbytes * EVP_NSTRESS, h->st));
+    if (h->tiled) {
+        // the loop runs on the strip-tiled layout: state and loop-invariant fields -> tiles (both copies)
+        if ((rc = pack_tiles(h))) return rc;
+    } else {
+        // second ping-pong copy: same ghost / masked-out values as copy 0; stresses outside the T list are 0
+        CU(cudaMemcpyAsync(p[P_U1], p[P_U0], pbytes, cudaMemcpyDeviceToDevice, h->st));
+        CU(cudaMemcpyAsync(p[P_V1], p[P_V0], pbytes, cudaMemcpyDeviceToDevice, h->st));
+        CU(cudaMemsetAsync(p[P_S1], 0, pbytes * EVP_NSTRESS, h->st));
+    }
     if (h->p2p) {
         // the neighbours store into the ghost rows of copy 1 from their first subcycle kernel on:
-        // exchanging those rows once more (same values) orders their stores after the copy above
+        // exchanging those rows once more (same values; with the tiled layout only as a two-sided ordering
+        // point) orders their stores after the copy / the packing above
         void *pp[2] = {p[P_U1], p[P_V1]};
         if ((rc = exchange_rows(h, pp, 2, sizeof(double)))) return rc;
     }
@@ -941,6 +1055,7 @@ static int do_run_impl(evp_b200_handle *h, const evp_b200_inputs *in, const doub
     CU(cudaEventRecord(h->ev_early_done, h->st2));
     // ---- :347-404 ------------------------------------------------------------------------------
     if ((rc = run_subcycle_loop(h))) return rc;
+    if ((rc = sync_planes(h))) return rc; // tiled layout: the result goes back into the planes
     CU(cudaEventRecord(h->ev[4], h->st));
     h->resident = true;
     // ---- evp_finish + u2tgrid_vector (:410-428) -------------------------------------------------
@@ -1068,6 +1183,7 @@ int evp_b200_diagnostics(evp_b200_handle *h, double out[4]) {
     if (!h || !out) return fail(EVP_B200_ERR_ARG, "NULL argument");
     if (!h->resident) return fail(EVP_B200_ERR_STATE, "no device-resident result: call evp_b200_step/run first");
     CU(cudaSetDevice(h->device));
+    if (int src = sync_planes(h)) return src;
     double *d = (double *)(h->sync + EVP_SYNC_INTS); // 4 doubles behind the sync block
     CU(cudaMemsetAsync(d, 0, 4 * sizeof(double), h->st));
     // lmask_s: ULAT < -puny  <=>  fcor = 2*omega*sin(ULAT) < 2*omega*sin(-puny)
@@ -1084,6 +1200,7 @@ int evp_b200_download_state(evp_b200_handle *h, evp_b200_state *st) {
     CU(cudaSetDevice(h->device));
     double **p = h->pl;
     int rc = 0;
+    if ((rc = sync_planes(h))) return rc;
     if ((rc = download_r8(h, st->uvel, SL_U, p[P_U0], PACK_FULL))) return rc;
     if ((rc = download_r8(h, st->vvel, SL_V, p[P_V0], PACK_FULL))) return rc;
     double *sh[EVP_NSTRESS] = {st->stressp_1, st->stressp_2, st->stressp_3, st->stressp_4,
@@ -1099,6 +1216,19 @@ int evp_b200_download_state(evp_b200_handle *h, evp_b200_state *st) {
 int evp_b200_invalidate_device_state(evp_b200_handle *h) {
     if (!h) return fail(EVP_B200_ERR_ARG, "NULL argument");
     h->stress_on_device = false;
+    return 0;
+}
+
+int evp_b200_get_info(const evp_b200_handle *h, int32_t out[8]) {
+    if (!h || !out) return fail(EVP_B200_ERR_ARG, "NULL argument");
+    out[0] = h->tiled ? 1 : 0;
+    out[1] = h->grid_x;
+    out[2] = h->grid_y;
+    out[3] = h->threads;
+    out[4] = h->strip_w;
+    out[5] = h->tiled ? h->tiled_stages : 0;
+    out[6] = h->p2p ? 1 : 0;
+    out[7] = h->persistent ? 1 : 0;
     return 0;
 }
 
@@ -1188,14 +1318,16 @@ int evp_b200_comm_init(evp_b200_handle *h, const uint8_t id[128]) {
         // neighbours (through the communicator just made), map them, and let the subcycle kernel
         // store its boundary rows straight into the neighbours' ghost rows.
         struct PeerInfo {
-            cudaIpcMemHandle_t pool, sync;
-            int nyl, pitch;
+            cudaIpcMemHandle_t pool, sync, tiles;
+            int nyl, pitch, tiled;
             unsigned long long cells;
         } mine, theirs[2];
         memset(&mine, 0, sizeof(mine));
         memset(theirs, 0, sizeof(theirs));
         CU(cudaIpcGetMemHandle(&mine.pool, h->pool));
         CU(cudaIpcGetMemHandle(&mine.sync, h->sync));
+        if (h->tiled) CU(cudaIpcGetMemHandle(&mine.tiles, h->tg.tiles));
+        mine.tiled = h->tiled ? 1 : 0;
         mine.nyl = h->pg.nyl;
         mine.pitch = h->pg.pitch;
         mine.cells = h->pg.cells;
@@ -1225,13 +1357,19 @@ int evp_b200_comm_init(evp_b200_handle *h, const uint8_t id[128]) {
                 void *pp = nullptr, *ps = nullptr;
                 if (ok && cudaIpcOpenMemHandle(&pp, theirs[k].pool, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) ok = false;
                 if (ok && cudaIpcOpenMemHandle(&ps, theirs[k].sync, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) ok = false;
+                if (ok && theirs[k].tiled != (h->tiled ? 1 : 0)) ok = false;
+                if (ok && h->tiled) {
+                    void *pt = nullptr;
+                    if (cudaIpcOpenMemHandle(&pt, theirs[k].tiles, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) ok = false;
+                    h->peer_tiles[k] = (double *)pt;
+                }
                 h->peer_pool[k] = (double *)pp;
                 h->peer_sync[k] = (int *)ps;
                 h->peer_nyl[k] = theirs[k].nyl;
                 h->peer_cells[k] = (size_t)theirs[k].cells;
             }
         cudaGetLastError();
-        if (h->grid_x > EVP_SYNC_MAXCX) ok = false;
+        if ((h->tiled ? h->tg.ns : h->grid_x) > EVP_SYNC_MAXCX) ok = false;
         // every rank must use the same exchange inside the loop: peer-to-peer only if ALL ranks can
         int mine_ok = ok ? 1 : 0, all_ok = 0;
         int *d_ok = (int *)(d + 3 * sizeof(PeerInfo));
@@ -1241,6 +1379,10 @@ int evp_b200_comm_init(evp_b200_handle *h, const uint8_t id[128]) {
         CU(cudaMemcpyAsync(&all_ok, d_ok, sizeof(int), cudaMemcpyDeviceToHost, h->st));
         CU(cudaStreamSynchronize(h->st));
         h->p2p = all_ok != 0; // otherwise the NCCL exchange stays in use (evp_b200_get_timings reports the mode)
+        if (!h->p2p && h->tiled) { // the tiled kernel has no NCCL exchange: back to the plane kernels
+            h->tiled = false;
+            if (int trc = choose_tiling(h)) return trc;
+        }
         decide_persistent(h);
     }
     return 0;
@@ -1262,8 +1404,12 @@ int evp_b200_finalize(evp_b200_handle *h) {
     cudaFree(h->d_cta_epoch);
     cudaFree(h->row_ht);
     if (h->comm && h->pCommDestroy) h->pCommDestroy(h->comm);
-    if (h->graph_exec) cudaGraphExecDestroy(h->graph_exec);
-    if (h->graph) cudaGraphDestroy(h->graph);
+    for (int k = 0; k < 2; ++k) {
+        if (h->graph_exec[k]) cudaGraphExecDestroy(h->graph_exec[k]);
+        if (h->graph[k]) cudaGraphDestroy(h->graph[k]);
+        if (h->peer_tiles[k]) cudaIpcCloseMemHandle(h->peer_tiles[k]);
+    }
+    cudaFree(h->tg.tiles);
     cudaFree(h->pool);
     cudaFree(h->cat);
     cudaFree(h->mpool);

@@ -584,6 +584,83 @@ __global__ void k_wait_peers(int *sync, int has_north, int has_south, int ncx) {
 }
 
 // ---------------------------------------------------------------------------------------------
+// strip-tiled layout (evp_tiled.cuh): one warp per (strip, tile row); lane = slot
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ bool tile_coords(const PlaneGeom &pg, const TileGeom &tg, int &w, int &j, int &lane, int &i) {
+    w = blockIdx.y;
+    j = blockIdx.x * blockDim.y + threadIdx.y;
+    lane = threadIdx.x;
+    i = EVT_UW * w + 1 + lane; // plane column of this slot
+    return j < tg.nr;
+}
+
+__global__ void k_tile_pack_static(PlaneGeom pg, TileGeom tg, TileStaticArgs a) {
+    int w, j, lane, i;
+    if (!tile_coords(pg, tg, w, j, lane, i)) return;
+    double *inv = tg.tiles + ((size_t)w * tg.nr + j) * EVT_ROW_D + evt_inv_off();
+    const bool colT = i <= pg.nx + 1;
+    const size_t idx = (size_t)j * pg.pitch + i;
+    const double *tp[9] = {a.dxt, a.dyt, a.dxhy, a.dyhx, a.cxp, a.cyp, a.cxm, a.cym, a.tinyarea};
+#pragma unroll
+    for (int q = 0; q < 9; ++q) inv[EVT_T(1 + q) + lane] = colT ? tp[q][idx] : 0.0;
+    const bool colU = lane < EVT_UW && i <= pg.nx && j >= 1;
+    inv[EVT_UF(9) + lane] = colU ? a.uarear[idx - pg.pitch] : 0.0;
+}
+
+__global__ void k_tile_pack_call(PlaneGeom pg, TileGeom tg, TileCallArgs a) {
+    int w, j, lane, i;
+    if (!tile_coords(pg, tg, w, j, lane, i)) return;
+    double *row = tg.tiles + ((size_t)w * tg.nr + j) * EVT_ROW_D;
+    double *inv = row + evt_inv_off();
+    const bool colT = i <= pg.nx + 1;
+    const bool colU = lane < EVT_UW && i <= pg.nx && j >= 1;
+    const size_t idx = (size_t)j * pg.pitch + i;
+    inv[EVT_T(0) + lane] = colT ? a.strength[idx] : 0.0;
+    const double *up[9] = {a.aiu, a.uocn, a.vocn, a.waterx, a.watery, a.forcex, a.forcey, a.umassdtei, a.fm};
+#pragma unroll
+    for (int q = 0; q < 9; ++q) inv[EVT_UF(q) + lane] = colU ? up[q][idx - pg.pitch] : 0.0;
+    unsigned char *mk = (unsigned char *)(inv + EVT_MASK);
+    // T cells are computed on [1..nx+1] x [1..nyl+1] (source/ice_dyn_evp.F90:850-859), U cells on the interior
+    mk[lane] = (colT && j >= 1 && a.icetmask[idx]) ? 1 : 0;
+    mk[32 + lane] = (colU && a.iceumask[idx - pg.pitch]) ? 1 : 0;
+    double *c0 = row + evt_state_off(0), *c1 = row + evt_state_off(1);
+    const double u = colT ? a.u[idx] : 0.0, v = colT ? a.v[idx] : 0.0;
+    c0[EVT_U + lane] = u; c0[EVT_V + lane] = v;
+    c1[EVT_U + lane] = u; c1[EVT_V + lane] = v;
+#pragma unroll
+    for (int k = 0; k < EVP_NSTRESS; ++k) {
+        c0[EVT_S(k) + lane] = colT ? a.s[k][idx] : 0.0;
+        c1[EVT_S(k) + lane] = 0.0;
+    }
+    if (lane < 4) { // halo words: U column 31 w (the last column of strip w-1, or the west ghost column)
+        const size_t hidx = (size_t)j * pg.pitch + EVT_UW * w;
+        const double h = lane == 0 ? a.u[hidx] : (lane == 1 ? a.v[hidx] : 0.0);
+        c0[EVT_HALO + lane] = h;
+        c1[EVT_HALO + lane] = h;
+    }
+}
+
+__global__ void k_tile_unpack_state(PlaneGeom pg, TileGeom tg, int copy, TileStateArgs a) {
+    int w, j, lane, i;
+    if (!tile_coords(pg, tg, w, j, lane, i)) return;
+    const double *c = tg.tiles + ((size_t)w * tg.nr + j) * EVT_ROW_D + evt_state_off(copy);
+    // every plane column 1 .. nx+1 once: the 31 own slots of a strip, and slot 31 only where it is column nx+1
+    const bool own = (lane < EVT_UW && i <= pg.nx + 1) || (i == pg.nx + 1);
+    const size_t idx = (size_t)j * pg.pitch + i;
+    if (own) {
+        a.u[idx] = c[EVT_U + lane];
+        a.v[idx] = c[EVT_V + lane];
+        if (j >= 1) { // T row 0 is never computed: the planes keep their south ghost stresses
+#pragma unroll
+            for (int k = 0; k < EVP_NSTRESS; ++k) a.s[k][idx] = c[EVT_S(k) + lane];
+        }
+    }
+    if (w == 0 && lane < 2) { // west ghost column of u, v
+        (lane == 0 ? a.u : a.v)[(size_t)j * pg.pitch] = c[EVT_HALO + lane];
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
 // self-test of evp_ieee.cuh against the compiler's own IEEE sqrt() and operator/
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ unsigned long long splitmix64(unsigned long long &x) {
@@ -746,6 +823,18 @@ void aux_principal_stress(size_t n, const double *sp1, const double *sm1, const 
 void aux_ice_strength(const PlaneGeom &pg, const StrengthArgs &a, cudaStream_t s) {
     dim3 grid(nblk(pg.nx + 2), pg.nyl + 2);
     k_ice_strength<<<grid, TPB, 0, s>>>(pg, a);
+}
+void aux_tile_pack_static(const PlaneGeom &pg, const TileGeom &tg, const TileStaticArgs &a, cudaStream_t s) {
+    dim3 grid((tg.nr + 3) / 4, tg.ns), block(32, 4);
+    k_tile_pack_static<<<grid, block, 0, s>>>(pg, tg, a);
+}
+void aux_tile_pack_call(const PlaneGeom &pg, const TileGeom &tg, const TileCallArgs &a, cudaStream_t s) {
+    dim3 grid((tg.nr + 3) / 4, tg.ns), block(32, 4);
+    k_tile_pack_call<<<grid, block, 0, s>>>(pg, tg, a);
+}
+void aux_tile_unpack_state(const PlaneGeom &pg, const TileGeom &tg, int copy, const TileStateArgs &a, cudaStream_t s) {
+    dim3 grid((tg.nr + 3) / 4, tg.ns), block(32, 4);
+    k_tile_unpack_state<<<grid, block, 0, s>>>(pg, tg, copy, a);
 }
 void aux_wait_peers(int *sync, int has_north, int has_south, int ncx, cudaStream_t s) {
     k_wait_peers<<<1, 128, 0, s>>>(sync, has_north, has_south, ncx);

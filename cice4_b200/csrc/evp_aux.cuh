@@ -6,6 +6,7 @@
 #include <cstdint>
 
 #include "evp_common.cuh"
+#include "evp_tiled.cuh"
 
 // geometry of one handle's slab planes
 struct PlaneGeom {
@@ -121,3 +122,26 @@ void aux_diagnostics(const PlaneGeom &pg, const double *u, const double *v, cons
 // evp_ieee.cuh (the straight-line IEEE sqrt / division of the subcycle kernel) against sqrt() and operator/
 // on n generated operands; see k_selftest_ieee for out[0..5].  Returns a cudaError_t value.
 int aux_selftest_ieee(long long n, unsigned long long seed, unsigned long long out[6]);
+
+// ---- strip-tiled layout of the subcycle loop (evp_tiled.cuh) -----------------------------------------
+// loop-invariant block, static part (once at init): the 9 T metrics of row j and uarear of U row j-1
+struct TileStaticArgs {
+    const double *dxt, *dyt, *dxhy, *dyhx, *cxp, *cyp, *cxm, *cym, *tinyarea, *uarear;
+};
+void aux_tile_pack_static(const PlaneGeom &pg, const TileGeom &tg, const TileStaticArgs &a, cudaStream_t s);
+// per call, before the ndte loop: strength, the 9 per-call U fields, the masks and the state.  State copy 0
+// receives u, v and the stresses of the planes (with the halo words and duplicated slots), copy 1 the same
+// velocities and zero stresses (what the plane path does with its second copy, evp_abi.cu).
+struct TileCallArgs {
+    const double *strength, *aiu, *uocn, *vocn, *waterx, *watery, *forcex, *forcey, *umassdtei, *fm;
+    const uint8_t *icetmask, *iceumask;
+    const double *u, *v;
+    const double *s[EVP_NSTRESS];
+};
+void aux_tile_pack_call(const PlaneGeom &pg, const TileGeom &tg, const TileCallArgs &a, cudaStream_t s);
+// after the loop: state copy `copy` of the tiles -> planes (u, v with their ghost ring; stresses)
+struct TileStateArgs {
+    double *u, *v;
+    double *s[EVP_NSTRESS];
+};
+void aux_tile_unpack_state(const PlaneGeom &pg, const TileGeom &tg, int copy, const TileStateArgs &a, cudaStream_t s);

@@ -12,7 +12,7 @@
 #include <cstdint>
 
 #define EVP_NSTRESS 12
-#define EVP_SYNC_MAXCX 128
+#define EVP_SYNC_MAXCX 512
 #define EVP_SYNC_FN 32
 #define EVP_SYNC_FS (EVP_SYNC_FN + EVP_SYNC_MAXCX)
 #define EVP_SYNC_INTS (EVP_SYNC_FS + EVP_SYNC_MAXCX)
@@ -73,6 +73,11 @@ struct SubArgs {
     // where this rank's boundary CTAs publish: the north neighbour's FS array, the south neighbour's FN array
     int *peer_n_flag, *peer_s_flag;
     int p2p;                         // 1 = the above are in use
+    // ---- strip-tiled layout of the TMA-fed kernel (evp_tiled.cuh); null when the plane kernels run ----
+    double *tiles;                   // [t_ns strips][t_nr = nyl + 2 rows][EVT_ROW_D]
+    int t_ns, t_nr;
+    double *peer_n_tiles, *peer_s_tiles; // the neighbours' tile pools (same strips; their own row counts)
+    int peer_n_nr, peer_s_nr;
     // ---- tripole u-fold of u_new/v_new inside the kernel (top slab only) ------------------------
     int fold;              // 1 = the last CTA of the northernmost chunk to finish applies the fold
     double *fold_scratch;  // 2 * pitch doubles: copy of the raw top physical row of u_new, v_new
@@ -120,4 +125,12 @@ int evp_persist_launch_fast(const SubArgs &a, int threads, unsigned grid_x, unsi
                             int *ctas_per_sm);
 int evp_subcycle_configure_strict(void);
 int evp_subcycle_configure_fast(void);
+// strip-tiled TMA-fed kernel (k_subcycle_tiled): stages = 2 (3 CTAs of 4 warps per SM) or 3 (2 CTAs per SM);
+// ctas_per_sm != nullptr: only the occupancy query.  Returns a cudaError_t value.
+typedef int (*tiled_launch_fn)(const SubArgs &a, bool last, int stages, bool pdl, unsigned grid_x, unsigned grid_y,
+                               void *stream, int *ctas_per_sm);
+int evp_tiled_launch_strict(const SubArgs &a, bool last, int stages, bool pdl, unsigned grid_x, unsigned grid_y,
+                            void *stream, int *ctas_per_sm);
+int evp_tiled_launch_fast(const SubArgs &a, bool last, int stages, bool pdl, unsigned grid_x, unsigned grid_y,
+                          void *stream, int *ctas_per_sm);
 int evp_subcycle_max_threads(void);

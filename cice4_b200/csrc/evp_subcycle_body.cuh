@@ -36,6 +36,7 @@
 
 #include "evp_common.cuh"
 #include "evp_ieee.cuh"
+#include "evp_tiled.cuh"
 
 namespace EVP_SUB_NS {
 
@@ -141,6 +142,68 @@ __device__ __forceinline__ void load_U(const SubArgs &a, URow &u, int i, int j, 
     }
 }
 
+// Where the results of stress_cell / stepu_cell go.  PlaneStore: the plane layout (one pointer per field,
+// 32-bit element offsets); TileStore (evp_tiled.cuh): the strip-tiled layout of the TMA-fed kernel.  The
+// arithmetic is shared; the policies only differ in addressing.
+struct PlaneStoreT {
+    const SubArgs &a;
+    idx_t sn, idx; // offset of the state copy that is written; plane index of the T cell
+    bool on;       // this thread owns the cell (stores its stresses / diagnostics)
+    __device__ __forceinline__ void diag(double divu, double rdg_conv, double rdg_shear, double shear) const {
+        a.divu[idx] = divu; a.rdg_conv[idx] = rdg_conv; a.rdg_shear[idx] = rdg_shear; a.shear[idx] = shear;
+    }
+    __device__ __forceinline__ void prs(double v) const { a.prs_sig[idx] = v; }
+    __device__ __forceinline__ void stress(int k, double v) const { a.s[k][idx + sn] = v; }
+};
+
+struct PlaneStoreU {
+    const SubArgs &a;
+    idx_t sn, idx;
+    int i, j;
+    __device__ __forceinline__ void uv(double unew, double vnew) const {
+        double *const u_new = a.u + sn, *const v_new = a.v + sn;
+        u_new[idx] = unew;
+        v_new[idx] = vnew;
+        if (a.ew_cyclic) { // east-west part of ice_HaloUpdate(uvel/vvel), serial/ice_boundary.F90:3629-3668
+            if (i == a.nx) {
+                u_new[idx - a.nx] = unew;
+                v_new[idx - a.nx] = vnew;
+            }
+            if (i == 1) {
+                u_new[idx + a.nx] = unew;
+                v_new[idx + a.nx] = vnew;
+            }
+        }
+        if (a.p2p) {
+            // slab-to-slab part of the halo update: the top / bottom physical row goes straight into the
+            // neighbour GPU's ghost row over NVLink (whole padded row: the wrap columns travel with it)
+            double *pu = nullptr, *pv = nullptr;
+            const bool second = sn != 0; // the neighbours' copies are laid out like ours
+            if (j == a.nyl && a.peer_n_flag) {
+                pu = a.peer_n_u + (second ? a.peer_n_stride : 0);
+                pv = a.peer_n_v + (second ? a.peer_n_stride : 0);
+            }
+            if (j == 1 && a.peer_s_flag) {
+                if (pu) { // one-row slab: both neighbours
+                    pu[i] = unew; pv[i] = vnew;
+                    if (a.ew_cyclic && i == a.nx) { pu[0] = unew; pv[0] = vnew; }
+                    if (a.ew_cyclic && i == 1) { pu[a.nx + 1] = unew; pv[a.nx + 1] = vnew; }
+                }
+                pu = a.peer_s_u + (second ? a.peer_s_stride : 0);
+                pv = a.peer_s_v + (second ? a.peer_s_stride : 0);
+            }
+            if (pu) {
+                pu[i] = unew; pv[i] = vnew;
+                if (a.ew_cyclic && i == a.nx) { pu[0] = unew; pv[0] = vnew; }
+                if (a.ew_cyclic && i == 1) { pu[a.nx + 1] = unew; pv[a.nx + 1] = vnew; }
+            }
+        }
+    }
+    __device__ __forceinline__ void last(double strintx, double strinty, double taux, double tauy) const {
+        a.strintx[idx] = strintx; a.strinty[idx] = strinty; a.strocnx[idx] = taux; a.strocny[idx] = tauy;
+    }
+};
+
 // n/d1 .. n/d4: four independent IEEE divisions, interleaved (evp_ieee.cuh); bit-identical to operator/
 __device__ __forceinline__ void div4(double n, double d1, double d2, double d3, double d4, double &q1,
                                      double &q2, double &q3, double &q4) {
@@ -161,10 +224,10 @@ __device__ __forceinline__ void div4(double n, double d1, double d2, double d3, 
 
 // source/ice_dyn_evp.F90:1056-1291 for one T cell.  (un,vn)=(i,j) (uw,vw)=(i-1,j) (us,vs)=(i,j-1)
 // (usw,vsw)=(i-1,j-1).  Operation order is the Fortran's.
-template <bool LAST>
-__device__ __forceinline__ void stress_cell(const SubArgs &a, idx_t sn, const TRow &t, double us, double vs,
-                                            double usw, double vsw, idx_t idx, bool store,
-                                            double (&str)[8]) {
+template <bool LAST, class ST>
+__device__ __forceinline__ void stress_cell(const SubArgs &a, const ST &out, const TRow &t, double us, double vs,
+                                            double usw, double vsw, double (&str)[8]) {
+    const bool store = out.on;
     const double p5 = 0.5, p25 = 0.25, c4 = 4.0;
     const double p166 = 1.0 / 6.0, p333 = 1.0 / 3.0, p111 = 1.0 / 9.0;
     const double p055 = p111 * 0.5, p027 = p055 * 0.5, p222 = 2.0 / 9.0;
@@ -207,12 +270,9 @@ __device__ __forceinline__ void stress_cell(const SubArgs &a, idx_t sn, const TR
     if (LAST && store) { // :1103-1115
         const double divu = p25 * (divune + divunw + divuse + divusw) * t.tarear;
         const double tmp = p25 * (Deltane + Deltanw + Deltase + Deltasw) * t.tarear;
-        a.divu[idx] = divu;
-        a.rdg_conv[idx] = -fmin(divu, 0.0);
-        a.rdg_shear[idx] = p5 * (tmp - fabs(divu));
         const double tsum = tensionne + tensionnw + tensionse + tensionsw;
         const double ssum = shearne + shearnw + shearse + shearsw;
-        a.shear[idx] = p25 * t.tarear * sqrt(tsum * tsum + ssum * ssum);
+        out.diag(divu, -fmin(divu, 0.0), p5 * (tmp - fabs(divu)), p25 * t.tarear * sqrt(tsum * tsum + ssum * ssum));
     }
 
     double c0ne, c0nw, c0sw, c0se;
@@ -224,11 +284,11 @@ __device__ __forceinline__ void stress_cell(const SubArgs &a, idx_t sn, const TR
         c0nw = fmin(c0nw, a.rcon);
         c0sw = fmin(c0sw, a.rcon);
         c0se = fmin(c0se, a.rcon);
-        if (LAST && store) a.prs_sig[idx] = t.strength * Deltane / fmax(Deltane, t4);
+        if (LAST && store) out.prs(t.strength * Deltane / fmax(Deltane, t4));
     } else { // :1131-1135
         div4(t.strength, fmax(Deltane, t.tiny), fmax(Deltanw, t.tiny), fmax(Deltasw, t.tiny), fmax(Deltase, t.tiny),
              c0ne, c0nw, c0sw, c0se);
-        if (LAST && store) a.prs_sig[idx] = c0ne * Deltane;
+        if (LAST && store) out.prs(c0ne * Deltane);
     }
     const double c1ne = c0ne * a.dte2T; // :1138-1141
     const double c1nw = c0nw * a.dte2T;
@@ -250,10 +310,9 @@ __device__ __forceinline__ void stress_cell(const SubArgs &a, idx_t sn, const TR
     const double s124 = (t.s[11] + c1se * shearse * p5) * a.denom2;
 
     if (store) {
-        const idx_t idn = idx + sn;
-        a.s[0][idn] = sp1; a.s[1][idn] = sp2; a.s[2][idn] = sp3; a.s[3][idn] = sp4;
-        a.s[4][idn] = sm1; a.s[5][idn] = sm2; a.s[6][idn] = sm3; a.s[7][idn] = sm4;
-        a.s[8][idn] = s121; a.s[9][idn] = s122; a.s[10][idn] = s123; a.s[11][idn] = s124;
+        out.stress(0, sp1); out.stress(1, sp2); out.stress(2, sp3); out.stress(3, sp4);
+        out.stress(4, sm1); out.stress(5, sm2); out.stress(6, sm3); out.stress(7, sm4);
+        out.stress(8, s121); out.stress(9, s122); out.stress(10, s123); out.stress(11, s124);
     }
 
     // :1196-1215
@@ -302,10 +361,9 @@ __device__ __forceinline__ void stress_cell(const SubArgs &a, idx_t sn, const TR
 }
 
 // source/ice_dyn_evp.F90:1386-1441 for one U cell; sx, sy are the two str sums of :1415-1418
-template <bool LAST>
-__device__ __forceinline__ void stepu_cell(const SubArgs &a, idx_t sn, const URow &u, double uold, double vold,
-                                           double sx, double sy, int i, int j, idx_t idx) {
-    double *const u_new = a.u + sn, *const v_new = a.v + sn;
+template <bool LAST, class SU>
+__device__ __forceinline__ void stepu_cell(const SubArgs &a, const SU &out, const URow &u, double uold, double vold,
+                                           double sx, double sy) {
     const double du = u.uocn - uold, dv = u.vocn - vold;
     const double vrel = u.aiu * a.dragw * sqrt(du * du + dv * dv); // :1394
     const double taux = vrel * u.waterx;                            // :1397-1398
@@ -331,48 +389,8 @@ __device__ __forceinline__ void stepu_cell(const SubArgs &a, idx_t sn, const URo
         unew = nu / ab2;
         vnew = nv / ab2;
     }
-    u_new[idx] = unew;
-    v_new[idx] = vnew;
-    if (a.ew_cyclic) { // east-west part of ice_HaloUpdate(uvel/vvel), serial/ice_boundary.F90:3629-3668
-        if (i == a.nx) {
-            u_new[idx - a.nx] = unew;
-            v_new[idx - a.nx] = vnew;
-        }
-        if (i == 1) {
-            u_new[idx + a.nx] = unew;
-            v_new[idx + a.nx] = vnew;
-        }
-    }
-    if (a.p2p) {
-        // slab-to-slab part of the halo update: the top / bottom physical row goes straight into the
-        // neighbour GPU's ghost row over NVLink (whole padded row: the wrap columns travel with it)
-        double *pu = nullptr, *pv = nullptr;
-        const bool second = sn != 0; // the neighbours' copies are laid out like ours
-        if (j == a.nyl && a.peer_n_flag) {
-            pu = a.peer_n_u + (second ? a.peer_n_stride : 0);
-            pv = a.peer_n_v + (second ? a.peer_n_stride : 0);
-        }
-        if (j == 1 && a.peer_s_flag) {
-            if (pu) { // one-row slab: both neighbours
-                pu[i] = unew; pv[i] = vnew;
-                if (a.ew_cyclic && i == a.nx) { pu[0] = unew; pv[0] = vnew; }
-                if (a.ew_cyclic && i == 1) { pu[a.nx + 1] = unew; pv[a.nx + 1] = vnew; }
-            }
-            pu = a.peer_s_u + (second ? a.peer_s_stride : 0);
-            pv = a.peer_s_v + (second ? a.peer_s_stride : 0);
-        }
-        if (pu) {
-            pu[i] = unew; pv[i] = vnew;
-            if (a.ew_cyclic && i == a.nx) { pu[0] = unew; pv[0] = vnew; }
-            if (a.ew_cyclic && i == 1) { pu[a.nx + 1] = unew; pv[a.nx + 1] = vnew; }
-        }
-    }
-    if (LAST) { // only the last subcycle's values are observable (:1415-1418,:1434-1435)
-        a.strintx[idx] = strintx;
-        a.strinty[idx] = strinty;
-        a.strocnx[idx] = taux;
-        a.strocny[idx] = tauy;
-    }
+    out.uv(unew, vnew); // + the east-west / slab-to-slab part of ice_HaloUpdate(uvel/vvel) (:397-402)
+    if (LAST) out.last(strintx, strinty, taux, tauy); // only the last subcycle's values are observable (:1415-1418,:1434-1435)
 }
 
 // Bounded spin on a flag that another CTA (or another GPU) advances: a protocol bug or a dead peer must
@@ -573,7 +591,7 @@ __device__ __forceinline__ void march(const SubArgs &a, idx_t so, idx_t sn, int 
         if (t.act) {
             derive_metrics<HT>(t);
             const bool store = ownT && (j < j0 + nrows || j == a.nyl + 1);
-            stress_cell<LAST>(a, sn, t, us, vs, usw, vsw, idx, store, str);
+            stress_cell<LAST>(a, PlaneStoreT{a, sn, idx, store}, t, us, vs, usw, vsw, str);
         } else {
 #pragma unroll
             for (int k = 0; k < 8; ++k) str[k] = 0.0; // str(:,:,:) = c0, :1051
@@ -596,7 +614,7 @@ __device__ __forceinline__ void march(const SubArgs &a, idx_t so, idx_t sn, int 
         if (uc.act) {
             const double sx = px + str[2] + s4r;          // ((s1 + s2) + s3) + s4
             const double sy = s5c + str[5] + s7c + s8r;    // ((s5 + s6) + s7) + s8
-            stepu_cell<LAST>(a, sn, uc, us, vs, sx, sy, i, j - 1, idx - a.pitch);
+            stepu_cell<LAST>(a, PlaneStoreU{a, sn, idx - a.pitch, i, j - 1}, uc, us, vs, sx, sy);
         }
         px = str[0] + s2r;
         s5c = str[4];
@@ -783,7 +801,7 @@ __device__ __forceinline__ void march_tma(const SubArgs &a, idx_t so, idx_t sn, 
             t.tiny = sg[23 * W + 1];
             if (LAST) t.tarear = sg[(NP - 1) * W + 1];
             const bool store = ownT && (j < j0 + nrows || j == a.nyl + 1);
-            stress_cell<LAST>(a, sn, t, us, vs, usw, vsw, idx, store, str);
+            stress_cell<LAST>(a, PlaneStoreT{a, sn, idx, store}, t, us, vs, usw, vsw, str);
         } else {
 #pragma unroll
             for (int k = 0; k < 8; ++k) str[k] = 0.0; // str(:,:,:) = c0, :1051
@@ -812,7 +830,7 @@ __device__ __forceinline__ void march_tma(const SubArgs &a, idx_t so, idx_t sn, 
         if (uc.act) {
             const double sx = px + str[2] + s4r;          // ((s1 + s2) + s3) + s4
             const double sy = s5c + str[5] + s7c + s8r;    // ((s5 + s6) + s7) + s8
-            stepu_cell<LAST>(a, sn, uc, us, vs, sx, sy, i, j - 1, idx - a.pitch);
+            stepu_cell<LAST>(a, PlaneStoreU{a, sn, idx - a.pitch, i, j - 1}, uc, us, vs, sx, sy);
         }
         px = str[0] + s2r;
         s5c = str[4];
@@ -852,6 +870,427 @@ __global__ void __launch_bounds__(NT, MINB) k_subcycle_tma(const __grid_constant
 template <int NT, int S>
 static constexpr size_t tma_smem_bytes() {
     return (size_t)(2 * 4 * NT + S * 25 * (NT + 2)) * sizeof(double) + S * sizeof(unsigned long long);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Strip-tiled, warp-autonomous, TMA-fed subcycle kernel (layout: evp_tiled.cuh).
+//
+// One WARP owns a strip of 31 U columns (32 T columns) and marches north over its row chunk on its own:
+//   * every tile row (the old state copy + all loop-invariant fields of T row j and U row j-1, 8800
+//     contiguous bytes) arrives in shared memory by ONE bulk copy (cp.async.bulk, completing on an
+//     mbarrier), S rows deep per warp -- no per-thread global address arithmetic, no register prefetch,
+//     no register rotation;
+//   * str(2,4,7,8) of the east neighbour cell come by warp shuffle, the west velocities too; there is
+//     no shared-memory exchange line and no CTA barrier in the loop, so the warps of an SM drift apart
+//     and overlap each other's copy and arithmetic phases;
+//   * the new stresses and velocities go straight from registers to the new state copy of the tile rows
+//     (one base pointer, immediate offsets; 256-byte coalesced segments).  The writer of a U column that a
+//     neighbouring strip also holds (its east slot 31 / its west halo word, the east-west wrap columns and,
+//     on several GPUs, the neighbour slab's ghost row) stores it there as well -- this is the per-subcycle
+//     ice_HaloUpdate(uvel, vvel) (source/ice_dyn_evp.F90:397-402).
+// The arithmetic is stress_cell / stepu_cell, shared with the plane kernels: results are bit-identical.
+// ------------------------------------------------------------------------------------------------
+#define EVT_STAGE_D 1104 // doubles per pipeline stage (EVT_WIN_D rounded up to a multiple of 128 bytes)
+
+struct TileStoreT {
+    const SubArgs &a;
+    double *row_new; // new state copy of tile row (strip, j)
+    idx_t pidx;      // plane index of the T cell (last subcycle's diagnostics stay in planes)
+    int lane;
+    bool on;
+    __device__ __forceinline__ void diag(double divu, double rdg_conv, double rdg_shear, double shear) const {
+        a.divu[pidx] = divu; a.rdg_conv[pidx] = rdg_conv; a.rdg_shear[pidx] = rdg_shear; a.shear[pidx] = shear;
+    }
+    __device__ __forceinline__ void prs(double v) const { a.prs_sig[pidx] = v; }
+    __device__ __forceinline__ void stress(int k, double v) const { row_new[EVT_S(k) + lane] = v; }
+};
+
+// which other places hold a copy of this lane's U column (constant over the rows of a strip)
+struct TileDup {
+    int flags;      // bit 0: an east-type slot (u, v 32 apart), bit 1: a west halo word (u, v adjacent)
+    int wdE, slotE; // strip and slot of the east-type duplicate
+    int wdW;        // strip whose west halo duplicates this column
+};
+
+__device__ __forceinline__ TileDup tile_dups(const SubArgs &a, int w, int lane, int i, bool colU) {
+    TileDup d = {0, 0, 0, 0};
+    if (!colU) return d;
+    const int ns = a.t_ns;
+    if (lane == 0) {
+        if (w > 0) { d.flags |= 1; d.wdE = w - 1; d.slotE = EVT_UW; }                                  // east slot of strip w-1
+        else if (a.ew_cyclic) { d.flags |= 1; d.wdE = ns - 1; d.slotE = a.nx - EVT_UW * (ns - 1); } // ghost column nx+1 <- U(1)
+    }
+    if (lane == EVT_UW - 1 && w < ns - 1) { d.flags |= 2; d.wdW = w + 1; }                             // west halo of strip w+1
+    if (i == a.nx && a.ew_cyclic) { d.flags |= 2; d.wdW = 0; }                                         // ghost column 0 <- U(nx)
+    return d;
+}
+
+// u, v of U column (strip w, lane) of tile row `row` of a tile pool, with its duplicates
+__device__ __forceinline__ void tile_store_uv(double *pool, int nr, int row, int copy, int w, int lane, const TileDup &d,
+                                              double u, double v) {
+    const int so = evt_state_off(copy);
+    double *p = pool + ((size_t)w * nr + row) * EVT_ROW_D + so;
+    p[EVT_U + lane] = u;
+    p[EVT_V + lane] = v;
+    if (d.flags & 1) {
+        double *q = pool + ((size_t)d.wdE * nr + row) * EVT_ROW_D + so + EVT_U + d.slotE;
+        q[0] = u; q[32] = v;
+    }
+    if (d.flags & 2) {
+        double *q = pool + ((size_t)d.wdW * nr + row) * EVT_ROW_D + so + EVT_HALO;
+        q[0] = u; q[1] = v;
+    }
+}
+
+struct TileStoreU {
+    const SubArgs &a;
+    double *u_new;        // this lane's u slot in the new copy of tile row (strip, j); v is 32 doubles behind
+    long long dupE, dupW; // offsets (doubles) from u_new to the duplicates
+    const TileDup &d;
+    idx_t pidx;
+    int w, lane, j, newc;
+    __device__ __forceinline__ void uv(double unew, double vnew) const {
+        u_new[0] = unew;
+        u_new[32] = vnew;
+        if (d.flags & 1) { u_new[dupE] = unew; u_new[dupE + 32] = vnew; }
+        if (d.flags & 2) { u_new[dupW] = unew; u_new[dupW + 1] = vnew; }
+        if (a.p2p) { // slab-to-slab part of the halo update: straight into the neighbour GPU's ghost tile rows
+            if (j == a.nyl && a.peer_n_flag) tile_store_uv(a.peer_n_tiles, a.peer_n_nr, 0, newc, w, lane, d, unew, vnew);
+            if (j == 1 && a.peer_s_flag)
+                tile_store_uv(a.peer_s_tiles, a.peer_s_nr, a.peer_s_nr - 1, newc, w, lane, d, unew, vnew);
+        }
+    }
+    __device__ __forceinline__ void last(double strintx, double strinty, double taux, double tauy) const {
+        a.strintx[pidx] = strintx; a.strinty[pidx] = strinty; a.strocnx[pidx] = taux; a.strocny[pidx] = tauy;
+    }
+};
+
+// lane 0: arm the stage's mbarrier with the byte count and issue the bulk copy of one read window
+__device__ __forceinline__ void tile_issue(const double *src, double *stage, unsigned bar) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"((unsigned)(EVT_WIN_D * 8))
+                 : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(stage)),
+                 "l"(src), "r"((unsigned)(EVT_WIN_D * 8)), "r"(bar)
+                 : "memory");
+}
+
+template <bool LAST, int S>
+__device__ __forceinline__ void march_tiled(const SubArgs &a, double *stages, unsigned long long *bars, int w, int lane,
+                                            int j0, int nrows, bool peer_top) {
+    const int nx = a.nx, nr = a.t_nr;
+    const int i = EVT_UW * w + 1 + lane;
+    const bool colT = i <= nx + 1;
+    const bool colU = lane < EVT_UW && i <= nx;
+    const int jlast = min(j0 + nrows, a.nyl + 1); // last T row of this warp
+    const int nT = jlast - j0 + 1;
+    const int oldc = a.flip ? 1 : 0, newc = oldc ^ 1;
+    // where the old state copy and the loop-invariant block sit inside a stage (evp_tiled.cuh)
+    const int st_s = oldc ? EVT_INV_D : 0, inv_s = oldc ? 0 : EVT_STATE_D;
+    double *const strip = a.tiles + (size_t)w * nr * EVT_ROW_D;
+    const double *const win = strip + (size_t)j0 * EVT_ROW_D + evt_window_off(oldc);
+
+    if (lane == 0) {
+#pragma unroll
+        for (int q = 0; q < S; ++q)
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(bars + q)) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        // stores of the previous kernel / of the neighbour GPU (generic proxy) before the bulk copies (async proxy)
+        asm volatile("fence.proxy.async;" ::: "memory");
+#pragma unroll
+        for (int q = 0; q < S; ++q)
+            if (q < nT) tile_issue(win + (size_t)q * EVT_ROW_D, stages + q * EVT_STAGE_D, smem_u32(bars + q));
+    }
+    __syncwarp();
+
+    // velocities of the row south of the chunk
+    double us = 0.0, vs = 0.0, usw, vsw;
+    {
+        const double *sr = strip + (size_t)(j0 - 1) * EVT_ROW_D + evt_state_off(oldc);
+        if (colT) {
+            us = __ldcg(sr + EVT_U + lane);
+            vs = __ldcg(sr + EVT_V + lane);
+        }
+        usw = __shfl_up_sync(0xffffffffu, us, 1);
+        vsw = __shfl_up_sync(0xffffffffu, vs, 1);
+        if (lane == 0) {
+            usw = __ldcg(sr + EVT_HALO);
+            vsw = __ldcg(sr + EVT_HALO + 1);
+        }
+    }
+    const TileDup dup = tile_dups(a, w, lane, i, colU);
+    const long long dupE = ((long long)(dup.wdE - w) * nr) * EVT_ROW_D + (dup.slotE - lane);
+    const long long dupW = ((long long)(dup.wdW - w) * nr) * EVT_ROW_D + (EVT_HALO - (EVT_U + lane));
+    double *rown = strip + (size_t)j0 * EVT_ROW_D + evt_state_off(newc); // new state copy of tile row j
+    double px = 0.0, s5c = 0.0, s7c = 0.0;
+    int st = 0;
+    unsigned phase = 0;
+
+    for (int r = 0; r < nT; ++r) {
+        const int j = j0 + r;
+        { // wait for the row's bulk copy (bounded: a protocol bug must not hang the device)
+            const unsigned bar = smem_u32(bars + st);
+            unsigned done = 0, spins = 0;
+            while (!done) {
+                asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                             : "=r"(done)
+                             : "r"(bar), "r"(phase)
+                             : "memory");
+                if (!done && ++spins > (1u << 22)) {
+                    *(volatile int *)(a.sync + 6) = 1;
+                    break;
+                }
+            }
+        }
+        double *const stage = stages + st * EVT_STAGE_D;
+        const double *sg = stage + st_s, *si = stage + inv_s;
+        const unsigned char *mk = (const unsigned char *)(si + EVT_MASK);
+        TRow t;
+        URow uc;
+        t.ht = false;
+        t.act = colT && mk[lane] != 0;
+        uc.act = colU && r > 0 && mk[32 + lane] != 0;
+        double hu, hv;
+        if (peer_top && j == a.nyl + 1) {
+            // ghost row written by the north neighbour GPU while this kernel runs: read it with coherent
+            // generic loads (after the flag wait) instead of trusting the bulk copy's view of it
+            const double *gr = strip + (size_t)j * EVT_ROW_D + evt_state_off(oldc);
+            t.u = colT ? __ldcg(gr + EVT_U + lane) : 0.0;
+            t.v = colT ? __ldcg(gr + EVT_V + lane) : 0.0;
+            hu = __ldcg(gr + EVT_HALO);
+            hv = __ldcg(gr + EVT_HALO + 1);
+        } else {
+            t.u = colT ? sg[EVT_U + lane] : 0.0;
+            t.v = colT ? sg[EVT_V + lane] : 0.0;
+            hu = sg[EVT_HALO];
+            hv = sg[EVT_HALO + 1];
+        }
+        t.uw = __shfl_up_sync(0xffffffffu, t.u, 1);
+        t.vw = __shfl_up_sync(0xffffffffu, t.v, 1);
+        if (lane == 0) {
+            t.uw = hu;
+            t.vw = hv;
+        }
+        const idx_t pidx = j * a.pitch + i;
+        if (t.act) {
+#pragma unroll
+            for (int k = 0; k < EVP_NSTRESS; ++k) t.s[k] = sg[EVT_S(k) + lane];
+            t.strength = si[EVT_T(0) + lane];
+            t.dxt = si[EVT_T(1) + lane];
+            t.dyt = si[EVT_T(2) + lane];
+            t.dxhy = si[EVT_T(3) + lane];
+            t.dyhx = si[EVT_T(4) + lane];
+            t.cxp = si[EVT_T(5) + lane];
+            t.cyp = si[EVT_T(6) + lane];
+            t.cxm = si[EVT_T(7) + lane];
+            t.cym = si[EVT_T(8) + lane];
+            t.tiny = si[EVT_T(9) + lane];
+            if (LAST) t.tarear = __ldg(a.tarear + pidx);
+        }
+        if (uc.act) {
+            uc.aiu = si[EVT_UF(0) + lane];
+            uc.uocn = si[EVT_UF(1) + lane];
+            uc.vocn = si[EVT_UF(2) + lane];
+            uc.waterx = si[EVT_UF(3) + lane];
+            uc.watery = si[EVT_UF(4) + lane];
+            uc.forcex = si[EVT_UF(5) + lane];
+            uc.forcey = si[EVT_UF(6) + lane];
+            uc.umassdtei = si[EVT_UF(7) + lane];
+            uc.fm = si[EVT_UF(8) + lane];
+            uc.uarear = si[EVT_UF(9) + lane];
+        }
+        // every lane holds its values in registers: the stage can be refilled with row j + S right away
+        __syncwarp();
+        if (lane == 0 && r + S < nT) {
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            tile_issue(win + (size_t)(r + S) * EVT_ROW_D, stage, smem_u32(bars + st));
+        }
+
+        double str[8];
+        if (t.act) {
+            const bool store = j < j0 + nrows || j == a.nyl + 1;
+            stress_cell<LAST>(a, TileStoreT{a, rown, pidx, lane, store}, t, us, vs, usw, vsw, str);
+        } else {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) str[k] = 0.0; // str(:,:,:) = c0, :1051
+        }
+        // str(2,4,7,8) of the T cell east of this lane's U point
+        const double s2r = __shfl_down_sync(0xffffffffu, str[1], 1);
+        const double s4r = __shfl_down_sync(0xffffffffu, str[3], 1);
+        const double s7r = __shfl_down_sync(0xffffffffu, str[6], 1);
+        const double s8r = __shfl_down_sync(0xffffffffu, str[7], 1);
+        if (uc.act) {
+            const double sx = px + str[2] + s4r;       // ((s1 + s2) + s3) + s4
+            const double sy = s5c + str[5] + s7c + s8r; // ((s5 + s6) + s7) + s8
+            stepu_cell<LAST>(a, TileStoreU{a, rown - EVT_ROW_D + EVT_U + lane, dupE, dupW, dup, pidx - a.pitch, w, lane, j - 1, newc},
+                             uc, us, vs, sx, sy);
+        }
+        px = str[0] + s2r;
+        s5c = str[4];
+        s7c = s7r;
+        us = t.u;
+        vs = t.v;
+        usw = t.uw;
+        vsw = t.vw;
+        rown += EVT_ROW_D;
+        if (++st == S) {
+            st = 0;
+            phase ^= 1u;
+        }
+    }
+}
+
+// Tripole u-fold on the tiled layout (north-south part of the halo update on the top slab): the last CTA of
+// the northernmost chunk to finish symmetrises the top physical row and fills the ghost row, through a scratch
+// copy of the raw top row (same arithmetic as k_halo_tripole / evp_fold_necorner).
+__device__ __forceinline__ void tile_write_col(const SubArgs &a, int copy, int cc, int row, double u, double v) {
+    int dv;
+    double *pool = a.tiles;
+    double *p = pool + evt_u_primary(cc, row, a.nx, a.t_ns, a.t_nr, copy, dv);
+    p[0] = u;
+    p[dv] = v;
+    if (cc >= 1 && cc <= a.nx) {
+        const int w = (cc - 1) / EVT_UW, l = (cc - 1) - w * EVT_UW;
+        const int so = evt_state_off(copy);
+        if (l == 0 && w > 0) {
+            double *q = pool + ((size_t)(w - 1) * a.t_nr + row) * EVT_ROW_D + so + EVT_U + EVT_UW;
+            q[0] = u; q[32] = v;
+        }
+        if (l == EVT_UW - 1 && w < a.t_ns - 1) {
+            double *q = pool + ((size_t)(w + 1) * a.t_nr + row) * EVT_ROW_D + so + EVT_HALO;
+            q[0] = u; q[1] = v;
+        }
+    }
+}
+
+template <int NT>
+__device__ __forceinline__ void tiled_epilogue(const SubArgs &a, int newc, int tid, bool top) {
+    if (a.fold && top) {
+        __shared__ int is_last;
+        __syncthreads();
+        if (tid == 0) {
+            __threadfence();
+            is_last = (atomicAdd((unsigned *)a.sync + 4, 1u) == gridDim.x - 1) ? 1 : 0;
+        }
+        __syncthreads();
+        if (is_last) {
+            __threadfence();
+            const int ncol = a.nx + 2, nyl = a.nyl;
+            for (int c = tid; c < 2 * ncol; c += NT) { // raw top row of u_new, v_new -> scratch
+                const int f = c >= ncol, cc = f ? c - ncol : c;
+                int dv;
+                const double *p = a.tiles + evt_u_primary(cc, nyl, a.nx, a.t_ns, a.t_nr, newc, dv);
+                a.fold_scratch[(size_t)f * a.pitch + cc] = __ldcg(p + (f ? dv : 0));
+            }
+            __syncthreads();
+            for (int cc = tid; cc < ncol; cc += NT) {
+                int ig = cc;
+                if (cc == 0) ig = a.ew_cyclic ? a.nx : 1;
+                if (cc == a.nx + 1) ig = a.ew_cyclic ? 1 : a.nx;
+                int k = a.nx - ig;
+                if (k == 0) k = a.nx;
+                double ut, vt, dummy;
+                evp_fold_necorner(a.fold_scratch, a.fold_scratch, cc, a.nx, a.ew_cyclic, -1.0, ut, dummy);
+                evp_fold_necorner(a.fold_scratch + a.pitch, a.fold_scratch + a.pitch, cc, a.nx, a.ew_cyclic, -1.0, vt, dummy);
+                int dv;
+                const double *pb = a.tiles + evt_u_primary(k, nyl - 1, a.nx, a.t_ns, a.t_nr, newc, dv);
+                const double ug = -__ldcg(pb), vg = -__ldcg(pb + dv);
+                tile_write_col(a, newc, cc, nyl, ut, vt);
+                tile_write_col(a, newc, cc, nyl + 1, ug, vg);
+            }
+            if (tid == 0) a.sync[4] = 0;
+        }
+    }
+    if (a.p2p) { // the last CTA of the grid to finish advances this rank's count of completed kernels
+        __syncthreads();
+        if (tid == 0) {
+            __threadfence();
+            const unsigned total = gridDim.x * gridDim.y;
+            const unsigned prev = atomicAdd((unsigned *)a.sync, 1u);
+            if (prev == total - 1) {
+                a.sync[0] = 0;
+                a.sync[1] = a.sync[1] + 1;
+            }
+        }
+    }
+}
+
+template <bool LAST, int S, int MINB>
+__global__ void __launch_bounds__(128, MINB) k_subcycle_tiled(const __grid_constant__ SubArgs a) {
+    asm volatile("griddepcontrol.launch_dependents;");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    extern __shared__ __align__(128) double evt_smem[]; // [4 warps][S stages][EVT_STAGE_D], then 4 * S mbarriers
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    double *const stages = evt_smem + (size_t)warp * S * EVT_STAGE_D;
+    unsigned long long *const bars = (unsigned long long *)(evt_smem + 4 * S * EVT_STAGE_D) + warp * S;
+    const int w = blockIdx.x * 4 + warp; // strip of this warp
+    const int j0 = __ldg(a.chunks + 2 * blockIdx.y);
+    const int nrows = __ldg(a.chunks + 2 * blockIdx.y + 1);
+    const bool top = (j0 + nrows - 1 == a.nyl), bot = (j0 == 1);
+    const bool live = w < a.t_ns && nrows > 0;
+    const bool peer_cta = a.p2p && ((top && a.peer_n_flag) || (bot && a.peer_s_flag));
+    int epoch = 0;
+    if (peer_cta && live) {
+        // wait until strips w-1, w, w+1 of the neighbour's adjacent chunk have published as many finished
+        // subcycles as this rank has completed (see p2p_wait)
+        epoch = *(volatile int *)(a.sync + 1);
+        if (lane < 3) {
+            const int x = (w + lane - 1 + a.t_ns) % a.t_ns;
+            if (top && a.peer_n_flag) wait_flag_ge(a.sync + EVP_SYNC_FN + x, epoch, a.sync);
+            if (bot && a.peer_s_flag) wait_flag_ge(a.sync + EVP_SYNC_FS + x, epoch, a.sync);
+            __threadfence_system();
+        }
+        __syncwarp();
+    }
+    if (live) march_tiled<LAST, S>(a, stages, bars, w, lane, j0, nrows, top && a.p2p && a.peer_n_flag != nullptr);
+    if (peer_cta && live) {
+        // this strip's boundary rows are in the neighbour's ghost tile rows: make them visible system-wide,
+        // then publish the strip's epoch in the neighbour's sync block
+        __syncwarp();
+        if (lane == 0) {
+            __threadfence_system();
+            if (top && a.peer_n_flag) *(volatile int *)(a.peer_n_flag + w) = epoch + 1;
+            if (bot && a.peer_s_flag) *(volatile int *)(a.peer_s_flag + w) = epoch + 1;
+        }
+    }
+    tiled_epilogue<128>(a, a.flip ? 0 : 1, tid, top);
+}
+
+template <int S>
+static constexpr size_t tiled_smem_bytes() {
+    return (size_t)4 * S * EVT_STAGE_D * sizeof(double) + 4 * S * sizeof(unsigned long long);
+}
+
+template <int S, int MINB>
+static int tiled_launch(const SubArgs &a, bool last, bool pdl, unsigned gx, unsigned gy, cudaStream_t s, int *ctas_per_sm) {
+    auto k0 = k_subcycle_tiled<false, S, MINB>;
+    auto k1 = k_subcycle_tiled<true, S, MINB>;
+    const size_t smem = tiled_smem_bytes<S>();
+    static bool configured = false; // once per process and instantiation (outside any stream capture)
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(k0, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(k1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return (int)e;
+        configured = true;
+    }
+    if (ctas_per_sm) {
+        int n0 = 0, n1 = 0;
+        cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n0, k0, 128, smem);
+        if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n1, k1, 128, smem);
+        *ctas_per_sm = n0 < n1 ? n0 : n1;
+        return (int)e;
+    }
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(gx, gy);
+    cfg.blockDim = dim3(128);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl ? 1 : 0;
+    return (int)(last ? cudaLaunchKernelEx(&cfg, k1, a) : cudaLaunchKernelEx(&cfg, k0, a));
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1046,6 +1485,14 @@ int EVP_SUB_CONFIGURE(void) {
     set(k_subcycle_tma<128, false, 2, 3>, tma_smem_bytes<128, 2>());
     set(k_subcycle_tma<128, true, 2, 3>, tma_smem_bytes<128, 2>());
     return (int)e;
+}
+
+// strip-tiled TMA-fed kernel: launch (ctas_per_sm == nullptr) or configure + occupancy query
+int EVP_TILED_LAUNCH(const SubArgs &a, bool last, int stages, bool pdl, unsigned grid_x, unsigned grid_y, void *stream,
+                     int *ctas_per_sm) {
+    cudaStream_t s = (cudaStream_t)stream;
+    if (stages == 3) return EVP_SUB_NS::tiled_launch<3, 2>(a, last, pdl, grid_x, grid_y, s, ctas_per_sm);
+    return EVP_SUB_NS::tiled_launch<2, 3>(a, last, pdl, grid_x, grid_y, s, ctas_per_sm);
 }
 
 // persistent kernel: launch (ctas_per_sm == nullptr) or occupancy query; returns a cudaError_t value

@@ -4,4 +4,5 @@
 #define EVP_SUB_LAUNCH evp_subcycle_launch_fast
 #define EVP_PERSIST_LAUNCH evp_persist_launch_fast
 #define EVP_SUB_CONFIGURE evp_subcycle_configure_fast
+#define EVP_TILED_LAUNCH evp_tiled_launch_fast
 #include "evp_subcycle_body.cuh"

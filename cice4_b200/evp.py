@@ -35,7 +35,7 @@ EXPORTS = [
     "evp_b200_prep", "evp_b200_run", "evp_b200_step", "evp_b200_subcycle_resident",
     "evp_b200_principal_stress", "evp_b200_get_timings", "evp_b200_diagnostics", "evp_b200_download_state",
     "evp_b200_invalidate_device_state", "evp_b200_comm_unique_id", "evp_b200_comm_init", "evp_b200_finalize",
-    "evp_b200_unpin", "evp_b200_selftest_ieee",
+    "evp_b200_unpin", "evp_b200_selftest_ieee", "evp_b200_get_info",
 ]
 
 
@@ -133,6 +133,7 @@ def load_library(path: str = LIB_PATH) -> C.CDLL:
     L.evp_b200_comm_init.argtypes = [H, C.POINTER(C.c_uint8)]
     L.evp_b200_finalize.argtypes = [H]
     L.evp_b200_unpin.argtypes = [H, C.c_void_p]
+    L.evp_b200_get_info.argtypes = [H, c_ip]
     L.evp_b200_selftest_ieee.argtypes = [C.c_int64, C.c_uint64, C.POINTER(C.c_uint64)]
     for n in EXPORTS:
         if n not in ("evp_b200_last_error", "evp_b200_default_params"):
@@ -468,6 +469,13 @@ class IceDynEvp:
         t = Timings()
         _check(load_library().evp_b200_get_timings(self._h, C.byref(t)))
         return {n: getattr(t, n) for n, _ in Timings._fields_}
+
+    def info(self) -> Dict[str, int]:
+        """How the ndte loop of this handle runs (evp_b200_get_info)."""
+        out = (C.c_int32 * 8)()
+        _check(load_library().evp_b200_get_info(self._h, out))
+        return dict(tiled=out[0], grid_x=out[1], grid_y=out[2], threads=out[3], strip_w=out[4], stages=out[5],
+                    p2p=out[6], persistent=out[7])
 
     def diagnostics(self) -> Dict[str, float]:
         """max ice speed / max strength per hemisphere of this slab, as runtime_diags prints them

@@ -105,7 +105,12 @@ typedef struct {
                                the default graph of per-subcycle launches); bit 8 (256) / bit 9
                                (512): T-row planes staged through shared memory by TMA bulk copies, 3 rows
                                deep with 2 CTAs per SM / 2 rows deep with 3 CTAs per SM; bit 10 (1024): no
-                               register prefetch across the arithmetic (<= 168 registers, 3 CTAs per SM) */
+                               register prefetch across the arithmetic (<= 168 registers, 3 CTAs per SM);
+                               bit 11 (2048): the strip-tiled layout + warp-autonomous TMA-fed kernel
+                               (csrc/evp_tiled.cuh; falls back to the plane kernels where it does not apply:
+                               north-south cyclic domains, exchange_mode 1, slabs too small for the in-kernel
+                               fold); bit 12 (4096): with bit 11, 3 pipeline stages per warp and 2 CTAs per SM
+                               instead of 2 stages and 3 CTAs */
     int32_t state_residency; /* 0 = the whole state is uploaded and downloaded by every call (host arrays always
                                current: restart-exact drop-in); 1 = the 12 stress arrays stay on the device
                                between calls: uploaded by the first call after init or after
@@ -206,6 +211,12 @@ int evp_b200_principal_stress(evp_b200_handle *h, const double *stressp_1, const
                               double *sig1, double *sig2);
 
 int evp_b200_get_timings(const evp_b200_handle *h, evp_b200_timings *t);
+
+/* How the ndte loop of this handle runs: out[0] = 1 when the strip-tiled TMA-fed kernel is in use (0: the
+ * plane kernels), out[1..2] = grid of the subcycle kernel, out[3] = threads per CTA, out[4] = U columns per
+ * strip, out[5] = pipeline stages per warp (tiled kernel), out[6] = 1 with the peer-to-peer halo, out[7] = 1
+ * with the persistent cooperative kernel. */
+int evp_b200_get_info(const evp_b200_handle *h, int32_t out[8]);
 
 /* pin_host = 1: forget (cudaHostUnregister) a caller array before the caller frees it; unknown pointers
  * are ignored.  Waits for the handle's streams first. */
