@@ -96,7 +96,7 @@ struct evp_b200_handle {
     // strip-tiled layout of the subcycle loop (evp_tiled.cuh) and the TMA-fed kernel that runs on it
     bool tiled = false;               // the ndte loop runs k_subcycle_tiled on `tiles`
     int tiled_stages = 2;             // pipeline depth per warp: 2 (3 CTAs per SM) or 3 (2 CTAs per SM)
-    TileGeom tg = {nullptr, 0, 0};
+    TileGeom tg = {nullptr, 0, 0, 0, 0};
     bool tiles_static = false;        // static part of the loop-invariant block packed
     bool planes_stale = false;        // the current state lives in the tiles only (after evp_b200_subcycle_resident)
     double *peer_tiles[2] = {nullptr, nullptr};
@@ -297,11 +297,24 @@ void fill_subargs(evp_b200_handle *h, SubArgs &a, int cur) {
     a.tiles = h->tiled ? h->tg.tiles : nullptr;
     a.t_ns = h->tg.ns;
     a.t_nr = h->tg.nr;
+    a.t_sw = h->tg.sw;
+    a.t_sj = h->tg.sj;
     a.peer_n_tiles = a.peer_s_tiles = nullptr;
     a.peer_n_nr = a.peer_s_nr = 0;
+    a.peer_n_sw = a.peer_n_sj = a.peer_s_sw = a.peer_s_sj = 0;
     if (h->p2p && h->tiled) {
-        if (h->north >= 0) { a.peer_n_tiles = h->peer_tiles[0]; a.peer_n_nr = h->peer_nyl[0] + 2; }
-        if (h->south >= 0) { a.peer_s_tiles = h->peer_tiles[1]; a.peer_s_nr = h->peer_nyl[1] + 2; }
+        const int row_major = h->tg.sw == EVT_ROW_D; // every rank of a chain uses the same order
+        TileGeom pgm = h->tg;
+        if (h->north >= 0) {
+            pgm.nr = h->peer_nyl[0] + 2;
+            evt_set_order(pgm, row_major);
+            a.peer_n_tiles = h->peer_tiles[0]; a.peer_n_nr = pgm.nr; a.peer_n_sw = pgm.sw; a.peer_n_sj = pgm.sj;
+        }
+        if (h->south >= 0) {
+            pgm.nr = h->peer_nyl[1] + 2;
+            evt_set_order(pgm, row_major);
+            a.peer_s_tiles = h->peer_tiles[1]; a.peer_s_nr = pgm.nr; a.peer_s_sw = pgm.sw; a.peer_s_sj = pgm.sj;
+        }
     }
     if (h->p2p) {
         // the neighbours' pools are laid out like ours (same plane ids, their own plane size)
@@ -329,8 +342,8 @@ int launch_subcycle(evp_b200_handle *h, int cur, bool last) {
     int e;
     if (h->tiled) {
         tiled_launch_fn fn = h->par.math_mode == 1 ? evp_tiled_launch_fast : evp_tiled_launch_strict;
-        e = fn(a, last, h->tiled_stages, (h->par.kernel_variant & 64) != 0, (unsigned)h->grid_x, (unsigned)h->grid_y,
-               (void *)h->st, nullptr);
+        const int flags = ((h->par.kernel_variant & 64) ? 1 : 0) | ((h->par.kernel_variant & 16384) ? 2 : 0);
+        e = fn(a, last, h->tiled_stages, flags, (unsigned)h->grid_x, (unsigned)h->grid_y, (void *)h->st, nullptr);
     } else {
         subcycle_launch_fn fn = h->par.math_mode == 1 ? evp_subcycle_launch_fast : evp_subcycle_launch_strict;
         e = fn(a, last, h->par.kernel_variant, h->threads, (unsigned)h->grid_x, (unsigned)h->grid_y, (void *)h->st);
@@ -514,7 +527,9 @@ int choose_tiling(evp_b200_handle *h) {
     if (h->tiled) {
         // strip-tiled TMA-fed kernel: one warp per strip of 31 U columns, 4 warps per CTA; resident CTAs per
         // SM from the occupancy of the kernel itself (shared memory: 2 or 3 pipeline stages per warp)
-        h->tiled_stages = (h->par.kernel_variant & 4096) ? 3 : 2;
+        // 3 stages / 2 CTAs per SM measured equal or better than 2 stages / 3 CTAs on every short slab but one
+        // (360 x 300: 13.7 vs 13.3 us); kernel_variant bit 12 selects the latter
+        h->tiled_stages = (h->par.kernel_variant & 4096) ? 2 : 3;
         nt = 128;
         strip_w = EVT_UW;
         ncx = (evt_nstrips(nx) + 3) / 4;
@@ -522,7 +537,7 @@ int choose_tiling(evp_b200_handle *h) {
         fill_subargs(h, a, 0);
         tiled_launch_fn fn = h->par.math_mode == 1 ? evp_tiled_launch_fast : evp_tiled_launch_strict;
         per_sm = 0;
-        const int e = fn(a, false, h->tiled_stages, false, 0, 0, nullptr, &per_sm);
+        const int e = fn(a, false, h->tiled_stages, 0, 0, 0, nullptr, &per_sm);
         if (e != 0 || per_sm < 1) {
             cudaGetLastError();
             return fail(EVP_B200_ERR_CUDA, "tiled subcycle kernel cannot be configured: %s", cudaGetErrorString((cudaError_t)e));
@@ -804,13 +819,24 @@ static int init_handle(evp_b200_handle *h, const evp_b200_dims *d, const evp_b20
     }
     if (rc) return rc;
     CU(cudaStreamSynchronize(h->st));
-    // The strip-tiled TMA-fed kernel (kernel_variant bit 11) needs everything of the per-subcycle halo update
-    // inside the kernel: no north-south cyclic wrap, no NCCL exchange in the loop, per-strip flags for all strips
-    h->tiled = (p->kernel_variant & 2048) != 0 && (p->kernel_variant & (16 | 128 | 256 | 512 | 1024)) == 0 &&
-               !pg.ns_cyclic && !(d->nranks > 1 && p->exchange_mode != 0) && evt_nstrips(pg.nx) <= EVP_SYNC_MAXCX;
+    // Which kernel runs the ndte loop.  The strip-tiled TMA-fed kernel needs everything of the per-subcycle halo
+    // update inside the kernel: no north-south cyclic wrap, no NCCL exchange in the loop, per-strip flags for all
+    // strips.  Measured on B200 (profiles/r02_*): it wins on short slabs -- 1440 x 135: 15.0 vs 19.2 us per
+    // subcycle, 1440 x 270: 28.9 vs 32.4, 3600 x 338: 95.7 vs 103.8, 100 x 116: 6.3 vs 6.8 -- where the plane
+    // kernel's few rows per CTA cost it redundant T rows and exposed row latency, and loses on tall ones (1440 x
+    // 540: 61.6 vs 57.0, 1440 x 1080: 123.6 vs 112.6), where the duplicated slot of every strip (+3 %), the
+    // shorter row chunks and the halo words make it stream 9 % more bytes.  Default: tiled below 450 rows per
+    // slab (decided from the mean slab height so that all ranks of a chain agree); kernel_variant bit 11 forces
+    // it, bit 15 forces the plane kernels.
+    const int kv = p->kernel_variant;
+    const bool tiled_ok = (kv & (16 | 128 | 256 | 512 | 1024 | 32768)) == 0 && !pg.ns_cyclic &&
+                          !(d->nranks > 1 && p->exchange_mode != 0) && evt_nstrips(pg.nx) <= EVP_SYNC_MAXCX;
+    const bool tiled_auto = p->tile_threads == 0 && d->ny_global / d->nranks < 450;
+    h->tiled = tiled_ok && ((kv & 2048) != 0 || tiled_auto);
     if (h->tiled) {
         h->tg.ns = evt_nstrips(pg.nx);
         h->tg.nr = pg.nyl + 2;
+        evt_set_order(h->tg, (p->kernel_variant & 8192) ? 0 : 1); // bit 13: strip-major instead of row-major
         const size_t tb = sizeof(double) * (size_t)h->tg.ns * h->tg.nr * EVT_ROW_D;
         CU(cudaMalloc(&h->tg.tiles, tb));
         CU(cudaMemsetAsync(h->tg.tiles, 0, tb, h->st));

@@ -597,7 +597,7 @@ __device__ __forceinline__ bool tile_coords(const PlaneGeom &pg, const TileGeom 
 __global__ void k_tile_pack_static(PlaneGeom pg, TileGeom tg, TileStaticArgs a) {
     int w, j, lane, i;
     if (!tile_coords(pg, tg, w, j, lane, i)) return;
-    double *inv = tg.tiles + ((size_t)w * tg.nr + j) * EVT_ROW_D + evt_inv_off();
+    double *inv = tg.tiles + (w * tg.sw + j * tg.sj) + evt_inv_off();
     const bool colT = i <= pg.nx + 1;
     const size_t idx = (size_t)j * pg.pitch + i;
     const double *tp[9] = {a.dxt, a.dyt, a.dxhy, a.dyhx, a.cxp, a.cyp, a.cxm, a.cym, a.tinyarea};
@@ -610,7 +610,7 @@ __global__ void k_tile_pack_static(PlaneGeom pg, TileGeom tg, TileStaticArgs a) 
 __global__ void k_tile_pack_call(PlaneGeom pg, TileGeom tg, TileCallArgs a) {
     int w, j, lane, i;
     if (!tile_coords(pg, tg, w, j, lane, i)) return;
-    double *row = tg.tiles + ((size_t)w * tg.nr + j) * EVT_ROW_D;
+    double *row = tg.tiles + (w * tg.sw + j * tg.sj);
     double *inv = row + evt_inv_off();
     const bool colT = i <= pg.nx + 1;
     const bool colU = lane < EVT_UW && i <= pg.nx && j >= 1;
@@ -643,7 +643,7 @@ __global__ void k_tile_pack_call(PlaneGeom pg, TileGeom tg, TileCallArgs a) {
 __global__ void k_tile_unpack_state(PlaneGeom pg, TileGeom tg, int copy, TileStateArgs a) {
     int w, j, lane, i;
     if (!tile_coords(pg, tg, w, j, lane, i)) return;
-    const double *c = tg.tiles + ((size_t)w * tg.nr + j) * EVT_ROW_D + evt_state_off(copy);
+    const double *c = tg.tiles + (w * tg.sw + j * tg.sj) + evt_state_off(copy);
     // every plane column 1 .. nx+1 once: the 31 own slots of a strip, and slot 31 only where it is column nx+1
     const bool own = (lane < EVT_UW && i <= pg.nx + 1) || (i == pg.nx + 1);
     const size_t idx = (size_t)j * pg.pitch + i;

@@ -74,10 +74,12 @@ struct SubArgs {
     int *peer_n_flag, *peer_s_flag;
     int p2p;                         // 1 = the above are in use
     // ---- strip-tiled layout of the TMA-fed kernel (evp_tiled.cuh); null when the plane kernels run ----
-    double *tiles;                   // [t_ns strips][t_nr = nyl + 2 rows][EVT_ROW_D]
-    int t_ns, t_nr;
-    double *peer_n_tiles, *peer_s_tiles; // the neighbours' tile pools (same strips; their own row counts)
+    double *tiles;                   // tile row (strip w, row j) at tiles + w * t_sw + j * t_sj
+    int t_ns, t_nr;                  // strips; rows per strip (nyl + 2)
+    long long t_sw, t_sj;
+    double *peer_n_tiles, *peer_s_tiles; // the neighbours' tile pools (same strips; their own row counts / strides)
     int peer_n_nr, peer_s_nr;
+    long long peer_n_sw, peer_n_sj, peer_s_sw, peer_s_sj;
     // ---- tripole u-fold of u_new/v_new inside the kernel (top slab only) ------------------------
     int fold;              // 1 = the last CTA of the northernmost chunk to finish applies the fold
     double *fold_scratch;  // 2 * pitch doubles: copy of the raw top physical row of u_new, v_new
@@ -127,10 +129,11 @@ int evp_subcycle_configure_strict(void);
 int evp_subcycle_configure_fast(void);
 // strip-tiled TMA-fed kernel (k_subcycle_tiled): stages = 2 (3 CTAs of 4 warps per SM) or 3 (2 CTAs per SM);
 // ctas_per_sm != nullptr: only the occupancy query.  Returns a cudaError_t value.
-typedef int (*tiled_launch_fn)(const SubArgs &a, bool last, int stages, bool pdl, unsigned grid_x, unsigned grid_y,
+// flags: bit 0 programmatic dependent launch, bit 1 memory-only measurement variant (results invalid)
+typedef int (*tiled_launch_fn)(const SubArgs &a, bool last, int stages, int flags, unsigned grid_x, unsigned grid_y,
                                void *stream, int *ctas_per_sm);
-int evp_tiled_launch_strict(const SubArgs &a, bool last, int stages, bool pdl, unsigned grid_x, unsigned grid_y,
+int evp_tiled_launch_strict(const SubArgs &a, bool last, int stages, int flags, unsigned grid_x, unsigned grid_y,
                             void *stream, int *ctas_per_sm);
-int evp_tiled_launch_fast(const SubArgs &a, bool last, int stages, bool pdl, unsigned grid_x, unsigned grid_y,
+int evp_tiled_launch_fast(const SubArgs &a, bool last, int stages, int flags, unsigned grid_x, unsigned grid_y,
                           void *stream, int *ctas_per_sm);
 int evp_subcycle_max_threads(void);

@@ -926,18 +926,18 @@ __device__ __forceinline__ TileDup tile_dups(const SubArgs &a, int w, int lane, 
 }
 
 // u, v of U column (strip w, lane) of tile row `row` of a tile pool, with its duplicates
-__device__ __forceinline__ void tile_store_uv(double *pool, int nr, int row, int copy, int w, int lane, const TileDup &d,
-                                              double u, double v) {
+__device__ __forceinline__ void tile_store_uv(double *pool, long long sw, long long sj, int row, int copy, int w, int lane,
+                                              const TileDup &d, double u, double v) {
     const int so = evt_state_off(copy);
-    double *p = pool + ((size_t)w * nr + row) * EVT_ROW_D + so;
+    double *p = pool + (w * sw + row * sj) + so;
     p[EVT_U + lane] = u;
     p[EVT_V + lane] = v;
     if (d.flags & 1) {
-        double *q = pool + ((size_t)d.wdE * nr + row) * EVT_ROW_D + so + EVT_U + d.slotE;
+        double *q = pool + (d.wdE * sw + row * sj) + so + EVT_U + d.slotE;
         q[0] = u; q[32] = v;
     }
     if (d.flags & 2) {
-        double *q = pool + ((size_t)d.wdW * nr + row) * EVT_ROW_D + so + EVT_HALO;
+        double *q = pool + (d.wdW * sw + row * sj) + so + EVT_HALO;
         q[0] = u; q[1] = v;
     }
 }
@@ -955,9 +955,10 @@ struct TileStoreU {
         if (d.flags & 1) { u_new[dupE] = unew; u_new[dupE + 32] = vnew; }
         if (d.flags & 2) { u_new[dupW] = unew; u_new[dupW + 1] = vnew; }
         if (a.p2p) { // slab-to-slab part of the halo update: straight into the neighbour GPU's ghost tile rows
-            if (j == a.nyl && a.peer_n_flag) tile_store_uv(a.peer_n_tiles, a.peer_n_nr, 0, newc, w, lane, d, unew, vnew);
+            if (j == a.nyl && a.peer_n_flag)
+                tile_store_uv(a.peer_n_tiles, a.peer_n_sw, a.peer_n_sj, 0, newc, w, lane, d, unew, vnew);
             if (j == 1 && a.peer_s_flag)
-                tile_store_uv(a.peer_s_tiles, a.peer_s_nr, a.peer_s_nr - 1, newc, w, lane, d, unew, vnew);
+                tile_store_uv(a.peer_s_tiles, a.peer_s_sw, a.peer_s_sj, a.peer_s_nr - 1, newc, w, lane, d, unew, vnew);
         }
     }
     __device__ __forceinline__ void last(double strintx, double strinty, double taux, double tauy) const {
@@ -975,10 +976,13 @@ __device__ __forceinline__ void tile_issue(const double *src, double *stage, uns
                  : "memory");
 }
 
-template <bool LAST, int S>
+// MEMONLY (measurement only, kernel_variant bit 14, results invalid): the same loads, copies and stores without
+// the stress / stepu arithmetic -- the streaming ceiling of this access pattern.
+template <bool LAST, int S, bool MEMONLY = false>
 __device__ __forceinline__ void march_tiled(const SubArgs &a, double *stages, unsigned long long *bars, int w, int lane,
                                             int j0, int nrows, bool peer_top) {
-    const int nx = a.nx, nr = a.t_nr;
+    const int nx = a.nx;
+    const long long sw = a.t_sw, sj = a.t_sj;
     const int i = EVT_UW * w + 1 + lane;
     const bool colT = i <= nx + 1;
     const bool colU = lane < EVT_UW && i <= nx;
@@ -987,26 +991,24 @@ __device__ __forceinline__ void march_tiled(const SubArgs &a, double *stages, un
     const int oldc = a.flip ? 1 : 0, newc = oldc ^ 1;
     // where the old state copy and the loop-invariant block sit inside a stage (evp_tiled.cuh)
     const int st_s = oldc ? EVT_INV_D : 0, inv_s = oldc ? 0 : EVT_STATE_D;
-    double *const strip = a.tiles + (size_t)w * nr * EVT_ROW_D;
-    const double *const win = strip + (size_t)j0 * EVT_ROW_D + evt_window_off(oldc);
+    double *const strip = a.tiles + w * sw;
+    const double *const win = strip + j0 * sj + evt_window_off(oldc);
 
     if (lane == 0) {
 #pragma unroll
         for (int q = 0; q < S; ++q)
             asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(bars + q)) : "memory");
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        // stores of the previous kernel / of the neighbour GPU (generic proxy) before the bulk copies (async proxy)
-        asm volatile("fence.proxy.async;" ::: "memory");
 #pragma unroll
         for (int q = 0; q < S; ++q)
-            if (q < nT) tile_issue(win + (size_t)q * EVT_ROW_D, stages + q * EVT_STAGE_D, smem_u32(bars + q));
+            if (q < nT) tile_issue(win + q * sj, stages + q * EVT_STAGE_D, smem_u32(bars + q));
     }
     __syncwarp();
 
     // velocities of the row south of the chunk
     double us = 0.0, vs = 0.0, usw, vsw;
     {
-        const double *sr = strip + (size_t)(j0 - 1) * EVT_ROW_D + evt_state_off(oldc);
+        const double *sr = strip + (j0 - 1) * sj + evt_state_off(oldc);
         if (colT) {
             us = __ldcg(sr + EVT_U + lane);
             vs = __ldcg(sr + EVT_V + lane);
@@ -1019,9 +1021,9 @@ __device__ __forceinline__ void march_tiled(const SubArgs &a, double *stages, un
         }
     }
     const TileDup dup = tile_dups(a, w, lane, i, colU);
-    const long long dupE = ((long long)(dup.wdE - w) * nr) * EVT_ROW_D + (dup.slotE - lane);
-    const long long dupW = ((long long)(dup.wdW - w) * nr) * EVT_ROW_D + (EVT_HALO - (EVT_U + lane));
-    double *rown = strip + (size_t)j0 * EVT_ROW_D + evt_state_off(newc); // new state copy of tile row j
+    const long long dupE = (dup.wdE - w) * sw + (dup.slotE - lane);
+    const long long dupW = (dup.wdW - w) * sw + (EVT_HALO - (EVT_U + lane));
+    double *rown = strip + j0 * sj + evt_state_off(newc); // new state copy of tile row j
     double px = 0.0, s5c = 0.0, s7c = 0.0;
     int st = 0;
     unsigned phase = 0;
@@ -1054,7 +1056,7 @@ __device__ __forceinline__ void march_tiled(const SubArgs &a, double *stages, un
         if (peer_top && j == a.nyl + 1) {
             // ghost row written by the north neighbour GPU while this kernel runs: read it with coherent
             // generic loads (after the flag wait) instead of trusting the bulk copy's view of it
-            const double *gr = strip + (size_t)j * EVT_ROW_D + evt_state_off(oldc);
+            const double *gr = strip + j * sj + evt_state_off(oldc);
             t.u = colT ? __ldcg(gr + EVT_U + lane) : 0.0;
             t.v = colT ? __ldcg(gr + EVT_V + lane) : 0.0;
             hu = __ldcg(gr + EVT_HALO);
@@ -1099,15 +1101,32 @@ __device__ __forceinline__ void march_tiled(const SubArgs &a, double *stages, un
             uc.fm = si[EVT_UF(8) + lane];
             uc.uarear = si[EVT_UF(9) + lane];
         }
-        // every lane holds its values in registers: the stage can be refilled with row j + S right away
+        // Every lane holds its values in registers: the stage can be refilled with row j + S right away.  The
+        // warp barrier orders the lanes' shared-memory reads before the issue of the copy (write-after-read
+        // across the proxies needs no proxy fence: the copy is issued after the barrier, like a TMA producer
+        // that acquired an "empty" mbarrier).
         __syncwarp();
-        if (lane == 0 && r + S < nT) {
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-            tile_issue(win + (size_t)(r + S) * EVT_ROW_D, stage, smem_u32(bars + st));
-        }
+        if (lane == 0 && r + S < nT) tile_issue(win + (r + S) * sj, stage, smem_u32(bars + st));
 
         double str[8];
-        if (t.act) {
+        if (MEMONLY) {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) str[k] = 0.0;
+            if (t.act) {
+                const double extra = t.strength + t.dxt + t.dyt + t.dxhy + t.dyhx + t.cxp + t.cyp + t.cxm + t.cym + t.tiny;
+                if (j < j0 + nrows || j == a.nyl + 1) {
+#pragma unroll
+                    for (int k = 0; k < EVP_NSTRESS; ++k) rown[EVT_S(k) + lane] = t.s[k] + (k == 0 ? extra * 1e-300 : 0.0);
+                }
+                str[0] = t.uw + t.vw;
+            }
+            if (uc.act) {
+                double *un = rown - sj + EVT_U + lane;
+                const double e2 = uc.aiu + uc.uocn + uc.vocn + uc.waterx + uc.watery + uc.forcex + uc.forcey + uc.umassdtei + uc.fm + uc.uarear;
+                un[0] = us + (e2 + usw) * 1e-300;
+                un[32] = vs + vsw * 1e-300;
+            }
+        } else if (t.act) {
             const bool store = j < j0 + nrows || j == a.nyl + 1;
             stress_cell<LAST>(a, TileStoreT{a, rown, pidx, lane, store}, t, us, vs, usw, vsw, str);
         } else {
@@ -1119,10 +1138,10 @@ __device__ __forceinline__ void march_tiled(const SubArgs &a, double *stages, un
         const double s4r = __shfl_down_sync(0xffffffffu, str[3], 1);
         const double s7r = __shfl_down_sync(0xffffffffu, str[6], 1);
         const double s8r = __shfl_down_sync(0xffffffffu, str[7], 1);
-        if (uc.act) {
+        if (!MEMONLY && uc.act) {
             const double sx = px + str[2] + s4r;       // ((s1 + s2) + s3) + s4
             const double sy = s5c + str[5] + s7c + s8r; // ((s5 + s6) + s7) + s8
-            stepu_cell<LAST>(a, TileStoreU{a, rown - EVT_ROW_D + EVT_U + lane, dupE, dupW, dup, pidx - a.pitch, w, lane, j - 1, newc},
+            stepu_cell<LAST>(a, TileStoreU{a, rown - sj + EVT_U + lane, dupE, dupW, dup, pidx - a.pitch, w, lane, j - 1, newc},
                              uc, us, vs, sx, sy);
         }
         px = str[0] + s2r;
@@ -1132,7 +1151,7 @@ __device__ __forceinline__ void march_tiled(const SubArgs &a, double *stages, un
         vs = t.v;
         usw = t.uw;
         vsw = t.vw;
-        rown += EVT_ROW_D;
+        rown += sj;
         if (++st == S) {
             st = 0;
             phase ^= 1u;
@@ -1146,59 +1165,102 @@ __device__ __forceinline__ void march_tiled(const SubArgs &a, double *stages, un
 __device__ __forceinline__ void tile_write_col(const SubArgs &a, int copy, int cc, int row, double u, double v) {
     int dv;
     double *pool = a.tiles;
-    double *p = pool + evt_u_primary(cc, row, a.nx, a.t_ns, a.t_nr, copy, dv);
+    double *p = pool + evt_u_primary(cc, row, a.nx, a.t_ns, a.t_sw, a.t_sj, copy, dv);
     p[0] = u;
     p[dv] = v;
     if (cc >= 1 && cc <= a.nx) {
         const int w = (cc - 1) / EVT_UW, l = (cc - 1) - w * EVT_UW;
         const int so = evt_state_off(copy);
         if (l == 0 && w > 0) {
-            double *q = pool + ((size_t)(w - 1) * a.t_nr + row) * EVT_ROW_D + so + EVT_U + EVT_UW;
+            double *q = pool + ((w - 1) * a.t_sw + row * a.t_sj) + so + EVT_U + EVT_UW;
             q[0] = u; q[32] = v;
         }
         if (l == EVT_UW - 1 && w < a.t_ns - 1) {
-            double *q = pool + ((size_t)(w + 1) * a.t_nr + row) * EVT_ROW_D + so + EVT_HALO;
+            double *q = pool + ((w + 1) * a.t_sw + row * a.t_sj) + so + EVT_HALO;
             q[0] = u; q[1] = v;
         }
     }
 }
 
+// Barrier among the CTAs of the northernmost chunk (they are all resident: the grid is one wave).  The counter
+// only grows; the target is the next multiple of the number of participants, so no reset is needed between
+// kernels.  Bounded like every other wait.
+__device__ __forceinline__ void top_chunk_barrier(int *counter, int tid, int *sync) {
+    __syncthreads();
+    if (tid == 0) {
+        __threadfence();
+        const unsigned n = gridDim.x;
+        const unsigned prev = atomicAdd((unsigned *)counter, 1u);
+        const unsigned target = (prev / n + 1u) * n;
+        unsigned spins = 0;
+        while ((int)((unsigned)ld_acquire(counter) - target) < 0) {
+            if (++spins > (1u << 24)) {
+                *(volatile int *)(sync + 6) = 1;
+                break;
+            }
+        }
+        __threadfence();
+    }
+    __syncthreads();
+}
+
+// End of a subcycle on the tiled layout.  Tripole u-fold (north-south part of the halo update on the top slab,
+// serial/ice_boundary.F90:777-866) by ALL CTAs of the northernmost chunk together: once every one of them has
+// finished its rows, each thread takes one column of its own strip, loads the raw top-row values of that
+// column's fold partner (and the row below it), and -- after a second barrier, because the update is in place --
+// writes the symmetrised top row and the ghost row.  Same arithmetic as evp_fold_necorner / k_halo_tripole.
 template <int NT>
 __device__ __forceinline__ void tiled_epilogue(const SubArgs &a, int newc, int tid, bool top) {
     if (a.fold && top) {
-        __shared__ int is_last;
-        __syncthreads();
-        if (tid == 0) {
-            __threadfence();
-            is_last = (atomicAdd((unsigned *)a.sync + 4, 1u) == gridDim.x - 1) ? 1 : 0;
+        top_chunk_barrier(a.sync + 4, tid, a.sync);
+        const int nx = a.nx, nyl = a.nyl, warp = tid >> 5, lane = tid & 31;
+        const int w = blockIdx.x * 4 + warp;
+        // lanes 0..30: the U columns of strip w; lane 31 of the first / last strip: the ghost columns 0 / nx+1
+        int cc = EVT_UW * w + 1 + lane;
+        bool mine = w < a.t_ns && lane < EVT_UW && cc <= nx;
+        if (lane == EVT_UW && w == 0) { cc = 0; mine = true; }
+        if (lane == EVT_UW && w == a.t_ns - 1 && a.t_ns > 1) { cc = nx + 1; mine = true; }
+        double ut = 0.0, vt = 0.0, ug = 0.0, vg = 0.0, ut2 = 0.0, vt2 = 0.0, ug2 = 0.0, vg2 = 0.0;
+        auto fold_col = [&](int c, double &o_ut, double &o_vt, double &o_ug, double &o_vg) {
+            int ig = c; // i_glob of the column (source/ice_blocks.F90:291-330)
+            if (c == 0) ig = a.ew_cyclic ? nx : 1;
+            if (c == nx + 1) ig = a.ew_cyclic ? 1 : nx;
+            int k = nx - ig; // iSrc = nxGlobal - i_glob + 1 - ioffset, ioffset = 1
+            if (k == 0) k = nx;
+            int dv, dv2 = 32, dvb;
+            const double *pk = a.tiles + evt_u_primary(k, nyl, nx, a.t_ns, a.t_sw, a.t_sj, newc, dv);
+            const bool pair = k >= 1 && k <= nx - 1;
+            const double *pn = pair ? a.tiles + evt_u_primary(nx - k, nyl, nx, a.t_ns, a.t_sw, a.t_sj, newc, dv2) : pk;
+            const double *pb = a.tiles + evt_u_primary(k, nyl - 1, nx, a.t_ns, a.t_sw, a.t_sj, newc, dvb);
+            const double uk = __ldcg(pk), vk = __ldcg(pk + dv), un = __ldcg(pn), vn = __ldcg(pn + (pair ? dv2 : dv));
+            const double ub = __ldcg(pb), vb = __ldcg(pb + dvb);
+            const double isign = -1.0;
+            double xu, xv;
+            if (k >= 1 && k <= nx / 2 - 1) {
+                xu = 0.5 * (uk + isign * un);
+                xv = 0.5 * (vk + isign * vn);
+            } else if (k >= nx - (nx / 2 - 1) && k <= nx - 1) {
+                xu = isign * (0.5 * (un + isign * uk)); // partner of the loop index i = nx - k
+                xv = isign * (0.5 * (vn + isign * vk));
+            } else {
+                xu = uk;
+                xv = vk;
+            }
+            o_ut = isign * xu; o_vt = isign * xv; // row nyl   <- isign * buf(iSrc, 2)
+            o_ug = isign * ub; o_vg = isign * vb; // row nyl+1 <- isign * buf(iSrc, 1)
+        };
+        // a single strip holds both ghost columns on lane 31: the second one goes through the *2 set
+        const bool both = a.t_ns == 1 && lane == EVT_UW && w == 0;
+        if (mine) fold_col(cc, ut, vt, ug, vg);
+        if (both) fold_col(nx + 1, ut2, vt2, ug2, vg2);
+        top_chunk_barrier(a.sync + 5, tid, a.sync);
+        if (mine) {
+            tile_write_col(a, newc, cc, nyl, ut, vt);
+            tile_write_col(a, newc, cc, nyl + 1, ug, vg);
         }
-        __syncthreads();
-        if (is_last) {
-            __threadfence();
-            const int ncol = a.nx + 2, nyl = a.nyl;
-            for (int c = tid; c < 2 * ncol; c += NT) { // raw top row of u_new, v_new -> scratch
-                const int f = c >= ncol, cc = f ? c - ncol : c;
-                int dv;
-                const double *p = a.tiles + evt_u_primary(cc, nyl, a.nx, a.t_ns, a.t_nr, newc, dv);
-                a.fold_scratch[(size_t)f * a.pitch + cc] = __ldcg(p + (f ? dv : 0));
-            }
-            __syncthreads();
-            for (int cc = tid; cc < ncol; cc += NT) {
-                int ig = cc;
-                if (cc == 0) ig = a.ew_cyclic ? a.nx : 1;
-                if (cc == a.nx + 1) ig = a.ew_cyclic ? 1 : a.nx;
-                int k = a.nx - ig;
-                if (k == 0) k = a.nx;
-                double ut, vt, dummy;
-                evp_fold_necorner(a.fold_scratch, a.fold_scratch, cc, a.nx, a.ew_cyclic, -1.0, ut, dummy);
-                evp_fold_necorner(a.fold_scratch + a.pitch, a.fold_scratch + a.pitch, cc, a.nx, a.ew_cyclic, -1.0, vt, dummy);
-                int dv;
-                const double *pb = a.tiles + evt_u_primary(k, nyl - 1, a.nx, a.t_ns, a.t_nr, newc, dv);
-                const double ug = -__ldcg(pb), vg = -__ldcg(pb + dv);
-                tile_write_col(a, newc, cc, nyl, ut, vt);
-                tile_write_col(a, newc, cc, nyl + 1, ug, vg);
-            }
-            if (tid == 0) a.sync[4] = 0;
+        if (both) {
+            tile_write_col(a, newc, nx + 1, nyl, ut2, vt2);
+            tile_write_col(a, newc, nx + 1, nyl + 1, ug2, vg2);
         }
     }
     if (a.p2p) { // the last CTA of the grid to finish advances this rank's count of completed kernels
@@ -1215,7 +1277,7 @@ __device__ __forceinline__ void tiled_epilogue(const SubArgs &a, int newc, int t
     }
 }
 
-template <bool LAST, int S, int MINB>
+template <bool LAST, int S, int MINB, bool MEMONLY = false>
 __global__ void __launch_bounds__(128, MINB) k_subcycle_tiled(const __grid_constant__ SubArgs a) {
     asm volatile("griddepcontrol.launch_dependents;");
     asm volatile("griddepcontrol.wait;" ::: "memory");
@@ -1242,7 +1304,7 @@ __global__ void __launch_bounds__(128, MINB) k_subcycle_tiled(const __grid_const
         }
         __syncwarp();
     }
-    if (live) march_tiled<LAST, S>(a, stages, bars, w, lane, j0, nrows, top && a.p2p && a.peer_n_flag != nullptr);
+    if (live) march_tiled<LAST, S, MEMONLY>(a, stages, bars, w, lane, j0, nrows, top && a.p2p && a.peer_n_flag != nullptr);
     if (peer_cta && live) {
         // this strip's boundary rows are in the neighbour's ghost tile rows: make them visible system-wide,
         // then publish the strip's epoch in the neighbour's sync block
@@ -1262,13 +1324,16 @@ static constexpr size_t tiled_smem_bytes() {
 }
 
 template <int S, int MINB>
-static int tiled_launch(const SubArgs &a, bool last, bool pdl, unsigned gx, unsigned gy, cudaStream_t s, int *ctas_per_sm) {
-    auto k0 = k_subcycle_tiled<false, S, MINB>;
+static int tiled_launch(const SubArgs &a, bool last, bool pdl, bool memonly, unsigned gx, unsigned gy, cudaStream_t s,
+                        int *ctas_per_sm) {
+    auto k0 = memonly ? k_subcycle_tiled<false, S, MINB, true> : k_subcycle_tiled<false, S, MINB>;
     auto k1 = k_subcycle_tiled<true, S, MINB>;
     const size_t smem = tiled_smem_bytes<S>();
     static bool configured = false; // once per process and instantiation (outside any stream capture)
     if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(k0, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e = cudaFuncSetAttribute(k_subcycle_tiled<false, S, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e == cudaSuccess)
+            e = cudaFuncSetAttribute(k_subcycle_tiled<false, S, MINB, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(k1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return (int)e;
         configured = true;
@@ -1488,11 +1553,12 @@ int EVP_SUB_CONFIGURE(void) {
 }
 
 // strip-tiled TMA-fed kernel: launch (ctas_per_sm == nullptr) or configure + occupancy query
-int EVP_TILED_LAUNCH(const SubArgs &a, bool last, int stages, bool pdl, unsigned grid_x, unsigned grid_y, void *stream,
+int EVP_TILED_LAUNCH(const SubArgs &a, bool last, int stages, int flags, unsigned grid_x, unsigned grid_y, void *stream,
                      int *ctas_per_sm) {
     cudaStream_t s = (cudaStream_t)stream;
-    if (stages == 3) return EVP_SUB_NS::tiled_launch<3, 2>(a, last, pdl, grid_x, grid_y, s, ctas_per_sm);
-    return EVP_SUB_NS::tiled_launch<2, 3>(a, last, pdl, grid_x, grid_y, s, ctas_per_sm);
+    const bool pdl = (flags & 1) != 0, memonly = (flags & 2) != 0;
+    if (stages == 3) return EVP_SUB_NS::tiled_launch<3, 2>(a, last, pdl, memonly, grid_x, grid_y, s, ctas_per_sm);
+    return EVP_SUB_NS::tiled_launch<2, 3>(a, last, pdl, memonly, grid_x, grid_y, s, ctas_per_sm);
 }
 
 // persistent kernel: launch (ctas_per_sm == nullptr) or occupancy query; returns a cudaError_t value

@@ -53,17 +53,26 @@ __host__ __device__ inline int evt_inv_off() { return EVT_STATE_D; }
 __host__ __device__ inline int evt_window_off(int old_copy) { return old_copy ? EVT_STATE_D : 0; }
 __host__ __device__ inline int evt_nstrips(int nx) { return (nx + EVT_UW - 1) / EVT_UW; }
 
+// Tile row (strip w, row j) starts at  w * sw + j * sj  doubles.  Two orders: strip-major (sw = nr * EVT_ROW_D,
+// sj = EVT_ROW_D: the rows a warp marches over are consecutive in memory) and row-major (sw = EVT_ROW_D,
+// sj = ns * EVT_ROW_D: the tile rows that the warps of one row chunk read at about the same time are
+// consecutive, i.e. every row front of the sweep is one long contiguous run for the DRAM pages).
 struct TileGeom {
-    double *tiles;   // [strip][row 0 .. nyl+1][EVT_ROW_D]
-    int ns, nr;      // strips, rows per strip (nyl + 2)
+    double *tiles;
+    int ns, nr;        // strips, rows per strip (nyl + 2)
+    long long sw, sj;  // strides (doubles) between strips / between rows
 };
+__host__ __device__ inline void evt_set_order(TileGeom &g, int row_major) {
+    g.sw = row_major ? (long long)EVT_ROW_D : (long long)g.nr * EVT_ROW_D;
+    g.sj = row_major ? (long long)g.ns * EVT_ROW_D : (long long)EVT_ROW_D;
+}
 
 // U column i (0 .. nx+1) of row j: where its PRIMARY copy lives.  Returns the offset (doubles) of u from
 // the start of the tile pool; v sits dv doubles behind it.
-__host__ __device__ inline size_t evt_u_primary(int i, int j, int nx, int ns, int nr, int copy, int &dv) {
+__host__ __device__ inline size_t evt_u_primary(int i, int j, int nx, int ns, long long sw, long long sj, int copy, int &dv) {
     if (i == 0) { // west ghost column: the halo word of strip 0
         dv = 1;
-        return ((size_t)0 * nr + j) * EVT_ROW_D + evt_state_off(copy) + EVT_HALO;
+        return (size_t)(j * sj) + evt_state_off(copy) + EVT_HALO;
     }
     int w = (i - 1) / EVT_UW, l = (i - 1) - w * EVT_UW;
     if (w >= ns) { // column nx+1 when nx is a multiple of 31: slot 31 of the last strip
@@ -71,5 +80,5 @@ __host__ __device__ inline size_t evt_u_primary(int i, int j, int nx, int ns, in
         l = i - 1 - w * EVT_UW;
     }
     dv = 32;
-    return ((size_t)w * nr + j) * EVT_ROW_D + evt_state_off(copy) + EVT_U + l;
+    return (size_t)(w * sw + j * sj) + evt_state_off(copy) + EVT_U + l;
 }

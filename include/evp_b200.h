@@ -106,11 +106,15 @@ typedef struct {
                                (512): T-row planes staged through shared memory by TMA bulk copies, 3 rows
                                deep with 2 CTAs per SM / 2 rows deep with 3 CTAs per SM; bit 10 (1024): no
                                register prefetch across the arithmetic (<= 168 registers, 3 CTAs per SM);
-                               bit 11 (2048): the strip-tiled layout + warp-autonomous TMA-fed kernel
-                               (csrc/evp_tiled.cuh; falls back to the plane kernels where it does not apply:
-                               north-south cyclic domains, exchange_mode 1, slabs too small for the in-kernel
-                               fold); bit 12 (4096): with bit 11, 3 pipeline stages per warp and 2 CTAs per SM
-                               instead of 2 stages and 3 CTAs */
+                               bit 11 (2048): force the strip-tiled layout + warp-autonomous TMA-fed kernel
+                               (csrc/evp_tiled.cuh), which is the default below 450 rows per slab; it falls
+                               back to the plane kernels where it does not apply (north-south cyclic domains,
+                               exchange_mode 1, slabs too small for the in-kernel fold, tile_threads set);
+                               bit 12 (4096): tiled kernel with 2 pipeline stages per warp and 3 CTAs per SM
+                               instead of 3 stages and 2 CTAs; bit 13 (8192): strip-major instead of row-major
+                               tile order; bit 14 (16384): MEASUREMENT ONLY, results invalid: tiled kernel
+                               without the arithmetic (streaming ceiling of the access pattern); bit 15
+                               (32768): force the plane kernels */
     int32_t state_residency; /* 0 = the whole state is uploaded and downloaded by every call (host arrays always
                                current: restart-exact drop-in); 1 = the 12 stress arrays stay on the device
                                between calls: uploaded by the first call after init or after

@@ -126,13 +126,17 @@ def test_cuda_block_layout_matches_reference_blocks(evp_lib):
     dyn.finalize()
 
 
+@pytest.mark.parametrize("kernel", [0, 32768], ids=["default-kernel", "plane-kernel"])
 @pytest.mark.parametrize("label,kw", CASES, ids=[c[0] for c in CASES])
-def test_bit_exact_vs_oracle_two_steps(oracle, evp_lib, label, kw):
-    """Cold start + warm second call (the timed configuration), unfused math: bit-exact."""
+def test_bit_exact_vs_oracle_two_steps(oracle, evp_lib, label, kw, kernel):
+    """Cold start + warm second call (the timed configuration), unfused math: bit-exact.  Once with the
+    kernel the library picks itself (the strip-tiled TMA-fed kernel on slabs this short) and once with the
+    plane kernel forced (kernel_variant bit 15), which is what the tall slabs run."""
     case = synth.make_case(**kw)
     st, f, strengths, _ = oracle_steps(oracle, case, nsteps=2)
     lay = E.BlockLayout.single_block(case.grid.nx, case.grid.ny)
-    dyn, out = cuda_steps(case, nsteps=2, strengths=strengths, math_mode=0)
+    dyn, out = cuda_steps(case, nsteps=2, strengths=strengths, math_mode=0, kernel_variant=kernel)
+    assert dyn.info()["tiled"] == (0 if kernel or label.startswith("cyclic-cyclic") else 1)
     _compare_exact(dyn, out, st, f, lay)
     assert np.abs(st["uvel"]).max() > 1e-3   # the case is not trivially zero
 
@@ -209,7 +213,7 @@ TILED_CASES = CASES + [
 ]
 
 
-@pytest.mark.parametrize("variant", [2048, 2048 + 4096], ids=["2-stages-3-ctas", "3-stages-2-ctas"])
+@pytest.mark.parametrize("variant", [2048 + 4096, 2048], ids=["2-stages-3-ctas", "3-stages-2-ctas"])
 @pytest.mark.parametrize("label,kw", TILED_CASES, ids=[c[0] for c in TILED_CASES])
 def test_tiled_kernel_bit_exact(oracle, evp_lib, label, kw, variant):
     """kernel_variant bit 11: the strip-tiled layout with the warp-autonomous TMA-fed kernel (one bulk copy
@@ -224,7 +228,7 @@ def test_tiled_kernel_bit_exact(oracle, evp_lib, label, kw, variant):
     if label.startswith("cyclic-cyclic"):
         assert info["tiled"] == 0      # north-south cyclic: the plane kernels run
     else:
-        assert info["tiled"] == 1 and info["strip_w"] == 31 and info["stages"] == (3 if variant & 4096 else 2), info
+        assert info["tiled"] == 1 and info["strip_w"] == 31 and info["stages"] == (2 if variant & 4096 else 3), info
     _compare_exact(dyn, out, st, f, lay)
     # the resident loop continues from the tiles; the state comes back through download_state
     if info["tiled"]:
