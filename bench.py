@@ -345,21 +345,24 @@ def parity_vs_one_gpu(ctx, case, args, ndte, dyn, rows, want):
     ctx.dist.gather_object((rows, mine), gathered if ctx.rank == 0 else None, 0)
     verdict = None
     if ctx.rank == 0:
-        one, lay1, rows1, inputs1 = make_dyn(ctx, case, args, ndte, world=1, rank=0)
-        dt = case_dt(case)
-        o = one.evp(dt, inputs1, strength=None, want=want)
-        s1 = o["strength"].copy(order="F")
-        one.evp(dt, inputs1, strength=s1, want=want)
-        bad = []
-        bounds = [gp[0] for gp in gathered]
-        for n in names:
-            full = slab.gather_slabs([gp[1][n] for gp in gathered], bounds, g.nx, g.ny)
-            ref = one.state[n][:, :, 0]
-            I = (slice(0, g.nx + 2), slice(0, g.ny + 2)) if n in ("uvel", "vvel") else (slice(1, g.nx + 1), slice(1, g.ny + 1))
-            if not np.array_equal(full[I], ref[I]):
-                bad.append(f"{n}: max|diff| {np.abs(full[I] - ref[I]).max():.3e}")
-        one.finalize()
-        verdict = "bit-exact (uvel, vvel, stressp_1 after cold + warm call)" if not bad else "MISMATCH " + "; ".join(bad)
+        try:
+            one, lay1, rows1, inputs1 = make_dyn(ctx, case, args, ndte, world=1, rank=0, pin_host=0)
+            dt = case_dt(case)
+            o = one.evp(dt, inputs1, strength=None, want=want)
+            s1 = o["strength"].copy(order="F")
+            one.evp(dt, inputs1, strength=s1, want=want)
+            bad = []
+            bounds = [gp[0] for gp in gathered]
+            for n in names:
+                full = slab.gather_slabs([gp[1][n] for gp in gathered], bounds, g.nx, g.ny)
+                ref = one.state[n][:, :, 0]
+                I = (slice(0, g.nx + 2), slice(0, g.ny + 2)) if n in ("uvel", "vvel") else (slice(1, g.nx + 1), slice(1, g.ny + 1))
+                if not np.array_equal(full[I], ref[I]):
+                    bad.append(f"{n}: max|diff| {np.abs(full[I] - ref[I]).max():.3e}")
+            one.finalize()
+            verdict = "bit-exact (uvel, vvel, stressp_1 after cold + warm call)" if not bad else "MISMATCH " + "; ".join(bad)
+        except Exception as e:   # the other ranks wait in the broadcast below: never leave them there
+            verdict = f"NOT CHECKED: {type(e).__name__}: {e}"
     obj = [verdict]
     ctx.dist.broadcast_object_list(obj, 0)
     return obj[0]
@@ -560,10 +563,21 @@ def main():
     ap.add_argument("--variant", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
-    if args.impl == "reference":
-        run_reference(args)
-    else:
-        run_b200(args)
+    try:
+        if args.impl == "reference":
+            run_reference(args)
+        else:
+            run_b200(args)
+    except BaseException:
+        # a rank that fails must not linger in destructors (NCCL teardown, stream syncs on peer flags) while
+        # the other ranks wait for it in a collective: report and leave at once so that the launcher ends the job
+        import traceback
+        traceback.print_exc()
+        sys.stderr.flush()
+        sys.stdout.flush()
+        if isinstance(sys.exc_info()[1], SystemExit) and sys.exc_info()[1].code in (0, None):
+            return
+        os._exit(1)
 
 
 if __name__ == "__main__":

@@ -105,6 +105,7 @@ struct evp_b200_handle {
     bool stress_on_device = false;    // state_residency = 1: copy 0 of the stress planes is current
     evp_b200_timings tm;
     std::unordered_map<const void *, size_t> pinned;
+    bool pin_enabled = false;         // false during evp_b200_init (static fields are not pinned)
     int grid_x = 0, grid_y = 0, threads = 128, strip_w = 0, rows = 0;
     int *d_chunks = nullptr;          // row-chunk table of the subcycle kernel (2 ints per chunk)
     int *d_cta_epoch = nullptr;       // persistent kernel: subcycles finished per CTA (grid_x * grid_y ints)
@@ -140,8 +141,13 @@ struct evp_b200_handle {
 
 namespace {
 
+// Page-lock a caller array on first use (pin_host = 1).  Only the per-call arrays are pinned -- the state, input
+// and output arrays of evp(), which the caller keeps for the whole run (Fortran module arrays; evp_b200_unpin
+// otherwise): the static grid fields of evp_b200_init are uploaded once from pageable memory, because their
+// arrays need not outlive the call and a registration left on freed memory poisons whatever the allocator
+// places there next (a partly registered range makes cudaMemcpyAsync fail with "invalid argument").
 void pin(evp_b200_handle *h, const void *p, size_t bytes) {
-    if (!h->par.pin_host || !p) return;
+    if (!h->par.pin_host || !h->pin_enabled || !p) return;
     auto it = h->pinned.find(p);
     if (it != h->pinned.end() && it->second >= bytes) return;
     if (it != h->pinned.end()) cudaHostUnregister(const_cast<void *>(p));
@@ -848,6 +854,7 @@ static int init_handle(evp_b200_handle *h, const evp_b200_dims *d, const evp_b20
     }
     decide_persistent(h); // multi-rank: decided again once the peer-to-peer halo is set up (comm_init)
     memset(&h->tm, 0, sizeof(h->tm));
+    h->pin_enabled = true;
     return EVP_B200_OK;
 }
 

@@ -398,7 +398,8 @@ def test_full_size_vs_oracle(oracle, evp_lib, label, kw, dt):
     <= 1e-10 (BASELINE north_star tolerance) -- except where contraction alone moves the CPU code by more
     than that: the same C code built with and without contraction (gcc -ffp-contract=fast vs off) differs
     by 1.6e-10 in the stresses of the warm gx1 call (rigid cells with Delta near tinyarea amplify
-    rounding), so there the bound is twice that measured freedom of the reference arithmetic itself."""
+    rounding), so where that happens the bound is twice the measured freedom of the reference arithmetic
+    itself on the same case (computed here, printed with -s)."""
     case = synth.make_case(**kw)
     assert synth.CONFIG_DT[kw["name"]] == dt
     st, f, strengths, _ = oracle_steps(oracle, case, nsteps=2, dt=dt)
@@ -414,12 +415,16 @@ def test_full_size_vs_oracle(oracle, evp_lib, label, kw, dt):
     for _ in range(2):
         oracle.run_evp(g, case.inputs, st_c, pc, lib_kind="fast")
     freedom = max(relerr(st_c[n], st[n]) for n in STATE[2:14])
+    freedom_u = max(maxabs(st_c[n], st[n]) for n in ("uvel", "vvel"))
     tol_s = max(TOL_S, 2.0 * freedom)
+    tol_u = max(TOL_U, 2.0 * freedom_u)
     dyn, out = cuda_steps(case, nsteps=2, strengths=strengths, math_mode=1, dt=dt)
-    for n in ("uvel", "vvel"):
-        assert maxabs(_merge(dyn.state[n], lay), st[n]) <= TOL_U, n
+    worst_u = max(maxabs(_merge(dyn.state[n], lay), st[n]) for n in ("uvel", "vvel"))
+    assert worst_u <= tol_u, f"velocity error {worst_u:.3e} m/s > {tol_u:.3e} (CPU contraction freedom {freedom_u:.3e})"
     worst = max(relerr(_merge(dyn.state[n], lay), st[n]) for n in STATE[2:14])
     assert worst <= tol_s, f"relative stress error {worst:.3e} > {tol_s:.3e} (CPU contraction freedom {freedom:.3e})"
+    print(f"\n[{label}] math_mode=1 vs strict oracle after cold + warm call: max|du| {worst_u:.3e} m/s (CPU contraction "
+          f"freedom {freedom_u:.3e}), relative stress error {worst:.3e} (CPU contraction freedom {freedom:.3e})")
     assert np.array_equal(_merge(dyn.state["iceumask"], lay), st["iceumask"])
     dyn.finalize()
 
