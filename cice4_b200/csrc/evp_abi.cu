@@ -78,7 +78,11 @@ struct evp_b200_handle {
     double dtei, ecci, dte2T, denom1, denom2, rcon, dragw;
     int device = 0;
     cudaStream_t st = nullptr;
-    cudaStream_t st2 = nullptr;       // early download of outputs that are final before the ndte loop
+    cudaStream_t st2 = nullptr;       // device-to-host copies (and the early outputs' pack kernels)
+    cudaStream_t st_up = nullptr;     // host-to-device copies: the copy engine runs ahead of the unpack kernels on st
+    cudaEvent_t ring[128] = {};       // events that order a copy on st_up / st2 against its kernel on st
+    int ring_pos = 0;
+    bool dn_pending = false;          // copies on st2 that st has not been ordered after yet
     cudaEvent_t ev_early = nullptr, ev_early_done = nullptr;
     double *pool = nullptr;
     double *pl[P_COUNT];
@@ -106,6 +110,8 @@ struct evp_b200_handle {
     evp_b200_timings tm;
     std::unordered_map<const void *, size_t> pinned;
     bool pin_enabled = false;         // false during evp_b200_init (static fields are not pinned)
+    bool io_device = false;           // evp_b200_step_device: the caller's arrays are DEVICE memory (block layout)
+    bool vel_on_device = false;       // state_residency = 2: uvel, vvel, iceumask of the planes are current
     int grid_x = 0, grid_y = 0, threads = 128, strip_w = 0, rows = 0;
     int *d_chunks = nullptr;          // row-chunk table of the subcycle kernel (2 ints per chunk)
     int *d_cta_epoch = nullptr;       // persistent kernel: subcycles finished per CTA (grid_x * grid_y ints)
@@ -130,6 +136,7 @@ struct evp_b200_handle {
     int *sync = nullptr;              // local sync block (64 ints): see SubArgs::sync
     uint8_t *row_ht = nullptr;        // per-row flag of the 2-plane metric path (nullptr = off)
     int rows_ht = 0;                  // rows on which it is active
+    double *d_energy = nullptr;       // scratch of evp_b200_diagnostics_energy
     double *fold_scratch = nullptr;   // 2 * pitch doubles
     bool fold_in_kernel = false;      // tripole fold done by the subcycle kernel (else k_halo_tripole)
     bool p2p = false;
@@ -157,22 +164,45 @@ void pin(evp_b200_handle *h, const void *p, size_t bytes) {
         cudaGetLastError(); // pageable copy still works
 }
 
+cudaEvent_t next_event(evp_b200_handle *h) {
+    cudaEvent_t &e = h->ring[h->ring_pos];
+    h->ring_pos = (h->ring_pos + 1) % 128;
+    if (!e) cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
+    return e;
+}
+
+// Host arrays reach the planes in two steps on two streams: the copy into the staging slot on st_up (the
+// copy engine works through all fields back to back) and the unpack kernel on st, ordered by an event.
 int upload_r8(evp_b200_handle *h, const double *host, int slot, double *plane) {
     if (!host) return fail(EVP_B200_ERR_ARG, "required host array is NULL (stage slot %d)", slot);
+    if (h->io_device) { // device-pointer hand-off: the block array is read where it lies
+        aux_unblock_r8(h->bg, h->pg, host, plane, h->st);
+        return 0;
+    }
     double *stg = h->stage + (size_t)slot * h->blocked_elems;
     const size_t bytes = h->blocked_elems * sizeof(double);
     pin(h, host, bytes);
-    CU(cudaMemcpyAsync(stg, host, bytes, cudaMemcpyHostToDevice, h->st));
+    CU(cudaMemcpyAsync(stg, host, bytes, cudaMemcpyHostToDevice, h->st_up));
+    cudaEvent_t e = next_event(h);
+    CU(cudaEventRecord(e, h->st_up));
+    CU(cudaStreamWaitEvent(h->st, e, 0));
     aux_unblock_r8(h->bg, h->pg, stg, plane, h->st);
     return 0;
 }
 
 int upload_mask(evp_b200_handle *h, const int32_t *host, int slot, uint8_t *plane) {
     if (!host) return fail(EVP_B200_ERR_ARG, "required host mask is NULL");
+    if (h->io_device) {
+        aux_unblock_mask(h->bg, h->pg, host, plane, h->st);
+        return 0;
+    }
     int32_t *stg = h->stage_i + (size_t)slot * h->blocked_elems;
     const size_t bytes = h->blocked_elems * sizeof(int32_t);
     pin(h, host, bytes);
-    CU(cudaMemcpyAsync(stg, host, bytes, cudaMemcpyHostToDevice, h->st));
+    CU(cudaMemcpyAsync(stg, host, bytes, cudaMemcpyHostToDevice, h->st_up));
+    cudaEvent_t e = next_event(h);
+    CU(cudaEventRecord(e, h->st_up));
+    CU(cudaStreamWaitEvent(h->st, e, 0));
     aux_unblock_mask(h->bg, h->pg, stg, plane, h->st);
     return 0;
 }
@@ -183,21 +213,50 @@ int download_r8(evp_b200_handle *h, double *host, int slot, const double *plane,
                 cudaStream_t s = nullptr) {
     if (!host) return 0;
     if (!s) s = h->st;
+    if (h->io_device) { // the KEEP policies leave the caller's other cells as they are
+        aux_block_r8(h->bg, h->pg, plane, h->mk[M_ICETMASK], host, policy, s);
+        if (s != h->st) h->dn_pending = true;
+        return 0;
+    }
     double *stg = h->stage + (size_t)slot * h->blocked_elems;
     const size_t bytes = h->blocked_elems * sizeof(double);
     pin(h, host, bytes);
     aux_block_r8(h->bg, h->pg, plane, h->mk[M_ICETMASK], stg, policy, s);
-    CU(cudaMemcpyAsync(host, stg, bytes, cudaMemcpyDeviceToHost, s));
+    if (s != h->st2) { // the pack kernels run on st, the copies follow on st2: the copy engine never waits for a kernel launch
+        cudaEvent_t e = next_event(h);
+        CU(cudaEventRecord(e, s));
+        CU(cudaStreamWaitEvent(h->st2, e, 0));
+    }
+    CU(cudaMemcpyAsync(host, stg, bytes, cudaMemcpyDeviceToHost, h->st2));
+    h->dn_pending = true;
+    return 0;
+}
+
+// every download issued so far is complete on st once this returns (orders st2 into st)
+int join_downloads(evp_b200_handle *h) {
+    if (!h->dn_pending) return 0;
+    cudaEvent_t e = next_event(h);
+    CU(cudaEventRecord(e, h->st2));
+    CU(cudaStreamWaitEvent(h->st, e, 0));
+    h->dn_pending = false;
     return 0;
 }
 
 int download_mask(evp_b200_handle *h, int32_t *host, int slot, const uint8_t *plane, int policy) {
     if (!host) return 0;
+    if (h->io_device) {
+        aux_block_mask(h->bg, h->pg, plane, host, policy, h->st);
+        return 0;
+    }
     int32_t *stg = h->stage_i + (size_t)slot * h->blocked_elems;
     const size_t bytes = h->blocked_elems * sizeof(int32_t);
     pin(h, host, bytes);
     aux_block_mask(h->bg, h->pg, plane, stg, policy, h->st);
-    CU(cudaMemcpyAsync(host, stg, bytes, cudaMemcpyDeviceToHost, h->st));
+    cudaEvent_t e = next_event(h);
+    CU(cudaEventRecord(e, h->st));
+    CU(cudaStreamWaitEvent(h->st2, e, 0));
+    CU(cudaMemcpyAsync(host, stg, bytes, cudaMemcpyDeviceToHost, h->st2));
+    h->dn_pending = true;
     return 0;
 }
 
@@ -767,6 +826,7 @@ static int init_handle(evp_b200_handle *h, const evp_b200_dims *d, const evp_b20
 
     CU(cudaStreamCreateWithFlags(&h->st, cudaStreamNonBlocking));
     CU(cudaStreamCreateWithFlags(&h->st2, cudaStreamNonBlocking));
+    CU(cudaStreamCreateWithFlags(&h->st_up, cudaStreamNonBlocking));
     CU(cudaEventCreateWithFlags(&h->ev_early, cudaEventDisableTiming));
     CU(cudaEventCreateWithFlags(&h->ev_early_done, cudaEventDisableTiming));
     for (auto &e : h->ev) CU(cudaEventCreate(&e));
@@ -907,6 +967,8 @@ static int drain_on_error(evp_b200_handle *h, int rc) {
         const std::string why = g_err;
         if (h->st) cudaStreamSynchronize(h->st);
         if (h->st2) cudaStreamSynchronize(h->st2);
+        if (h->st_up) cudaStreamSynchronize(h->st_up);
+        h->dn_pending = false;
         cudaGetLastError();
         g_err = why;
     }
@@ -936,15 +998,21 @@ static int do_prep_impl(evp_b200_handle *h, const evp_b200_inputs *in, evp_b200_
         if ((rc = upload_r8(h, in->ss_tltx, SL_SSTLTX, p[P_SSTLTX]))) return rc;
         if ((rc = upload_r8(h, in->ss_tlty, SL_SSTLTY, p[P_SSTLTY]))) return rc;
     }
-    if ((rc = upload_r8(h, st->uvel, SL_U, p[P_U0]))) return rc;
-    if ((rc = upload_r8(h, st->vvel, SL_V, p[P_V0]))) return rc;
+    // state_residency: 0 = the whole state travels both ways every call; 1 = the stresses stay on the device;
+    // 2 = uvel, vvel and iceumask too (the planes hold the result of the previous call)
+    const bool keep_vel = h->par.state_residency == 2 && h->vel_on_device;
+    const bool keep_stress = h->par.state_residency >= 1 && h->stress_on_device;
+    if (!keep_vel) {
+        if ((rc = upload_r8(h, st->uvel, SL_U, p[P_U0]))) return rc;
+        if ((rc = upload_r8(h, st->vvel, SL_V, p[P_V0]))) return rc;
+    }
     double *sh[EVP_NSTRESS] = {st->stressp_1, st->stressp_2, st->stressp_3, st->stressp_4,
                                st->stressm_1, st->stressm_2, st->stressm_3, st->stressm_4,
                                st->stress12_1, st->stress12_2, st->stress12_3, st->stress12_4};
-    if (!(h->par.state_residency == 1 && h->stress_on_device))
+    if (!keep_stress)
         for (int k = 0; k < EVP_NSTRESS; ++k)
             if ((rc = upload_r8(h, sh[k], SL_S0 + k, p[P_S0 + k]))) return rc;
-    if ((rc = upload_mask(h, st->iceumask, 0, h->mk[M_ICEUMASK]))) return rc;
+    if (!keep_vel && (rc = upload_mask(h, st->iceumask, 0, h->mk[M_ICEUMASK]))) return rc;
     CU(cudaEventRecord(h->ev[1], h->st));
 
     // ---- :214-224 and init_history_dyn (source/ice_flux.F90:585-602) ---------------------------
@@ -989,6 +1057,7 @@ static int do_prep_impl(evp_b200_handle *h, const evp_b200_inputs *in, evp_b200_
     h->tm.kernel_launches = 0;
     if (icetmask_out) {
         if ((rc = download_mask(h, icetmask_out, 1, h->mk[M_ICETMASK], PACK_FULL))) return rc;
+        if ((rc = join_downloads(h))) return rc;
         CU(cudaStreamSynchronize(h->st));
     }
     h->prepared = true;
@@ -1028,11 +1097,11 @@ static int do_run_impl(evp_b200_handle *h, const evp_b200_inputs *in, const doub
         const size_t be = (size_t)h->dims.nx_block * h->dims.ny_block;
         for (int which = 0; which < 2; ++which) {
             const double *src = which == 0 ? in->aicen : in->vicen;
-            pin(h, src, be * ncat * h->dims.max_blocks * sizeof(double));
+            if (!h->io_device) pin(h, src, be * ncat * h->dims.max_blocks * sizeof(double));
             for (int n = 0; n < ncat; ++n) {
                 for (int b = 0; b < h->dims.nblocks; ++b)
                     CU(cudaMemcpyAsync(h->stage_cat + (size_t)b * be, src + ((size_t)b * ncat + n) * be,
-                                       be * sizeof(double), cudaMemcpyHostToDevice, h->st));
+                                       be * sizeof(double), cudaMemcpyDefault, h->st));
                 aux_unblock_r8(h->bg, pg, h->stage_cat, h->cat + (size_t)(which * ncat + n) * pg.cells, h->st);
             }
         }
@@ -1112,16 +1181,19 @@ static int do_run_impl(evp_b200_handle *h, const evp_b200_inputs *in, const doub
     CU(cudaGetLastError());
     CU(cudaEventRecord(h->ev[5], h->st));
     // ---- download ------------------------------------------------------------------------------
-    if ((rc = download_r8(h, st->uvel, SL_U, p[P_U0], PACK_FULL))) return rc;
-    if ((rc = download_r8(h, st->vvel, SL_V, p[P_V0], PACK_FULL))) return rc;
+    if (h->par.state_residency != 2) {
+        if ((rc = download_r8(h, st->uvel, SL_U, p[P_U0], PACK_FULL))) return rc;
+        if ((rc = download_r8(h, st->vvel, SL_V, p[P_V0], PACK_FULL))) return rc;
+    }
     double *sh[EVP_NSTRESS] = {st->stressp_1, st->stressp_2, st->stressp_3, st->stressp_4,
                                st->stressm_1, st->stressm_2, st->stressm_3, st->stressm_4,
                                st->stress12_1, st->stress12_2, st->stress12_3, st->stress12_4};
-    if (h->par.state_residency != 1)
+    if (h->par.state_residency == 0)
         for (int k = 0; k < EVP_NSTRESS; ++k)
             if ((rc = download_r8(h, sh[k], SL_S0 + k, p[P_S0 + k], PACK_TNE_KEEP))) return rc;
     h->stress_on_device = true;
-    if ((rc = download_mask(h, st->iceumask, 0, h->mk[M_ICEUMASK], PACK_INT_KEEP))) return rc;
+    h->vel_on_device = true;
+    if (h->par.state_residency != 2 && (rc = download_mask(h, st->iceumask, 0, h->mk[M_ICEUMASK], PACK_INT_KEEP))) return rc;
     if (out) {
         struct { double *dst; int id; int policy; } outs[] = {
             {out->strairx, P_STRAIRX, PACK_INT_ZERO}, {out->strairy, P_STRAIRY, PACK_INT_ZERO},
@@ -1142,7 +1214,7 @@ static int do_run_impl(evp_b200_handle *h, const evp_b200_inputs *in, const doub
             ++slot;
         }
     }
-    CU(cudaStreamWaitEvent(h->st, h->ev_early_done, 0));
+    if ((rc = join_downloads(h))) return rc; // early and late outputs, state: all copies on st2
     CU(cudaEventRecord(h->ev[6], h->st));
     if ((rc = check_wait_flag(h))) return rc;
     CU(cudaEventElapsedTime(&h->tm.upload_ms, h->ev[0], h->ev[1]));
@@ -1212,6 +1284,22 @@ int evp_b200_principal_stress(evp_b200_handle *h, const double *sp1, const doubl
     return 0;
 }
 
+int evp_b200_principal_stress_n(evp_b200_handle *h, int64_t n, const double *sp1, const double *sm1, const double *s12,
+                                const double *prs, double *sig1, double *sig2) {
+    if (!h || !sp1 || !sm1 || !s12 || !prs || !sig1 || !sig2) return fail(EVP_B200_ERR_ARG, "NULL argument");
+    if (n < 1 || (size_t)n > h->blocked_elems) return fail(EVP_B200_ERR_ARG, "n must be 1 .. nx_block*ny_block*max_blocks");
+    CU(cudaSetDevice(h->device));
+    const size_t bytes = (size_t)n * sizeof(double), m = h->blocked_elems;
+    double *s = h->stage;
+    const double *src[4] = {sp1, sm1, s12, prs};
+    for (int k = 0; k < 4; ++k) CU(cudaMemcpyAsync(s + k * m, src[k], bytes, cudaMemcpyHostToDevice, h->st));
+    aux_principal_stress((size_t)n, s, s + m, s + 2 * m, s + 3 * m, h->par.puny, s + 4 * m, s + 5 * m, h->st);
+    CU(cudaMemcpyAsync(sig1, s + 4 * m, bytes, cudaMemcpyDeviceToHost, h->st));
+    CU(cudaMemcpyAsync(sig2, s + 5 * m, bytes, cudaMemcpyDeviceToHost, h->st));
+    CU(cudaStreamSynchronize(h->st));
+    return 0;
+}
+
 int evp_b200_diagnostics(evp_b200_handle *h, double out[4]) {
     if (!h || !out) return fail(EVP_B200_ERR_ARG, "NULL argument");
     if (!h->resident) return fail(EVP_B200_ERR_STATE, "no device-resident result: call evp_b200_step/run first");
@@ -1224,6 +1312,31 @@ int evp_b200_diagnostics(evp_b200_handle *h, double out[4]) {
     aux_diagnostics(h->pg, h->pl[P_U0], h->pl[P_V0], h->pl[P_STRENGTH], h->pl[P_FCOR], fcor_south, d, h->st);
     CU(cudaMemcpyAsync(out, d, 4 * sizeof(double), cudaMemcpyDeviceToHost, h->st));
     CU(cudaStreamSynchronize(h->st));
+    return 0;
+}
+
+int evp_b200_diagnostics_energy(evp_b200_handle *h, double out[8]) {
+    if (!h || !out) return fail(EVP_B200_ERR_ARG, "NULL argument");
+    if (!h->resident) return fail(EVP_B200_ERR_STATE, "no device-resident result: call evp_b200_step/run first");
+    CU(cudaSetDevice(h->device));
+    if (int src = sync_planes(h)) return src;
+    if (!h->d_energy) CU(cudaMalloc(&h->d_energy, sizeof(double) * (6 * (size_t)(h->pg.nyl + 2) + 8)));
+    EnergyArgs ea;
+    ea.u = h->pl[P_U0]; ea.v = h->pl[P_V0]; ea.vice = h->pl[P_VICE]; ea.vsno = h->pl[P_VSNO];
+    ea.tarea = h->pl[P_TAREA]; ea.fcor = h->pl[P_FCOR]; ea.tmask = h->mk[M_TMASK];
+    ea.rhoi = h->par.rhoi; ea.rhos = h->par.rhos;
+    ea.fcor_south = 2.0 * 7.292e-5 * sin(-h->par.puny);
+    ea.rowsum = h->d_energy;
+    ea.out6 = h->d_energy + 6 * (size_t)(h->pg.nyl + 2);
+    aux_energy_sums(h->pg, ea, h->st);
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(out, ea.out6, 6 * sizeof(double), cudaMemcpyDeviceToHost, h->st));
+    CU(cudaStreamSynchronize(h->st));
+    // rms ice speed, source/ice_diagnostics.F90:221-234 (for one slab; several slabs: sum out[0..5], then this)
+    for (int k = 0; k < 2; ++k) {
+        double urms = 2.0 * out[k] / (h->par.rhoi * out[2 + k] + h->par.rhos * out[4 + k] + h->par.puny);
+        out[6 + k] = urms > h->par.puny ? sqrt(urms) : 0.0;
+    }
     return 0;
 }
 
@@ -1242,6 +1355,7 @@ int evp_b200_download_state(evp_b200_handle *h, evp_b200_state *st) {
     for (int k = 0; k < EVP_NSTRESS; ++k)
         if ((rc = download_r8(h, sh[k], SL_S0 + k, p[P_S0 + k], PACK_TNE_KEEP))) return rc;
     if ((rc = download_mask(h, st->iceumask, 0, h->mk[M_ICEUMASK], PACK_INT_KEEP))) return rc;
+    if ((rc = join_downloads(h))) return rc;
     CU(cudaStreamSynchronize(h->st));
     return 0;
 }
@@ -1249,7 +1363,45 @@ int evp_b200_download_state(evp_b200_handle *h, evp_b200_state *st) {
 int evp_b200_invalidate_device_state(evp_b200_handle *h) {
     if (!h) return fail(EVP_B200_ERR_ARG, "NULL argument");
     h->stress_on_device = false;
+    h->vel_on_device = false;
     return 0;
+}
+
+int evp_b200_download_velocity(evp_b200_handle *h, double *uvel, double *vvel) {
+    if (!h || !uvel || !vvel) return fail(EVP_B200_ERR_ARG, "NULL argument");
+    if (!h->vel_on_device) return fail(EVP_B200_ERR_STATE, "no device state yet: call evp_b200_step/run first");
+    CU(cudaSetDevice(h->device));
+    int rc = 0;
+    if ((rc = sync_planes(h))) return rc;
+    if ((rc = download_r8(h, uvel, SL_U, h->pl[P_U0], PACK_FULL))) return drain_on_error(h, rc);
+    if ((rc = download_r8(h, vvel, SL_V, h->pl[P_V0], PACK_FULL))) return drain_on_error(h, rc);
+    if ((rc = join_downloads(h))) return rc;
+    CU(cudaStreamSynchronize(h->st));
+    return 0;
+}
+
+int evp_b200_device_velocity(evp_b200_handle *h, const double **uvel, const double **vvel, int32_t *pitch,
+                             int32_t *nrows) {
+    if (!h || !uvel || !vvel || !pitch || !nrows) return fail(EVP_B200_ERR_ARG, "NULL argument");
+    if (!h->vel_on_device) return fail(EVP_B200_ERR_STATE, "no device state yet: call evp_b200_step/run first");
+    CU(cudaSetDevice(h->device));
+    if (int rc = sync_planes(h)) return rc;
+    CU(cudaStreamSynchronize(h->st));
+    *uvel = h->pl[P_U0];
+    *vvel = h->pl[P_V0];
+    *pitch = h->pg.pitch;
+    *nrows = h->pg.nyl + 2;
+    return 0;
+}
+
+int evp_b200_step_device(evp_b200_handle *h, const evp_b200_inputs *in, const double *strength, evp_b200_state *st,
+                         evp_b200_outputs *out) {
+    if (!h) return fail(EVP_B200_ERR_ARG, "NULL argument");
+    h->io_device = true;
+    int rc = do_prep(h, in, st, nullptr);
+    if (!rc) rc = do_run(h, in, strength, st, out);
+    h->io_device = false;
+    return rc;
 }
 
 int evp_b200_get_info(const evp_b200_handle *h, int32_t out[8]) {
@@ -1286,6 +1438,7 @@ int evp_b200_unpin(evp_b200_handle *h, const void *host_ptr) {
     CU(cudaSetDevice(h->device));
     CU(cudaStreamSynchronize(h->st));
     CU(cudaStreamSynchronize(h->st2));
+    CU(cudaStreamSynchronize(h->st_up));
     cudaHostUnregister(const_cast<void *>(host_ptr));
     cudaGetLastError();
     h->pinned.erase(it);
@@ -1431,6 +1584,7 @@ int evp_b200_finalize(evp_b200_handle *h) {
         if (h->peer_sync[k]) cudaIpcCloseMemHandle(h->peer_sync[k]);
     }
     cudaFree(h->sync);
+    cudaFree(h->d_energy);
     cudaFree(h->fold_scratch);
     cudaFree(h->d_chunks);
     cudaFree(h->d_rowcnt);
@@ -1455,6 +1609,9 @@ int evp_b200_finalize(evp_b200_handle *h) {
     if (h->ev_early) cudaEventDestroy(h->ev_early);
     if (h->ev_early_done) cudaEventDestroy(h->ev_early_done);
     if (h->st2) cudaStreamDestroy(h->st2);
+    if (h->st_up) cudaStreamDestroy(h->st_up);
+    for (auto &e : h->ring)
+        if (e) cudaEventDestroy(e);
     if (h->st) cudaStreamDestroy(h->st);
     cudaGetLastError();
     delete h;

@@ -556,6 +556,56 @@ __global__ void k_diagnostics(PlaneGeom pg, const double *__restrict__ u, const 
     }
 }
 
+// ---- kinetic energy / ice and snow volume sums of runtime_diags (source/ice_diagnostics.F90:199-234) ----
+// Deterministic, fixed-order sums: row j is summed by one CTA of 256 threads -- thread t adds columns
+// t+1, t+257, ... in that order, then a binary tree (stride 128, 64, .. 1) combines the 256 partial sums --
+// and one CTA sums the rows the same way.  tests/helpers.py restates exactly this order in numpy.
+// q: 0/1 kinetic energy north/south, 2/3 ice volume, 4/5 snow volume (all times the hemisphere's T-cell area).
+__device__ __forceinline__ double tree256(double v, double *sh) {
+    const int t = threadIdx.x;
+    sh[t] = v;
+    __syncthreads();
+    for (int s2 = 128; s2 > 0; s2 >>= 1) {
+        if (t < s2) sh[t] = sh[t] + sh[t + s2];
+        __syncthreads();
+    }
+    const double r = sh[0];
+    __syncthreads();
+    return r;
+}
+
+__global__ void __launch_bounds__(256) k_energy_rows(PlaneGeom pg, EnergyArgs a) {
+    __shared__ double sh[256];
+    const int j = 1 + blockIdx.x; // physical rows 1..nyl
+    double acc[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+    for (int i = 1 + threadIdx.x; i <= pg.nx; i += 256) {
+        const size_t idx = (size_t)j * pg.pitch + i;
+        const double area = a.tmask[idx] ? a.tarea[idx] : 0.0; // tarea * hm (source/ice_grid.F90:1386-1391)
+        const int south = a.fcor[idx] < a.fcor_south ? 1 : 0;  // lmask_s: ULAT < -puny
+        const double vsno = a.vsno[idx], vice = a.vice[idx], u = a.u[idx], v = a.v[idx];
+        const double ke = 0.5 * (a.rhos * vsno + a.rhoi * vice) * (u * u + v * v); // :210-212
+        acc[0 + south] = acc[0 + south] + ke * area;
+        acc[2 + south] = acc[2 + south] + vice * area;
+        acc[4 + south] = acc[4 + south] + vsno * area;
+        // the other hemisphere's mask is zero there: adding array * 0 leaves its sum unchanged
+    }
+#pragma unroll
+    for (int q = 0; q < 6; ++q) {
+        const double r = tree256(acc[q], sh);
+        if (threadIdx.x == 0) a.rowsum[(size_t)q * (pg.nyl + 2) + j] = r;
+    }
+}
+
+__global__ void __launch_bounds__(256) k_energy_total(PlaneGeom pg, EnergyArgs a) {
+    __shared__ double sh[256];
+    for (int q = 0; q < 6; ++q) {
+        double acc = 0.0;
+        for (int j = 1 + threadIdx.x; j <= pg.nyl; j += 256) acc = acc + a.rowsum[(size_t)q * (pg.nyl + 2) + j];
+        const double r = tree256(acc, sh);
+        if (threadIdx.x == 0) a.out6[q] = r;
+    }
+}
+
 // Bounded like the in-kernel waits (wait_flag_ge in evp_subcycle_body.cuh): a neighbour that returned
 // early on an error, crashed or timed out must not hang this GPU.  After ~2^24 polls (seconds) the error
 // flag sync[6] is raised and the host reports EVP_B200_ERR_STATE.
@@ -848,6 +898,10 @@ void aux_balance_chunks(const PlaneGeom &pg, const uint8_t *icetmask, const uint
     k_row_active<<<pg.nyl + 2, 128, 0, s>>>(pg, icetmask, iceumask, rowcnt);
     k_balance_chunks<<<1, 256, sizeof(int) * (pg.nyl + 2), s>>>(pg, rowcnt, chunks, ncy, w_bot, w_top, min_top,
                                                                  row_overhead);
+}
+void aux_energy_sums(const PlaneGeom &pg, const EnergyArgs &a, cudaStream_t s) {
+    k_energy_rows<<<pg.nyl, 256, 0, s>>>(pg, a);
+    k_energy_total<<<1, 256, 0, s>>>(pg, a);
 }
 void aux_diagnostics(const PlaneGeom &pg, const double *u, const double *v, const double *strength,
                      const double *fcor, double fcor_south, double *out4, cudaStream_t s) {

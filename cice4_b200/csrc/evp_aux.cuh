@@ -145,3 +145,13 @@ struct TileStateArgs {
     double *s[EVP_NSTRESS];
 };
 void aux_tile_unpack_state(const PlaneGeom &pg, const TileGeom &tg, int copy, const TileStateArgs &a, cudaStream_t s);
+
+// kinetic-energy / volume sums of runtime_diags (source/ice_diagnostics.F90:199-234), fixed summation order
+struct EnergyArgs {
+    const double *u, *v, *vice, *vsno, *tarea, *fcor;
+    const uint8_t *tmask;
+    double rhoi, rhos, fcor_south;
+    double *rowsum; // 6 * (nyl + 2) doubles of scratch
+    double *out6;   // ke north, ke south, ice volume north, south, snow volume north, south
+};
+void aux_energy_sums(const PlaneGeom &pg, const EnergyArgs &a, cudaStream_t s);

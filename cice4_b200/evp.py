@@ -35,7 +35,8 @@ EXPORTS = [
     "evp_b200_prep", "evp_b200_run", "evp_b200_step", "evp_b200_subcycle_resident",
     "evp_b200_principal_stress", "evp_b200_get_timings", "evp_b200_diagnostics", "evp_b200_download_state",
     "evp_b200_invalidate_device_state", "evp_b200_comm_unique_id", "evp_b200_comm_init", "evp_b200_finalize",
-    "evp_b200_unpin", "evp_b200_selftest_ieee", "evp_b200_get_info",
+    "evp_b200_unpin", "evp_b200_selftest_ieee", "evp_b200_get_info", "evp_b200_download_velocity",
+    "evp_b200_device_velocity", "evp_b200_step_device", "evp_b200_principal_stress_n", "evp_b200_diagnostics_energy",
 ]
 
 
@@ -134,6 +135,11 @@ def load_library(path: str = LIB_PATH) -> C.CDLL:
     L.evp_b200_finalize.argtypes = [H]
     L.evp_b200_unpin.argtypes = [H, C.c_void_p]
     L.evp_b200_get_info.argtypes = [H, c_ip]
+    L.evp_b200_download_velocity.argtypes = [H, c_dp, c_dp]
+    L.evp_b200_device_velocity.argtypes = [H, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), c_ip, c_ip]
+    L.evp_b200_step_device.argtypes = [H, C.POINTER(Inputs), C.c_void_p, C.POINTER(State), C.POINTER(Outputs)]
+    L.evp_b200_principal_stress_n.argtypes = [H, C.c_int64, c_dp, c_dp, c_dp, c_dp, c_dp, c_dp]
+    L.evp_b200_diagnostics_energy.argtypes = [H, c_dp]
     L.evp_b200_selftest_ieee.argtypes = [C.c_int64, C.c_uint64, C.POINTER(C.c_uint64)]
     for n in EXPORTS:
         if n not in ("evp_b200_last_error", "evp_b200_default_params"):
@@ -444,9 +450,45 @@ class IceDynEvp:
         st = self._state_struct()
         _check(load_library().evp_b200_download_state(self._h, C.byref(st)))
 
+    def download_velocity(self) -> None:
+        """state_residency = 2: bring uvel / vvel (with their ghost ring) into `self.state` -- what the
+        transport scheme reads right after evp (/root/reference/source/ice_step_mod.F90:575-585)."""
+        _check(load_library().evp_b200_download_velocity(self._h, _dptr(self.state["uvel"]), _dptr(self.state["vvel"])))
+
+    def device_velocity(self):
+        """(uvel_ptr, vvel_ptr, pitch, nrows): the device planes of this slab (transport hand-off on the GPU)."""
+        pu, pv = C.c_void_p(None), C.c_void_p(None)
+        pitch, nrows = C.c_int32(0), C.c_int32(0)
+        _check(load_library().evp_b200_device_velocity(self._h, C.byref(pu), C.byref(pv), C.byref(pitch), C.byref(nrows)))
+        return pu.value, pv.value, pitch.value, nrows.value
+
+    def evp_device(self, inputs: Dict[str, int], state: Dict[str, int], outputs: Dict[str, int],
+                   strength: Optional[int] = None) -> None:
+        """evp_b200_step_device: every argument is a DEVICE address (int) of an array in the block layout
+        (nx_block, ny_block[, ncat], max_blocks): inputs by INPUT_D name, state by STATE_D name + 'iceumask'
+        (int32), outputs by OUTPUT_D name.  `strength=None` runs ice_strength on the device."""
+        inp, st, out = Inputs(), State(), Outputs()
+        for n, a in inputs.items():
+            setattr(inp, n, C.cast(C.c_void_p(a), c_dp))
+        for n in STATE_D:
+            setattr(st, n, C.cast(C.c_void_p(state[n]), c_dp))
+        st.iceumask = C.cast(C.c_void_p(state["iceumask"]), c_ip)
+        for n, a in outputs.items():
+            setattr(out, n, C.cast(C.c_void_p(a), c_dp))
+        _check(load_library().evp_b200_step_device(self._h, C.byref(inp), C.c_void_p(strength), C.byref(st), C.byref(out)))
+
     def invalidate_device_state(self) -> None:
         """The host arrays of `self.state` were changed by the caller (restartfile): upload them again."""
         _check(load_library().evp_b200_invalidate_device_state(self._h))
+
+    def principal_stress_block(self, stressp_1, stressm_1, stress12_1, prs_sig):
+        """principal_stress on one (nx_block, ny_block) slice, as ice_history calls it block by block
+        (/root/reference/source/ice_history.F90:1939-1945) -> (sig1, sig2)."""
+        a = [np.asfortranarray(x, dtype=np.float64) for x in (stressp_1, stressm_1, stress12_1, prs_sig)]
+        sig1 = np.zeros(a[0].shape, order="F")
+        sig2 = np.zeros(a[0].shape, order="F")
+        _check(load_library().evp_b200_principal_stress_n(self._h, a[0].size, *[_dptr(x) for x in a], _dptr(sig1), _dptr(sig2)))
+        return sig1, sig2
 
     def principal_stress(self, stressp_1, stressm_1, stress12_1, prs_sig):
         """source/ice_dyn_evp.F90:1558-1609 -> (sig1, sig2)."""
@@ -476,6 +518,14 @@ class IceDynEvp:
         _check(load_library().evp_b200_get_info(self._h, out))
         return dict(tiled=out[0], grid_x=out[1], grid_y=out[2], threads=out[3], strip_w=out[4], stages=out[5],
                     p2p=out[6], persistent=out[7])
+
+    def diagnostics_energy(self) -> Dict[str, float]:
+        """total ice-snow kinetic energy, ice / snow volume and rms ice speed per hemisphere of this slab
+        (/root/reference/source/ice_diagnostics.F90:199-234), deterministic fixed-order sums."""
+        out = (C.c_double * 8)()
+        _check(load_library().evp_b200_diagnostics_energy(self._h, out))
+        return dict(ketotn=out[0], ketots=out[1], shmaxn=out[2], shmaxs=out[3], snwmxn=out[4], snwmxs=out[5],
+                    urmsn=out[6], urmss=out[7])
 
     def diagnostics(self) -> Dict[str, float]:
         """max ice speed / max strength per hemisphere of this slab, as runtime_diags prints them

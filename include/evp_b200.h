@@ -119,7 +119,10 @@ typedef struct {
                                current: restart-exact drop-in); 1 = the 12 stress arrays stay on the device
                                between calls: uploaded by the first call after init or after
                                evp_b200_invalidate_device_state, brought back only by evp_b200_download_state
-                               (before dumpfile / ice_write_hist); uvel, vvel, iceumask still round-trip */
+                               (before dumpfile / ice_write_hist); uvel, vvel, iceumask still round-trip;
+                               2 = uvel, vvel and iceumask stay on the device as well: nothing of the state
+                               travels in either direction; the transport scheme gets the velocities from
+                               evp_b200_download_velocity or, on the device, evp_b200_device_velocity */
     int32_t exchange_mode;  /* multi-rank velocity halo inside the ndte loop: 0 = peer-to-peer stores from the
                                subcycle kernel into the neighbour's ghost rows (CUDA IPC over NVLink, flags for
                                ordering), 1 = NCCL send/recv after every subcycle */
@@ -214,6 +217,21 @@ int evp_b200_principal_stress(evp_b200_handle *h, const double *stressp_1, const
                               const double *stress12_1, const double *prs_sig,
                               double *sig1, double *sig2);
 
+/* principal_stress on the first n elements of the arrays (the reference calls it block by block with
+ * (nx_block, ny_block) slices, source/ice_history.F90:1939-1945); n <= nx_block*ny_block*max_blocks */
+int evp_b200_principal_stress_n(evp_b200_handle *h, int64_t n, const double *stressp_1, const double *stressm_1,
+                                const double *stress12_1, const double *prs_sig, double *sig1, double *sig2);
+
+/* Kinetic energy and rms ice speed of runtime_diags (source/ice_diagnostics.F90:199-234) from the device-
+ * resident result and the vice / vsno of the last call, this slab only: out[0] / out[1] = total ice-snow
+ * kinetic energy north / south (sum of 0.5*(rhos*vsno + rhoi*vice)*(uvel**2 + vvel**2) * tarean|tareas),
+ * out[2] / out[3] = ice volume, out[4] / out[5] = snow volume, out[6] / out[7] = rms ice speed computed from
+ * them (several slabs: add out[0..5] over the slabs -- the reference's global_sum -- and apply :221-234).
+ * The sums are deterministic with a fixed order (csrc/evp_aux.cu k_energy_rows): thread-strided partial sums
+ * of a row combined by a binary tree, rows combined the same way; a value depends on the summation order
+ * exactly as the reference's does on its block decomposition (serial/ice_global_reductions.F90:222-246). */
+int evp_b200_diagnostics_energy(evp_b200_handle *h, double out[8]);
+
 int evp_b200_get_timings(const evp_b200_handle *h, evp_b200_timings *t);
 
 /* How the ndte loop of this handle runs: out[0] = 1 when the strip-tiled TMA-fed kernel is in use (0: the
@@ -237,6 +255,22 @@ int evp_b200_diagnostics(evp_b200_handle *h, double out[4]);
  * that the caller changed the host arrays (restartfile, :427-487) so the next call uploads them again. */
 int evp_b200_download_state(evp_b200_handle *h, evp_b200_state *st);
 int evp_b200_invalidate_device_state(evp_b200_handle *h);
+
+/* state_residency = 2, transport hand-off (source/ice_step_mod.F90:575-585, source/ice_transport_driver.F90:
+ * 498-505 read uvel / vvel with their ghost ring right after evp): only the two velocity arrays into the
+ * caller's host arrays (block layout) ... */
+int evp_b200_download_velocity(evp_b200_handle *h, double *uvel, double *vvel);
+/* ... or where they lie on the device: the library's planes of this slab, element (i, j) of plane row j at
+ * ptr[j * pitch + i], i in 0 .. nx_global+1, j in 0 .. nrows-1 (ghost ring included; plane (i, j) is Fortran
+ * (i+1, j+1) of one block spanning the slab).  Valid until the next call on this handle. */
+int evp_b200_device_velocity(evp_b200_handle *h, const double **uvel, const double **vvel, int32_t *pitch,
+                             int32_t *nrows);
+
+/* evp_b200_step with every array pointer of in / strength / st / out being DEVICE memory of this handle's
+ * device (same block layout (nx_block, ny_block, max_blocks) as the host arrays): for a caller whose
+ * thermodynamics / transport already live on the GPU.  No host traffic; the call still synchronises. */
+int evp_b200_step_device(evp_b200_handle *h, const evp_b200_inputs *in, const double *strength,
+                         evp_b200_state *st, evp_b200_outputs *out);
 
 /* multi-GPU: one handle per rank (y-slab).  id is the 128-byte ncclUniqueId made by rank 0
  * (evp_b200_comm_unique_id) and broadcast by the host (MPI_Bcast in the Fortran world,

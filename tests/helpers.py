@@ -115,3 +115,44 @@ def block_region_mismatches(name, got_blk, want_blk, layout):
         if not np.array_equal(got_blk[i0:i1, j0:j1, b], want_blk[i0:i1, j0:j1, b]):
             bad.append(b)
     return bad
+
+
+def energy_sums_fixed_order(grid, inputs, state, rhoi=917.0, rhos=330.0, puny=1e-11):
+    """runtime_diags' kinetic energy / volume sums and rms ice speed (/root/reference/source/
+    ice_diagnostics.F90:199-234) with the summation order of the device reduction (csrc/evp_aux.cu
+    k_energy_rows / k_energy_total): per row, thread t of 256 adds columns t+1, t+257, ... in order, a binary
+    tree (stride 128 .. 1) combines the 256 partial sums; the rows are combined the same way."""
+    nx, ny = grid.nx, grid.ny
+    I = (slice(1, nx + 1), slice(1, ny + 1))
+    u, v = state["uvel"][I], state["vvel"][I]
+    vice, vsno = inputs["vice"][I], inputs["vsno"][I]
+    area = np.where(grid.f["tmask"][I] != 0, grid.f["tarea"][I], 0.0)
+    south = grid.f["ULAT"][I] < -puny
+    ke = 0.5 * (rhos * vsno + rhoi * vice) * (u * u + v * v)
+    terms = [ke * area, vice * area, vsno * area]
+
+    def tree(part):            # part: (256, n)
+        s = 128
+        part = part.copy()
+        while s > 0:
+            part[:s] = part[:s] + part[s:2 * s]
+            s >>= 1
+        return part[0]
+
+    def strided(a):            # a: (n_items, n_lines): sum over items in the device order, per line
+        n = a.shape[0]
+        part = np.zeros((256, a.shape[1]))
+        for k in range(0, n, 256):
+            chunk = a[k:k + 256]
+            part[:chunk.shape[0]] = part[:chunk.shape[0]] + chunk
+        return tree(part)
+
+    out = {}
+    for name, t in zip(("ketot", "shmax", "snwmx"), terms):
+        for hemi, m in (("n", ~south), ("s", south)):
+            rows = strided(np.where(m, t, 0.0))          # one value per row j
+            out[name + hemi] = float(strided(rows[:, None])[0])
+    for hemi in ("n", "s"):
+        ur = 2.0 * out["ketot" + hemi] / (rhoi * out["shmax" + hemi] + rhos * out["snwmx" + hemi] + puny)
+        out["urms" + hemi] = float(np.sqrt(ur)) if ur > puny else 0.0
+    return out

@@ -540,6 +540,97 @@ def test_stress_residency(oracle, evp_lib):
     _compare_exact(dyn, out2, st_h, f2, lay)
 
 
+def test_full_state_residency_and_velocity_handoff(oracle, evp_lib):
+    """state_residency = 2: nothing of the state travels; the transport hand-off gets
+    uvel / vvel through download_velocity or as device planes; download_state brings everything back."""
+    import torch
+    case = synth.make_case("om1deg", nx=64, ny=48, realistic=True)
+    lay = E.BlockLayout.cartesian(64, 48, 32, 24)
+    st, f, strengths, _ = oracle_steps(oracle, case, nsteps=3)
+    dyn, out = cuda_steps(case, nsteps=3, strengths=strengths, layout=lay, state_residency=2)
+    assert np.all(dyn.state["stressp_1"] == 0.0) and np.all(dyn.state["uvel"] == 0.0)   # never downloaded so far
+    for n in OUT_CMP:                                          # outputs do travel
+        assert np.array_equal(_merge(out[n], lay), f[n]), n
+    dyn.download_velocity()
+    for n in ("uvel", "vvel"):
+        assert np.array_equal(_merge(dyn.state[n], lay), st[n]), n
+    pu, pv, pitch, nrows = dyn.device_velocity()
+    assert pitch >= 66 and nrows == 50
+    # the device planes themselves: plane (i, j) is element (i, j) of the padded single-block array
+    buf = torch.empty(pitch * nrows, dtype=torch.float64, device="cuda")
+    from cuda import cudart
+    err, = cudart.cudaMemcpy(buf.data_ptr(), pu, 8 * pitch * nrows, cudart.cudaMemcpyKind.cudaMemcpyDeviceToDevice)
+    assert int(err) == 0
+    torch.cuda.synchronize()
+    plane = buf.cpu().numpy().reshape(nrows, pitch)[:, :66].T
+    assert np.array_equal(plane, st["uvel"])
+    dyn.download_state()
+    _compare_exact(dyn, out, st, f, lay)
+    dyn.finalize()
+
+
+def test_step_device_pointers(oracle, evp_lib):
+    """evp_b200_step_device: inputs, state and outputs as DEVICE arrays in the block layout (a caller whose
+    other components already live on the GPU); bit-exact against the host-pointer path's oracle result."""
+    import torch
+    case = synth.make_case("om1deg", nx=64, ny=48, realistic=True)
+    lay = E.BlockLayout.cartesian(64, 48, 23, 19)
+    st, f, strengths, _ = oracle_steps(oracle, case, nsteps=2)
+    dyn = E.IceDynEvp(lay, "cyclic", "tripole")
+    dyn.init_evp(3600.0, E.grid_fields_in_blocks(case.grid, lay, "cyclic", "tripole"))
+    dev = lambda a: torch.from_numpy(np.ascontiguousarray(a.reshape(-1, order="F"))).cuda()
+    inputs = {k: dev(E.split_blocks(v, lay, "cyclic", "tripole")) for k, v in case.inputs.items()
+              if k in E.INPUT_D and k not in ("aice0", "aicen", "vicen")}
+    n = lay.nx_block * lay.ny_block * lay.max_blocks
+    state = {k: torch.zeros(n, dtype=torch.float64, device="cuda") for k in E.STATE_D}
+    state["iceumask"] = torch.zeros(n, dtype=torch.int32, device="cuda")
+    outs = {k: torch.zeros(n, dtype=torch.float64, device="cuda") for k in OUT_CMP}
+    for k in range(2):
+        sdev = dev(E.split_blocks(strengths[k], lay, "cyclic", "tripole"))
+        dyn.evp_device({k2: v.data_ptr() for k2, v in inputs.items()}, {k2: v.data_ptr() for k2, v in state.items()},
+                       {k2: v.data_ptr() for k2, v in outs.items()}, strength=sdev.data_ptr())
+    back = lambda t: t.cpu().numpy().reshape(lay.shape, order="F")
+    for k in STATE:
+        assert np.array_equal(_merge(back(state[k]), lay), st[k]), k
+    for k in OUT_CMP:
+        assert np.array_equal(_merge(back(outs[k]), lay), f[k]), k
+    dyn.finalize()
+
+
+def test_energy_diagnostics_fixed_order(oracle, evp_lib):
+    """Kinetic energy, ice / snow volume and rms ice speed per hemisphere (runtime_diags,
+    ice_diagnostics.F90:199-234) reduced on the device in a fixed order: bit-identical to the same order in
+    numpy, and equal to the reference's sequential global_sum order within rounding."""
+    from helpers import energy_sums_fixed_order
+    for kw in (dict(name="om1deg", nx=300, ny=90), dict(name="gx3", realistic=True, gx3_fixture=GX3_FIXTURE)):
+        case = synth.make_case(**kw)
+        st, f, strengths, _ = oracle_steps(oracle, case, nsteps=1)
+        dyn, out = cuda_steps(case, strengths=strengths)
+        d = dyn.diagnostics_energy()
+        ref = energy_sums_fixed_order(case.grid, case.inputs, st)
+        for k in ref:
+            assert d[k] == ref[k], (k, d[k], ref[k])
+        # the reference's own (sequential, j outer / i inner) order agrees to rounding
+        g = case.grid
+        I = (slice(1, g.nx + 1), slice(1, g.ny + 1))
+        ke = 0.5 * (330.0 * case.inputs["vsno"][I] + 917.0 * case.inputs["vice"][I]) * (st["uvel"][I] ** 2 + st["vvel"][I] ** 2)
+        area_n = np.where((g.f["tmask"][I] != 0) & (g.f["ULAT"][I] >= -1e-11), g.f["tarea"][I], 0.0)
+        seq = float(np.sum((ke * area_n).T.ravel()))
+        assert abs(d["ketotn"] - seq) <= 1e-12 * abs(seq)
+        assert d["urmsn"] > 0.0
+        dyn.finalize()
+
+
+def test_principal_stress_per_block(oracle, evp_lib):
+    case = synth.make_case("om1deg", nx=48, ny=40)
+    st, f, strengths, _ = oracle_steps(oracle, case, nsteps=1)
+    dyn, out = cuda_steps(case, strengths=strengths, want=["prs_sig"])
+    s1, s2 = oracle.principal_stress(st["stressp_1"], st["stressm_1"], st["stress12_1"], f["prs_sig"])
+    g1, g2 = dyn.principal_stress_block(st["stressp_1"], st["stressm_1"], st["stress12_1"], f["prs_sig"])
+    np.testing.assert_array_equal(g1, s1)
+    np.testing.assert_array_equal(g2, s2)
+
+
 def test_edge_no_ice_and_all_land(oracle, evp_lib):
     """Empty inputs: an ice-free ocean and an all-land domain give all-zero dynamics, and the state
     left by a previous call is cleared exactly as evp_prep2 does (:827-840, :886-894)."""
