@@ -635,7 +635,8 @@ int choose_tiling(evp_b200_handle *h) {
     int ncy = (per_sm * sms) / ncx; // one wave
     if (ncy < 1) ncy = 1;
     if (ncy > nyl) ncy = nyl;
-    const bool fold_wanted = h->pg.tripole && (h->par.kernel_variant & 4) == 0;
+    // the in-kernel fold is the u-fold; the T-fold (rows nyl, nyl+1 mirror rows nyl-1, nyl-2) runs as k_halo_tripole
+    const bool fold_wanted = h->pg.tripole && !h->pg.tfold && (h->par.kernel_variant & 4) == 0;
     // relative length of the boundary chunks: the northernmost chunk of the top slab also folds, a
     // chunk next to another slab waits for that slab's flag at its start
     const bool multi = h->dims.nranks > 1 && h->par.exchange_mode == 0;
@@ -803,7 +804,8 @@ static int init_handle(evp_b200_handle *h, const evp_b200_dims *d, const evp_b20
     pg.pitch = ((pg.nx + 2 + 15) / 16) * 16;
     pg.ew_cyclic = d->ew_boundary == EVP_B200_BND_CYCLIC;
     pg.ns_cyclic = d->ns_boundary == EVP_B200_BND_CYCLIC;
-    pg.tripole = d->ns_boundary == EVP_B200_BND_TRIPOLE && d->rank == d->nranks - 1;
+    pg.tfold = d->ns_boundary == EVP_B200_BND_TRIPOLET;
+    pg.tripole = (d->ns_boundary == EVP_B200_BND_TRIPOLE || pg.tfold) && d->rank == d->nranks - 1;
     h->north = (d->rank < d->nranks - 1) ? d->rank + 1 : -1;
     h->south = (d->rank > 0) ? d->rank - 1 : -1;
     pg.cells = (size_t)pg.pitch * (pg.nyl + 2);
@@ -926,9 +928,11 @@ int evp_b200_init(const evp_b200_dims *d, const evp_b200_params *p, const evp_b2
     if (d->nx_block < 3 || d->ny_block < 3) return fail(EVP_B200_ERR_ARG, "bad block size");
     if (!d->ilo || !d->ihi || !d->jlo || !d->jhi || !d->iglob_lo || !d->jglob_lo)
         return fail(EVP_B200_ERR_ARG, "block index arrays are NULL");
-    if (d->ns_boundary > EVP_B200_BND_TRIPOLE || d->ew_boundary > EVP_B200_BND_CYCLIC || d->ew_boundary < 0 ||
+    if (d->ns_boundary > EVP_B200_BND_TRIPOLET || d->ew_boundary > EVP_B200_BND_CYCLIC || d->ew_boundary < 0 ||
         d->ns_boundary < 0)
-        return fail(EVP_B200_ERR_UNSUPPORTED, "boundary type not supported (tripoleT is not implemented)");
+        return fail(EVP_B200_ERR_UNSUPPORTED, "boundary type not supported");
+    if (d->ns_boundary == EVP_B200_BND_TRIPOLET && d->rank == d->nranks - 1 && d->slab_jhi - d->slab_jlo + 1 < 3)
+        return fail(EVP_B200_ERR_ARG, "the T-fold needs at least 3 rows in the top slab");
     if (d->nranks < 1 || d->rank < 0 || d->rank >= d->nranks) return fail(EVP_B200_ERR_ARG, "bad rank/nranks");
     if (d->slab_jlo < 1 || d->slab_jhi > d->ny_global || d->slab_jhi - d->slab_jlo + 1 < 2)
         return fail(EVP_B200_ERR_ARG, "bad slab rows (each slab needs at least 2 rows)");
@@ -940,7 +944,7 @@ int evp_b200_init(const evp_b200_dims *d, const evp_b200_params *p, const evp_b2
         return fail(EVP_B200_ERR_ARG, "slabs must be ordered south to north by rank");
     if (p->ndte < 1 || !(p->dt > 0.0)) return fail(EVP_B200_ERR_ARG, "bad dt/ndte");
     if (p->ncat < 1 || p->ncat > 16) return fail(EVP_B200_ERR_ARG, "ncat out of range");
-    if (d->ns_boundary == EVP_B200_BND_TRIPOLE && d->nx_global + 2 > 8 * 1024)
+    if ((d->ns_boundary == EVP_B200_BND_TRIPOLE || d->ns_boundary == EVP_B200_BND_TRIPOLET) && d->nx_global + 2 > 8 * 1024)
         return fail(EVP_B200_ERR_UNSUPPORTED, "tripole fold kernel supports nx_global <= 8190");
 
     int ndev = 0;

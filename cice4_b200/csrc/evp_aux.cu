@@ -112,13 +112,19 @@ __global__ void k_halo_ns_cyclic(PlaneGeom pg, T *__restrict__ a, int with_corne
 // row nyl is safe.  loc 1 = centre (ghost row only), 2 = NE corner (symmetrise + overwrite the
 // top physical row, :777-800, :837-866).
 constexpr int TRIP_MAXC = 8;
+// average of two degenerate points: floating point 0.5*(x1 + isign*x2); integer fields nint(...) (serial/
+// ice_boundary.F90:1318) -- for the 0/1 masks that travel here nint(0.5*(x1 + x2)) = x1 | x2
+template <typename T> __device__ __forceinline__ T trip_avg(T x1, T x2, int isign) { return (T)(0.5 * (x1 + isign * x2)); }
+template <> __device__ __forceinline__ uint8_t trip_avg<uint8_t>(uint8_t x1, uint8_t x2, int) { return (uint8_t)(x1 | x2); }
+
 template <typename T>
 __global__ void __launch_bounds__(1024) k_halo_tripole(PlaneGeom pg, T *a0, T *a1, int loc, int isign) {
     T *a = blockIdx.x == 0 ? a0 : a1;
     const int nx = pg.nx, nyl = pg.nyl;
     const size_t rtop = (size_t)nyl * pg.pitch, rbelow = (size_t)(nyl - 1) * pg.pitch,
-                 rghost = (size_t)(nyl + 1) * pg.pitch;
+                 rbelow2 = (size_t)(nyl - 2) * pg.pitch, rghost = (size_t)(nyl + 1) * pg.pitch;
     T vtop[TRIP_MAXC], vghost[TRIP_MAXC];
+    bool wtop = false;
 #pragma unroll
     for (int c = 0; c < TRIP_MAXC; ++c) {
         const int i = threadIdx.x + c * 1024; // plane column 0..nx+1
@@ -128,7 +134,31 @@ __global__ void __launch_bounds__(1024) k_halo_tripole(PlaneGeom pg, T *a0, T *a
         int ig = i; // i_glob of the column (source/ice_blocks.F90:291-330)
         if (i == 0) ig = pg.ew_cyclic ? nx : 1;
         if (i == nx + 1) ig = pg.ew_cyclic ? 1 : nx;
-        if (loc == 2) {
+        if (pg.tfold) {
+            // T-fold (:725-773): the buffer holds rows nyl-2, nyl-1, nyl; iSrc = nx - i_glob + 1 - ioffset
+            if (loc == 2) { // NE corner: ioffset 0, joffset 1 -- rows nyl and nyl+1 mirror rows nyl-1 and nyl-2
+                int k = nx - ig + 1;
+                if (k == 0) k = nx;
+                if (k > nx) k -= nx;
+                vtop[c] = (T)(isign * a[rbelow + k]);
+                vghost[c] = (T)(isign * a[rbelow2 + k]);
+                wtop = true;
+            } else { // centre: ioffset -1, joffset 0 -- the top row is degenerate: symmetrise pairs (k, nx-k+2), k = 2..nx/2
+                int k = nx - ig + 2;
+                if (k == 0) k = nx;
+                if (k > nx) k -= nx;
+                T x = a[rtop + k];
+                if (k >= 2 && k <= nx / 2) {
+                    x = trip_avg<T>(a[rtop + k], a[rtop + (nx - k + 2)], isign);
+                } else if (k >= nx - nx / 2 + 2 && k <= nx) { // the partner iDst = nx - i + 2 of the loop index i
+                    const int kk = nx - k + 2;
+                    x = (T)(isign * trip_avg<T>(a[rtop + kk], a[rtop + k], isign));
+                }
+                vtop[c] = (T)(isign * x);
+                vghost[c] = (T)(isign * a[rbelow + k]);
+                wtop = true;
+            }
+        } else if (loc == 2) {
             int k = nx - ig; // iSrc = nxGlobal - i_glob + 1 - ioffset, ioffset = 1
             if (k == 0) k = nx;
             // bufTripole(k, 2) after symmetrisation of the top physical row
@@ -145,6 +175,7 @@ __global__ void __launch_bounds__(1024) k_halo_tripole(PlaneGeom pg, T *a0, T *a
             }
             vtop[c] = (T)(isign * x);                  // j=1: row jhi   <- isign*buf(iSrc, 2)
             vghost[c] = (T)(isign * a[rbelow + k]);    // j=2: row jhi+1 <- isign*buf(iSrc, 1)
+            wtop = true;
         } else {
             int k = nx - ig + 1; // ioffset = 0
             if (k > nx) k -= nx;
@@ -156,7 +187,7 @@ __global__ void __launch_bounds__(1024) k_halo_tripole(PlaneGeom pg, T *a0, T *a
     for (int c = 0; c < TRIP_MAXC; ++c) {
         const int i = threadIdx.x + c * 1024;
         if (i > nx + 1) continue;
-        if (loc == 2) a[rtop + i] = vtop[c];
+        if (wtop) a[rtop + i] = vtop[c];
         a[rghost + i] = vghost[c];
     }
 }

@@ -12,7 +12,8 @@
 struct PlaneGeom {
     int nx, nyl, pitch;
     int ew_cyclic, ns_cyclic;
-    int tripole;   // 1 when this slab holds the tripole fold (top rank, ns = tripole)
+    int tripole;   // 1 when this slab holds the tripole fold (top rank, ns = tripole or tripoleT)
+    int tfold;     // 1: the fold is a T-fold (ns = tripoleT), else a u-fold
     size_t cells;  // pitch * (nyl + 2)
 };
 

@@ -28,7 +28,7 @@ LIB_PATH = os.path.join(HERE, "lib", "libevp_b200.so")
 c_dp = C.POINTER(C.c_double)
 c_ip = C.POINTER(C.c_int32)
 
-BND = {"open": 0, "closed": 1, "cyclic": 2, "tripole": 3}
+BND = {"open": 0, "closed": 1, "cyclic": 2, "tripole": 3, "tripoleT": 4}
 
 EXPORTS = [
     "evp_b200_abi_version", "evp_b200_last_error", "evp_b200_default_params", "evp_b200_init",

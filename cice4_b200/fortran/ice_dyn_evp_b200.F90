@@ -115,10 +115,37 @@
             type(evp_b200_state), intent(in) :: st
             type(evp_b200_outputs), intent(in) :: outp
          end function
-         integer(c_int) function evp_b200_principal_stress(handle, sp1, sm1, s12, prs, s1, s2) &
-               bind(C, name='evp_b200_principal_stress')
+         integer(c_int) function evp_b200_principal_stress_n(handle, n, sp1, sm1, s12, prs, s1, s2) &
+               bind(C, name='evp_b200_principal_stress_n')
+            import :: c_int, c_int64_t, c_ptr
+            type(c_ptr), value :: handle
+            integer(c_int64_t), value :: n
+            type(c_ptr), value :: sp1, sm1, s12, prs, s1, s2
+         end function
+         integer(c_int) function evp_b200_download_state(handle, st) bind(C, name='evp_b200_download_state')
+            import :: c_int, c_ptr, evp_b200_state
+            type(c_ptr), value :: handle
+            type(evp_b200_state), intent(in) :: st
+         end function
+         integer(c_int) function evp_b200_invalidate_device_state(handle) &
+               bind(C, name='evp_b200_invalidate_device_state')
             import :: c_int, c_ptr
-            type(c_ptr), value :: handle, sp1, sm1, s12, prs, s1, s2
+            type(c_ptr), value :: handle
+         end function
+         integer(c_int) function evp_b200_download_velocity(handle, uvel, vvel) &
+               bind(C, name='evp_b200_download_velocity')
+            import :: c_int, c_ptr
+            type(c_ptr), value :: handle, uvel, vvel
+         end function
+         integer(c_int) function evp_b200_diagnostics(handle, out4) bind(C, name='evp_b200_diagnostics')
+            import :: c_int, c_ptr, c_double
+            type(c_ptr), value :: handle
+            real(c_double), intent(out) :: out4(4)
+         end function
+         integer(c_int) function evp_b200_diagnostics_energy(handle, out8) bind(C, name='evp_b200_diagnostics_energy')
+            import :: c_int, c_ptr, c_double
+            type(c_ptr), value :: handle
+            real(c_double), intent(out) :: out8(8)
          end function
          integer(c_int) function evp_b200_comm_unique_id(id) bind(C, name='evp_b200_comm_unique_id')
             import :: c_int, c_int8_t
@@ -139,6 +166,11 @@
       end interface
 
       type(c_ptr), private :: b200_handle = c_null_ptr
+
+      ! 0: the whole state travels every call (host arrays always current); 1: the stresses stay on the
+      ! device; 2: uvel, vvel, iceumask too.  With 1 or 2 dumpfile / ice_write_hist must be preceded by
+      ! `call evp_state_to_host` and restartfile followed by `call evp_state_from_host` (INTEGRATION.md).
+      integer (kind=int_kind) :: evp_b200_residency = 0
 
       ! int32 0/1 copies of the Fortran logical masks (compiler-independent .true. pattern)
       integer(c_int32_t), allocatable, target, private :: &
@@ -248,7 +280,7 @@
       p%ncat = ncat; p%mu_rdg = mu_rdg
       p%math_mode = 0; p%pin_host = 1; p%use_graph = 1
       p%tile_threads = 0; p%tile_rows = 0; p%kernel_variant = 0
-      p%state_residency = 0; p%exchange_mode = 0
+      p%state_residency = evp_b200_residency; p%exchange_mode = 0
 
       g%dxt = c_loc(dxt); g%dyt = c_loc(dyt); g%dxhy = c_loc(dxhy); g%dyhx = c_loc(dyhx)
       g%cxp = c_loc(cxp); g%cyp = c_loc(cyp); g%cxm = c_loc(cxm); g%cym = c_loc(cym)
@@ -275,7 +307,8 @@
       case ('closed');  b200_bnd = 1
       case ('cyclic');  b200_bnd = 2
       case ('tripole'); b200_bnd = 3
-      case default;     b200_bnd = -1      ! tripoleT: rejected by evp_b200_init
+      case ('tripoleT'); b200_bnd = 4
+      case default;     b200_bnd = -1      ! rejected by evp_b200_init
       end select
       end function b200_bnd
 
@@ -327,14 +360,7 @@
       inp%ss_tltx = c_loc(ss_tltx); inp%ss_tlty = c_loc(ss_tlty)
       inp%aice0 = c_null_ptr; inp%aicen = c_null_ptr; inp%vicen = c_null_ptr
 
-      st%uvel = c_loc(uvel); st%vvel = c_loc(vvel)
-      st%stressp_1 = c_loc(stressp_1); st%stressp_2 = c_loc(stressp_2)
-      st%stressp_3 = c_loc(stressp_3); st%stressp_4 = c_loc(stressp_4)
-      st%stressm_1 = c_loc(stressm_1); st%stressm_2 = c_loc(stressm_2)
-      st%stressm_3 = c_loc(stressm_3); st%stressm_4 = c_loc(stressm_4)
-      st%stress12_1 = c_loc(stress12_1); st%stress12_2 = c_loc(stress12_2)
-      st%stress12_3 = c_loc(stress12_3); st%stress12_4 = c_loc(stress12_4)
-      st%iceumask = c_loc(iceumask_i4)
+      call b200_state_ptrs(st)
 
       ! phase 1 on the device: evp_prep1, HALO icetmask, to_ugrid, t2ugrid_vector, evp_prep2
       call b200_check(evp_b200_prep(b200_handle, inp, st, c_loc(icetmask_i4)), 'evp_b200_prep')
@@ -378,31 +404,64 @@
       ! phase 2 on the device: HALO strength,u,v ; ndte x (stress, stepu, HALO) ; evp_finish ; u2tgrid_vector
       call b200_check(evp_b200_run(b200_handle, c_loc(strength), st, outp), 'evp_b200_run')
 
-      iceumask = (iceumask_i4 == 1)
+      if (evp_b200_residency /= 2) iceumask = (iceumask_i4 == 1)
 
       call ice_timer_stop(timer_dynamics)
       end subroutine evp
 
 !=======================================================================
-! principal_stress: same argument list as source/ice_dyn_evp.F90:1558-1561
+! state_residency = 1 / 2: bring the device-resident state into the module arrays (call before dumpfile,
+! source/ice_restart.F90:197-246, and before ice_write_hist) ...
+      subroutine evp_state_to_host
+      use ice_state
+      use ice_flux
+      type (evp_b200_state) :: st
+      if (evp_b200_residency == 0) return
+      call b200_state_ptrs(st)
+      call b200_check(evp_b200_download_state(b200_handle, st), 'evp_b200_download_state')
+      iceumask = (iceumask_i4 == 1)
+      end subroutine evp_state_to_host
+
+! ... and tell the library that the module arrays were changed by the host (after restartfile,
+! source/ice_restart.F90:427-487): the next evp call uploads them again
+      subroutine evp_state_from_host
+      if (evp_b200_residency == 0) return
+      call b200_check(evp_b200_invalidate_device_state(b200_handle), 'evp_b200_invalidate_device_state')
+      end subroutine evp_state_from_host
+
+! state_residency = 2: only the velocities, for the transport scheme right after evp
+! (source/ice_step_mod.F90:575-585)
+      subroutine evp_velocity_to_host
+      use ice_state, only: uvel, vvel
+      if (evp_b200_residency /= 2) return
+      call b200_check(evp_b200_download_velocity(b200_handle, c_loc(uvel), c_loc(vvel)), 'evp_b200_download_velocity')
+      end subroutine evp_velocity_to_host
+
+      subroutine b200_state_ptrs(st)
+      use ice_state
+      use ice_flux
+      type (evp_b200_state), intent(out) :: st
+      st%uvel = c_loc(uvel); st%vvel = c_loc(vvel)
+      st%stressp_1 = c_loc(stressp_1); st%stressp_2 = c_loc(stressp_2)
+      st%stressp_3 = c_loc(stressp_3); st%stressp_4 = c_loc(stressp_4)
+      st%stressm_1 = c_loc(stressm_1); st%stressm_2 = c_loc(stressm_2)
+      st%stressm_3 = c_loc(stressm_3); st%stressm_4 = c_loc(stressm_4)
+      st%stress12_1 = c_loc(stress12_1); st%stress12_2 = c_loc(stress12_2)
+      st%stress12_3 = c_loc(stress12_3); st%stress12_4 = c_loc(stress12_4)
+      st%iceumask = c_loc(iceumask_i4)
+      end subroutine b200_state_ptrs
+
+!=======================================================================
+! principal_stress: same argument list as source/ice_dyn_evp.F90:1558-1561; computed by the library
+! (evp_b200_principal_stress_n on one (nx_block, ny_block) slice, as ice_history calls it block by block)
       subroutine principal_stress(nx_block, ny_block, stressp_1, stressm_1, stress12_1, prs_sig, sig1, sig2)
       integer (kind=int_kind), intent(in) :: nx_block, ny_block
       real (kind=dbl_kind), dimension (nx_block,ny_block), intent(in), target :: &
          stressp_1, stressm_1, stress12_1, prs_sig
       real (kind=dbl_kind), dimension (nx_block,ny_block), intent(out), target :: sig1, sig2
-      integer (kind=int_kind) :: i, j
-      ! one block at a time is too small to be worth a device round trip: same arithmetic on the host
-      do j = 1, ny_block
-      do i = 1, nx_block
-         if (prs_sig(i,j) > puny) then
-            sig1(i,j) = (p5*(stressp_1(i,j) + sqrt(stressm_1(i,j)**2+c4*stress12_1(i,j)**2))) / prs_sig(i,j)
-            sig2(i,j) = (p5*(stressp_1(i,j) - sqrt(stressm_1(i,j)**2+c4*stress12_1(i,j)**2))) / prs_sig(i,j)
-         else
-            sig1(i,j) = spval_dbl
-            sig2(i,j) = spval_dbl
-         endif
-      enddo
-      enddo
+      call b200_check(evp_b200_principal_stress_n(b200_handle, int(nx_block*ny_block, c_int64_t), &
+                         c_loc(stressp_1), c_loc(stressm_1), c_loc(stress12_1), c_loc(prs_sig), &
+                         c_loc(sig1), c_loc(sig2)), 'evp_b200_principal_stress_n')
       end subroutine principal_stress
 
       end module ice_dyn_evp

@@ -19,8 +19,9 @@ from typing import Dict
 import numpy as np
 
 # boundary types (same numeric values as include/evp_b200.h)
-BND_OPEN, BND_CLOSED, BND_CYCLIC, BND_TRIPOLE = 0, 1, 2, 3
-BND_NAMES = {"open": BND_OPEN, "closed": BND_CLOSED, "cyclic": BND_CYCLIC, "tripole": BND_TRIPOLE}
+BND_OPEN, BND_CLOSED, BND_CYCLIC, BND_TRIPOLE, BND_TRIPOLET = 0, 1, 2, 3, 4
+BND_NAMES = {"open": BND_OPEN, "closed": BND_CLOSED, "cyclic": BND_CYCLIC, "tripole": BND_TRIPOLE,
+             "tripoleT": BND_TRIPOLET}
 LOC_CENTER, LOC_NECORNER, LOC_NFACE, LOC_EFACE = 1, 2, 3, 4
 TYPE_SCALAR, TYPE_VECTOR, TYPE_ANGLE = 1, 2, 3
 
@@ -43,7 +44,7 @@ def _ghost_index(n: int, bnd: int, north: bool):
     # low side
     if bnd == BND_CYCLIC:
         out[0] = n
-    elif bnd in (BND_OPEN, BND_TRIPOLE):
+    elif bnd in (BND_OPEN, BND_TRIPOLE, BND_TRIPOLET):
         out[0] = 1  # nghost - j + 1
     else:
         out[0] = 0
@@ -52,7 +53,7 @@ def _ghost_index(n: int, bnd: int, north: bool):
         out[n + 1] = 1
     elif bnd == BND_OPEN:
         out[n + 1] = n  # 2*n - (n+1) + 1
-    elif bnd == BND_TRIPOLE and north:
+    elif bnd in (BND_TRIPOLE, BND_TRIPOLET) and north:
         out[n + 1] = -(n + 1)
     else:
         out[n + 1] = 0
@@ -62,39 +63,48 @@ def _ghost_index(n: int, bnd: int, north: bool):
 def scatter_global(a_g: np.ndarray, ew: int, ns: int, loc: int = LOC_CENTER,
                    kind: int = TYPE_SCALAR) -> np.ndarray:
     """Global (nx,ny) -> padded single block with ghost fill
-    (serial/ice_gather_scatter.F90:404-534, u-fold offsets :426-443)."""
+    (serial/ice_gather_scatter.F90:404-534; u-fold offsets :426-443, T-fold offsets :407-425 with the
+    second source row `yoffset2` for U rows on the T-fold, :520-534)."""
     nx, ny = a_g.shape
     out = fzeros((nx + 2, ny + 2), a_g.dtype)
     ig = _ghost_index(nx, ew, north=False)
     jg = _ghost_index(ny, ns, north=True)
-    xoff, yoff = {LOC_CENTER: (1, 1), LOC_NECORNER: (0, 0), LOC_EFACE: (0, 1), LOC_NFACE: (1, 0)}[loc]
+    if ns == BND_TRIPOLET:
+        xoff, yoff = {LOC_CENTER: (2, 0), LOC_NECORNER: (1, -1), LOC_EFACE: (1, 0), LOC_NFACE: (2, -1)}[loc]
+    else:
+        xoff, yoff = {LOC_CENTER: (1, 1), LOC_NECORNER: (0, 0), LOC_EFACE: (0, 1), LOC_NFACE: (1, 0)}[loc]
     isign = 1 if kind == TYPE_SCALAR else -1
     for j in range(ny + 2):
         if jg[j] > 0:
             cols = ig != 0
             out[cols, j] = a_g[ig[cols] - 1, jg[j] - 1]
-        elif jg[j] < 0:
-            jsrc = ny + yoff + (jg[j] + ny)  # yoffset2 = 0 on the u-fold
-            for i in range(nx + 2):
-                if ig[i] != 0:
-                    isrc = nx + xoff - ig[i]
-                    if isrc < 1:
-                        isrc += nx
-                    if isrc > nx:
-                        isrc -= nx
-                    out[i, j] = isign * a_g[isrc - 1, jsrc - 1]
+    for j in range(ny + 2):      # fold rows last: on the T-fold they also overwrite the row below (:531)
+        if jg[j] < 0:
+            for yoff2 in range(0, max(yoff, 0) - yoff + 1):
+                jsrc = ny + yoff + yoff2 + (jg[j] + ny)
+                for i in range(nx + 2):
+                    if ig[i] != 0:
+                        isrc = nx + xoff - ig[i]
+                        if isrc < 1:
+                            isrc += nx
+                        if isrc > nx:
+                            isrc -= nx
+                        out[i, j - yoff2] = isign * a_g[isrc - 1, jsrc - 1]
     return out
 
 
 def halo_update(a: np.ndarray, ew: int, ns: int, loc: int = LOC_CENTER,
                 kind: int = TYPE_SCALAR) -> None:
     """In-place ghost update of one padded block holding the whole domain
-    (serial/ice_boundary.F90:591-873 with the address lists of :3494-4202)."""
+    (serial/ice_boundary.F90:591-873 with the address lists of :3494-4202): independent numpy restatement,
+    used to build the grids and to cross-check oracle/evp_oracle.c's halo update."""
     nxb, nyb = a.shape
     nx, ny = nxb - 2, nyb - 2
-    trip = ns == BND_TRIPOLE
+    tfold = ns == BND_TRIPOLET
+    trip = ns == BND_TRIPOLE or tfold
+    trows = 3 if tfold else 2
     if trip:
-        buf = a[1:nx + 1, ny - 1:ny + 1].copy()  # rows jhi-1, jhi
+        buf = a[1:nx + 1, ny - trows + 1:ny + 1].copy()  # rows jhi-trows+1 .. jhi
     if ew == BND_CYCLIC:
         a[0, 1:ny + 1] = a[nx, 1:ny + 1]
         a[nx + 1, 1:ny + 1] = a[1, 1:ny + 1]
@@ -108,26 +118,38 @@ def halo_update(a: np.ndarray, ew: int, ns: int, loc: int = LOC_CENTER,
         a[nx + 1, ny + 1] = a[1, 1]
     if trip:
         isign = 1 if kind == TYPE_SCALAR else -1
-        ioff, joff = {LOC_CENTER: (0, 0), LOC_NECORNER: (1, 1), LOC_EFACE: (1, 0), LOC_NFACE: (0, 1)}[loc]
-        if loc == LOC_NECORNER:
-            for i in range(1, nx // 2):
-                idst = nx - i
-                x1, x2 = buf[i - 1, 1], buf[idst - 1, 1]
-                xavg = 0.5 * (x1 + isign * x2)
-                buf[i - 1, 1] = xavg
-                buf[idst - 1, 1] = isign * xavg
-        elif loc == LOC_NFACE:
-            for i in range(1, nx // 2 + 1):
-                idst = nx + 1 - i
-                x1, x2 = buf[i - 1, 1], buf[idst - 1, 1]
-                xavg = 0.5 * (x1 + isign * x2)
-                buf[i - 1, 1] = xavg
-                buf[idst - 1, 1] = isign * xavg
+        integer = np.issubdtype(a.dtype, np.integer)
+
+        def avg(x1, x2):
+            v = 0.5 * (float(x1) + isign * float(x2))
+            if integer:   # nint: half away from zero
+                return int(np.floor(v + 0.5)) if v >= 0 else -int(np.floor(-v + 0.5))
+            return v
+
+        def symmetrise(lo, hi, mirror):
+            for i in range(lo, hi + 1):
+                idst = mirror - i
+                xavg = avg(buf[i - 1, trows - 1], buf[idst - 1, trows - 1])
+                buf[i - 1, trows - 1] = xavg
+                buf[idst - 1, trows - 1] = isign * xavg
+
+        if tfold:   # :725-773
+            ioff, joff = {LOC_CENTER: (-1, 0), LOC_NECORNER: (0, 1), LOC_EFACE: (0, 0), LOC_NFACE: (-1, 1)}[loc]
+            if loc == LOC_CENTER:
+                symmetrise(2, nx // 2, nx + 2)
+            elif loc == LOC_EFACE:
+                symmetrise(1, nx // 2, nx + 1)
+        else:       # :777-827
+            ioff, joff = {LOC_CENTER: (0, 0), LOC_NECORNER: (1, 1), LOC_EFACE: (1, 0), LOC_NFACE: (0, 1)}[loc]
+            if loc == LOC_NECORNER:
+                symmetrise(1, nx // 2 - 1, nx)
+            elif loc == LOC_NFACE:
+                symmetrise(1, nx // 2, nx + 1)
         ig = _ghost_index(nx, ew, north=False)
         for j in (1, 2):
             jsrc = 4 - j - joff
             jdst = ny + j - 1  # local 1-based row jhi + j - 1 -> 0-based index
-            if not (0 < jsrc <= 2):
+            if not (0 < jsrc <= trows):
                 continue
             for i in range(nx + 2):
                 isrc = nx - ig[i] + 1 - ioff
@@ -239,9 +261,10 @@ def build_grid(htn_m: np.ndarray, hte_m: np.ndarray, ulat: np.ndarray, hm: np.nd
 # ---------------------------------------------------------------------------
 
 def analytic_global(nx: int, ny: int, lat_s: float = -78.0, lat_n: float = 89.5,
-                    lat_cap: float = 65.0):
+                    lat_cap: float = 65.0, tfold: bool = False):
     """Lat-lon-like metrics, periodic in x, symmetric under the tripole fold
-    (i -> nx+1-i for T columns, i -> nx-i for U columns).  Cell widths follow
+    (u-fold: i -> nx+1-i for T columns, i -> nx-i for U columns; T-fold (`tfold`): i -> nx+2-i for T
+    columns, i -> nx+1-i for U columns).  Cell widths follow
     cos(lat) up to |lat| = lat_cap and stay constant poleward of it (a real
     tripole grid keeps cells finite by putting its poles on land)."""
     dlam = 2.0 * np.pi / nx
@@ -249,8 +272,9 @@ def analytic_global(nx: int, ny: int, lat_s: float = -78.0, lat_n: float = 89.5,
     j = np.arange(1, ny + 1)
     ulat_1d = np.deg2rad(lat_s) + dphi * j  # latitude of the N edge / U points of row j
     lat_eff = np.clip(ulat_1d, -np.deg2rad(lat_cap), np.deg2rad(lat_cap))
-    xt = (np.arange(1, nx + 1) - 0.5) / nx
-    xu = np.arange(1, nx + 1) / nx
+    shift = 0.5 if tfold else 0.0      # the fold axis passes through T points instead of U points
+    xt = (np.arange(1, nx + 1) - 0.5 - shift) / nx
+    xu = (np.arange(1, nx + 1) - shift) / nx
     htn = RADIUS * np.cos(lat_eff)[None, :] * dlam * (1.0 + 0.05 * np.cos(4.0 * np.pi * xt))[:, None]
     tlat_1d = ulat_1d - 0.5 * dphi
     hte = RADIUS * dphi * (1.0 + 0.03 * np.sin(2.0 * tlat_1d))[None, :] * \
@@ -272,10 +296,11 @@ def synthetic_land(nx: int, ny: int, ulat: np.ndarray, ulon: np.ndarray, ns: int
         hm[(lon > 20) & (lon < 60) & (lat > -35) & (lat < 72)] = 0
         hm[(lon > 190) & (lon < 250) & (lat > -55) & (lat < 68)] = 0
         hm[lat < -74] = 0
-    if ns == BND_TRIPOLE:
+    if ns in (BND_TRIPOLE, BND_TRIPOLET):
         w = max(2, nx // 60)
         h = max(2, ny // 60)
-        for ic in (nx // 2, nx):
+        # the two pole points of the fold row: U columns nx/2 and nx (u-fold), T columns nx/2+1 and 1 (T-fold)
+        for ic in ((nx // 2 + 1, 1) if ns == BND_TRIPOLET else (nx // 2, nx)):
             cols = np.arange(ic - w, ic + w + 1) % nx
             hm[cols, ny - h:] = 0
     else:

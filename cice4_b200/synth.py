@@ -101,7 +101,7 @@ def make_case(name: str = "gx3", nx: Optional[int] = None, ny: Optional[int] = N
         if not realistic:
             hm[:, 1:-1] = 1.0
     else:
-        htn, hte, ulat, ulon = G.analytic_global(nx, ny)
+        htn, hte, ulat, ulon = G.analytic_global(nx, ny, tfold=(nsb == G.BND_TRIPOLET))
         hm = G.synthetic_land(nx, ny, ulat, ulon, nsb, realistic)
     grid = G.build_grid(htn, hte, ulat, hm, ewb, nsb)
 

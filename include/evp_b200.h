@@ -44,9 +44,13 @@ enum {
 };
 
 /* ew_boundary_type / ns_boundary_type of domain_nml (source/ice_domain.F90:126-131,
- * index maps source/ice_blocks.F90:237-343).  'tripole' is the u-fold;
- * 'tripoleT' is not implemented (EVP_B200_ERR_UNSUPPORTED). */
-enum { EVP_B200_BND_OPEN = 0, EVP_B200_BND_CLOSED = 1, EVP_B200_BND_CYCLIC = 2, EVP_B200_BND_TRIPOLE = 3 };
+ * index maps source/ice_blocks.F90:237-343).  'tripole' is the u-fold, 'tripoleT' the T-fold
+ * (serial/ice_boundary.F90:725-773: three buffer rows, U rows jhi and jhi+1 mirror rows jhi-1 and
+ * jhi-2, the degenerate top T row is symmetrised); the T-fold needs at least 3 rows in the top slab and
+ * is folded by a separate kernel after every subcycle (the in-kernel fold and the tiled kernel are
+ * u-fold only). */
+enum { EVP_B200_BND_OPEN = 0, EVP_B200_BND_CLOSED = 1, EVP_B200_BND_CYCLIC = 2, EVP_B200_BND_TRIPOLE = 3,
+       EVP_B200_BND_TRIPOLET = 4 };
 
 /* Replaces: nx_block/ny_block/max_blocks (source/ice_blocks.F90:56-61,
  * source/ice_domain_size.F90:34-64), nblocks + blocks_ice (source/ice_domain.F90),

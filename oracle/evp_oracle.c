@@ -92,7 +92,12 @@ void orc_set_evp_parameters(orc_params *p, double dt, int ndte) {
 /*     returns at :3580, ghost cells are left untouched;                 */
 /*   - tripole (u-fold): :3699-3733 copy-in of the top nghost+1 physical */
 /*     rows, :777-827 symmetrisation, :3735-3763 + :837-866 copy-out     */
-/*     over local i = 1..ihi+nghost, rows jhi and jhi+1.                 */
+/*     over local i = 1..ihi+nghost, rows jhi and jhi+1;                 */
+/*   - tripoleT (T-fold): tripoleRows = nghost+2 (:199-205), so the top  */
+/*     THREE physical rows go into the buffer; symmetrisation and        */
+/*     offsets of :725-773 (integer fields: nint of the average,         */
+/*     :1303-1321); the copy-out message of buffer row 3 has jDst = -1   */
+/*     and is skipped (:3753-3757).                                      */
 /* All regular copies read physical cells and write ghost cells, so      */
 /* their order is immaterial; the tripole copy-out runs last (:837).     */
 /* ------------------------------------------------------------------ */
@@ -102,15 +107,17 @@ void orc_set_evp_parameters(orc_params *p, double dt, int ndte) {
     const int nxg = ihi - ilo + 1;                                                          \
     const int ewc = (g->ew_boundary == ORC_BND_CYCLIC);                                     \
     const int nsc = (g->ns_boundary == ORC_BND_CYCLIC);                                     \
-    const int trip = (g->ns_boundary == ORC_BND_TRIPOLE);                                   \
+    const int tfold = (g->ns_boundary == ORC_BND_TRIPOLET);                                 \
+    const int trip = (g->ns_boundary == ORC_BND_TRIPOLE) || tfold;                          \
+    const int trows = tfold ? 3 : 2; /* tripoleRows, :199-205 */                            \
     T *buf = NULL;                                                                          \
     int i, j;                                                                               \
     if (trip) {                                                                             \
-        /* copy-in: buf(i_glob, 1:2) = array(:, jhi-1:jhi), :3717-3731 */                   \
-        buf = (T *)malloc(sizeof(T) * (size_t)nxg * 2);                                     \
-        for (j = 1; j <= 2; ++j)                                                            \
+        /* copy-in: buf(i_glob, 1:trows) = array(:, jhi-trows+1:jhi), :3717-3731 */         \
+        buf = (T *)malloc(sizeof(T) * (size_t)nxg * trows);                                 \
+        for (j = 1; j <= trows; ++j)                                                        \
             for (i = 1; i <= nxg; ++i)                                                      \
-                buf[(size_t)(j - 1) * nxg + (i - 1)] = a[IX(ilo + i - 1, jhi - 2 + j)];     \
+                buf[(size_t)(j - 1) * nxg + (i - 1)] = a[IX(ilo + i - 1, jhi - trows + j)]; \
     }                                                                                       \
     if (ewc) {                                                                              \
         for (j = jlo; j <= jhi; ++j) {                                                      \
@@ -133,15 +140,40 @@ void orc_set_evp_parameters(orc_params *p, double dt, int ndte) {
     if (trip) {                                                                             \
         int isign = (kind == ORC_TYPE_SCALAR) ? 1 : -1; /* :713-723 */                      \
         int ioffset = 0, joffset = 0;                                                       \
-        T *row2 = buf + nxg; /* bufTripole(:, tripoleRows) */                               \
-        switch (loc) { /* u-fold branch, :777-827 */                                        \
+        T *row2 = buf + (size_t)(trows - 1) * nxg; /* bufTripole(:, tripoleRows) */         \
+        if (tfold) switch (loc) { /* T-fold branch, :725-773 */                             \
+        case ORC_LOC_CENTER:                                                                \
+            ioffset = -1; joffset = 0;                                                      \
+            for (i = 2; i <= nxg / 2; ++i) {                                                \
+                int iDst = nxg - i + 2;                                                     \
+                T x1 = row2[i - 1], x2 = row2[iDst - 1];                                    \
+                T xavg = (T)AVG(x1, isign * x2);                                            \
+                row2[i - 1] = xavg;                                                         \
+                row2[iDst - 1] = isign * xavg;                                              \
+            }                                                                               \
+            break;                                                                          \
+        case ORC_LOC_NECORNER: ioffset = 0; joffset = 1; break;                             \
+        case ORC_LOC_EFACE:                                                                 \
+            ioffset = 0; joffset = 0;                                                       \
+            for (i = 1; i <= nxg / 2; ++i) {                                                \
+                int iDst = nxg + 1 - i;                                                     \
+                T x1 = row2[i - 1], x2 = row2[iDst - 1];                                    \
+                T xavg = (T)AVG(x1, isign * x2);                                            \
+                row2[i - 1] = xavg;                                                         \
+                row2[iDst - 1] = isign * xavg;                                              \
+            }                                                                               \
+            break;                                                                          \
+        case ORC_LOC_NFACE: ioffset = -1; joffset = 1; break;                               \
+        default: break;                                                                     \
+        }                                                                                   \
+        else switch (loc) { /* u-fold branch, :777-827 */                                   \
         case ORC_LOC_CENTER: ioffset = 0; joffset = 0; break;                               \
         case ORC_LOC_NECORNER:                                                              \
             ioffset = 1; joffset = 1;                                                       \
             for (i = 1; i <= nxg / 2 - 1; ++i) {                                            \
                 int iDst = nxg - i;                                                         \
                 T x1 = row2[i - 1], x2 = row2[iDst - 1];                                    \
-                T xavg = (T)(HALF * (x1 + isign * x2));                                     \
+                T xavg = (T)AVG(x1, isign * x2);                                            \
                 row2[i - 1] = xavg;                                                         \
                 row2[iDst - 1] = isign * xavg;                                              \
             }                                                                               \
@@ -152,14 +184,14 @@ void orc_set_evp_parameters(orc_params *p, double dt, int ndte) {
             for (i = 1; i <= nxg / 2; ++i) {                                                \
                 int iDst = nxg + 1 - i;                                                     \
                 T x1 = row2[i - 1], x2 = row2[iDst - 1];                                    \
-                T xavg = (T)(HALF * (x1 + isign * x2));                                     \
+                T xavg = (T)AVG(x1, isign * x2);                                            \
                 row2[i - 1] = xavg;                                                         \
                 row2[iDst - 1] = isign * xavg;                                              \
             }                                                                               \
             break;                                                                          \
         default: break;                                                                     \
         }                                                                                   \
-        /* copy-out, :3743-3761 and :837-866 */                                             \
+        /* copy-out, :3743-3761 and :837-866 (the message of buffer row 3 has jDst = -1) */ \
         for (j = 1; j <= 2; ++j) {                                                          \
             for (i = 1; i <= ihi + 1; ++i) {                                                \
                 int ig = i - ilo + 1; /* i_glob(i), source/ice_blocks.F90:291-330 */        \
@@ -173,7 +205,7 @@ void orc_set_evp_parameters(orc_params *p, double dt, int ndte) {
                 jSrc -= joffset;                                                            \
                 if (iSrc == 0) iSrc = nxg;                                                  \
                 if (iSrc > nxg) iSrc -= nxg;                                                \
-                if (jSrc <= 2 && jSrc > 0 && jDst > 0)                                      \
+                if (jSrc <= trows && jSrc > 0 && jDst > 0)                                  \
                     a[IX(i, jDst)] = isign * buf[(size_t)(jSrc - 1) * nxg + (iSrc - 1)];    \
             }                                                                               \
         }                                                                                   \
@@ -181,18 +213,19 @@ void orc_set_evp_parameters(orc_params *p, double dt, int ndte) {
     }                                                                                       \
     (void)fill;
 
-#define HALF 0.5
+#define AVG(x1, x2) (0.5 * ((x1) + (x2)))
 void orc_halo_r8(double *a, const orc_grid *g, int loc, int kind, double fill) {
     HALO_BODY(double)
 }
-#undef HALF
-/* integer variant (serial/ice_boundary.F90:1169-1451): xavg = nint(0.5*(x1+isign*x2)),
- * only reached for corner/face fields; icetmask is a centre scalar. */
-#define HALF 0.5
+#undef AVG
+/* integer variant (serial/ice_boundary.F90:1169-1451): xavg = nint(0.5*(x1+isign*x2)) -- Fortran nint rounds
+ * half away from zero.  Reached by icetmask (a centre scalar) on the T-fold only. */
+static int32_t orc_nint(double x) { return (int32_t)(x >= 0.0 ? floor(x + 0.5) : -floor(-x + 0.5)); }
+#define AVG(x1, x2) orc_nint(0.5 * ((double)(x1) + (double)(x2)))
 void orc_halo_i4(int32_t *a, const orc_grid *g, int loc, int kind, int32_t fill) {
     HALO_BODY(int32_t)
 }
-#undef HALF
+#undef AVG
 
 /* ------------------------------------------------------------------ */
 /* source/ice_grid.F90:1580-1633                                        */

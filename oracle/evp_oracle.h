@@ -36,7 +36,7 @@ extern "C" {
 #endif
 
 /* boundary types, source/ice_blocks.F90:237-343 */
-enum { ORC_BND_OPEN = 0, ORC_BND_CLOSED = 1, ORC_BND_CYCLIC = 2, ORC_BND_TRIPOLE = 3 };
+enum { ORC_BND_OPEN = 0, ORC_BND_CLOSED = 1, ORC_BND_CYCLIC = 2, ORC_BND_TRIPOLE = 3, ORC_BND_TRIPOLET = 4 };
 /* field locations / kinds, drivers/cice4/ice_constants.F90 (field_loc_*, field_type_*) */
 enum { ORC_LOC_CENTER = 1, ORC_LOC_NECORNER = 2, ORC_LOC_NFACE = 3, ORC_LOC_EFACE = 4 };
 enum { ORC_TYPE_SCALAR = 1, ORC_TYPE_VECTOR = 2, ORC_TYPE_ANGLE = 3 };

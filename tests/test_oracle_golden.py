@@ -84,9 +84,10 @@ def test_gx3_grid_fixture_known_answers():
 
 
 @pytest.mark.parametrize("ew,ns", [("cyclic", "open"), ("cyclic", "tripole"), ("cyclic", "cyclic"),
-                                   ("open", "open")])
+                                   ("open", "open"), ("cyclic", "tripoleT"), ("open", "tripoleT")])
 @pytest.mark.parametrize("loc,kind", [(G.LOC_CENTER, G.TYPE_SCALAR), (G.LOC_CENTER, G.TYPE_VECTOR),
-                                      (G.LOC_NECORNER, G.TYPE_VECTOR), (G.LOC_NECORNER, G.TYPE_SCALAR)])
+                                      (G.LOC_NECORNER, G.TYPE_VECTOR), (G.LOC_NECORNER, G.TYPE_SCALAR),
+                                      (G.LOC_NFACE, G.TYPE_SCALAR), (G.LOC_EFACE, G.TYPE_VECTOR)])
 def test_numpy_halo_equals_oracle_halo(oracle, ew, ns, loc, kind):
     """The host-side numpy halo (grid construction) and the oracle's C halo restate the same
     reference routine independently; they must agree bit for bit."""
@@ -121,6 +122,52 @@ def test_tripole_fold_semantics(oracle):
     b = a.copy(order="F")
     oracle.halo_r8(b, G.BND_CYCLIC, G.BND_TRIPOLE, G.LOC_NECORNER, G.TYPE_VECTOR)
     np.testing.assert_array_equal(b[1:nx // 2, ny], a[1:nx // 2, ny])
+
+
+def test_tripoleT_fold_semantics(oracle):
+    """T-fold (serial/ice_boundary.F90:725-773, address lists :3699-3763): for a NE-corner vector the top
+    physical row and the ghost row become the sign-flipped mirror images of the two rows below them, without
+    any averaging; for a centre field the degenerate top row is symmetrised about the two pole T points
+    (columns 1 and nx/2+1 keep their values) and the ghost row mirrors the row below the top."""
+    nx, ny = 16, 7
+    rng = np.random.default_rng(4)
+    a = np.asfortranarray(rng.standard_normal((nx + 2, ny + 2)))
+    a0 = a.copy()
+    oracle.halo_r8(a, G.BND_CYCLIC, G.BND_TRIPOLET, G.LOC_NECORNER, G.TYPE_VECTOR)
+    for i in range(1, nx + 1):                       # U column i <-> nx + 1 - i
+        assert a[i, ny] == -a0[nx + 1 - i, ny - 1]
+        assert a[i, ny + 1] == -a0[nx + 1 - i, ny - 2]
+    np.testing.assert_array_equal(a[1:nx + 1, 1:ny], a0[1:nx + 1, 1:ny])
+    c = np.asfortranarray(rng.standard_normal((nx + 2, ny + 2)))
+    c0 = c.copy()
+    oracle.halo_r8(c, G.BND_CYCLIC, G.BND_TRIPOLET, G.LOC_CENTER, G.TYPE_SCALAR)
+    top = c[1:nx + 1, ny]
+    for i in range(2, nx // 2 + 1):                  # T column i <-> nx + 2 - i, averaged
+        assert top[i - 1] == top[nx + 2 - i - 1] == 0.5 * (c0[i, ny] + c0[nx + 2 - i, ny])
+    assert top[0] == c0[1, ny] and top[nx // 2] == c0[nx // 2 + 1, ny]     # the pole points map onto themselves
+    for i in range(2, nx + 1):
+        assert c[i, ny + 1] == c0[nx + 2 - i, ny - 1]
+    # integer fields average with nint (:1318): a 0/1 mask becomes the OR of the pair
+    import ctypes as C
+    m = np.asfortranarray(rng.integers(0, 2, (nx + 2, ny + 2)).astype(np.int32))
+    m0 = m.copy()
+    g = oracle.make_grid(nx + 2, ny + 2, G.BND_CYCLIC, G.BND_TRIPOLET)
+    oracle.lib().orc_halo_i4(m.ctypes.data_as(oracle.c_ip), C.byref(g), G.LOC_CENTER, G.TYPE_SCALAR, 0)
+    for i in range(2, nx // 2 + 1):
+        assert m[i, ny] == m[nx + 2 - i, ny] == (m0[i, ny] | m0[nx + 2 - i, ny])
+
+
+def test_tripoleT_evp_invariants(oracle):
+    """One evp step on a T-fold grid: the velocity rows at and above the fold are the mirror images of the
+    rows below it after the final halo update."""
+    case = synth.make_case("x", nx=48, ny=30, ew="cyclic", ns="tripoleT")
+    st, f = _run(oracle, case)
+    u, v = st["uvel"], st["vvel"]
+    nx, ny = 48, 30
+    assert np.abs(u).max() > 1e-3
+    for i in range(1, nx + 1):
+        assert u[i, ny] == -u[nx + 1 - i, ny - 1] and v[i, ny] == -v[nx + 1 - i, ny - 1]
+        assert u[i, ny + 1] == -u[nx + 1 - i, ny - 2]
 
 
 def _run(oracle, case, **kw):

@@ -26,6 +26,8 @@ DOMAINS = [
     ("cyclic-cyclic-40x33", dict(name="x", nx=40, ny=33, ew="cyclic", ns="cyclic")),
     ("open-open-37x29", dict(name="x", nx=37, ny=29, ew="open", ns="open")),
     ("closed-closed-30x31", dict(name="x", nx=30, ny=31, ew="closed", ns="closed")),
+    ("tripoleT-64x48-realistic", dict(name="x", nx=64, ny=48, ew="cyclic", ns="tripoleT", realistic=True)),
+    ("tripoleT-45x31", dict(name="x", nx=45, ny=31, ew="cyclic", ns="tripoleT")),
 ]
 TURN = dict(cosw=0.9063077870366499, sinw=0.42261826174069944)
 VARIANTS = [

@@ -54,6 +54,8 @@ CASES = [
     ("tripole-130x70-realistic", dict(name="om1deg", nx=130, ny=70, realistic=True)),
     ("cyclic-cyclic-40x33", dict(name="x", nx=40, ny=33, ew="cyclic", ns="cyclic")),
     ("open-open-37x29", dict(name="x", nx=37, ny=29, ew="open", ns="open")),
+    ("tripoleT-64x48", dict(name="x", nx=64, ny=48, ew="cyclic", ns="tripoleT")),
+    ("tripoleT-130x70-realistic", dict(name="x", nx=130, ny=70, ew="cyclic", ns="tripoleT", realistic=True)),
 ]
 
 
@@ -136,7 +138,8 @@ def test_bit_exact_vs_oracle_two_steps(oracle, evp_lib, label, kw, kernel):
     st, f, strengths, _ = oracle_steps(oracle, case, nsteps=2)
     lay = E.BlockLayout.single_block(case.grid.nx, case.grid.ny)
     dyn, out = cuda_steps(case, nsteps=2, strengths=strengths, math_mode=0, kernel_variant=kernel)
-    assert dyn.info()["tiled"] == (0 if kernel or label.startswith("cyclic-cyclic") else 1)
+    # north-south cyclic domains and the T-fold run the plane kernels (the in-kernel fold is the u-fold)
+    assert dyn.info()["tiled"] == (0 if kernel or label.startswith("cyclic-cyclic") or "tripoleT" in label else 1)
     _compare_exact(dyn, out, st, f, lay)
     assert np.abs(st["uvel"]).max() > 1e-3   # the case is not trivially zero
 
@@ -225,8 +228,8 @@ def test_tiled_kernel_bit_exact(oracle, evp_lib, label, kw, variant):
     lay = E.BlockLayout.single_block(case.grid.nx, case.grid.ny)
     dyn, out = cuda_steps(case, nsteps=2, strengths=strengths, math_mode=0, ndte=ndte, kernel_variant=variant)
     info = dyn.info()
-    if label.startswith("cyclic-cyclic"):
-        assert info["tiled"] == 0      # north-south cyclic: the plane kernels run
+    if label.startswith("cyclic-cyclic") or "tripoleT" in label:
+        assert info["tiled"] == 0      # north-south cyclic / T-fold: the plane kernels run
     else:
         assert info["tiled"] == 1 and info["strip_w"] == 31 and info["stages"] == (2 if variant & 4096 else 3), info
     _compare_exact(dyn, out, st, f, lay)
@@ -299,6 +302,18 @@ def test_block_decomposition_invariance(oracle, evp_lib, bx, by):
     for b in range(lay.nblocks):
         ni, nj = lay.ihi[b] - lay.ilo[b] + 3, lay.jhi[b] - lay.jlo[b] + 3
         np.testing.assert_array_equal(ublk[:ni, :nj, b], want[:ni, :nj, b])
+
+
+def test_tripoleT_block_layout(oracle, evp_lib):
+    """T-fold behind a reference block decomposition (padded edge blocks), two calls: bit-exact."""
+    case = synth.make_case("x", nx=64, ny=48, ew="cyclic", ns="tripoleT", realistic=True)
+    st, f, strengths, _ = oracle_steps(oracle, case, nsteps=2)
+    lay = E.BlockLayout.cartesian(64, 48, 23, 19)
+    dyn, out = cuda_steps(case, nsteps=2, strengths=strengths, layout=lay)
+    _compare_exact(dyn, out, st, f, lay)
+    u = _merge(dyn.state["uvel"], lay)
+    for i in range(1, 65):
+        assert u[i, 48] == -u[65 - i, 47]
 
 
 def test_land_block_elimination(oracle, evp_lib):
