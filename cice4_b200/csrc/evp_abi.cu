@@ -171,8 +171,9 @@ cudaEvent_t next_event(evp_b200_handle *h) {
     return e;
 }
 
-// Host arrays reach the planes in two steps on two streams: the copy into the staging slot on st_up (the
-// copy engine works through all fields back to back) and the unpack kernel on st, ordered by an event.
+// Host arrays reach the planes in two steps on the handle's stream: the copy into the staging slot and the unpack
+// kernel.  (Running the copies on a second stream ahead of the kernels gained 0.3 ms of a 28 ms call and was
+// taken out again.)
 int upload_r8(evp_b200_handle *h, const double *host, int slot, double *plane) {
     if (!host) return fail(EVP_B200_ERR_ARG, "required host array is NULL (stage slot %d)", slot);
     if (h->io_device) { // device-pointer hand-off: the block array is read where it lies
@@ -182,10 +183,7 @@ int upload_r8(evp_b200_handle *h, const double *host, int slot, double *plane) {
     double *stg = h->stage + (size_t)slot * h->blocked_elems;
     const size_t bytes = h->blocked_elems * sizeof(double);
     pin(h, host, bytes);
-    CU(cudaMemcpyAsync(stg, host, bytes, cudaMemcpyHostToDevice, h->st_up));
-    cudaEvent_t e = next_event(h);
-    CU(cudaEventRecord(e, h->st_up));
-    CU(cudaStreamWaitEvent(h->st, e, 0));
+    CU(cudaMemcpyAsync(stg, host, bytes, cudaMemcpyHostToDevice, h->st));
     aux_unblock_r8(h->bg, h->pg, stg, plane, h->st);
     return 0;
 }
@@ -199,10 +197,7 @@ int upload_mask(evp_b200_handle *h, const int32_t *host, int slot, uint8_t *plan
     int32_t *stg = h->stage_i + (size_t)slot * h->blocked_elems;
     const size_t bytes = h->blocked_elems * sizeof(int32_t);
     pin(h, host, bytes);
-    CU(cudaMemcpyAsync(stg, host, bytes, cudaMemcpyHostToDevice, h->st_up));
-    cudaEvent_t e = next_event(h);
-    CU(cudaEventRecord(e, h->st_up));
-    CU(cudaStreamWaitEvent(h->st, e, 0));
+    CU(cudaMemcpyAsync(stg, host, bytes, cudaMemcpyHostToDevice, h->st));
     aux_unblock_mask(h->bg, h->pg, stg, plane, h->st);
     return 0;
 }
@@ -222,17 +217,12 @@ int download_r8(evp_b200_handle *h, double *host, int slot, const double *plane,
     const size_t bytes = h->blocked_elems * sizeof(double);
     pin(h, host, bytes);
     aux_block_r8(h->bg, h->pg, plane, h->mk[M_ICETMASK], stg, policy, s);
-    if (s != h->st2) { // the pack kernels run on st, the copies follow on st2: the copy engine never waits for a kernel launch
-        cudaEvent_t e = next_event(h);
-        CU(cudaEventRecord(e, s));
-        CU(cudaStreamWaitEvent(h->st2, e, 0));
-    }
-    CU(cudaMemcpyAsync(host, stg, bytes, cudaMemcpyDeviceToHost, h->st2));
-    h->dn_pending = true;
+    CU(cudaMemcpyAsync(host, stg, bytes, cudaMemcpyDeviceToHost, s));
+    if (s != h->st) h->dn_pending = true;
     return 0;
 }
 
-// every download issued so far is complete on st once this returns (orders st2 into st)
+// the early outputs travel on st2 while the ndte loop runs: order them into st (no-op when there were none)
 int join_downloads(evp_b200_handle *h) {
     if (!h->dn_pending) return 0;
     cudaEvent_t e = next_event(h);
@@ -252,11 +242,7 @@ int download_mask(evp_b200_handle *h, int32_t *host, int slot, const uint8_t *pl
     const size_t bytes = h->blocked_elems * sizeof(int32_t);
     pin(h, host, bytes);
     aux_block_mask(h->bg, h->pg, plane, stg, policy, h->st);
-    cudaEvent_t e = next_event(h);
-    CU(cudaEventRecord(e, h->st));
-    CU(cudaStreamWaitEvent(h->st2, e, 0));
-    CU(cudaMemcpyAsync(host, stg, bytes, cudaMemcpyDeviceToHost, h->st2));
-    h->dn_pending = true;
+    CU(cudaMemcpyAsync(host, stg, bytes, cudaMemcpyDeviceToHost, h->st));
     return 0;
 }
 
