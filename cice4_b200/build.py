@@ -22,10 +22,12 @@ COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "-Xcompiler",
 UNITS = [
     ("evp_subcycle_strict.cu", ["-fmad=false"]),
     ("evp_subcycle_fast.cu", ["-fmad=true"]),
+    ("evp_fused_strict.cu", ["-fmad=false"]),
+    ("evp_fused_fast.cu", ["-fmad=true"]),
     ("evp_aux.cu", ["-fmad=false"]),
     ("evp_abi.cu", ["-fmad=false"]),
 ]
-DEPS = ["evp_common.cuh", "evp_aux.cuh", "evp_subcycle_body.cuh", "evp_ieee.cuh", "evp_tiled.cuh", os.path.join("..", "..", "include", "evp_b200.h")]
+DEPS = ["evp_common.cuh", "evp_aux.cuh", "evp_subcycle_body.cuh", "evp_ieee.cuh", "evp_tiled.cuh", "evp_fused.cuh", os.path.join("..", "..", "include", "evp_b200.h")]
 
 
 def _nvcc() -> str:

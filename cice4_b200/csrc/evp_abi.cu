@@ -56,7 +56,9 @@ enum PlaneId {
     P_SIG1, P_SIG2,
     // ping-pong state: u, v, 12 stresses, two copies each
     // state copy 0 (u, v, 12 stresses) and, EVP_STATE_PLANES planes behind each, copy 1 (SubArgs::copy_stride)
-    P_U0, P_V0, P_S0, P_U1 = P_S0 + EVP_NSTRESS, P_V1, P_S1, P_COUNT = P_S1 + EVP_NSTRESS
+    // copy 2 (2 * copy_stride behind copy 0): intermediate rows of the tripole top chunk of the two-subcycle kernel
+    P_U0, P_V0, P_S0, P_U1 = P_S0 + EVP_NSTRESS, P_V1, P_S1, P_U2 = P_S1 + EVP_NSTRESS, P_V2, P_S2,
+    P_COUNT = P_S2 + EVP_NSTRESS
 };
 enum MaskId { M_TMASK, M_UMASK, M_TMPHM, M_ICETMASK, M_ICEUMASK, M_COUNT };
 
@@ -116,6 +118,8 @@ struct evp_b200_handle {
     int *d_chunks = nullptr;          // row-chunk table of the subcycle kernel (2 ints per chunk)
     int *d_cta_epoch = nullptr;       // persistent kernel: subcycles finished per CTA (grid_x * grid_y ints)
     bool persistent = false;          // run the ndte loop as one cooperative launch (k_persist)
+    bool fused = false;               // two subcycles per launch (k_subcycle2, evp_fused.cuh)
+    int *d_wstrips = nullptr;         // its per-warp strip table (4 ints per warp strip)
     int epoch_count = 0;              // subcycles completed on this rank since init (== sync[1] with p2p)
     long eliminated_cells = 0;        // cells of the slab without a block (eliminated land blocks)
     int *d_rowcnt = nullptr;          // active T cells per row (load balance of the chunks)
@@ -311,6 +315,7 @@ void fill_subargs(evp_b200_handle *h, SubArgs &a, int cur) {
     a.uarear = p[P_UAREAR];
     a.icetmask = h->mk[M_ICETMASK]; a.iceumask = h->mk[M_ICEUMASK];
     static_assert(P_U1 - P_U0 == P_V1 - P_V0 && P_U1 - P_U0 == P_S1 - P_S0, "state copies must be equidistant");
+    static_assert(P_U2 - P_U1 == P_U1 - P_U0 && P_V2 - P_V1 == P_U1 - P_U0 && P_S2 - P_S1 == P_U1 - P_U0, "state copies must be equidistant");
     a.u = p[P_U0];
     a.v = p[P_V0];
     for (int k = 0; k < EVP_NSTRESS; ++k) a.s[k] = p[P_S0 + k];
@@ -340,6 +345,7 @@ void fill_subargs(evp_b200_handle *h, SubArgs &a, int cur) {
     a.dragw = h->dragw; a.cosw = h->par.cosw; a.sinw = h->par.sinw;
     a.fold = h->fold_in_kernel ? 1 : 0;
     a.fold_scratch = h->fold_scratch;
+    a.wstrips = h->d_wstrips;
     a.peer_n_u = a.peer_n_v = a.peer_s_u = a.peer_s_v = nullptr;
     a.peer_n_stride = a.peer_s_stride = 0;
     a.peer_n_flag = a.peer_s_flag = nullptr;
@@ -417,6 +423,49 @@ int launch_subcycle(evp_b200_handle *h, int cur, bool last) {
     return n;
 }
 
+// two subcycles in one launch (k_subcycle2): east-west wrap and tripole fold of both are inside the kernel
+int launch_fused(evp_b200_handle *h, int cur, bool last) {
+    SubArgs a;
+    fill_subargs(h, a, cur);
+    fused_launch_fn fn = h->par.math_mode == 1 ? evp_fused_launch_fast : evp_fused_launch_strict;
+    const int e = fn(a, last, 0, (unsigned)h->grid_x, (unsigned)h->grid_y, (void *)h->st, nullptr);
+    if (e != 0) {
+        fail(EVP_B200_ERR_CUDA, "two-subcycle kernel launch: %s", cudaGetErrorString((cudaError_t)e));
+        return -1;
+    }
+    return 1;
+}
+
+// the launches of one ndte loop starting from state copy `cur`; returns the number of kernels (< 0: error) and
+// leaves the copy that holds the result in `cur`
+int launch_loop(evp_b200_handle *h, int &cur) {
+    const int ndte = h->par.ndte;
+    int n = 0, k = 1;
+    if (h->fused) {
+        if (ndte & 1) { // an odd ndte starts with one single subcycle
+            const int m = launch_subcycle(h, cur, ndte == 1);
+            if (m < 0) return -1;
+            n += m;
+            cur ^= 1;
+            k = 2;
+        }
+        for (; k + 1 <= ndte; k += 2) {
+            const int m = launch_fused(h, cur, k + 1 == ndte);
+            if (m < 0) return -1;
+            n += m;
+            cur ^= 1;
+        }
+        return n;
+    }
+    for (; k <= ndte; ++k) {
+        const int m = launch_subcycle(h, cur, k == ndte);
+        if (m < 0) return -1;
+        n += m;
+        cur ^= 1;
+    }
+    return n;
+}
+
 int run_subcycle_loop(evp_b200_handle *h) {
     const int ndte = h->par.ndte;
     // the plane kernels always start from state copy 0 (an odd ndte is copied back below); the tiled
@@ -441,14 +490,9 @@ int run_subcycle_loop(evp_b200_handle *h) {
     } else if (graph_ok) {
         if (!h->graph_exec[c0]) {
             CU(cudaStreamBeginCapture(h->st, cudaStreamCaptureModeThreadLocal));
-            int cur = c0, n = 0;
-            bool bad = false;
-            for (int k = 1; k <= ndte; ++k) {
-                const int m = launch_subcycle(h, cur, k == ndte);
-                if (m < 0) { bad = true; break; }
-                n += m;
-                cur ^= 1;
-            }
+            int cur = c0;
+            const int n = launch_loop(h, cur);
+            const bool bad = n < 0;
             h->sub_launches_per_loop = n;
             const std::string why = g_err;
             CU(cudaStreamEndCapture(h->st, &h->graph[c0]));
@@ -462,15 +506,10 @@ int run_subcycle_loop(evp_b200_handle *h) {
             CU(cudaGraphInstantiate(&h->graph_exec[c0], h->graph[c0], 0));
         }
         CU(cudaGraphLaunch(h->graph_exec[c0], h->st));
-        h->cur = c0 ^ (ndte & 1);
+        h->cur = c0 ^ ((h->fused ? (ndte + 1) / 2 : ndte) & 1);
     } else {
-        int n = 0;
-        for (int k = 1; k <= ndte; ++k) {
-            const int m = launch_subcycle(h, h->cur, k == ndte);
-            if (m < 0) return EVP_B200_ERR_CUDA;
-            n += m;
-            h->cur ^= 1;
-        }
+        const int n = launch_loop(h, h->cur);
+        if (n < 0) return EVP_B200_ERR_CUDA;
         h->sub_launches_per_loop = n;
     }
     CU(cudaGetLastError());
@@ -575,7 +614,22 @@ int choose_tiling(evp_b200_handle *h) {
     const int nx = h->pg.nx, nyl = h->pg.nyl;
     int nt, ncx, strip_w, per_sm;
     bool tma = false;
-    if (h->tiled) {
+    if (h->fused) {
+        // two-subcycle kernel: one warp per strip of up to 29 U columns, 4 warps per CTA (at most 112 columns: every
+        // warp can own at least 28, see the strip table below), two CTAs per SM (255 registers, 102 KB of rings)
+        nt = 128;
+        ncx = (nx + 111) / 112;
+        strip_w = (nx + ncx - 1) / ncx;
+        SubArgs a;
+        fill_subargs(h, a, 0);
+        fused_launch_fn fn = h->par.math_mode == 1 ? evp_fused_launch_fast : evp_fused_launch_strict;
+        per_sm = 0;
+        const int e = fn(a, false, 0, 0, 0, nullptr, &per_sm);
+        if (e != 0 || per_sm < 1) {
+            cudaGetLastError();
+            return fail(EVP_B200_ERR_CUDA, "two-subcycle kernel cannot be configured: %s", cudaGetErrorString((cudaError_t)e));
+        }
+    } else if (h->tiled) {
         // strip-tiled TMA-fed kernel: one warp per strip of 31 U columns, 4 warps per CTA; resident CTAs per
         // SM from the occupancy of the kernel itself (shared memory: 2 or 3 pipeline stages per warp)
         // 3 stages / 2 CTAs per SM measured equal or better than 2 stages / 3 CTAs on every short slab but one
@@ -617,6 +671,8 @@ int choose_tiling(evp_b200_handle *h) {
         per_sm = (nt == 256) ? 1 : (nt == 128 ? 2 : 4);
         if (tma && (h->par.kernel_variant & 256) == 0) per_sm = 3;
         if (!tma && nt == 128 && (h->par.kernel_variant & 1024)) per_sm = 3; // late-load kernel: 3 CTAs per SM
+        if (!tma && nt == 128 && (h->par.kernel_variant & 1024) && (h->par.kernel_variant & 262144)) per_sm = 4;
+        if (!tma && nt == 128 && (h->par.kernel_variant & 1024) && (h->par.kernel_variant & 524288)) per_sm = 5;
     }
     int ncy = (per_sm * sms) / ncx; // one wave
     if (ncy < 1) ncy = 1;
@@ -628,7 +684,9 @@ int choose_tiling(evp_b200_handle *h) {
     const bool multi = h->dims.nranks > 1 && h->par.exchange_mode == 0;
     double w_top = 1.0, w_bot = 1.0;
     if (ncy >= 3 && h->par.tile_rows <= 0) {
-        if (fold_wanted) w_top = 0.5;
+        // (two-subcycle kernel: the fold chunk runs two one-subcycle passes over its rows + 1 and waits for its
+        // neighbours twice, against one fused pass over rows + 3 at ~1.7 x the cost per row)
+        if (fold_wanted) w_top = h->fused ? 0.6 : 0.5;
         else if (multi && h->north >= 0) w_top = 0.6;
         if (multi && h->south >= 0) w_bot = 0.6;
     }
@@ -663,6 +721,12 @@ int choose_tiling(evp_b200_handle *h) {
         }
         ncy = (int)tab.size() / 2;
     }
+    if (h->par.kernel_variant & 65536) {
+        // MEASUREMENT ONLY (results invalid): every chunk marches the same rows in the middle of the slab, so the
+        // whole grid works on an L2-resident set -- the kernel's time without DRAM
+        const int n = std::min(rows, std::max(2, nyl - 4));
+        for (int k = 0; k < ncy; ++k) { tab[2 * k] = std::max(2, nyl / 2 - n / 2); tab[2 * k + 1] = n; }
+    }
     h->threads = nt;
     h->strip_w = strip_w;
     h->rows = rows;
@@ -672,7 +736,52 @@ int choose_tiling(evp_b200_handle *h) {
     int top_rows = 0;
     for (int k = 0; k < ncy; ++k)
         if (tab[2 * k] + tab[2 * k + 1] - 1 == nyl) top_rows = tab[2 * k + 1];
-    h->fold_in_kernel = fold_wanted && top_rows >= 2;
+    h->fold_in_kernel = fold_wanted && (top_rows >= 2 || (h->par.kernel_variant & 65536));
+    if (h->fused) {
+        // the fold chunk reads two rows below itself; every chunk of the table must be one wave (the fold chunk's
+        // CTAs wait for each other)
+        int top_j0 = 0;
+        for (int k = 0; k < ncy; ++k)
+            if (tab[2 * k] + tab[2 * k + 1] - 1 == nyl) top_j0 = tab[2 * k];
+        const bool ok = (!h->pg.tripole || (h->fold_in_kernel && (top_j0 >= 3 || (h->par.kernel_variant & 65536)))) &&
+                        (long)ncx * ncy <= (long)per_sm * sms;
+        if (!ok) {
+            h->fused = false;
+            return choose_tiling(h);
+        }
+        // Strip table.  Per warp: virtual column of lane 0; owned lanes; lane G of the ghost T column nx+1 where the
+        // warp holds the seam of a cyclic domain (lanes .., nx, nx+1, 1, 2, ..); lanes in use.  A warp owns lanes
+        // 1..29 (a first cyclic warp 2..29 behind its two seam lanes), a warp that owns column nx of a cyclic domain
+        // at most up to lane 28 (three seam lanes follow), so four warps always cover a CTA's <= 112 columns.
+        std::vector<int> ws((size_t)ncx * 16, 0);
+        const bool cyc = h->pg.ew_cyclic != 0;
+        for (int x = 0; x < ncx; ++x) {
+            const int ca = 1 + strip_w * x, cb = std::min(strip_w * (x + 1), nx);
+            int c = ca;
+            for (int w = 0; w < 4; ++w) {
+                int *e = &ws[((size_t)x * 4 + w) * 4];
+                if (c > cb) { e[0] = 0; e[1] = 1 | (0 << 8); e[2] = -1; e[3] = 1 | (0 << 8); continue; }
+                const bool first_cyc = cyc && c == 1;
+                const int l0 = first_cyc ? 2 : 1;
+                int n = std::min(cb - c + 1, 29 - l0 + 1);
+                if (cyc && c + n - 1 == nx && l0 + n - 1 > 28) --n; // column nx moves to the next warp
+                const int lo = l0, hi = l0 + n - 1;
+                const bool owns_nx = c + n - 1 == nx;
+                int G = -1, v0 = c - l0, llo = lo - 1, lhi = hi + 2;
+                if (first_cyc) { G = 1; v0 = nx; llo = 0; }
+                else if (cyc && owns_nx) { G = hi + 1; lhi = hi + 3; }
+                e[0] = v0; e[1] = lo | (hi << 8); e[2] = G; e[3] = llo | (lhi << 8);
+                c += n;
+            }
+            if (c <= cb) { // cannot happen for strips of <= 112 columns
+                h->fused = false;
+                return choose_tiling(h);
+            }
+        }
+        if (h->d_wstrips) cudaFree(h->d_wstrips);
+        CU(cudaMalloc(&h->d_wstrips, sizeof(int) * ws.size()));
+        CU(cudaMemcpy(h->d_wstrips, ws.data(), sizeof(int) * ws.size(), cudaMemcpyHostToDevice));
+    }
     if (h->tiled && h->pg.tripole && !h->fold_in_kernel) {
         // the separate fold kernel works on planes: tiny slabs / variant bit 2 fall back to the plane kernels
         h->tiled = false;
@@ -681,7 +790,7 @@ int choose_tiling(evp_b200_handle *h) {
     h->w_bot = (float)w_bot;
     h->w_top = (float)w_top;
     // with the default tiling the chunk table is re-balanced by active cells on the device each call
-    h->balance = h->par.tile_rows <= 0 && ncy >= 3 && (h->par.kernel_variant & 32) == 0;
+    h->balance = h->par.tile_rows <= 0 && ncy >= 3 && (h->par.kernel_variant & (32 | 65536)) == 0;
     if (h->d_chunks) cudaFree(h->d_chunks);
     if (h->d_rowcnt) cudaFree(h->d_rowcnt);
     if (h->d_cta_epoch) cudaFree(h->d_cta_epoch);
@@ -807,7 +916,7 @@ static int init_handle(evp_b200_handle *h, const evp_b200_dims *d, const evp_b20
     }
     // the subcycle kernel addresses a plane and its second copy with 32-bit element offsets: the largest
     // one is copy_stride (P_U1 - P_U0 planes) plus an index inside the last plane
-    if ((unsigned long long)(P_U1 - P_U0 + 1) * pg.cells + (unsigned long long)pg.pitch >= (1ull << 31))
+    if ((unsigned long long)(P_U2 - P_U0 + 1) * pg.cells + (unsigned long long)pg.pitch >= (1ull << 31))
         return fail(EVP_B200_ERR_ARG, "slab too large for 32-bit plane offsets (%zu cells per plane): use more ranks",
                     pg.cells);
     h->blocked_elems = (size_t)d->nx_block * d->ny_block * d->max_blocks;
@@ -887,6 +996,12 @@ static int init_handle(evp_b200_handle *h, const evp_b200_dims *d, const evp_b20
                           !(d->nranks > 1 && p->exchange_mode != 0) && evt_nstrips(pg.nx) <= EVP_SYNC_MAXCX;
     const bool tiled_auto = p->tile_threads == 0 && d->ny_global / d->nranks < 450;
     h->tiled = tiled_ok && ((kv & 2048) != 0 || tiled_auto);
+    // Two subcycles per launch (evp_fused.cuh): single rank, no north-south wrap, u-fold or no fold, plane layout.
+    // kernel_variant bit 17 (131072) selects it.
+    const bool fused_ok = (kv & (4 | 16 | 128 | 256 | 512 | 1024 | 2048)) == 0 && d->nranks == 1 && !pg.ns_cyclic &&
+                          !pg.tfold && p->ndte >= 2 && pg.nx >= 64 && pg.nyl >= 16 && p->tile_threads == 0;
+    h->fused = fused_ok && (kv & 131072) != 0;
+    if (h->fused) h->tiled = false;
     if (h->tiled) {
         h->tg.ns = evt_nstrips(pg.nx);
         h->tg.nr = pg.nyl + 2;
@@ -1116,6 +1231,11 @@ static int do_run_impl(evp_b200_handle *h, const evp_b200_inputs *in, const doub
         CU(cudaMemcpyAsync(p[P_U1], p[P_U0], pbytes, cudaMemcpyDeviceToDevice, h->st));
         CU(cudaMemcpyAsync(p[P_V1], p[P_V0], pbytes, cudaMemcpyDeviceToDevice, h->st));
         CU(cudaMemsetAsync(p[P_S1], 0, pbytes * EVP_NSTRESS, h->st));
+        if (h->fused && h->pg.tripole) { // third copy: the rows of the fold chunk (ghost / masked-out values)
+            CU(cudaMemcpyAsync(p[P_U2], p[P_U0], pbytes, cudaMemcpyDeviceToDevice, h->st));
+            CU(cudaMemcpyAsync(p[P_V2], p[P_V0], pbytes, cudaMemcpyDeviceToDevice, h->st));
+            CU(cudaMemsetAsync(p[P_S2], 0, pbytes * EVP_NSTRESS, h->st));
+        }
     }
     if (h->p2p) {
         // the neighbours store into the ghost rows of copy 1 from their first subcycle kernel on:
@@ -1396,7 +1516,7 @@ int evp_b200_step_device(evp_b200_handle *h, const evp_b200_inputs *in, const do
 
 int evp_b200_get_info(const evp_b200_handle *h, int32_t out[8]) {
     if (!h || !out) return fail(EVP_B200_ERR_ARG, "NULL argument");
-    out[0] = h->tiled ? 1 : 0;
+    out[0] = h->tiled ? 1 : (h->fused ? 2 : 0); // kernel of the ndte loop: 0 plane, 1 strip-tiled, 2 two subcycles per launch
     out[1] = h->grid_x;
     out[2] = h->grid_y;
     out[3] = h->threads;
@@ -1577,6 +1697,7 @@ int evp_b200_finalize(evp_b200_handle *h) {
     cudaFree(h->d_energy);
     cudaFree(h->fold_scratch);
     cudaFree(h->d_chunks);
+    cudaFree(h->d_wstrips);
     cudaFree(h->d_rowcnt);
     cudaFree(h->d_cta_epoch);
     cudaFree(h->row_ht);

@@ -83,6 +83,12 @@ struct SubArgs {
     // ---- tripole u-fold of u_new/v_new inside the kernel (top slab only) ------------------------
     int fold;              // 1 = the last CTA of the northernmost chunk to finish applies the fold
     double *fold_scratch;  // 2 * pitch doubles: copy of the raw top physical row of u_new, v_new
+    // ---- two subcycles per launch (evp_fused.cuh) ------------------------------------------------
+    // per warp strip (4 per CTA, index 4 * blockIdx.x + warp) four ints: virtual column of lane 0; first | last << 8
+    // owned lane; lane that holds the ghost T column nx+1 next to the east-west wrap (-1: none); first | last << 8
+    // lane in use.  A third state copy (2 * copy_stride behind copy 0) holds the intermediate rows of the tripole
+    // top chunk.
+    const int *wstrips;
 };
 
 // Tripole u-fold of a NE-corner vector field (serial/ice_boundary.F90:777-800 symmetrisation,
@@ -136,4 +142,12 @@ int evp_tiled_launch_strict(const SubArgs &a, bool last, int stages, int flags, 
                             void *stream, int *ctas_per_sm);
 int evp_tiled_launch_fast(const SubArgs &a, bool last, int stages, int flags, unsigned grid_x, unsigned grid_y,
                           void *stream, int *ctas_per_sm);
+// two subcycles per launch (k_subcycle2): reads state copy a.flip, writes copy a.flip ^ 1; `last`: the second of
+// the two is subcycle ndte.  ctas_per_sm != nullptr: only configure + occupancy query.  Returns a cudaError_t value.
+typedef int (*fused_launch_fn)(const SubArgs &a, bool last, int flags, unsigned grid_x, unsigned grid_y, void *stream,
+                               int *ctas_per_sm);
+int evp_fused_launch_strict(const SubArgs &a, bool last, int flags, unsigned grid_x, unsigned grid_y, void *stream,
+                            int *ctas_per_sm);
+int evp_fused_launch_fast(const SubArgs &a, bool last, int flags, unsigned grid_x, unsigned grid_y, void *stream,
+                          int *ctas_per_sm);
 int evp_subcycle_max_threads(void);

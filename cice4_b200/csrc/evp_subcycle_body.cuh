@@ -428,6 +428,67 @@ __device__ __forceinline__ void p2p_wait(const SubArgs &a, int tid, bool top, bo
     __syncthreads();
 }
 
+// Tripole u-fold of the rows nyl (symmetrised in place) and nyl+1 (ghost row) of the planes u_new, v_new by ONE CTA,
+// for the whole width (north-south part of the halo update on the top slab, serial/ice_boundary.F90:777-866).
+// The raw top row goes through a scratch copy because the update is in place.  All other CTAs' stores to these
+// rows must be complete and visible (the caller orders that).
+template <int NT>
+__device__ __forceinline__ void fold_top_rows(const SubArgs &a, double *u_new, double *v_new, int tid) {
+    const size_t rtop = (size_t)a.nyl * a.pitch;
+    const int ncol = a.nx + 2;
+    // raw top row of u_new and v_new -> scratch (independent loads, issued in batches)
+    for (int c0 = 0; c0 < 2 * ncol; c0 += 4 * NT) {
+        double val[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const int c = c0 + q * NT + tid;
+            if (c < 2 * ncol) {
+                const int f = c >= ncol, cc = f ? c - ncol : c;
+                val[q] = __ldcg((f ? v_new : u_new) + rtop + cc);
+            }
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const int c = c0 + q * NT + tid;
+            if (c < 2 * ncol) {
+                const int f = c >= ncol, cc = f ? c - ncol : c;
+                a.fold_scratch[(size_t)f * a.pitch + cc] = val[q];
+            }
+        }
+    }
+    __syncthreads();
+    for (int c0 = 0; c0 < 2 * ncol; c0 += 4 * NT) {
+        double vt[4], vg[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const int c = c0 + q * NT + tid;
+            if (c < 2 * ncol) {
+                const int f = c >= ncol, cc = f ? c - ncol : c;
+                const double *fld = f ? v_new : u_new;
+                int ig = cc;
+                if (cc == 0) ig = a.ew_cyclic ? a.nx : 1;
+                if (cc == a.nx + 1) ig = a.ew_cyclic ? 1 : a.nx;
+                int k = a.nx - ig;
+                if (k == 0) k = a.nx;
+                const double *scr = a.fold_scratch + (size_t)f * a.pitch;
+                double dummy;
+                evp_fold_necorner(scr, scr, cc, a.nx, a.ew_cyclic, -1.0, vt[q], dummy);
+                vg[q] = -__ldcg(fld + rtop - a.pitch + k);
+            }
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const int c = c0 + q * NT + tid;
+            if (c < 2 * ncol) {
+                const int f = c >= ncol, cc = f ? c - ncol : c;
+                double *fld = f ? v_new : u_new;
+                fld[rtop + cc] = vt[q];
+                fld[rtop + a.pitch + cc] = vg[q];
+            }
+        }
+    }
+}
+
 // End of a subcycle: publication of this rank's epoch to the neighbours (peer-to-peer halo), then the
 // tripole fold by the last CTA of the northernmost chunk (top slab).  `sn` = offset of the copy just written.
 // PERSIST: the fold's completion is published in sync[5] (the top chunk waits for it before the next
@@ -459,59 +520,7 @@ __device__ __forceinline__ void subcycle_epilogue(const SubArgs &a, idx_t sn, in
         __syncthreads();
         if (is_last) {
             __threadfence();
-            const size_t rtop = (size_t)a.nyl * a.pitch;
-            const int ncol = a.nx + 2;
-            // raw top row of u_new and v_new -> scratch (independent loads, issued in batches)
-            for (int c0 = 0; c0 < 2 * ncol; c0 += 4 * NT) {
-                double val[4];
-#pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    const int c = c0 + q * NT + tid;
-                    if (c < 2 * ncol) {
-                        const int f = c >= ncol, cc = f ? c - ncol : c;
-                        val[q] = __ldcg((f ? v_new : u_new) + rtop + cc);
-                    }
-                }
-#pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    const int c = c0 + q * NT + tid;
-                    if (c < 2 * ncol) {
-                        const int f = c >= ncol, cc = f ? c - ncol : c;
-                        a.fold_scratch[(size_t)f * a.pitch + cc] = val[q];
-                    }
-                }
-            }
-            __syncthreads();
-            for (int c0 = 0; c0 < 2 * ncol; c0 += 4 * NT) {
-                double vt[4], vg[4];
-#pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    const int c = c0 + q * NT + tid;
-                    if (c < 2 * ncol) {
-                        const int f = c >= ncol, cc = f ? c - ncol : c;
-                        const double *fld = f ? v_new : u_new;
-                        int ig = cc;
-                        if (cc == 0) ig = a.ew_cyclic ? a.nx : 1;
-                        if (cc == a.nx + 1) ig = a.ew_cyclic ? 1 : a.nx;
-                        int k = a.nx - ig;
-                        if (k == 0) k = a.nx;
-                        const double *scr = a.fold_scratch + (size_t)f * a.pitch;
-                        double dummy;
-                        evp_fold_necorner(scr, scr, cc, a.nx, a.ew_cyclic, -1.0, vt[q], dummy);
-                        vg[q] = -__ldcg(fld + rtop - a.pitch + k);
-                    }
-                }
-#pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    const int c = c0 + q * NT + tid;
-                    if (c < 2 * ncol) {
-                        const int f = c >= ncol, cc = f ? c - ncol : c;
-                        double *fld = f ? v_new : u_new;
-                        fld[rtop + cc] = vt[q];
-                        fld[rtop + a.pitch + cc] = vg[q];
-                    }
-                }
-            }
+            fold_top_rows<NT>(a, u_new, v_new, tid);
             if (PERSIST) {
                 __syncthreads();
                 if (tid == 0) {
@@ -1474,6 +1483,14 @@ template <int NT>
 static int launch_nt(const SubArgs &a, bool last, bool pdl, int variant, unsigned gx, unsigned gy, cudaStream_t s) {
     dim3 grid(gx, gy), block(NT);
     if constexpr (NT == 128) {
+        if ((variant & 1024) && (variant & 262144) && !a.p2p) { // ... capped at 128 registers: 4 CTAs per SM (spills)
+            if (last) return launch_k(k_subcycle<NT, true, false, true, 4>, a, grid, block, pdl, s);
+            return launch_k(k_subcycle<NT, false, false, true, 4>, a, grid, block, pdl, s);
+        }
+        if ((variant & 1024) && (variant & 524288) && !a.p2p) { // ... at 96 registers: 5 CTAs per SM
+            if (last) return launch_k(k_subcycle<NT, true, false, true, 5>, a, grid, block, pdl, s);
+            return launch_k(k_subcycle<NT, false, false, true, 5>, a, grid, block, pdl, s);
+        }
         if (variant & 1024) { // no prefetch across the arithmetic, 3 CTAs per SM (<= 168 registers)
             if (a.p2p) {
                 if (last) return launch_k(k_subcycle<NT, true, false, true, 3, true>, a, grid, block, pdl, s);
@@ -1524,6 +1541,7 @@ static int persist_nt(const SubArgs &a, unsigned gx, unsigned gy, cudaStream_t s
 
 } // namespace EVP_SUB_NS
 
+#ifndef EVP_BODY_NO_LAUNCHERS
 // returns a cudaError_t value (the launch status)
 int EVP_SUB_LAUNCH(const SubArgs &a, bool last, int variant, int threads, unsigned grid_x,
                    unsigned grid_y, void *stream) {
@@ -1571,3 +1589,4 @@ int EVP_PERSIST_LAUNCH(const SubArgs &a, int threads, unsigned grid_x, unsigned 
     default: return EVP_SUB_NS::persist_nt<128>(a, grid_x, grid_y, s, ctas_per_sm);
     }
 }
+#endif // EVP_BODY_NO_LAUNCHERS

@@ -241,6 +241,62 @@ def test_tiled_kernel_bit_exact(oracle, evp_lib, label, kw, variant):
     dyn.finalize()
 
 
+FUSED_CASES = [
+    ("gx3-real-grid", dict(name="gx3", realistic=True, gx3_fixture=GX3_FIXTURE), dict()),
+    ("gx3-dense", dict(name="gx3", realistic=False, gx3_fixture=GX3_FIXTURE), dict()),
+    ("tripole-64x48", dict(name="om1deg", nx=64, ny=48), dict()),
+    ("tripole-130x70-realistic", dict(name="om1deg", nx=130, ny=70, realistic=True), dict()),
+    ("tripole-300x200", dict(name="om1deg", nx=300, ny=200), dict()),
+    ("tripole-112x40-one-cta", dict(name="om1deg", nx=112, ny=40), dict()),
+    ("tripole-113x33", dict(name="om1deg", nx=113, ny=33), dict()),
+    ("tripole-225x30-rows3", dict(name="om1deg", nx=225, ny=30), dict(tile_rows=3)),
+    ("tripole-170x64-rows2", dict(name="om1deg", nx=170, ny=64), dict(tile_rows=2)),
+    ("open-open-70x40", dict(name="x", nx=70, ny=40, ew="open", ns="open"), dict()),
+    ("closed-closed-90x35", dict(name="x", nx=90, ny=35, ew="closed", ns="closed"), dict(tile_rows=4)),
+    ("cyclic-open-150x40-odd-ndte", dict(name="gx3", nx=150, ny=40, ew="cyclic", ns="open"), dict(ndte=7)),
+    ("cyclic-closed-84x50-ndte2", dict(name="x", nx=84, ny=50, ew="cyclic", ns="closed"), dict(ndte=2)),
+    ("open-tripole-100x36", dict(name="x", nx=100, ny=36, ew="open", ns="tripole"), dict(ndte=12)),
+]
+
+
+@pytest.mark.parametrize("label,kw,par", FUSED_CASES, ids=[c[0] for c in FUSED_CASES])
+def test_fused_two_subcycle_kernel_bit_exact(oracle, evp_lib, label, kw, par):
+    """kernel_variant bit 17: TWO subcycles per launch (csrc/evp_fused.cuh) -- the second subcycle runs two rows
+    behind the first one on values kept in shared memory; east-west seam, closed / open boundaries and the tripole
+    fold of the intermediate velocities included.  Same arithmetic as the one-subcycle kernels: cold + warm call
+    bit-exact against the strict oracle, every state and output field."""
+    par = dict(par)
+    case = synth.make_case(**kw)
+    ndte = par.pop("ndte", 120)
+    st, f, strengths, _ = oracle_steps(oracle, case, nsteps=2, ndte=ndte)
+    lay = E.BlockLayout.single_block(case.grid.nx, case.grid.ny)
+    dyn, out = cuda_steps(case, nsteps=2, strengths=strengths, math_mode=0, ndte=ndte, kernel_variant=131072, **par)
+    info = dyn.info()
+    assert info["fused"] == 1 and info["threads"] == 128 and info["strip_w"] <= 112, info
+    _compare_exact(dyn, out, st, f, lay)
+    dyn.subcycle_resident(1)
+    assert np.isfinite(dyn.diagnostics()["umaxn"])
+    dyn.finalize()
+
+
+def test_fused_kernel_fma_mode_and_blocks(oracle, evp_lib):
+    """The two-subcycle kernel behind a block layout, with evp_damping, and its FMA build within the tolerance."""
+    case = synth.make_case("om1deg", nx=130, ny=70, realistic=True)
+    st, f, strengths, _ = oracle_steps(oracle, case, nsteps=2)
+    lay = E.BlockLayout.cartesian(130, 70, 23, 19)
+    dyn, out = cuda_steps(case, nsteps=2, strengths=strengths, layout=lay, kernel_variant=131072)
+    assert dyn.info()["fused"] == 1
+    _compare_exact(dyn, out, st, f, lay)
+    dyn.finalize()
+    dyn, out = cuda_steps(case, nsteps=2, strengths=strengths, math_mode=1, kernel_variant=131072)
+    _compare_tol(dyn, out, st, f, E.BlockLayout.single_block(130, 70))
+    dyn.finalize()
+    st, f, strengths, _ = oracle_steps(oracle, case, nsteps=1, evp_damping=1)
+    dyn, out = cuda_steps(case, strengths=strengths, kernel_variant=131072, evp_damping=1)
+    _compare_exact(dyn, out, st, f, E.BlockLayout.single_block(130, 70))
+    dyn.finalize()
+
+
 @pytest.mark.parametrize("rows", [1, 3, 1000])
 def test_tiled_kernel_tiling_invariance(oracle, evp_lib, rows):
     case = synth.make_case("om1deg", nx=300, ny=90)
