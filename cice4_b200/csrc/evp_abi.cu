@@ -671,8 +671,6 @@ int choose_tiling(evp_b200_handle *h) {
         per_sm = (nt == 256) ? 1 : (nt == 128 ? 2 : 4);
         if (tma && (h->par.kernel_variant & 256) == 0) per_sm = 3;
         if (!tma && nt == 128 && (h->par.kernel_variant & 1024)) per_sm = 3; // late-load kernel: 3 CTAs per SM
-        if (!tma && nt == 128 && (h->par.kernel_variant & 1024) && (h->par.kernel_variant & 262144)) per_sm = 4;
-        if (!tma && nt == 128 && (h->par.kernel_variant & 1024) && (h->par.kernel_variant & 524288)) per_sm = 5;
     }
     int ncy = (per_sm * sms) / ncx; // one wave
     if (ncy < 1) ncy = 1;

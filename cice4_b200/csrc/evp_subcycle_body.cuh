@@ -1483,14 +1483,6 @@ template <int NT>
 static int launch_nt(const SubArgs &a, bool last, bool pdl, int variant, unsigned gx, unsigned gy, cudaStream_t s) {
     dim3 grid(gx, gy), block(NT);
     if constexpr (NT == 128) {
-        if ((variant & 1024) && (variant & 262144) && !a.p2p) { // ... capped at 128 registers: 4 CTAs per SM (spills)
-            if (last) return launch_k(k_subcycle<NT, true, false, true, 4>, a, grid, block, pdl, s);
-            return launch_k(k_subcycle<NT, false, false, true, 4>, a, grid, block, pdl, s);
-        }
-        if ((variant & 1024) && (variant & 524288) && !a.p2p) { // ... at 96 registers: 5 CTAs per SM
-            if (last) return launch_k(k_subcycle<NT, true, false, true, 5>, a, grid, block, pdl, s);
-            return launch_k(k_subcycle<NT, false, false, true, 5>, a, grid, block, pdl, s);
-        }
         if (variant & 1024) { // no prefetch across the arithmetic, 3 CTAs per SM (<= 168 registers)
             if (a.p2p) {
                 if (last) return launch_k(k_subcycle<NT, true, false, true, 3, true>, a, grid, block, pdl, s);
