@@ -1245,7 +1245,8 @@ static int do_run_impl(evp_b200_handle *h, const evp_b200_inputs *in, const doub
     h->cur = 0;
     if (h->balance) // chunks of equal ACTIVE work; an inactive row inside a chunk still costs ~30 % of an active one
         aux_balance_chunks(pg, h->mk[M_ICETMASK], h->mk[M_ICEUMASK], h->d_rowcnt, h->d_chunks, h->grid_y,
-                           h->w_bot, h->w_top, h->fold_in_kernel ? 2 : 1, 0.3f * (float)(pg.nx + 1), h->st);
+                           h->w_bot, h->w_top, h->fold_in_kernel ? 2 : 1, 0.3f * (float)(pg.nx + 1),
+                           h->south >= 0 ? 1 : 0, (h->fold_in_kernel || h->north >= 0) ? 1 : 0, h->st);
     CU(cudaEventRecord(h->ev[3], h->st));
     // Outputs that are final before the subcycle loop travel to the host on a second stream while
     // the loop runs (copy engine and SMs overlap): strairx/y, strtltx/y, fm, strength, sicemass.

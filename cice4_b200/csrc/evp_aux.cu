@@ -489,13 +489,18 @@ __global__ void k_row_active(PlaneGeom pg, const uint8_t *__restrict__ icetmask,
 // one CTA: the row costs are staged in shared memory by all threads, then thread 0 walks them (a few
 // thousand rows at most; the serial pass over global memory took 110 us at 1080 rows)
 __global__ void k_balance_chunks(PlaneGeom pg, const int *__restrict__ rowcnt_g, int *__restrict__ chunks, int ncy,
-                                 float w_bot, float w_top, int min_top, float row_overhead) {
+                                 float w_bot, float w_top, int min_top, float row_overhead, int keep_bot, int keep_top) {
     extern __shared__ int rowcnt[]; // nyl + 2 entries
     for (int j = threadIdx.x; j <= pg.nyl + 1; j += blockDim.x) rowcnt[j] = rowcnt_g[j];
     __syncthreads();
     if (threadIdx.x != 0) return;
     const int nyl = pg.nyl;
-    auto cost = [&](int j) { return row_overhead + (float)rowcnt[j]; };
+    // A row without any active cell costs ~30 % of an active one when a CTA has to march through it (a boundary
+    // chunk that keeps its rows, or a gap between two ice bands inside a chunk), and nothing where it is trimmed
+    // from the end of a chunk: long ice-free stretches must not be given chunks of their own (they would all be
+    // trimmed to nothing while the few chunks left over share the ice).
+    auto cost_b = [&](int j) { return row_overhead + (float)rowcnt[j]; };
+    auto cost = [&](int j) { return rowcnt[j] > 0 ? row_overhead + (float)rowcnt[j] : 0.02f * row_overhead; };
     if (ncy == 1) {
         chunks[0] = 1; chunks[1] = nyl;
         return;
@@ -508,7 +513,7 @@ __global__ void k_balance_chunks(PlaneGeom pg, const int *__restrict__ rowcnt_g,
     int n_top = 0;
     float acc = 0.f;
     while (n_top < nyl - (ncy - 1) && (n_top < min_top || acc < w_top * unit)) {
-        acc += cost(nyl - n_top);
+        acc += keep_top ? cost_b(nyl - n_top) : cost(nyl - n_top);
         ++n_top;
     }
     if (n_top < 1) n_top = 1;
@@ -516,7 +521,7 @@ __global__ void k_balance_chunks(PlaneGeom pg, const int *__restrict__ rowcnt_g,
     int n_bot = 0;
     acc = 0.f;
     while (n_bot < nyl - n_top - n_int && (n_bot < 1 || acc < w_bot * unit)) {
-        acc += cost(1 + n_bot);
+        acc += keep_bot ? cost_b(1 + n_bot) : cost(1 + n_bot);
         ++n_bot;
     }
     chunks[0] = 1; chunks[1] = n_bot;
@@ -544,14 +549,15 @@ __global__ void k_balance_chunks(PlaneGeom pg, const int *__restrict__ rowcnt_g,
         j += n;
         rest -= acc;
     }
-    // Trim rows without any active T or U cell from both ends of the interior chunks: such rows
-    // belong to no chunk (nothing is computed there; velocities and stresses are 0 in both copies),
-    // and an all-inactive chunk becomes empty (its CTAs exit at once).  The boundary chunks keep
-    // their rows: they carry the fold and the peer-to-peer halo.
-    for (int k = 2; k < ncy; ++k) {
+    // Trim rows without any active T or U cell from both ends of the chunks: such rows belong to no chunk
+    // (nothing is computed there; velocities and stresses are 0 in both copies), and an all-inactive chunk
+    // becomes empty (its CTAs exit at once).  A boundary chunk that carries the tripole fold or the
+    // peer-to-peer halo keeps its rows; the northernmost chunk also owns the ghost T row nyl+1.
+    for (int k = 0; k < ncy; ++k) {
+        if ((k == 0 && keep_bot) || (k == 1 && keep_top)) continue;
         int j0 = chunks[2 * k], n = chunks[2 * k + 1];
         while (n > 0 && rowcnt[j0] == 0) { ++j0; --n; }
-        while (n > 0 && rowcnt[j0 + n - 1] == 0) --n;
+        while (n > 0 && rowcnt[j0 + n - 1] == 0 && !(j0 + n - 1 == nyl && rowcnt[nyl + 1] != 0)) --n;
         chunks[2 * k] = j0;
         chunks[2 * k + 1] = n;
     }
@@ -925,10 +931,10 @@ void aux_check_metrics(const PlaneGeom &pg, const MetricCheckArgs &a, cudaStream
 }
 void aux_balance_chunks(const PlaneGeom &pg, const uint8_t *icetmask, const uint8_t *iceumask, int *rowcnt,
                         int *chunks, int ncy, float w_bot, float w_top, int min_top, float row_overhead,
-                        cudaStream_t s) {
+                        int keep_bot, int keep_top, cudaStream_t s) {
     k_row_active<<<pg.nyl + 2, 128, 0, s>>>(pg, icetmask, iceumask, rowcnt);
     k_balance_chunks<<<1, 256, sizeof(int) * (pg.nyl + 2), s>>>(pg, rowcnt, chunks, ncy, w_bot, w_top, min_top,
-                                                                 row_overhead);
+                                                                 row_overhead, keep_bot, keep_top);
 }
 void aux_energy_sums(const PlaneGeom &pg, const EnergyArgs &a, cudaStream_t s) {
     k_energy_rows<<<pg.nyl, 256, 0, s>>>(pg, a);

@@ -114,7 +114,7 @@ void aux_check_metrics(const PlaneGeom &pg, const MetricCheckArgs &a, cudaStream
 // no chunk); an all-inactive chunk becomes empty.
 void aux_balance_chunks(const PlaneGeom &pg, const uint8_t *icetmask, const uint8_t *iceumask, int *rowcnt,
                         int *chunks, int ncy, float w_bot, float w_top, int min_top, float row_overhead,
-                        cudaStream_t s);
+                        int keep_bot, int keep_top, cudaStream_t s);
 
 // max ice speed / max strength per hemisphere (source/ice_diagnostics.F90:294-346); out4 must be zeroed
 void aux_diagnostics(const PlaneGeom &pg, const double *u, const double *v, const double *strength,
