@@ -111,6 +111,12 @@ def build_case(workload: str, realistic: bool, world: int = 1):
         c = synth.make_case("p01", nx=3600, ny=338 * world, realistic=realistic)
         c.name = "p01w"
         return c
+    if "@" in workload:      # development: NAME@NXxNY = the named configuration on another grid size
+        name, dims = workload.split("@")
+        nx, ny = (int(v) for v in dims.split("x"))
+        c = synth.make_case(name, nx=nx, ny=ny, realistic=realistic)
+        c.name = name
+        return c
     fixture = os.path.join(ROOT, "tests", "golden", "gx3_grid.npz") if workload == "gx3" else None
     return synth.make_case(workload, realistic=realistic, gx3_fixture=fixture)
 

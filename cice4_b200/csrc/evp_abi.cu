@@ -684,9 +684,25 @@ int choose_tiling(evp_b200_handle *h) {
     if (ncy >= 3 && h->par.tile_rows <= 0) {
         // (two-subcycle kernel: the fold chunk runs two one-subcycle passes over its rows + 1 and waits for its
         // neighbours twice, against one fused pass over rows + 3 at ~1.7 x the cost per row)
+        // A chunk next to another slab pays a fixed cost per kernel (flag wait, coherent ghost-row loads, remote
+        // stores, system fence before its flag): ~1.5 rows' worth in the plane kernels, ~4.5 rows' worth in the tiled
+        // kernel, whose rows are twice as fast (measured on 4 x B200, 135 rows per slab: 22.4 / 19.8 / 17.4 us per
+        // subcycle with boundary chunks of 1.0 / 0.6 / 0.3 interior lengths)
+        double w_peer = 0.6;
+        if (h->tiled) {
+            const double r0 = (double)nyl / ncy;
+            w_peer = std::min(1.0, std::max(0.2, 1.0 - 4.5 / r0));
+        }
         if (fold_wanted) w_top = h->fused ? 0.6 : 0.5;
-        else if (multi && h->north >= 0) w_top = 0.6;
-        if (multi && h->south >= 0) w_bot = 0.6;
+        else if (multi && h->north >= 0) w_top = w_peer;
+        if (multi && h->south >= 0) w_bot = w_peer;
+    }
+    if (const char *e = getenv("EVP_B200_WBND")) { // development: relative length of the chunks next to another slab
+        const double w = atof(e);
+        if (w > 0.05 && w <= 2.0 && multi) {
+            if (h->north >= 0 && !fold_wanted) w_top = w;
+            if (h->south >= 0) w_bot = w;
+        }
     }
     std::vector<int> tab; // (j0, n) in launch order: bottom, top, then interior south to north
     int rows = h->par.tile_rows;
