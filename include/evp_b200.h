@@ -118,7 +118,12 @@ typedef struct {
                                instead of 3 stages and 2 CTAs; bit 13 (8192): strip-major instead of row-major
                                tile order; bit 14 (16384): MEASUREMENT ONLY, results invalid: tiled kernel
                                without the arithmetic (streaming ceiling of the access pattern); bit 15
-                               (32768): force the plane kernels */
+                               (32768): force the plane kernels; bit 16 (65536): MEASUREMENT ONLY, results
+                               invalid: every row chunk marches the same L2-resident rows (the kernel's time
+                               without DRAM traffic); bit 17 (131072): TWO subcycles per launch (temporal
+                               blocking, csrc/evp_fused.cuh; bit-identical; single rank, no north-south wrap,
+                               no T-fold; halves the DRAM traffic but is issue-bound and measured slower,
+                               DESIGN.md 4) */
     int32_t state_residency; /* 0 = the whole state is uploaded and downloaded by every call (host arrays always
                                current: restart-exact drop-in); 1 = the 12 stress arrays stay on the device
                                between calls: uploaded by the first call after init or after
