@@ -122,7 +122,7 @@ __global__ void __launch_bounds__(1024) k_halo_tripole(PlaneGeom pg, T *a0, T *a
     T *a = blockIdx.x == 0 ? a0 : a1;
     const int nx = pg.nx, nyl = pg.nyl;
     const size_t rtop = (size_t)nyl * pg.pitch, rbelow = (size_t)(nyl - 1) * pg.pitch,
-                 rbelow2 = (size_t)(nyl - 2) * pg.pitch, rghost = (size_t)(nyl + 1) * pg.pitch;
+                 rghost = (size_t)(nyl + 1) * pg.pitch;
     T vtop[TRIP_MAXC], vghost[TRIP_MAXC];
     bool wtop = false;
 #pragma unroll
@@ -135,13 +135,17 @@ __global__ void __launch_bounds__(1024) k_halo_tripole(PlaneGeom pg, T *a0, T *a
         if (i == 0) ig = pg.ew_cyclic ? nx : 1;
         if (i == nx + 1) ig = pg.ew_cyclic ? 1 : nx;
         if (pg.tfold) {
-            // T-fold (:725-773): the buffer holds rows nyl-2, nyl-1, nyl; iSrc = nx - i_glob + 1 - ioffset
-            if (loc == 2) { // NE corner: ioffset 0, joffset 1 -- rows nyl and nyl+1 mirror rows nyl-1 and nyl-2
+            // T-fold (:725-773), iSrc = nx - i_glob + 1 - ioffset.  The three-row buffer the reference works on holds
+            // the physical rows nyl-1, nyl, nyl: the 'north' message fills it with rows nyl-2 .. nyl, then the
+            // 'northeast' / 'northwest' messages of the tripole blocks -- last in ice_HaloCreate's list, written
+            // for the two-row u-fold buffer -- overwrite buffer rows 1 and 2 with rows nyl-1, nyl
+            // (serial/ice_boundary.F90:3833-3848; seen by running the reference's own translated halo).
+            if (loc == 2) { // NE corner: ioffset 0, joffset 1 -- row nyl <- buffer row 2 (raw row nyl), row nyl+1 <- buffer row 1
                 int k = nx - ig + 1;
                 if (k == 0) k = nx;
                 if (k > nx) k -= nx;
-                vtop[c] = (T)(isign * a[rbelow + k]);
-                vghost[c] = (T)(isign * a[rbelow2 + k]);
+                vtop[c] = (T)(isign * a[rtop + k]);
+                vghost[c] = (T)(isign * a[rbelow + k]);
                 wtop = true;
             } else { // centre: ioffset -1, joffset 0 -- the top row is degenerate: symmetrise pairs (k, nx-k+2), k = 2..nx/2
                 int k = nx - ig + 2;
@@ -154,8 +158,8 @@ __global__ void __launch_bounds__(1024) k_halo_tripole(PlaneGeom pg, T *a0, T *a
                     const int kk = nx - k + 2;
                     x = (T)(isign * trip_avg<T>(a[rtop + kk], a[rtop + k], isign));
                 }
-                vtop[c] = (T)(isign * x);
-                vghost[c] = (T)(isign * a[rbelow + k]);
+                vtop[c] = (T)(isign * x);                  // row nyl   <- buffer row 3 (symmetrised row nyl)
+                vghost[c] = (T)(isign * a[rtop + k]);      // row nyl+1 <- buffer row 2 (RAW row nyl)
                 wtop = true;
             }
         } else if (loc == 2) {

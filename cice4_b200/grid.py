@@ -104,7 +104,11 @@ def halo_update(a: np.ndarray, ew: int, ns: int, loc: int = LOC_CENTER,
     trip = ns == BND_TRIPOLE or tfold
     trows = 3 if tfold else 2
     if trip:
-        buf = a[1:nx + 1, ny - trows + 1:ny + 1].copy()  # rows jhi-trows+1 .. jhi
+        buf = a[1:nx + 1, ny - trows + 1:ny + 1].copy()  # rows jhi-trows+1 .. jhi ('north' message, :3699-3733)
+        # the 'northeast' / 'northwest' messages of a tripole block (:3833-3848) come last in the list and copy
+        # rows jhi-1, jhi into buffer rows 1, 2 whatever tripoleRows is: a repeat on the u-fold, an overwrite of
+        # rows 1 and 2 on the T-fold -- the reference's actual behaviour (its own translated halo shows it)
+        buf[:, 0:2] = a[1:nx + 1, ny - 1:ny + 1]
     if ew == BND_CYCLIC:
         a[0, 1:ny + 1] = a[nx, 1:ny + 1]
         a[nx + 1, 1:ny + 1] = a[1, 1:ny + 1]

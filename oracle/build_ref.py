@@ -85,10 +85,52 @@ def translate(defines, driver, omp=False):
             # timing build: the cell loops of stress / stepu (independent iterations over the index lists,
             # as the OpenMP directives of later CICE versions assume) run on all host threads
             missing.update(tr.subroutine(path, s, omp={"ij"} if omp and s in ("stress", "stepu") else None))
-    missing -= set(tr.subs) | {"get_block", "ice_haloupdate", "ice_timer_start", "ice_timer_stop"}
+    missing.update(translate_halo(tr))
+    missing -= set(tr.subs) | {"get_block", "ice_haloupdate", "ice_timer_start", "ice_timer_stop",
+                               "get_block_parameter", "abort_ice"}
     if missing:
         raise T.TranslateError("unresolved names: " + ", ".join(sorted(missing)))
     return tr.emit_file()
+
+
+def translate_halo(tr):
+    """The reference's own block decomposition and halo machinery (serial build): the block loop of `create_blocks`,
+    `ice_blocksGetNbrID` (source/ice_blocks.F90), `ice_distributionGetBlockLoc` (source/ice_distribution.F90), the
+    message-configuration loop of `ice_HaloCreate`, `ice_HaloMsgCreate`, `ice_HaloUpdate2DR8` and `ice_HaloUpdate2DI4`
+    (serial/ice_boundary.F90), with the derived types `block`, `distrb` and `ice_halo`.  Allocation (the head of
+    create_blocks / ice_HaloCreate, whose sizes come from a counting pass over the same loop) and
+    `get_block_parameter` (optional pointer results) are hosted by oracle/ref_glue.c."""
+    src = os.path.join(REF, "source")
+    blk = os.path.join(src, "ice_blocks.F90")
+    dst = os.path.join(src, "ice_distribution.F90")
+    bnd = os.path.join(REF, "serial", "ice_boundary.F90")
+    for n in ("my_task", "nblocks_tot", "nblocks_x", "nblocks_y", "block_size_x", "block_size_y", "buf_nx", "buf_rows"):
+        tr.add_global(T.Decl(n, "integer"))
+    tr.module_decls(blk, only={"nghost", "ice_blocksnorth", "ice_blockssouth", "ice_blockseast", "ice_blockswest",
+                               "ice_blocksnortheast", "ice_blocksnorthwest", "ice_blockssoutheast",
+                               "ice_blockssouthwest", "ice_blockseast2", "ice_blockswest2",
+                               "ice_blockseastnortheast", "ice_blockswestnorthwest"})
+    tr.type_def(blk, "block", {"i_glob": [None], "j_glob": [None]})
+    tr.type_def(dst, "distrb", {"blocklocation": [None], "blocklocalid": [None], "blockglobalid": [None]})
+    tr.type_def(bnd, "ice_halo", {"srclocaladdr": ["3", None], "dstlocaladdr": ["3", None]})
+    tr.add_global(T.Decl("all_blocks", "type", ["nblocks_tot"], tname="block", pointer=True))
+    tr.add_global(T.Decl("all_blocks_ij", "integer", ["nblocks_x", "nblocks_y"], pointer=True))
+    tr.add_global(T.Decl("i_global", "integer", ["nx_block", "nblocks_tot"], pointer=True))
+    tr.add_global(T.Decl("j_global", "integer", ["ny_block", "nblocks_tot"], pointer=True))
+    tr.add_global(T.Decl("buftripoler8", "real", ["buf_nx", "buf_rows"], pointer=True))
+    tr.add_global(T.Decl("buftripolei4", "integer", ["buf_nx", "buf_rows"], pointer=True))
+    missing = set()
+    missing.update(tr.translate_range(blk, "create_blocks", "subroutine", r"^do\s+jblock\s*=", None,
+                                      "create_blocks_loop",
+                                      ["nx_global", "ny_global", "ew_boundary_type", "ns_boundary_type"]))
+    missing.update(tr.function(blk, "ice_blocksgetnbrid"))
+    missing.update(tr.subroutine(dst, "ice_distributiongetblockloc"))
+    missing.update(tr.subroutine(bnd, "ice_halomsgcreate"))
+    missing.update(tr.translate_range(bnd, "ice_halocreate", "function", r"^msgconfigloop\s*:", r"^end\s*do\s+msgconfigloop$",
+                                      "ice_halocreate_msgconfig", ["halo", "dist", "nsboundarytype", "ewboundarytype"]))
+    missing.update(tr.subroutine(bnd, "ice_haloupdate2dr8", dims_override={"array": BLOCK3}))
+    missing.update(tr.subroutine(bnd, "ice_haloupdate2di4", dims_override={"array": BLOCK3}))
+    return missing
 
 
 def build(verbose=False):

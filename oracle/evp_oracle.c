@@ -94,10 +94,11 @@ void orc_set_evp_parameters(orc_params *p, double dt, int ndte) {
 /*     rows, :777-827 symmetrisation, :3735-3763 + :837-866 copy-out     */
 /*     over local i = 1..ihi+nghost, rows jhi and jhi+1;                 */
 /*   - tripoleT (T-fold): tripoleRows = nghost+2 (:199-205), so the top  */
-/*     THREE physical rows go into the buffer; symmetrisation and        */
-/*     offsets of :725-773 (integer fields: nint of the average,         */
-/*     :1303-1321); the copy-out message of buffer row 3 has jDst = -1   */
-/*     and is skipped (:3753-3757).                                      */
+/*     THREE physical rows go into the buffer, and the corner messages   */
+/*     then overwrite buffer rows 1-2 with rows jhi-1, jhi (see below);  */
+/*     symmetrisation and offsets of :725-773 (integer fields: nint of   */
+/*     the average, :1303-1321); the copy-out message of buffer row 3    */
+/*     has jDst = -1 and is skipped (:3753-3757).                        */
 /* All regular copies read physical cells and write ghost cells, so      */
 /* their order is immaterial; the tripole copy-out runs last (:837).     */
 /* ------------------------------------------------------------------ */
@@ -118,6 +119,15 @@ void orc_set_evp_parameters(orc_params *p, double dt, int ndte) {
         for (j = 1; j <= trows; ++j)                                                        \
             for (i = 1; i <= nxg; ++i)                                                      \
                 buf[(size_t)(j - 1) * nxg + (i - 1)] = a[IX(ilo + i - 1, jhi - trows + j)]; \
+        /* The 'northeast' / 'northwest' messages of a tripole block (:3833-3848, :3868-3883) copy the top \
+         * nghost+1 rows into buffer rows 1 .. nghost+1 -- whatever tripoleRows is -- and they are the last \
+         * copies into the buffer in ice_HaloCreate's list order (:519-580).  On the u-fold that repeats the \
+         * 'north' message; on the T-fold (3 buffer rows) it OVERWRITES rows 1 and 2, so the buffer the update \
+         * works on holds the physical rows jhi-1, jhi, jhi (found by running the reference's own translated \
+         * halo, tests/test_oracle_vs_ref.py). */                                             \
+        for (j = 1; j <= 2; ++j)                                                            \
+            for (i = 1; i <= nxg; ++i)                                                      \
+                buf[(size_t)(j - 1) * nxg + (i - 1)] = a[IX(ilo + i - 1, jhi - 2 + j)];     \
     }                                                                                       \
     if (ewc) {                                                                              \
         for (j = jlo; j <= jhi; ++j) {                                                      \

@@ -217,6 +217,13 @@ def ref_lib(variant: str) -> C.CDLL:
     return _ref_libs[variant]
 
 
+def ref_abort_message(params: OrcParams) -> str:
+    """what the translated reference passed to abort_ice, or why the host refused the domain"""
+    L = ref_lib(ref_variant(params))
+    L.ref_abort_message.restype = C.c_char_p
+    return L.ref_abort_message().decode()
+
+
 def run_evp_ref(grid, inputs, state, params: OrcParams, dt: float):
     """One `evp(dt)` call of the translated reference (same contract as run_evp; the locals of the
     reference's `evp` -- icetmask, tmass, umass, aiu, ... -- are not exported)."""
@@ -224,7 +231,7 @@ def run_evp_ref(grid, inputs, state, params: OrcParams, dt: float):
     g = make_grid(grid.nx_block, grid.ny_block, grid.ew, grid.ns)
     rc = ref_lib(ref_variant(params)).ref_evp(C.byref(g), C.byref(params), C.byref(f.c), dt)
     if rc != 0:
-        raise RuntimeError("ref_evp failed")
+        raise RuntimeError("ref_evp failed: " + ref_abort_message(params))
     return f
 
 
@@ -250,8 +257,31 @@ def run_evp_ref_blocks(layout, ew: int, ns: int, grid_fields_blk, inputs_blk, st
                                                       layout.iglob_lo, layout.jglob_lo)])
     rc = L.ref_evp_blocks(C.byref(g), C.byref(lay), C.byref(params), C.byref(f.c), dt)
     if rc != 0:
-        raise RuntimeError("ref_evp_blocks failed")
+        raise RuntimeError("ref_evp_blocks failed: " + ref_abort_message(params))
     return f
+
+
+def ref_halo(a: np.ndarray, ew: int, ns: int, loc: int, kind: int, layout=None, variant: str = "cice4") -> None:
+    """The REFERENCE's own halo update (translated ice_HaloCreate message loop / ice_HaloMsgCreate /
+    ice_HaloUpdate2DR8|2DI4, serial/ice_boundary.F90) applied in place to `a`: one block (nx_block, ny_block) or, with
+    `layout` (a cice4_b200.evp.BlockLayout), a block array (nx_block, ny_block, nblocks)."""
+    L = ref_lib(variant)
+    is_int = a.dtype == np.int32
+    fn = L.ref_halo_update_i4 if is_int else L.ref_halo_update_r8
+    fn.restype = C.c_int
+    fn.argtypes = [C.POINTER(OrcGrid), C.POINTER(RefLayout), c_ip if is_int else c_dp, C.c_int32, C.c_int32]
+    if layout is None:
+        g = make_grid(a.shape[0], a.shape[1], ew, ns)
+        rc = fn(C.byref(g), None, _ptr(a, is_int), loc, kind)
+    else:
+        g = OrcGrid(layout.nx_block, layout.ny_block, 2, layout.nx_block - 1, 2, layout.ny_block - 1, ew, ns)
+        lay = RefLayout(layout.nblocks, layout.nx_global, layout.ny_global,
+                        *[x.ctypes.data_as(c_ip) for x in (layout.ilo, layout.ihi, layout.jlo, layout.jhi,
+                                                          layout.iglob_lo, layout.jglob_lo)])
+        rc = fn(C.byref(g), C.byref(lay), _ptr(a, is_int), loc, kind)
+    if rc != 0:
+        L.ref_abort_message.restype = C.c_char_p
+        raise RuntimeError("reference halo update failed: " + L.ref_abort_message().decode())
 
 
 def omp_set_num_threads(n: int) -> None:

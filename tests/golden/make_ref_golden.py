@@ -7,8 +7,10 @@ The reference is Fortran and the image has no Fortran compiler, so "the referenc
 oracle/_ref/libevp_ref_<variant>.so: the reference's own source text of `evp` and everything it calls
 (source/ice_dyn_evp.F90, source/ice_grid.F90, source/ice_mechred.F90, drivers/*/ice_constants.F90),
 translated statement by statement into C by oracle/f90_to_c.py at build time and compiled with gcc
--O2 -ffp-contract=off (oracle/build_ref.py; the hand-written parts are get_block and the index
-copying of ice_HaloUpdate, oracle/ref_glue.c).
+-O2 -ffp-contract=off (oracle/build_ref.py).  Since round 2 the halo updates are the reference's own too: the
+block loop of create_blocks, ice_blocksGetNbrID, the message loop of ice_HaloCreate, ice_HaloMsgCreate and
+ice_HaloUpdate2DR8 / 2DI4 (serial/ice_boundary.F90) are translated as well; hand-written in oracle/ref_glue.c are only
+the allocations, get_block / get_block_parameter and abort_ice.
 
 Each fixture holds the complete problem (grid fields, inputs, initial state = init_evp zeros, the
 run-time options) and the reference's state and outputs after `nsteps` consecutive calls, so the
@@ -35,6 +37,10 @@ CASES = {
     "auscom_cyclic_open_26x20": (dict(name="x", nx=26, ny=20, ew="cyclic", ns="open"),
                                  dict(auscom=1, coupled=1, use_ocnslope=0, cosw=0.9063077870366499,
                                       sinw=0.42261826174069944), 3600.0, 120, 2),
+    # T-fold: the fold as the reference's own halo executes it (the corner messages overwrite two rows of the
+    # three-row tripole buffer, serial/ice_boundary.F90:3833-3848)
+    "cice4_tripoleT_26x20": (dict(name="x", nx=26, ny=20, ew="cyclic", ns="tripoleT", realistic=True), dict(),
+                             3600.0, 120, 2),
     "access_tripole_damping_24x20": (dict(name="om1deg", nx=24, ny=20),
                                      dict(auscom=1, coupled=1, use_ocnslope=1, access_wind=1, evp_damping=1),
                                      1800.0, 120, 2),

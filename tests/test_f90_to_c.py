@@ -225,3 +225,208 @@ def test_cpp_nested_conditionals():
     assert keep([]) == ["a", "e", "f"]
     assert keep(["X"]) == ["a", "b", "c", "f"]
     assert keep(["X", "Y"]) == ["a", "b", "d", "f"]
+
+
+# ------------------------------------------------------------------------------------------------
+# round 2: the constructs of the reference's block / halo machinery (serial/ice_boundary.F90, ice_blocks.F90)
+# ------------------------------------------------------------------------------------------------
+HALO_LIKE = """
+      module halo_mod
+      implicit none
+      integer (int_kind), parameter :: dir_north = 1, dir_south = 2, dir_east = 3
+      type, public :: table
+         integer (int_kind) :: count, rows
+         logical (log_kind) :: flag
+         integer (int_kind), dimension(:,:), pointer :: addr
+      end type
+      real (dbl_kind), dimension(:,:), allocatable :: buf
+      contains
+
+      function neighbour(id, direction, bndy) result (nbr)
+      integer (int_kind), intent(in) :: id, direction
+      character (*), intent(in) :: bndy
+      integer (int_kind) :: nbr
+      integer (int_kind) :: step
+      call get_param(id, step=step)
+      select case (direction)
+      case (dir_north)
+         nbr = id + step
+         if (nbr > 10) then
+            select case (bndy)
+            case ('open', 'closed')
+               nbr = 0
+            case ('cyclic')
+               nbr = nbr - 10
+            case ('tripole':'tripoleT')
+               nbr = -id
+            case default
+               call stop_it('unknown boundary')
+            end select
+         endif
+      case (dir_south:dir_east)
+         nbr = id - step
+      case default
+         nbr = -999
+      end select
+      end function neighbour
+
+      subroutine fill (t, kind, scale, total, opt)
+      type (table), intent(inout) :: t
+      character (*), intent(in) :: kind
+      real (dbl_kind), intent(in) :: scale
+      real (dbl_kind), intent(out) :: total
+      real (dbl_kind), intent(in), optional :: opt
+      integer (int_kind) :: i, j, n, nx
+      integer (int_kind), dimension(:), pointer :: glob
+      real (dbl_kind) :: f
+      if (present(opt)) then
+         f = opt
+      else
+         f = 0.5_dbl_kind
+      endif
+      nx = 0
+      if (allocated(buf)) nx = size(buf,dim=1)
+      call get_param(abs(-3), list=glob)
+      n = t%count
+      outer: do j = 1, t%rows
+         do i = 1, 3
+            n = n + 1
+            t%addr(1,n) = glob(i) + neighbour(i, dir_north, kind)
+            t%addr(2,n) = j
+            if (kind == 'cyclic' .and. .not. t%flag) t%addr(2,n) = -j
+         end do
+      end do outer
+      t%count = n
+      buf = scale
+      total = f * nx
+      call helper2(t, -n, 'tag')
+      end subroutine fill
+
+      subroutine helper2 (t, m, label)
+      type (table), intent(inout) :: t
+      integer (int_kind), intent(in) :: m
+      character (*), intent(in) :: label
+      if (label /= 'tag') call stop_it('bad label')
+      t%rows = t%rows + m
+      end subroutine helper2
+      end module halo_mod
+"""
+
+HALO_HOST = r"""
+static int g_stopped;
+static void v_stop_it(const char *m) { (void)m; g_stopped = 1; }
+struct f_kw_get_param { int32_t *v_step; int32_t **v_list; };
+static int32_t g_list[3] = {100, 200, 300};
+static void v_get_param(int32_t *id, struct f_kw_get_param kw) {
+    if (kw.v_step) *kw.v_step = *id == 9 ? 5 : 1;
+    if (kw.v_list) *kw.v_list = g_list;
+}
+int stopped(void) { return g_stopped; }
+"""
+
+
+def test_halo_machinery_constructs(tmp_path):
+    """select case on integers (value, range, default) and strings (list, range, default), named do, character
+    dummies and string literals, == / /= on strings, derived type with a pointer-array component, optional dummy
+    with present(), allocated() / size(a,dim=n) of a module allocatable, pointer array attached by the callee through
+    a keyword argument, expression and string actual arguments, a function with a result clause called inside an
+    expression, whole-array assignment to an allocatable -- translated, compiled and executed."""
+    src = tmp_path / "halo_mod.F90"
+    src.write_text(HALO_LIKE)
+    tr = T.Translator(())
+    for n in ("buf_n1", "buf_n2"):
+        tr.add_global(T.Decl(n, "integer"))
+    tr.module_decls(str(src), only={"dir_north", "dir_south", "dir_east"})
+    tr.type_def(str(src), "table", {"addr": ["2", None]})
+    tr.add_global(T.Decl("buf", "real", ["buf_n1", "buf_n2"], pointer=True))
+    missing = set(tr.function(str(src), "neighbour"))
+    missing |= set(tr.subroutine(str(src), "helper2"))
+    missing |= set(tr.subroutine(str(src), "fill"))
+    assert missing - set(tr.subs) == {"get_param", "stop_it"}
+    code = tr.emit_file()
+    # host functions must precede the generated routines: put them right after the prelude + types
+    k = code.index("void ref_init_parameters")
+    cfile = tmp_path / "halo.c"
+    cfile.write_text(code[:k] + HALO_HOST + code[k:])
+    lib = tmp_path / "libhalo.so"
+    cc = "/usr/bin/gcc" if os.access("/usr/bin/gcc", os.X_OK) else "gcc"
+    subprocess.check_call([cc, "-std=gnu11", "-O2", "-fPIC", "-shared", "-Wno-unused", "-Wno-parentheses", "-o",
+                           str(lib), str(cfile), "-lm"])
+    L = C.CDLL(str(lib))
+    L.ref_init_parameters()
+    L.v_neighbour.restype = C.c_int32
+    L.v_neighbour.argtypes = [C.c_int32, C.c_int32, C.c_char_p]
+    assert L.v_neighbour(4, 1, b"open") == 5
+    assert L.v_neighbour(10, 1, b"open") == 0 and L.v_neighbour(10, 1, b"closed") == 0
+    assert L.v_neighbour(10, 1, b"cyclic") == 1
+    assert L.v_neighbour(9, 1, b"cyclic") == 4            # step 5 from the keyword call
+    assert L.v_neighbour(10, 1, b"tripole") == -10 and L.v_neighbour(10, 1, b"tripolet") == -10
+    assert L.v_neighbour(7, 2, b"x") == 6 and L.v_neighbour(7, 3, b"x") == 6 and L.v_neighbour(7, 4, b"x") == -999
+    assert L.stopped() == 0
+    L.v_neighbour(10, 1, b"weird")
+    assert L.stopped() == 1
+
+    class Table(C.Structure):
+        _fields_ = [("count", C.c_int32), ("rows", C.c_int32), ("flag", C.c_int32), ("addr", C.POINTER(C.c_int32))]
+
+    addr = np.zeros((2, 40), dtype=np.int32, order="F")
+    t = Table(2, 2, 0, addr.ctypes.data_as(C.POINTER(C.c_int32)))
+    buf = np.zeros((4, 3), order="F")
+    C.c_int32.in_dll(L, "v_buf_n1").value = 4
+    C.c_int32.in_dll(L, "v_buf_n2").value = 3
+    C.c_void_p.in_dll(L, "v_buf_").value = buf.ctypes.data
+    total = C.c_double(0.0)
+    L.v_fill(C.byref(t), b"cyclic", C.byref(C.c_double(2.5)), C.byref(total), None)
+    assert total.value == 0.5 * 4 and np.all(buf == 2.5)
+    assert t.count == 8 and t.rows == 2 - 8
+    want1 = [100 + 2, 200 + 3, 300 + 4] * 2               # glob(i) + neighbour(i, north, 'cyclic')
+    assert addr[0, 2:8].tolist() == want1
+    assert addr[1, 2:8].tolist() == [-1, -1, -1, -2, -2, -2]   # flag false and kind == 'cyclic'
+    L.v_fill(C.byref(t), b"open", C.byref(C.c_double(1.0)), C.byref(total), C.byref(C.c_double(3.0)))
+    assert total.value == 3.0 * 4
+
+
+def test_translate_range_of_a_routine(tmp_path):
+    """A statement range of a routine as a function of its own: the construct that starts at a given statement
+    (to its matching end) and a range between two labelled statements; untouched locals are not declared."""
+    src = tmp_path / "rng.F90"
+    src.write_text("""
+      module rng_mod
+      contains
+      subroutine big (n, acc, other)
+      integer (int_kind), intent(in) :: n
+      integer (int_kind), intent(inout) :: acc
+      real (dbl_kind), dimension(:,:), intent(in) :: other
+      integer (int_kind) :: i, j, unused
+      unused = 7
+      acc = 1000
+      do j = 1, n
+         do i = 1, j
+            if (i == j) then
+               acc = acc + i
+            endif
+         end do
+      end do
+      acc = -1
+      tail: do i = 1, n
+         acc = acc + 2
+      end do tail
+      end subroutine big
+      end module rng_mod
+""")
+    tr = T.Translator(())
+    tr.translate_range(str(src), "big", "subroutine", r"^do\s+j\s*=", None, "big_loop", ["n", "acc"])
+    tr.translate_range(str(src), "big", "subroutine", r"^tail\s*:", r"^end\s*do\s+tail$", "big_tail", ["n", "acc"])
+    code = tr.emit_file()
+    assert "v_unused" not in code and "v_other" not in code
+    cfile = tmp_path / "rng.c"
+    cfile.write_text(code)
+    lib = tmp_path / "librng.so"
+    cc = "/usr/bin/gcc" if os.access("/usr/bin/gcc", os.X_OK) else "gcc"
+    subprocess.check_call([cc, "-std=gnu11", "-O2", "-fPIC", "-shared", "-Wno-unused", "-o", str(lib), str(cfile)])
+    L = C.CDLL(str(lib))
+    acc = C.c_int32(5)
+    L.v_big_loop(C.byref(C.c_int32(4)), C.byref(acc))
+    assert acc.value == 5 + 1 + 2 + 3 + 4
+    L.v_big_tail(C.byref(C.c_int32(3)), C.byref(acc))
+    assert acc.value == 15 + 6

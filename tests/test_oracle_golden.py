@@ -125,18 +125,23 @@ def test_tripole_fold_semantics(oracle):
 
 
 def test_tripoleT_fold_semantics(oracle):
-    """T-fold (serial/ice_boundary.F90:725-773, address lists :3699-3763): for a NE-corner vector the top
-    physical row and the ghost row become the sign-flipped mirror images of the two rows below them, without
-    any averaging; for a centre field the degenerate top row is symmetrised about the two pole T points
-    (columns 1 and nx/2+1 keep their values) and the ghost row mirrors the row below the top."""
+    """T-fold AS THE REFERENCE EXECUTES IT (serial/ice_boundary.F90:725-773 with the address lists of
+    ice_HaloCreate / ice_HaloMsgCreate, established by running the reference's own translated halo,
+    tests/test_oracle_vs_ref.py::test_oracle_halo_equals_reference_halo): the 'north' message fills the three-row
+    buffer with the rows ny-2 .. ny, then the 'northeast' / 'northwest' messages of the tripole blocks (:3833-3848,
+    written for the two-row u-fold buffer and last in the list) overwrite buffer rows 1 and 2 with the rows ny-1, ny.
+    So for a NE-corner vector the top physical row becomes the sign-flipped mirror image of ITSELF and the ghost
+    row that of the row below it (not of rows ny-1 / ny-2, which a geometric T-fold would give); for a centre
+    field the degenerate top row is symmetrised about the two pole T points (columns 1 and nx/2+1 keep their
+    values) and the ghost row mirrors the RAW top row."""
     nx, ny = 16, 7
     rng = np.random.default_rng(4)
     a = np.asfortranarray(rng.standard_normal((nx + 2, ny + 2)))
     a0 = a.copy()
     oracle.halo_r8(a, G.BND_CYCLIC, G.BND_TRIPOLET, G.LOC_NECORNER, G.TYPE_VECTOR)
     for i in range(1, nx + 1):                       # U column i <-> nx + 1 - i
-        assert a[i, ny] == -a0[nx + 1 - i, ny - 1]
-        assert a[i, ny + 1] == -a0[nx + 1 - i, ny - 2]
+        assert a[i, ny] == -a0[nx + 1 - i, ny]
+        assert a[i, ny + 1] == -a0[nx + 1 - i, ny - 1]
     np.testing.assert_array_equal(a[1:nx + 1, 1:ny], a0[1:nx + 1, 1:ny])
     c = np.asfortranarray(rng.standard_normal((nx + 2, ny + 2)))
     c0 = c.copy()
@@ -146,7 +151,7 @@ def test_tripoleT_fold_semantics(oracle):
         assert top[i - 1] == top[nx + 2 - i - 1] == 0.5 * (c0[i, ny] + c0[nx + 2 - i, ny])
     assert top[0] == c0[1, ny] and top[nx // 2] == c0[nx // 2 + 1, ny]     # the pole points map onto themselves
     for i in range(2, nx + 1):
-        assert c[i, ny + 1] == c0[nx + 2 - i, ny - 1]
+        assert c[i, ny + 1] == c0[nx + 2 - i, ny]                          # the raw top row (buffer row 2)
     # integer fields average with nint (:1318): a 0/1 mask becomes the OR of the pair
     import ctypes as C
     m = np.asfortranarray(rng.integers(0, 2, (nx + 2, ny + 2)).astype(np.int32))
@@ -158,16 +163,16 @@ def test_tripoleT_fold_semantics(oracle):
 
 
 def test_tripoleT_evp_invariants(oracle):
-    """One evp step on a T-fold grid: the velocity rows at and above the fold are the mirror images of the
-    rows below it after the final halo update."""
+    """One evp step on a T-fold grid, with the fold as the reference executes it (see
+    test_tripoleT_fold_semantics): after the final halo update the ghost row is the sign-flipped mirror image of
+    the row below the top physical row (which no halo update touches)."""
     case = synth.make_case("x", nx=48, ny=30, ew="cyclic", ns="tripoleT")
     st, f = _run(oracle, case)
     u, v = st["uvel"], st["vvel"]
     nx, ny = 48, 30
     assert np.abs(u).max() > 1e-3
     for i in range(1, nx + 1):
-        assert u[i, ny] == -u[nx + 1 - i, ny - 1] and v[i, ny] == -v[nx + 1 - i, ny - 1]
-        assert u[i, ny + 1] == -u[nx + 1 - i, ny - 2]
+        assert u[i, ny + 1] == -u[nx + 1 - i, ny - 1] and v[i, ny + 1] == -v[nx + 1 - i, ny - 1]
 
 
 def _run(oracle, case, **kw):

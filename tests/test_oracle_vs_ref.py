@@ -92,7 +92,7 @@ def test_time_step_and_ndte_bit_exact_vs_reference(dt, ndte):
     assert not bad, f"oracle differs from the reference in {bad}"
 
 
-@pytest.mark.parametrize("bx,by", [(10, 8), (7, 11), (14, 5), (28, 22), (9, 22)])
+@pytest.mark.parametrize("bx,by", [(10, 8), (7, 11), (14, 5), (28, 22), (13, 22)])
 @pytest.mark.parametrize("var", [VARIANTS[0], VARIANTS[4]], ids=["cice4", "access"])
 def test_reference_on_block_decompositions(bx, by, var):
     """The translated reference itself run on create_blocks decompositions (padded edge blocks included;
@@ -240,3 +240,84 @@ def test_reference_timing_build_is_thread_invariant():
         assert np.array_equal(res[0][0][n], res[1][0][n]), n
     for n in ("divu", "strintx", "strocnxT", "prs_sig"):
         assert np.array_equal(res[0][1][n], res[1][1][n]), n
+
+
+# ------------------------------------------------------------------------------------------------
+# the reference's OWN halo machinery (translated create_blocks loop, ice_blocksGetNbrID, message loop of
+# ice_HaloCreate, ice_HaloMsgCreate, ice_HaloUpdate2DR8 / 2DI4): what pins oracle/evp_oracle.c's halo
+# ------------------------------------------------------------------------------------------------
+BND_ALL = {"open": 0, "closed": 1, "cyclic": 2, "tripole": 3, "tripoleT": 4}
+
+
+@pytest.mark.parametrize("ns", ["open", "closed", "cyclic", "tripole", "tripoleT"])
+@pytest.mark.parametrize("ew", ["open", "closed", "cyclic"])
+def test_oracle_halo_equals_reference_halo(ew, ns):
+    """Every boundary combination x field location x field kind x three sizes (even, odd, tiny), real and integer
+    fields: the oracle's halo update, its independent numpy restatement and the reference's own translated halo
+    update give the same array bit for bit -- ghost ring, fill cells and, on the tripole, the top physical row."""
+    from cice4_b200 import grid as G
+    rng = np.random.default_rng(7)
+    for nx, ny in ((12, 9), (13, 7), (8, 6)):
+        for loc in (1, 2, 3, 4):
+            for kind in (1, 2, 3):
+                a = np.asfortranarray(rng.standard_normal((nx + 2, ny + 2)))
+                b, c, d = a.copy(order="F"), a.copy(order="F"), a.copy(order="F")
+                O.halo_r8(b, BND_ALL[ew], BND_ALL[ns], loc, kind)
+                O.ref_halo(c, BND_ALL[ew], BND_ALL[ns], loc, kind)
+                G.halo_update(d, BND_ALL[ew], BND_ALL[ns], loc, kind)
+                assert np.array_equal(b, c), (nx, ny, loc, kind, np.argwhere(b != c)[:5].tolist())
+                assert np.array_equal(d, c), (nx, ny, loc, kind, np.argwhere(d != c)[:5].tolist())
+        m = np.asfortranarray(rng.integers(0, 2, (nx + 2, ny + 2)).astype(np.int32))   # icetmask: centre scalar
+        mb, mc = m.copy(order="F"), m.copy(order="F")
+        import ctypes as C
+        g = O.make_grid(nx + 2, ny + 2, BND_ALL[ew], BND_ALL[ns])
+        O.lib().orc_halo_i4(mb.ctypes.data_as(O.c_ip), C.byref(g), 1, 1, 0)
+        O.ref_halo(mc, BND_ALL[ew], BND_ALL[ns], 1, 1)
+        assert np.array_equal(mb, mc)
+
+
+@pytest.mark.parametrize("ew,ns", [("cyclic", "tripole"), ("cyclic", "tripoleT"), ("cyclic", "open"), ("open", "closed"),
+                                   ("cyclic", "cyclic")])
+@pytest.mark.parametrize("bx,by", [(10, 8), (7, 11), (14, 5), (13, 22)])
+def test_reference_multiblock_halo_equals_single_block(ew, ns, bx, by):
+    """The reference's halo update on create_blocks decompositions (its own address lists, several blocks, padded
+    edge blocks, corner neighbours, tripole buffer): every block ends up with the ring -- and on the tripole the
+    top physical row -- that the one-block update gives the same field."""
+    from cice4_b200 import evp as E
+    nx, ny = 28, 22
+    rng = np.random.default_rng(3)
+    lay = E.BlockLayout.cartesian(nx, ny, bx, by)
+    if ns == "tripoleT" and by == 5:      # top blocks of 2 rows < tripoleRows = 3: the reference itself stops
+        with pytest.raises(RuntimeError, match="not enough points in block for tripole"):
+            O.ref_halo(np.zeros(lay.shape, order="F"), BND_ALL[ew], BND_ALL[ns], 1, 1, layout=lay)
+        return
+    for loc, kind in ((1, 1), (2, 2), (1, 2)):
+        glob = np.zeros((nx + 2, ny + 2), order="F")     # ghost cells no update defines (open / closed) stay 0 in both
+        glob[1:nx + 1, 1:ny + 1] = rng.standard_normal((nx, ny))
+        one = glob.copy(order="F")
+        O.ref_halo(one, BND_ALL[ew], BND_ALL[ns], loc, kind)
+        blk = np.zeros(lay.shape, order="F")
+        for b in range(lay.nblocks):   # physical cells only: the update must produce every ghost cell itself
+            i0, j0 = lay.iglob_lo[b], lay.jglob_lo[b]
+            for j in range(lay.jlo[b], lay.jhi[b] + 1):
+                for i in range(lay.ilo[b], lay.ihi[b] + 1):
+                    blk[i - 1, j - 1, b] = glob[i0 + i - lay.ilo[b], j0 + j - lay.jlo[b]]
+        O.ref_halo(blk, BND_ALL[ew], BND_ALL[ns], loc, kind, layout=lay)
+        for b in range(lay.nblocks):
+            i0, j0 = lay.iglob_lo[b], lay.jglob_lo[b]
+            for j in range(lay.jlo[b] - 1, lay.jhi[b] + 2):
+                for i in range(lay.ilo[b] - 1, lay.ihi[b] + 2):
+                    want = one[i0 + i - lay.ilo[b], j0 + j - lay.jlo[b]]
+                    assert blk[i - 1, j - 1, b] == want, (loc, kind, b, i, j)
+
+
+def test_reference_create_blocks_one_column_edge_block():
+    """A quirk of the reference that the translated create_blocks exposes: a padded edge block of exactly ONE physical
+    column keeps its full width, because ihi is only shrunk for i > ilo (source/ice_blocks.F90:332-335).  The host
+    refuses a caller layout that differs from what create_blocks makes instead of silently using either."""
+    from cice4_b200 import evp as E
+    lay = E.BlockLayout.cartesian(28, 22, 9, 22)      # 28 = 3 x 9 + 1
+    assert lay.ihi[-1] == lay.ilo[-1]
+    a = np.zeros(lay.shape, order="F")
+    with pytest.raises(RuntimeError, match="not what create_blocks makes"):
+        O.ref_halo(a, 2, 3, 2, 2, layout=lay)
