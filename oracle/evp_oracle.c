@@ -769,6 +769,14 @@ void orc_principal_stress(int nx_block, int ny_block, const double *stressp_1,
 /* ------------------------------------------------------------------ */
 /* driver: source/ice_dyn_evp.F90:119-432                               */
 /* ------------------------------------------------------------------ */
+static double *g_strength_pre;
+static size_t g_strength_pre_n;
+/* copies the strength array of the last orc_evp call as it was BEFORE the halo update; returns its size */
+size_t orc_last_strength_prehalo(double *out) {
+    if (out && g_strength_pre) memcpy(out, g_strength_pre, sizeof(double) * g_strength_pre_n);
+    return g_strength_pre_n;
+}
+
 int orc_evp(const orc_grid *g, const orc_params *p, const orc_fields *f, double *subcycle_seconds) {
     const int nxb = g->nx_block, nyb = g->ny_block;
     const size_t plane = (size_t)nxb * nyb;
@@ -811,6 +819,12 @@ int orc_evp(const orc_grid *g, const orc_params *p, const orc_fields *f, double 
     else
         orc_ice_strength(g, p, f, icellt, indxti, indxtj); /* :322-332 */
 
+    /* tests: what ice_strength returned, before evp's halo update of it (the array a host that runs
+     * ice_strength itself passes to the two-phase entry; on the T-fold the update is not idempotent) */
+    free(g_strength_pre);
+    g_strength_pre = (double *)malloc(sizeof(double) * plane);
+    g_strength_pre_n = g_strength_pre ? plane : 0;
+    if (g_strength_pre) memcpy(g_strength_pre, f->strength, sizeof(double) * plane);
     orc_halo_r8(f->strength, g, ORC_LOC_CENTER, ORC_TYPE_SCALAR, 0.0); /* :337-343 */
     orc_halo_r8(f->uvel, g, ORC_LOC_NECORNER, ORC_TYPE_VECTOR, 0.0);
     orc_halo_r8(f->vvel, g, ORC_LOC_NECORNER, ORC_TYPE_VECTOR, 0.0);

@@ -29,6 +29,7 @@
 #ifndef EVP_ORACLE_H
 #define EVP_ORACLE_H
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -129,6 +130,8 @@ void orc_principal_stress(int nx_block, int ny_block, const double *stressp_1,
 /* full driver, source/ice_dyn_evp.F90:119-432.  Returns 0, or -1 on allocation failure.
  * subcycle_seconds (may be NULL) receives the wall time of the ndte loop only. */
 int orc_evp(const orc_grid *g, const orc_params *p, const orc_fields *f, double *subcycle_seconds);
+/* tests: the strength array of the last orc_evp call before evp's halo update of it; returns its size */
+size_t orc_last_strength_prehalo(double *out);
 
 /* ndte subcycles of stress+stepu+halo only, on prepared fields; for CPU timing.
  * nthreads>1 splits the T/U lists into j-bands (OpenMP) with a barrier per phase. */

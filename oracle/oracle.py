@@ -172,10 +172,24 @@ def run_evp(grid, inputs, state, params: Optional[OrcParams] = None, strength_in
     f = Fields(grid.f, inputs, state, strength_in)
     g = make_grid(grid.nx_block, grid.ny_block, grid.ew, grid.ns)
     sec = C.c_double(0.0)
-    rc = lib(lib_kind).orc_evp(C.byref(g), C.byref(p), C.byref(f.c), C.byref(sec))
+    L = lib(lib_kind)
+    rc = L.orc_evp(C.byref(g), C.byref(p), C.byref(f.c), C.byref(sec))
     if rc != 0:
         raise RuntimeError("orc_evp failed")
+    f.strength_pre = _strength_pre(L.orc_last_strength_prehalo, f["strength"])
     return f, sec.value
+
+
+def _strength_pre(fn, like: np.ndarray) -> np.ndarray:
+    """ice_strength's result of the last call BEFORE evp's halo update of it: what a host that runs ice_strength
+    itself hands to the two-phase entry (on the T-fold the halo update is not idempotent, so the post-halo array
+    would not do)"""
+    out = np.zeros(like.shape, order="F")
+    fn.restype = C.c_size_t
+    fn.argtypes = [c_dp]
+    n = fn(_ptr(out))
+    assert n == out.size, (n, out.size)
+    return out
 
 
 # ---------------------------------------------------------------------------------------------
@@ -229,9 +243,11 @@ def run_evp_ref(grid, inputs, state, params: OrcParams, dt: float):
     reference's `evp` -- icetmask, tmass, umass, aiu, ... -- are not exported)."""
     f = Fields(grid.f, inputs, state, None)
     g = make_grid(grid.nx_block, grid.ny_block, grid.ew, grid.ns)
-    rc = ref_lib(ref_variant(params)).ref_evp(C.byref(g), C.byref(params), C.byref(f.c), dt)
+    L = ref_lib(ref_variant(params))
+    rc = L.ref_evp(C.byref(g), C.byref(params), C.byref(f.c), dt)
     if rc != 0:
         raise RuntimeError("ref_evp failed: " + ref_abort_message(params))
+    f.strength_pre = _strength_pre(L.ref_last_strength_prehalo, f["strength"])
     return f
 
 
@@ -258,6 +274,7 @@ def run_evp_ref_blocks(layout, ew: int, ns: int, grid_fields_blk, inputs_blk, st
     rc = L.ref_evp_blocks(C.byref(g), C.byref(lay), C.byref(params), C.byref(f.c), dt)
     if rc != 0:
         raise RuntimeError("ref_evp_blocks failed: " + ref_abort_message(params))
+    f.strength_pre = _strength_pre(L.ref_last_strength_prehalo, f["strength"])
     return f
 
 

@@ -208,9 +208,22 @@ static int build_decomposition(const orc_grid *g, const ref_layout *lay) {
 
 /* ice_HaloUpdate (generic interface, serial/ice_boundary.F90:71-81) -> the translated specific routines on the
  * halo structure built above; fillValue is absent in every call of the path */
+static double *g_strength_pre;
+static size_t g_strength_pre_n;
 static void shim_halo_r8(double *a, int32_t *halo, int32_t *loc, int32_t *kind) {
     (void)halo;
+    if (a == v_strength_) { /* tests: ice_strength's result before evp halo-updates it (:337-343) */
+        const size_t n = (size_t)v_nx_block * v_ny_block * v_max_blocks;
+        free(g_strength_pre);
+        g_strength_pre = (double *)malloc(sizeof(double) * n);
+        g_strength_pre_n = g_strength_pre ? n : 0;
+        if (g_strength_pre) memcpy(g_strength_pre, a, sizeof(double) * n);
+    }
     v_ice_haloupdate2dr8(a, &g_halo, loc, kind, NULL);
+}
+size_t ref_last_strength_prehalo(double *out) {
+    if (out && g_strength_pre) memcpy(out, g_strength_pre, sizeof(double) * g_strength_pre_n);
+    return g_strength_pre_n;
 }
 static void shim_halo_i4(int32_t *a, int32_t *halo, int32_t *loc, int32_t *kind) {
     (void)halo;

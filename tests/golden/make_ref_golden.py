@@ -86,7 +86,7 @@ def blocks_golden():
         strengths = []
         for _ in range(nsteps):
             fb = O.run_evp_ref_blocks(lay, g.ew, g.ns, gfb, inb, stb, p, dt)
-            strengths.append(fb["strength"].copy(order="F"))
+            strengths.append(fb.strength_pre)
         out = {"meta_bx": bx, "meta_by": by}
         for k, a in enumerate(strengths):
             out["ref_strength_%d" % k] = a
@@ -114,7 +114,7 @@ def main():
         strengths = []
         for _ in range(nsteps):
             f = O.run_evp_ref(g, inp, st, p, dt)
-            strengths.append(f["strength"].copy(order="F"))
+            strengths.append(f.strength_pre)   # ice_strength's result before evp's halo update (input of the two-phase ABI)
         out = {"meta_nx": g.nx, "meta_ny": g.ny, "meta_ew": g.ew, "meta_ns": g.ns, "meta_dt": dt,
                "meta_ndte": ndte, "meta_nsteps": nsteps}
         for k, v in over.items():

@@ -22,13 +22,14 @@ def oracle_steps(O, case, nsteps=1, strength_from_oracle=True, **pover):
     strengths = []
     for _ in range(nsteps):
         f, _sec = O.run_evp(g, case.inputs, st, p)
-        strengths.append(f["strength"].copy(order="F"))
+        strengths.append(f.strength_pre)    # what ice_strength returned, BEFORE evp's halo update of it
     return st, f, strengths, p
 
 
 def cuda_steps(case, nsteps=1, strengths=None, layout=None, two_phase=False, want=None, **params):
-    """Same through the C ABI.  strengths: list of host strength arrays (pre-halo values are fine:
-    evp halo-updates strength itself) or None for the device ice_strength."""
+    """Same through the C ABI.  strengths: list of host strength arrays as ice_strength returns them (evp
+    halo-updates strength itself; on the T-fold that update is not idempotent, so pre-halo values are required) or
+    None for the device ice_strength."""
     g = case.grid
     lay = layout or E.BlockLayout.single_block(g.nx, g.ny)
     ew = {v: k for k, v in E.BND.items()}[g.ew]
