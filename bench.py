@@ -467,7 +467,8 @@ def measure(ctx, case, args, ndte, steps, warmup, full):
 def extra_configs(world: int):
     """(workload, ndte) of the `configs` table at this GPU count (BASELINE.json configs 0-2 and 4)."""
     if world == 1:
-        return [("gx3", 120), ("gx1", 120), ("om1deg", 120), ("p01", 120), ("p01", 240), ("p01w", 120)]
+        return [("gx3", 120), ("gx1", 120), ("om1deg", 120), ("p01", 120), ("p01", 240), ("p01w", 120),
+                ("om025:realistic", 120)]   # the headline grid with a realistic ice mask (20 % of the cells active)
     if world == 2:
         return [("om1deg", 120), ("p01", 120), ("p01w", 120)]
     if world == 4:
@@ -497,9 +498,11 @@ def run_b200(args):
     table = []
     if args.configs == "auto" and args.workload == "om025" and not args.realistic:
         for wl, nd in extra_configs(world):
-            c = build_case(wl, False, world)
+            realistic = wl.endswith(":realistic")
+            wl = wl.split(":")[0]
+            c = build_case(wl, realistic, world)
             x = measure(ctx, c, args, nd, max(2, min(args.steps, 5)), warmup, full=False)
-            table.append({"workload": workload_string(c, nd, False), "n_gpus": world, "value": x["value"], "unit": UNIT,
+            table.append({"workload": workload_string(c, nd, realistic), "n_gpus": world, "value": x["value"], "unit": UNIT,
                           "us_per_subcycle": x["kernel_us"], "roofline_frac_per_gpu": x["frac"],
                           "l2_resident": x["l2_resident"], "active_T_cells": x["icellt"], "active_U_cells": x["icellu"],
                           "e2e_value": c.grid.nx * c.grid.ny * nd / x["e2e_s"],
