@@ -64,7 +64,7 @@ def add_variant_inputs(case, over):
 
 
 # block decompositions of one of the problems above: (label of the problem, bx, by)
-BLOCK_CASES = [("cice4_tripole_28x22", 10, 8)]
+BLOCK_CASES = [("cice4_tripole_28x22", 10, 8), ("cice4_tripoleT_26x20", 10, 8)]
 
 
 def blocks_golden():

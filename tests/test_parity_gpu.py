@@ -96,7 +96,8 @@ def test_cuda_matches_reference_golden(evp_lib, path):
         dyn.finalize()
 
 
-def test_cuda_block_layout_matches_reference_blocks(evp_lib):
+@pytest.mark.parametrize("label,nb", [("cice4_tripole_28x22", 9), ("cice4_tripoleT_26x20", 9)])
+def test_cuda_block_layout_matches_reference_blocks(evp_lib, label, nb):
     """The caller's block layout against THE REFERENCE RUN ON THE SAME BLOCKS (committed outputs of the
     translated reference on a 10 x 8 create_blocks decomposition of the 28 x 22 tripole problem, padded
     edge blocks included): on the cells evp defines in every block -- velocities with their ghost ring,
@@ -105,11 +106,11 @@ def test_cuda_block_layout_matches_reference_blocks(evp_lib):
     import os
     from types import SimpleNamespace
     from helpers import BLOCK_REGION, GOLDEN_DIR, block_region_mismatches
-    base = [p for p in REF_GOLDEN if p.endswith("ref_evp_cice4_tripole_28x22.npz")][0]
+    base = [p for p in REF_GOLDEN if p.endswith("ref_evp_%s.npz" % label)][0]
     c = load_ref_golden(base)
-    z = np.load(os.path.join(GOLDEN_DIR, "refblocks_cice4_tripole_28x22_b10x8.npz"))
+    z = np.load(os.path.join(GOLDEN_DIR, "refblocks_%s_b10x8.npz" % label))
     lay = E.BlockLayout.cartesian(c.grid.nx, c.grid.ny, int(z["meta_bx"]), int(z["meta_by"]))
-    assert lay.nblocks == 9
+    assert lay.nblocks == nb
     case = SimpleNamespace(grid=c.grid, inputs={k: v for k, v in c.inputs.items() if k in E.INPUT_D})
     want = [n for n in BLOCK_REGION if "ref_out_" + n in z.files]
     dyn, out = cuda_steps(case, nsteps=c.nsteps, strengths=c.ref_strengths, layout=lay, want=want, dt=c.dt,
