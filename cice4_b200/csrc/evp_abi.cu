@@ -338,9 +338,15 @@ void fill_subargs(evp_b200_handle *h, SubArgs &a, int cur) {
     a.strip_w = h->strip_w; a.rows = h->rows; a.chunks = h->d_chunks;
     a.evp_damping = h->par.evp_damping; a.hemisphere_turning = h->par.hemisphere_turning;
     a.hte = p[P_HTE]; a.htn = p[P_HTN];
-    // the 2-plane metric path is opt-in (kernel_variant bit 4): it removes 6 of 48 words of DRAM
-    // traffic but the kernel is not purely bandwidth-bound, so it does not run faster
-    a.row_ht = (h->par.kernel_variant & 16) ? h->row_ht : nullptr;
+    // The 2-plane metric path removes 6 of 48 words of DRAM traffic.  In a burst the kernel is not purely
+    // bandwidth-bound and does not run faster for it, but sustained at the box's power cap the saved DRAM power goes
+    // to the SM clock: 113.4 instead of 116.0 us per subcycle at 1440 x 1080 inside bench.py's timed region
+    // (profiles/r02_experiments.txt 7).  Default on the plane kernels of tall slabs (>= 450 rows; short slabs are
+    // issue-bound, where the ~14 extra fp64 operations per cell cost more than the bytes save) when HTE / HTN were
+    // given and verified; kernel_variant bit 4 forces it on, bit 19 off.
+    const bool ht_auto = !h->tiled && !h->fused && h->dims.ny_global / h->dims.nranks >= 450 &&
+                         (h->par.kernel_variant & (256 | 512 | 1024 | 524288)) == 0;
+    a.row_ht = ((h->par.kernel_variant & 16) || ht_auto) ? h->row_ht : nullptr;
     a.ecci = h->ecci; a.dte2T = h->dte2T; a.denom1 = h->denom1; a.denom2 = h->denom2; a.rcon = h->rcon;
     a.dragw = h->dragw; a.cosw = h->par.cosw; a.sinw = h->par.sinw;
     a.fold = h->fold_in_kernel ? 1 : 0;

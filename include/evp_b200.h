@@ -101,8 +101,9 @@ typedef struct {
     int32_t use_graph;      /* 1 = replay the ndte loop as one CUDA graph */
     int32_t tile_threads;   /* 0 = default; threads per CTA of the subcycle kernel */
     int32_t tile_rows;      /* 0 = default; U rows marched per CTA */
-    int32_t kernel_variant; /* 0 = default; bit 2 (4): tripole fold as a separate kernel; bit 4 (16): 2-plane
-                               metric path (needs HTE/HTN); bit 5 (32): uniform row chunks instead of the
+    int32_t kernel_variant; /* 0 = default; bit 2 (4): tripole fold as a separate kernel; bit 4 (16): force the 2-plane
+                               metric path (needs HTE/HTN; the default on plane kernels of slabs >= 450 rows; bit 19
+                               (524288) switches it off); bit 5 (32): uniform row chunks instead of the
                                per-call active-work balance; bit 6 (64): programmatic dependent launch;
                                bit 7 (128): run the ndte loop as one persistent cooperative launch whose CTAs
                                synchronise with their neighbours only (bit-identical; measured slower than
