@@ -48,14 +48,17 @@ def build(force: bool = False, verbose: bool = False) -> str:
     os.makedirs(OUT, exist_ok=True)
     nvcc = _nvcc()
     deps = [os.path.join(CSRC, d) for d in DEPS]
-    objs = []
+    objs, cmds = [], []
     for src, flags in UNITS:
         s = os.path.join(CSRC, src)
         o = os.path.join(OUT, src.replace(".cu", ".o"))
         objs.append(o)
         if force or _stale(o, [s] + deps):
-            cmd = [nvcc] + ARCH + COMMON + flags + (["-Xptxas", "-v"] if verbose else []) + ["-c", s, "-o", o]
-            subprocess.check_call(cmd)
+            cmds.append([nvcc] + ARCH + COMMON + flags + (["-Xptxas", "-v"] if verbose else []) + ["-c", s, "-o", o])
+    if cmds:  # the translation units are independent: compile them side by side
+        from concurrent.futures import ThreadPoolExecutor
+        with ThreadPoolExecutor(max_workers=min(len(cmds), os.cpu_count() or 1)) as ex:
+            list(ex.map(subprocess.check_call, cmds))
     if force or _stale(LIB, objs):
         cmd = [nvcc] + ARCH + ["-shared", "-o", LIB] + objs + ["-lcudart", "-ldl"]
         subprocess.check_call(cmd)

@@ -33,6 +33,11 @@ int fail(int code, const char *fmt, ...) {
     return code;
 }
 
+// default of the plane kernels with 128-thread CTAs: one strip per warp (1) or one strip per CTA (0)
+#ifndef EVP_WARPX_DEFAULT
+#define EVP_WARPX_DEFAULT 1
+#endif
+
 #define CU(call)                                                                                   \
     do {                                                                                           \
         cudaError_t e_ = (call);                                                                   \
@@ -115,6 +120,7 @@ struct evp_b200_handle {
     bool io_device = false;           // evp_b200_step_device: the caller's arrays are DEVICE memory (block layout)
     bool vel_on_device = false;       // state_residency = 2: uvel, vvel, iceumask of the planes are current
     int grid_x = 0, grid_y = 0, threads = 128, strip_w = 0, rows = 0;
+    bool warpx = false; // plane kernels with one strip per warp (shuffles, no row barrier)
     int *d_chunks = nullptr;          // row-chunk table of the subcycle kernel (2 ints per chunk)
     int *d_cta_epoch = nullptr;       // persistent kernel: subcycles finished per CTA (grid_x * grid_y ints)
     bool persistent = false;          // run the ndte loop as one cooperative launch (k_persist)
@@ -305,6 +311,16 @@ int halo_r8(evp_b200_handle *h, double *plane, int loc, int isign) {
     return exchange_rows(h, pp, 1, sizeof(double));
 }
 
+// evp_finish (:1510-1547) runs as an epilogue of the last subcycle kernel (stepu's thread completes strocnx/y and
+// writes strocnxT/yT's input; the in-kernel tripole fold does it for the row it rewrites) unless the velocities of
+// physical cells still change after that kernel -- a tripole fold outside the kernel (T-fold, kernel_variant bit 2,
+// tiny slabs) -- or the two-subcycle kernel runs; kernel_variant bit 22 (4194304) keeps the separate k_finish launch.
+static bool fuse_finish(const evp_b200_handle *h) {
+    if (h->par.kernel_variant & 4194304) return false;
+    if (h->fused) return false;
+    return !h->pg.tripole || h->fold_in_kernel;
+}
+
 void fill_subargs(evp_b200_handle *h, SubArgs &a, int cur) {
     double **p = h->pl;
     a.dxt = p[P_DXT]; a.dyt = p[P_DYT]; a.dxhy = p[P_DXHY]; a.dyhx = p[P_DYHX];
@@ -333,6 +349,7 @@ void fill_subargs(evp_b200_handle *h, SubArgs &a, int cur) {
     a.divu = p[P_DIVU]; a.shear = p[P_SHEAR]; a.rdg_conv = p[P_RDG_CONV]; a.rdg_shear = p[P_RDG_SHEAR];
     a.prs_sig = p[P_PRS_SIG]; a.strintx = p[P_STRINTX]; a.strinty = p[P_STRINTY];
     a.strocnx = p[P_STROCNX]; a.strocny = p[P_STROCNY];
+    a.fuse_finish = fuse_finish(h) ? 1 : 0; a.finx = p[P_WRKX]; a.finy = p[P_WRKY];
     a.nx = h->pg.nx; a.nyl = h->pg.nyl; a.pitch = h->pg.pitch;
     a.ew_cyclic = h->pg.ew_cyclic;
     a.strip_w = h->strip_w; a.rows = h->rows; a.chunks = h->d_chunks;
@@ -409,7 +426,8 @@ int launch_subcycle(evp_b200_handle *h, int cur, bool last) {
         e = fn(a, last, h->tiled_stages, flags, (unsigned)h->grid_x, (unsigned)h->grid_y, (void *)h->st, nullptr);
     } else {
         subcycle_launch_fn fn = h->par.math_mode == 1 ? evp_subcycle_launch_fast : evp_subcycle_launch_strict;
-        e = fn(a, last, h->par.kernel_variant, h->threads, (unsigned)h->grid_x, (unsigned)h->grid_y, (void *)h->st);
+        const int kv = (h->par.kernel_variant & ~1048576) | (h->warpx ? 1048576 : 0);
+        e = fn(a, last, kv, h->threads, (unsigned)h->grid_x, (unsigned)h->grid_y, (void *)h->st);
     }
     if (e != 0) {
         fail(EVP_B200_ERR_CUDA, "subcycle kernel launch: %s", cudaGetErrorString((cudaError_t)e));
@@ -615,6 +633,7 @@ void decide_persistent(evp_b200_handle *h) {
 // Tiling of the subcycle kernel: balanced strips in x, one wave of CTAs in total, row chunks in
 // launch order with short boundary chunks.  Returns 0 or a CUDA error code via fail().
 int choose_tiling(evp_b200_handle *h) {
+    h->warpx = false;
     int sms = 148;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device);
     const int nx = h->pg.nx, nyl = h->pg.nyl;
@@ -668,11 +687,18 @@ int choose_tiling(evp_b200_handle *h) {
             const int e = h->par.math_mode == 1 ? evp_subcycle_configure_fast() : evp_subcycle_configure_strict();
             if (e != 0) return fail(EVP_B200_ERR_CUDA, "TMA-staged subcycle kernel: %s", cudaGetErrorString((cudaError_t)e));
         }
+        // Warp-autonomous strips (k_subcycle<.., WARPX>): each of the 4 warps of a 128-thread CTA owns strip_w / 4 <= 31
+        // U columns of its own, shuffles replace the exchange line and the per-row CTA barrier.  kernel_variant
+        // bit 20 (1048576) selects it, bit 21 (2097152) forbids it; see h->warpx below for the default.
+        const int kvv = h->par.kernel_variant;
+        h->warpx = nt == 128 && !tma && (kvv & (128 | 1024 | 2097152)) == 0 &&
+                   ((kvv & 1048576) != 0 || EVP_WARPX_DEFAULT);
         // balanced strips: ncx strips of strip_w U columns, strip_w + 1 <= nt threads hold T columns
-        const int wmax = tma ? nt - 2 : nt - 1;
+        const int wmax = h->warpx ? 124 : (tma ? nt - 2 : nt - 1);
         ncx = (nx + wmax - 1) / wmax;
         strip_w = (nx + ncx - 1) / ncx;
         if (tma && (strip_w & 1)) ++strip_w;
+        if (h->warpx) strip_w = (strip_w + 3) & ~3;
         // resident CTAs per SM at ~210 registers per thread: 256 threads
         per_sm = (nt == 256) ? 1 : (nt == 128 ? 2 : 4);
         if (tma && (h->par.kernel_variant & 256) == 0) per_sm = 3;
@@ -1287,6 +1313,11 @@ static int do_run_impl(evp_b200_handle *h, const evp_b200_inputs *in, const doub
         if ((rc = download_r8(h, e.dst, e.slot, p[e.id], e.policy, h->st2))) return rc;
     CU(cudaEventRecord(h->ev_early_done, h->st2));
     // ---- :347-404 ------------------------------------------------------------------------------
+    const bool fin_fused = fuse_finish(h);
+    if (fin_fused) { // evp_finish inside the last subcycle kernel: strocnxT / strocnyT = 0 everywhere first (:1512-1513)
+        CU(cudaMemsetAsync(p[P_WRKX], 0, pbytes, h->st));
+        CU(cudaMemsetAsync(p[P_WRKY], 0, pbytes, h->st));
+    }
     if ((rc = run_subcycle_loop(h))) return rc;
     if ((rc = sync_planes(h))) return rc; // tiled layout: the result goes back into the planes
     CU(cudaEventRecord(h->ev[4], h->st));
@@ -1298,7 +1329,7 @@ static int do_run_impl(evp_b200_handle *h, const evp_b200_inputs *in, const doub
     fa.strocnx = p[P_STROCNX]; fa.strocny = p[P_STROCNY]; fa.strocnxT = p[P_WRKX]; fa.strocnyT = p[P_WRKY];
     fa.dragw = h->dragw; fa.cosw = h->par.cosw; fa.sinw = h->par.sinw;
     fa.hemisphere_turning = h->par.hemisphere_turning;
-    aux_finish(pg, fa, h->st);
+    if (!fin_fused) aux_finish(pg, fa, h->st);
     // work1 = strocnxT; HALO(work1); to_tgrid(work1, strocnxT): the ghosts of strocnxT keep the 0 of :1512
     CU(cudaMemsetAsync(p[P_STROCNXT], 0, pbytes, h->st));
     CU(cudaMemsetAsync(p[P_STROCNYT], 0, pbytes, h->st));
@@ -1544,7 +1575,7 @@ int evp_b200_get_info(const evp_b200_handle *h, int32_t out[8]) {
     out[4] = h->strip_w;
     out[5] = h->tiled ? h->tiled_stages : 0;
     out[6] = h->p2p ? 1 : 0;
-    out[7] = h->persistent ? 1 : 0;
+    out[7] = (h->persistent ? 1 : 0) | (h->warpx ? 2 : 0) | (fuse_finish(h) ? 4 : 0);
     return 0;
 }
 

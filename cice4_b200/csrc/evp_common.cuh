@@ -37,6 +37,11 @@ struct SubArgs {
     int flip;
     // written on the last subcycle only (ksub == ndte, :1103-1115; :1415-1418,:1434-1435)
     double *divu, *shear, *rdg_conv, *rdg_shear, *prs_sig, *strintx, *strinty, *strocnx, *strocny;
+    // evp_finish (:1510-1547) as an epilogue of the last subcycle: 1 = the thread that produces the final u, v of a U
+    // cell also completes strocnx/y and writes strocnxT/yT = strocnx/y / aiu into finx / finy (zero-filled by the
+    // host, like :1512-1513); on the row that the in-kernel tripole fold rewrites, the fold does it
+    int fuse_finish;
+    double *finx, *finy;
     int nx, nyl, pitch;
     int ew_cyclic;
     int strip_w;   // U columns produced per CTA (threads 0..strip_w hold T columns)

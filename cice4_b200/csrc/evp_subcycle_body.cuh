@@ -202,6 +202,9 @@ struct PlaneStoreU {
     __device__ __forceinline__ void last(double strintx, double strinty, double taux, double tauy) const {
         a.strintx[idx] = strintx; a.strinty[idx] = strinty; a.strocnx[idx] = taux; a.strocny[idx] = tauy;
     }
+    // fused evp_finish: not on the row whose velocities the in-kernel tripole fold is still going to change
+    __device__ __forceinline__ bool finish_here() const { return a.fuse_finish && !(a.fold && j == a.nyl); }
+    __device__ __forceinline__ void finish(double xT, double yT) const { a.finx[idx] = xT; a.finy[idx] = yT; }
 };
 
 // n/d1 .. n/d4: four independent IEEE divisions, interleaved (evp_ieee.cuh); bit-identical to operator/
@@ -360,6 +363,37 @@ __device__ __forceinline__ void stress_cell(const SubArgs &a, const ST &out, con
     str[7] = strp_tmp - strm_tmp + str12sn - t.dyhx * (csigpsw + csigmsw) + t.dxhy * csig12sw;
 }
 
+// evp_finish (source/ice_dyn_evp.F90:1520-1546) for one U cell of the U list: (u, v) are the final velocities (after
+// the halo update of the last subcycle), sx / sy come in as taux / tauy of the last stepu (:1434-1435) and leave as
+// strocnx / strocny; xT / yT = strocnx / aiu, strocny / aiu (the input of u2tgrid_vector).  Same expressions as k_finish.
+__device__ __forceinline__ void finish_cell(const SubArgs &a, double u, double v, double uocn, double vocn, double aiu,
+                                            double fm, double &sx, double &sy, double &xT, double &yT) {
+    const double du = uocn - u, dv = vocn - v;
+    const double vrel = a.dragw * sqrt(du * du + dv * dv); // :1522
+    if (a.hemisphere_turning && fm < 0.0) {                 // :1525-1530
+        sx = sx - vrel * (u * a.cosw + v * a.sinw) * aiu;
+        sy = sy - vrel * (v * a.cosw - u * a.sinw) * aiu;
+    } else {                                                // :1532-1541
+        sx = sx - vrel * (u * a.cosw - v * a.sinw) * aiu;
+        sy = sy - vrel * (v * a.cosw + u * a.sinw) * aiu;
+    }
+    xT = sx / aiu; // :1545-1546
+    yT = sy / aiu;
+}
+
+// evp_finish for U column c of the top physical row, by the thread(s) that applied the in-kernel tripole fold to it
+// (the fold changes u, v of that row after stepu): strocnx / strocny still hold the raw taux / tauy of the last stepu.
+__device__ __forceinline__ void finish_fold_column(const SubArgs &a, int c, double u, double v) {
+    const size_t idx = (size_t)a.nyl * a.pitch + c;
+    if (__ldg(a.iceumask + idx) == 0) return;
+    double sx = __ldcg(a.strocnx + idx), sy = __ldcg(a.strocny + idx), xT, yT;
+    finish_cell(a, u, v, __ldg(a.uocn + idx), __ldg(a.vocn + idx), __ldg(a.aiu + idx), __ldg(a.fm + idx), sx, sy, xT, yT);
+    a.strocnx[idx] = sx;
+    a.strocny[idx] = sy;
+    a.finx[idx] = xT;
+    a.finy[idx] = yT;
+}
+
 // source/ice_dyn_evp.F90:1386-1441 for one U cell; sx, sy are the two str sums of :1415-1418
 template <bool LAST, class SU>
 __device__ __forceinline__ void stepu_cell(const SubArgs &a, const SU &out, const URow &u, double uold, double vold,
@@ -390,7 +424,15 @@ __device__ __forceinline__ void stepu_cell(const SubArgs &a, const SU &out, cons
         vnew = nv / ab2;
     }
     out.uv(unew, vnew); // + the east-west / slab-to-slab part of ice_HaloUpdate(uvel/vvel) (:397-402)
-    if (LAST) out.last(strintx, strinty, taux, tauy); // only the last subcycle's values are observable (:1415-1418,:1434-1435)
+    if constexpr (LAST) { // only the last subcycle's values are observable (:1415-1418,:1434-1435)
+        double ox = taux, oy = tauy;
+        if (out.finish_here()) { // evp_finish as an epilogue of the thread that holds the final u, v
+            double xT, yT;
+            finish_cell(a, unew, vnew, u.uocn, u.vocn, u.aiu, u.fm, ox, oy, xT, yT);
+            out.finish(xT, yT);
+        }
+        out.last(strintx, strinty, ox, oy);
+    }
 }
 
 // Bounded spin on a flag that another CTA (or another GPU) advances: a protocol bug or a dead peer must
@@ -433,7 +475,7 @@ __device__ __forceinline__ void p2p_wait(const SubArgs &a, int tid, bool top, bo
 // The raw top row goes through a scratch copy because the update is in place.  All other CTAs' stores to these
 // rows must be complete and visible (the caller orders that).
 template <int NT>
-__device__ __forceinline__ void fold_top_rows(const SubArgs &a, double *u_new, double *v_new, int tid) {
+__device__ __forceinline__ void fold_top_rows(const SubArgs &a, double *u_new, double *v_new, int tid, bool finish = false) {
     const size_t rtop = (size_t)a.nyl * a.pitch;
     const int ncol = a.nx + 2;
     // raw top row of u_new and v_new -> scratch (independent loads, issued in batches)
@@ -487,6 +529,10 @@ __device__ __forceinline__ void fold_top_rows(const SubArgs &a, double *u_new, d
             }
         }
     }
+    if (finish) { // last subcycle: evp_finish of the row whose velocities have just been folded
+        __syncthreads();
+        for (int c = 1 + tid; c <= a.nx; c += NT) finish_fold_column(a, c, u_new[rtop + c], v_new[rtop + c]);
+    }
 }
 
 // End of a subcycle: publication of this rank's epoch to the neighbours (peer-to-peer halo), then the
@@ -494,7 +540,8 @@ __device__ __forceinline__ void fold_top_rows(const SubArgs &a, double *u_new, d
 // PERSIST: the fold's completion is published in sync[5] (the top chunk waits for it before the next
 // subcycle) and the rank-level counter is left to the end of the persistent kernel.
 template <int NT, bool PERSIST>
-__device__ __forceinline__ void subcycle_epilogue(const SubArgs &a, idx_t sn, int tid, bool top, bool bot, int epoch) {
+__device__ __forceinline__ void subcycle_epilogue(const SubArgs &a, idx_t sn, int tid, bool top, bool bot, int epoch,
+                                                  bool last = false) {
     double *const u_new = a.u + sn, *const v_new = a.v + sn;
     if (a.p2p && ((top && a.peer_n_flag) || (bot && a.peer_s_flag))) {
         // boundary CTA done: its stores into the neighbour's ghost row are made visible system-wide,
@@ -520,7 +567,7 @@ __device__ __forceinline__ void subcycle_epilogue(const SubArgs &a, idx_t sn, in
         __syncthreads();
         if (is_last) {
             __threadfence();
-            fold_top_rows<NT>(a, u_new, v_new, tid);
+            fold_top_rows<NT>(a, u_new, v_new, tid, last && a.fuse_finish);
             if (PERSIST) {
                 __syncthreads();
                 if (tid == 0) {
@@ -554,13 +601,18 @@ __device__ __forceinline__ void subcycle_epilogue(const SubArgs &a, idx_t sn, in
 // LATE: the loads of T row j+1 are issued after the arithmetic of row j instead of before it: nothing is
 // prefetched across the stress computation, which frees ~50 registers (three warps per scheduler fit)
 // at the price of an exposed load latency per row that the third warp has to hide.
-template <int NT, bool LAST, bool HT, bool COH, bool LATE = false>
+// WARPX: every WARP owns its own strip of strip_w / 4 <= 31 U columns (lane strip_w / 4 supplies the T column east
+// of it, recomputed redundantly like the column east of a CTA strip) and takes str(2,4,7,8) of the east neighbour by
+// warp shuffle: no exchange line, no CTA barrier in the row loop, the warps of a CTA drift apart freely.
+template <int NT, bool LAST, bool HT, bool COH, bool LATE = false, bool WARPX = false>
 __device__ __forceinline__ void march(const SubArgs &a, idx_t so, idx_t sn, int tid, int i, int j0, int nrows) {
-    extern __shared__ double evp_xch[]; // [2][4][NT]: str(2,4,7,8) handed to the west neighbour thread
+    extern __shared__ double evp_xch[]; // [2][4][NT]: str(2,4,7,8) handed to the west neighbour thread (not WARPX)
     const int jlast = min(j0 + nrows, a.nyl + 1); // last T row of this CTA
-    const bool colT = (tid <= a.strip_w) && (i <= a.nx + 1);
-    const bool colU = (tid < a.strip_w) && (i <= a.nx);
-    const bool ownT = colT && (tid < a.strip_w || i == a.nx + 1);
+    const int lt = WARPX ? (tid & 31) : tid;              // position inside the strip of this thread's owner
+    const int lw = WARPX ? a.strip_w / (NT / 32) : a.strip_w; // U columns of that strip
+    const bool colT = (lt <= lw) && (i <= a.nx + 1);
+    const bool colU = (lt < lw) && (i <= a.nx);
+    const bool ownT = colT && (lt < lw || i == a.nx + 1);
 
     double us = 0.0, vs = 0.0, usw = 0.0, vsw = 0.0;
     if (colT) {
@@ -605,20 +657,27 @@ __device__ __forceinline__ void march(const SubArgs &a, idx_t so, idx_t sn, int 
 #pragma unroll
             for (int k = 0; k < 8; ++k) str[k] = 0.0; // str(:,:,:) = c0, :1051
         }
-        double *const xl = evp_xch + par * 4 * NT + tid;
-        xl[0 * NT] = str[1];
-        xl[1 * NT] = str[3];
-        xl[2 * NT] = str[6];
-        xl[3 * NT] = str[7];
-        __syncthreads();
         double s2r = 0.0, s4r = 0.0, s7r = 0.0, s8r = 0.0;
-        if (tid < NT - 1) {
-            s2r = xl[0 * NT + 1];
-            s4r = xl[1 * NT + 1];
-            s7r = xl[2 * NT + 1];
-            s8r = xl[3 * NT + 1];
+        if (WARPX) { // str(2,4,7,8) of the T cell east of this lane's U point (lane 31 never holds a U column)
+            s2r = __shfl_down_sync(0xffffffffu, str[1], 1);
+            s4r = __shfl_down_sync(0xffffffffu, str[3], 1);
+            s7r = __shfl_down_sync(0xffffffffu, str[6], 1);
+            s8r = __shfl_down_sync(0xffffffffu, str[7], 1);
+        } else {
+            double *const xl = evp_xch + par * 4 * NT + tid;
+            xl[0 * NT] = str[1];
+            xl[1 * NT] = str[3];
+            xl[2 * NT] = str[6];
+            xl[3 * NT] = str[7];
+            __syncthreads();
+            if (tid < NT - 1) {
+                s2r = xl[0 * NT + 1];
+                s4r = xl[1 * NT + 1];
+                s7r = xl[2 * NT + 1];
+                s8r = xl[3 * NT + 1];
+            }
+            par ^= 1;
         }
-        par ^= 1;
 
         if (uc.act) {
             const double sx = px + str[2] + s4r;          // ((s1 + s2) + s3) + s4
@@ -645,14 +704,16 @@ __device__ __forceinline__ void march(const SubArgs &a, idx_t so, idx_t sn, int 
 // Needed with the peer-to-peer halo: the neighbour GPU stores into this slab's ghost rows while this
 // kernel may already be running (the boundary CTAs only wait on the flag before READING those rows), and
 // ld.global.nc requires the data to be read-only for the whole kernel.
-template <int NT, bool LAST, bool HT, bool LATE = false, int MINB = 1, bool COH = false>
+template <int NT, bool LAST, bool HT, bool LATE = false, int MINB = 1, bool COH = false, bool WARPX = false>
 __global__ void __launch_bounds__(NT, MINB) k_subcycle(const __grid_constant__ SubArgs a) {
     // programmatic dependent launch: let the next subcycle kernel be scheduled as SMs drain, and
     // wait here until the previous grid has completed and flushed (no-ops without the attribute)
     asm volatile("griddepcontrol.launch_dependents;");
     asm volatile("griddepcontrol.wait;" ::: "memory");
     const int tid = threadIdx.x;
-    const int i = 1 + blockIdx.x * a.strip_w + tid;
+    // WARPX: the CTA's strip_w columns are shared out among its warps, strip_w / (NT / 32) <= 31 to each
+    const int i = WARPX ? 1 + blockIdx.x * a.strip_w + (tid >> 5) * (a.strip_w / (NT / 32)) + (tid & 31)
+                        : 1 + blockIdx.x * a.strip_w + tid;
     // Row chunks come from a table in launch order: the southernmost and northernmost chunk first
     // (with the peer-to-peer halo the rows the neighbours wait for are produced first), and they are
     // shorter than the interior ones, so that the wait for the neighbours / the tripole fold at their
@@ -667,8 +728,8 @@ __global__ void __launch_bounds__(NT, MINB) k_subcycle(const __grid_constant__ S
     }
     // an empty chunk (all rows inactive, trimmed by the load balancer) has nothing to do
     const idx_t so = a.flip ? (idx_t)a.copy_stride : 0, sn = a.flip ? 0 : (idx_t)a.copy_stride;
-    if (nrows > 0) march<NT, LAST, HT, COH, LATE>(a, so, sn, tid, i, j0, nrows);
-    subcycle_epilogue<NT, false>(a, sn, tid, top, bot, epoch);
+    if (nrows > 0) march<NT, LAST, HT, COH, LATE, WARPX>(a, so, sn, tid, i, j0, nrows);
+    subcycle_epilogue<NT, false>(a, sn, tid, top, bot, epoch, LAST);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -873,7 +934,7 @@ __global__ void __launch_bounds__(NT, MINB) k_subcycle_tma(const __grid_constant
     }
     const idx_t so = a.flip ? (idx_t)a.copy_stride : 0, sn = a.flip ? 0 : (idx_t)a.copy_stride;
     if (nrows > 0) march_tma<NT, LAST, S>(a, so, sn, tid, i, j0, nrows);
-    subcycle_epilogue<NT, false>(a, sn, tid, top, bot, epoch);
+    subcycle_epilogue<NT, false>(a, sn, tid, top, bot, epoch, LAST);
 }
 
 template <int NT, int S>
@@ -973,6 +1034,8 @@ struct TileStoreU {
     __device__ __forceinline__ void last(double strintx, double strinty, double taux, double tauy) const {
         a.strintx[pidx] = strintx; a.strinty[pidx] = strinty; a.strocnx[pidx] = taux; a.strocny[pidx] = tauy;
     }
+    __device__ __forceinline__ bool finish_here() const { return a.fuse_finish && !(a.fold && j == a.nyl); }
+    __device__ __forceinline__ void finish(double xT, double yT) const { a.finx[pidx] = xT; a.finy[pidx] = yT; }
 };
 
 // lane 0: arm the stage's mbarrier with the byte count and issue the bulk copy of one read window
@@ -1219,7 +1282,7 @@ __device__ __forceinline__ void top_chunk_barrier(int *counter, int tid, int *sy
 // column's fold partner (and the row below it), and -- after a second barrier, because the update is in place --
 // writes the symmetrised top row and the ghost row.  Same arithmetic as evp_fold_necorner / k_halo_tripole.
 template <int NT>
-__device__ __forceinline__ void tiled_epilogue(const SubArgs &a, int newc, int tid, bool top) {
+__device__ __forceinline__ void tiled_epilogue(const SubArgs &a, int newc, int tid, bool top, bool last) {
     if (a.fold && top) {
         top_chunk_barrier(a.sync + 4, tid, a.sync);
         const int nx = a.nx, nyl = a.nyl, warp = tid >> 5, lane = tid & 31;
@@ -1266,6 +1329,8 @@ __device__ __forceinline__ void tiled_epilogue(const SubArgs &a, int newc, int t
         if (mine) {
             tile_write_col(a, newc, cc, nyl, ut, vt);
             tile_write_col(a, newc, cc, nyl + 1, ug, vg);
+            // last subcycle: evp_finish of the row whose velocities have just been folded
+            if (last && a.fuse_finish && cc >= 1 && cc <= nx) finish_fold_column(a, cc, ut, vt);
         }
         if (both) {
             tile_write_col(a, newc, nx + 1, nyl, ut2, vt2);
@@ -1324,7 +1389,7 @@ __global__ void __launch_bounds__(128, MINB) k_subcycle_tiled(const __grid_const
             if (bot && a.peer_s_flag) *(volatile int *)(a.peer_s_flag + w) = epoch + 1;
         }
     }
-    tiled_epilogue<128>(a, a.flip ? 0 : 1, tid, top);
+    tiled_epilogue<128>(a, a.flip ? 0 : 1, tid, top, LAST);
 }
 
 template <int S>
@@ -1392,7 +1457,7 @@ __device__ __forceinline__ void persist_step(const SubArgs &a, int k, const int 
     }
     if (p2p_cta) p2p_wait(a, tid, top, bot, a.epoch0 + k);
     march<NT, LAST, HT, true>(a, so, sn, tid, i, j0, nrows);
-    subcycle_epilogue<NT, true>(a, sn, tid, top, bot, a.epoch0 + k);
+    subcycle_epilogue<NT, true>(a, sn, tid, top, bot, a.epoch0 + k, LAST);
     __syncthreads();
     if (tid == 0) {
         __threadfence();
@@ -1457,11 +1522,11 @@ __global__ void __launch_bounds__(NT) k_persist(const __grid_constant__ SubArgs 
 // this one drains; its CTAs block in griddepcontrol.wait at their first instruction until this grid
 // has completed and its stores are visible, so only launch latency and ramp-up overlap.
 template <typename K>
-static int launch_k(K kernel, const SubArgs &a, dim3 grid, dim3 block, bool pdl, cudaStream_t s) {
+static int launch_k(K kernel, const SubArgs &a, dim3 grid, dim3 block, bool pdl, cudaStream_t s, int xch = 1) {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = grid;
     cfg.blockDim = block;
-    cfg.dynamicSmemBytes = 2 * 4 * block.x * sizeof(double); // evp_xch
+    cfg.dynamicSmemBytes = xch ? 2 * 4 * block.x * sizeof(double) : 0; // evp_xch
     cfg.stream = s;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
@@ -1498,6 +1563,24 @@ static int launch_nt(const SubArgs &a, bool last, bool pdl, int variant, unsigne
         if (variant & 512) {
             if (last) return launch_tma(k_subcycle_tma<NT, true, 2, 3>, tma_smem_bytes<NT, 2>(), a, grid, block, s);
             return launch_tma(k_subcycle_tma<NT, false, 2, 3>, tma_smem_bytes<NT, 2>(), a, grid, block, s);
+        }
+    }
+    if constexpr (NT == 128) {
+        if (variant & 1048576) { // warp-autonomous strips: shuffles instead of the exchange line, no row barrier
+            if (a.p2p) {
+                if (a.row_ht) {
+                    if (last) return launch_k(k_subcycle<NT, true, true, false, 1, true, true>, a, grid, block, pdl, s, 0);
+                    return launch_k(k_subcycle<NT, false, true, false, 1, true, true>, a, grid, block, pdl, s, 0);
+                }
+                if (last) return launch_k(k_subcycle<NT, true, false, false, 1, true, true>, a, grid, block, pdl, s, 0);
+                return launch_k(k_subcycle<NT, false, false, false, 1, true, true>, a, grid, block, pdl, s, 0);
+            }
+            if (a.row_ht) {
+                if (last) return launch_k(k_subcycle<NT, true, true, false, 1, false, true>, a, grid, block, pdl, s, 0);
+                return launch_k(k_subcycle<NT, false, true, false, 1, false, true>, a, grid, block, pdl, s, 0);
+            }
+            if (last) return launch_k(k_subcycle<NT, true, false, false, 1, false, true>, a, grid, block, pdl, s, 0);
+            return launch_k(k_subcycle<NT, false, false, false, 1, false, true>, a, grid, block, pdl, s, 0);
         }
     }
     if (a.p2p) { // the neighbours write this slab's ghost rows during the kernel: coherent state loads

@@ -517,7 +517,8 @@ class IceDynEvp:
         out = (C.c_int32 * 8)()
         _check(load_library().evp_b200_get_info(self._h, out))
         return dict(tiled=int(out[0] == 1), fused=int(out[0] == 2), grid_x=out[1], grid_y=out[2], threads=out[3],
-                    strip_w=out[4], stages=out[5], p2p=out[6], persistent=out[7])
+                    strip_w=out[4], stages=out[5], p2p=out[6], persistent=out[7] & 1, warp_strips=(out[7] >> 1) & 1,
+                    finish_fused=(out[7] >> 2) & 1)
 
     def diagnostics_energy(self) -> Dict[str, float]:
         """total ice-snow kinetic energy, ice / snow volume and rms ice speed per hemisphere of this slab

@@ -124,7 +124,12 @@ typedef struct {
                                without DRAM traffic); bit 17 (131072): TWO subcycles per launch (temporal
                                blocking, csrc/evp_fused.cuh; bit-identical; single rank, no north-south wrap,
                                no T-fold; halves the DRAM traffic but is issue-bound and measured slower,
-                               DESIGN.md 4) */
+                               DESIGN.md 4); bit 20 (1048576): plane kernel of 128-thread CTAs with one strip of
+                               <= 31 U columns per WARP (east-neighbour str terms by warp shuffle, no exchange
+                               line and no CTA barrier in the row loop), bit 21 (2097152): one strip per CTA
+                               with the shared-memory exchange line and a barrier per row instead (DESIGN.md 4
+                               says which of the two is the default); bit 22 (4194304): evp_finish as a separate
+                               kernel after the loop instead of an epilogue of the last subcycle kernel */
     int32_t state_residency; /* 0 = the whole state is uploaded and downloaded by every call (host arrays always
                                current: restart-exact drop-in); 1 = the 12 stress arrays stay on the device
                                between calls: uploaded by the first call after init or after
@@ -246,8 +251,9 @@ int evp_b200_get_timings(const evp_b200_handle *h, evp_b200_timings *t);
 
 /* How the ndte loop of this handle runs: out[0] = 1 when the strip-tiled TMA-fed kernel is in use (0: the
  * plane kernels), out[1..2] = grid of the subcycle kernel, out[3] = threads per CTA, out[4] = U columns per
- * strip, out[5] = pipeline stages per warp (tiled kernel), out[6] = 1 with the peer-to-peer halo, out[7] = 1
- * with the persistent cooperative kernel. */
+ * strip, out[5] = pipeline stages per warp (tiled kernel), out[6] = 1 with the peer-to-peer halo, out[7] = bit 0
+ * the persistent cooperative kernel, bit 1 the plane kernel with one strip per warp (shuffles, no row barrier),
+ * bit 2 evp_finish runs as an epilogue of the last subcycle kernel. */
 int evp_b200_get_info(const evp_b200_handle *h, int32_t out[8]);
 
 /* pin_host = 1: forget (cudaHostUnregister) a caller array before the caller frees it; unknown pointers

@@ -154,8 +154,66 @@ def test_fma_mode_within_tolerance(oracle, evp_lib, label, kw):
     _compare_tol(dyn, out, st, f, lay)
 
 
+WARP_STRIPS, CTA_STRIPS, FINISH_KERNEL = 1048576, 2097152, 4194304   # kernel_variant bits 20, 21, 22
+
+
+@pytest.mark.parametrize("variant", [WARP_STRIPS, CTA_STRIPS, WARP_STRIPS + FINISH_KERNEL, CTA_STRIPS + FINISH_KERNEL,
+                                     WARP_STRIPS + 16, WARP_STRIPS + 4],
+                         ids=["warp-strips", "cta-strips", "warp-strips-finish-kernel", "cta-strips-finish-kernel",
+                              "warp-strips-2plane", "warp-strips-fold-kernel"])
+@pytest.mark.parametrize("label,kw", CASES, ids=[c[0] for c in CASES])
+def test_plane_kernel_strip_and_finish_variants(oracle, evp_lib, label, kw, variant):
+    """The plane kernel of 128-thread CTAs with one strip per warp (bit 20: shuffles, no row barrier) or one strip
+    per CTA (bit 21: exchange line + barrier), evp_finish as an epilogue of the last subcycle kernel (default) or
+    as its own kernel (bit 22): every combination is bit-exact, cold + warm call, on every domain type."""
+    case = synth.make_case(**kw)
+    st, f, strengths, _ = oracle_steps(oracle, case, nsteps=2)
+    lay = E.BlockLayout.single_block(case.grid.nx, case.grid.ny)
+    dyn, out = cuda_steps(case, nsteps=2, strengths=strengths, math_mode=0, tile_threads=128,
+                          kernel_variant=32768 + variant)
+    info = dyn.info()
+    assert info["tiled"] == 0 and info["threads"] == 128
+    assert info["warp_strips"] == (1 if variant & WARP_STRIPS else 0), info
+    if variant & WARP_STRIPS:
+        assert info["strip_w"] % 4 == 0 and info["strip_w"] <= 124, info
+    # the fused finish needs the final velocities inside the kernel: not with a fold outside it (T-fold, bit 2)
+    fold_outside = "tripoleT" in label or (label.startswith("tripole-") and (variant & 4))
+    assert info["finish_fused"] == (0 if (variant & FINISH_KERNEL) or fold_outside else 1), info
+    _compare_exact(dyn, out, st, f, lay)
+
+
+@pytest.mark.parametrize("variant", [0, FINISH_KERNEL], ids=["finish-fused", "finish-kernel"])
+def test_finish_epilogue_tiled_and_variants(oracle, evp_lib, variant):
+    """evp_finish inside the last subcycle kernel on the strip-tiled layout (fold row completed by the fold), with the
+    AusCOM hemisphere turning (sign flip where fm < 0), in the FMA build, behind a block layout, with the TMA-staged and
+    the persistent kernel -- against the same call with the separate k_finish launch and against the oracle."""
+    case = synth.make_case("om1deg", nx=130, ny=70, realistic=True)
+    lay1 = E.BlockLayout.single_block(130, 70)
+    st, f, strengths, _ = oracle_steps(oracle, case, nsteps=2)
+    dyn, out = cuda_steps(case, nsteps=2, strengths=strengths, kernel_variant=2048 + variant)
+    assert dyn.info()["tiled"] == 1 and dyn.info()["finish_fused"] == (0 if variant else 1)
+    _compare_exact(dyn, out, st, f, lay1)
+    lay = E.BlockLayout.cartesian(130, 70, 33, 18)
+    dyn, out = cuda_steps(case, nsteps=2, strengths=strengths, layout=lay, kernel_variant=variant)
+    _compare_exact(dyn, out, st, f, lay)
+    for kv, par in ((256, {}), (128, dict(tile_threads=64)), (1024, dict(tile_threads=128))):
+        dyn, out = cuda_steps(case, nsteps=2, strengths=strengths, kernel_variant=32768 + kv + variant, **par)
+        _compare_exact(dyn, out, st, f, lay1)
+    pover = dict(auscom=1, coupled=1, use_ocnslope=0, cosw=0.9063077870366499, sinw=0.42261826174069944)
+    cpar = {{"auscom": "hemisphere_turning", "coupled": "coupled_tilt"}.get(k, k): v for k, v in pover.items()}
+    st, f, strengths, _ = oracle_steps(oracle, case, **dict(pover))
+    for kv in (0, 32768 + WARP_STRIPS):
+        dyn, out = cuda_steps(case, strengths=strengths, kernel_variant=kv + variant,
+                              **(dict(tile_threads=128) if kv else {}), **cpar)
+        _compare_exact(dyn, out, st, f, lay1)
+    st, f, strengths, _ = oracle_steps(oracle, case, nsteps=2)
+    dyn, out = cuda_steps(case, nsteps=2, strengths=strengths, math_mode=1, kernel_variant=variant)
+    _compare_tol(dyn, out, st, f, lay1)
+
+
 @pytest.mark.parametrize("threads,rows,variant", [(64, 5, 0), (128, 7, 4), (256, 0, 0), (128, 1000, 0),
-                                                  (128, 0, 16), (64, 9, 16 + 4), (128, 0, 64), (256, 11, 64), (128, 0, 1024)])
+                                                  (128, 0, 16), (64, 9, 16 + 4), (128, 0, 64), (256, 11, 64), (128, 0, 1024),
+                                                  (128, 3, WARP_STRIPS), (128, 0, WARP_STRIPS + 64), (128, 1, CTA_STRIPS)])
 def test_tiling_invariance(oracle, evp_lib, threads, rows, variant):
     """Strip width, rows per CTA and the prefetch variant must not change a single bit."""
     case = synth.make_case("om1deg", nx=300, ny=90)
