@@ -362,7 +362,8 @@ void fill_subargs(evp_b200_handle *h, SubArgs &a, int cur) {
     // issue-bound, where the ~14 extra fp64 operations per cell cost more than the bytes save) when HTE / HTN were
     // given and verified; kernel_variant bit 4 forces it on, bit 19 off.
     const bool ht_auto = !h->tiled && !h->fused && h->dims.ny_global / h->dims.nranks >= 450 &&
-                         (h->par.kernel_variant & (256 | 512 | 1024 | 524288)) == 0;
+                         (h->par.kernel_variant & (256 | 512 | 524288)) == 0 &&
+                         ((h->par.kernel_variant & 1024) == 0 || h->warpx); // late loads: only the warp-strip instances have it
     a.row_ht = ((h->par.kernel_variant & 16) || ht_auto) ? h->row_ht : nullptr;
     a.ecci = h->ecci; a.dte2T = h->dte2T; a.denom1 = h->denom1; a.denom2 = h->denom2; a.rcon = h->rcon;
     a.dragw = h->dragw; a.cosw = h->par.cosw; a.sinw = h->par.sinw;
@@ -691,7 +692,7 @@ int choose_tiling(evp_b200_handle *h) {
         // U columns of its own, shuffles replace the exchange line and the per-row CTA barrier.  kernel_variant
         // bit 20 (1048576) selects it, bit 21 (2097152) forbids it; see h->warpx below for the default.
         const int kvv = h->par.kernel_variant;
-        h->warpx = nt == 128 && !tma && (kvv & (128 | 1024 | 2097152)) == 0 &&
+        h->warpx = nt == 128 && !tma && (kvv & (128 | 2097152)) == 0 &&
                    ((kvv & 1048576) != 0 || EVP_WARPX_DEFAULT);
         // balanced strips: ncx strips of strip_w U columns, strip_w + 1 <= nt threads hold T columns
         const int wmax = h->warpx ? 124 : (tma ? nt - 2 : nt - 1);

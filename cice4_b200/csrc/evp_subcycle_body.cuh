@@ -1542,12 +1542,34 @@ static int launch_tma(K kernel, size_t smem, const SubArgs &a, dim3 grid, dim3 b
     return (int)cudaPeekAtLastError();
 }
 
+// run-time selection of the LAST / HT (2-plane metric path, a.row_ht) / COH (peer-to-peer halo) instances
+template <int NT, bool LATE, int MINB, bool WARPX>
+static int launch_sel(const SubArgs &a, bool last, dim3 grid, dim3 block, bool pdl, cudaStream_t s) {
+    const int xch = WARPX ? 0 : 1;
+    if (a.p2p) {
+        if (a.row_ht) {
+            if (last) return launch_k(k_subcycle<NT, true, true, LATE, MINB, true, WARPX>, a, grid, block, pdl, s, xch);
+            return launch_k(k_subcycle<NT, false, true, LATE, MINB, true, WARPX>, a, grid, block, pdl, s, xch);
+        }
+        if (last) return launch_k(k_subcycle<NT, true, false, LATE, MINB, true, WARPX>, a, grid, block, pdl, s, xch);
+        return launch_k(k_subcycle<NT, false, false, LATE, MINB, true, WARPX>, a, grid, block, pdl, s, xch);
+    }
+    if (a.row_ht) {
+        if (last) return launch_k(k_subcycle<NT, true, true, LATE, MINB, false, WARPX>, a, grid, block, pdl, s, xch);
+        return launch_k(k_subcycle<NT, false, true, LATE, MINB, false, WARPX>, a, grid, block, pdl, s, xch);
+    }
+    if (last) return launch_k(k_subcycle<NT, true, false, LATE, MINB, false, WARPX>, a, grid, block, pdl, s, xch);
+    return launch_k(k_subcycle<NT, false, false, LATE, MINB, false, WARPX>, a, grid, block, pdl, s, xch);
+}
+
 // HT (2-plane metric path) is chosen by a.row_ht; variant bit 8 (256): TMA staging, 3 rows deep, 2 CTAs
 // per SM; bit 9 (512): TMA staging, 2 rows deep, 3 CTAs per SM (<= 168 registers) -- 128 threads only
 template <int NT>
 static int launch_nt(const SubArgs &a, bool last, bool pdl, int variant, unsigned gx, unsigned gy, cudaStream_t s) {
     dim3 grid(gx, gy), block(NT);
     if constexpr (NT == 128) {
+        if ((variant & 1024) && (variant & 1048576)) // the same with one strip per warp (2-plane path allowed)
+            return launch_sel<NT, true, 3, true>(a, last, grid, block, pdl, s);
         if (variant & 1024) { // no prefetch across the arithmetic, 3 CTAs per SM (<= 168 registers)
             if (a.p2p) {
                 if (last) return launch_k(k_subcycle<NT, true, false, true, 3, true>, a, grid, block, pdl, s);
@@ -1566,22 +1588,8 @@ static int launch_nt(const SubArgs &a, bool last, bool pdl, int variant, unsigne
         }
     }
     if constexpr (NT == 128) {
-        if (variant & 1048576) { // warp-autonomous strips: shuffles instead of the exchange line, no row barrier
-            if (a.p2p) {
-                if (a.row_ht) {
-                    if (last) return launch_k(k_subcycle<NT, true, true, false, 1, true, true>, a, grid, block, pdl, s, 0);
-                    return launch_k(k_subcycle<NT, false, true, false, 1, true, true>, a, grid, block, pdl, s, 0);
-                }
-                if (last) return launch_k(k_subcycle<NT, true, false, false, 1, true, true>, a, grid, block, pdl, s, 0);
-                return launch_k(k_subcycle<NT, false, false, false, 1, true, true>, a, grid, block, pdl, s, 0);
-            }
-            if (a.row_ht) {
-                if (last) return launch_k(k_subcycle<NT, true, true, false, 1, false, true>, a, grid, block, pdl, s, 0);
-                return launch_k(k_subcycle<NT, false, true, false, 1, false, true>, a, grid, block, pdl, s, 0);
-            }
-            if (last) return launch_k(k_subcycle<NT, true, false, false, 1, false, true>, a, grid, block, pdl, s, 0);
-            return launch_k(k_subcycle<NT, false, false, false, 1, false, true>, a, grid, block, pdl, s, 0);
-        }
+        // warp-autonomous strips: shuffles instead of the exchange line, no row barrier
+        if (variant & 1048576) return launch_sel<NT, false, 1, true>(a, last, grid, block, pdl, s);
     }
     if (a.p2p) { // the neighbours write this slab's ghost rows during the kernel: coherent state loads
         if (a.row_ht) {

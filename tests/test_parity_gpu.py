@@ -213,7 +213,8 @@ def test_finish_epilogue_tiled_and_variants(oracle, evp_lib, variant):
 
 @pytest.mark.parametrize("threads,rows,variant", [(64, 5, 0), (128, 7, 4), (256, 0, 0), (128, 1000, 0),
                                                   (128, 0, 16), (64, 9, 16 + 4), (128, 0, 64), (256, 11, 64), (128, 0, 1024),
-                                                  (128, 3, WARP_STRIPS), (128, 0, WARP_STRIPS + 64), (128, 1, CTA_STRIPS)])
+                                                  (128, 3, WARP_STRIPS), (128, 0, WARP_STRIPS + 64), (128, 1, CTA_STRIPS),
+                                                  (128, 0, WARP_STRIPS + 1024), (128, 5, WARP_STRIPS + 1024 + 16)])
 def test_tiling_invariance(oracle, evp_lib, threads, rows, variant):
     """Strip width, rows per CTA and the prefetch variant must not change a single bit."""
     case = synth.make_case("om1deg", nx=300, ny=90)
