@@ -35,6 +35,7 @@ def main():
     ap.add_argument("--use-graph", type=int, default=1)
     ap.add_argument("--exchange-mode", type=int, default=0)
     ap.add_argument("--kernel-variant", type=int, default=0, help="evp_b200_params.kernel_variant (128 = persistent kernel)")
+    ap.add_argument("--tile-threads", type=int, default=0, help="evp_b200_params.tile_threads (128 + variant 32768: warp-strip plane kernel)")
     ap.add_argument("--blocks", default="", help="bx,by: reference block layout regrouped into slabs")
     args = ap.parse_args()
 
@@ -61,7 +62,7 @@ def main():
 
     dyn = E.IceDynEvp(lay, ew, ns, device=local, rank=rank, nranks=world, slab=rows, ndte=args.ndte,
                       math_mode=args.math_mode, use_graph=args.use_graph, exchange_mode=args.exchange_mode,
-                      kernel_variant=args.kernel_variant)
+                      kernel_variant=args.kernel_variant, tile_threads=args.tile_threads)
     gf = E.grid_fields_in_blocks(g, lay, ew, ns)
     dyn.init_evp(3600.0, gf)
     uid = torch.zeros(128, dtype=torch.uint8, device="cuda")
@@ -107,7 +108,7 @@ def main():
                 ok = False
                 print(f"MISMATCH {n}: max abs diff {np.abs(full[I] - ref[I]).max():.3e}")
         print(f"multigpu_parity: world={world} {args.case} {nx}x{ny} steps={args.steps} blocks='{args.blocks}' "
-              f"graph={args.use_graph} variant={args.kernel_variant} launches/loop={dyn.timings()['subcycle_launches']} exchange_mode_used={dyn.timings()['exchange_mode_used']}: "
+              f"graph={args.use_graph} variant={args.kernel_variant} info={dyn.info()} launches/loop={dyn.timings()['subcycle_launches']} exchange_mode_used={dyn.timings()['exchange_mode_used']}: "
               f"{'BIT-EXACT vs oracle' if ok else 'FAILED'}; "
               f"resident loop {ms:.3f} ms on rank 0", flush=True)
     flag = torch.tensor([1 if ok else 0], device="cuda")

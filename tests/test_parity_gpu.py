@@ -617,7 +617,10 @@ def test_two_gpus_bit_exact_vs_oracle(evp_lib):
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
            "--master-addr", "127.0.0.1", "--master-port", "29533", os.path.join(root, "tests", "multigpu_parity.py"),
            "--realistic"]
-    for extra in ([], ["--kernel-variant", "128"], ["--kernel-variant", "2048"]):   # graph of launches; persistent; tiled
+    # graph of launches; persistent; tiled; plane kernel with warp strips / CTA strips
+    for extra in ([], ["--kernel-variant", "128"], ["--kernel-variant", "2048"],
+                  ["--kernel-variant", "32768", "--tile-threads", "128"],
+                  ["--kernel-variant", str(32768 + 2097152), "--tile-threads", "128"]):
         r = subprocess.run(cmd + extra, capture_output=True, text=True, timeout=240)
         assert r.returncode == 0 and "BIT-EXACT" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
 
