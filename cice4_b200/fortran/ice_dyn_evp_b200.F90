@@ -27,7 +27,7 @@
       use, intrinsic :: iso_c_binding
       use ice_kinds_mod
       use ice_fileunits
-      use ice_communicate, only: my_task, master_task
+      use ice_communicate, only: my_task, master_task, get_num_procs
       use ice_domain_size
       use ice_constants
 #ifdef AusCOM
@@ -183,12 +183,25 @@
       contains
 
 !=======================================================================
-      subroutine b200_check(rc, where)
+      subroutine b200_check(rc, what)
       use ice_exit, only: abort_ice
       integer(c_int), intent(in) :: rc
-      character(*), intent(in) :: where
-      if (rc /= 0) call abort_ice('ice_dyn_evp(b200): '//where//' failed, see libevp_b200 last_error')
+      character(*), intent(in) :: what
+      if (rc /= 0) call abort_ice('ice_dyn_evp(b200): '//what//' failed, see libevp_b200 last_error')
       end subroutine b200_check
+
+!=======================================================================
+! Address of a module array of ice_state / ice_flux / ice_grid.  C_LOC needs an argument with the TARGET (or
+! POINTER) attribute, and those modules -- which stay unchanged -- declare their arrays without it.  An
+! assumed-size TARGET dummy is associated with a contiguous whole-array actual by reference (sequence association,
+! no copy-in / copy-out for an explicit-shape module array), so C_LOC of the dummy is the address of the array
+! itself; the arrays are SAVEd module variables, their storage does not move.  (Formally a pointer taken from a
+! TARGET dummy whose actual has no TARGET attribute is not guaranteed beyond the call -- the alternative is to add
+! `target` to the declarations in ice_state.F90, ice_flux.F90 and ice_grid.F90, see INTEGRATION.md.)
+      type(c_ptr) function b200_addr(x)
+      real (kind=dbl_kind), target, intent(in) :: x(*)
+      b200_addr = c_loc(x)
+      end function b200_addr
 
 !=======================================================================
 ! init_evp: same duties as source/ice_dyn_evp.F90:441-526, plus the device setup.
@@ -282,12 +295,12 @@
       p%tile_threads = 0; p%tile_rows = 0; p%kernel_variant = 0
       p%state_residency = evp_b200_residency; p%exchange_mode = 0
 
-      g%dxt = c_loc(dxt); g%dyt = c_loc(dyt); g%dxhy = c_loc(dxhy); g%dyhx = c_loc(dyhx)
-      g%cxp = c_loc(cxp); g%cyp = c_loc(cyp); g%cxm = c_loc(cxm); g%cym = c_loc(cym)
-      g%tarea = c_loc(tarea); g%tarear = c_loc(tarear); g%tinyarea = c_loc(tinyarea)
-      g%uarea = c_loc(uarea); g%uarear = c_loc(uarear); g%fcor = c_loc(fcor_blk)
+      g%dxt = b200_addr(dxt); g%dyt = b200_addr(dyt); g%dxhy = b200_addr(dxhy); g%dyhx = b200_addr(dyhx)
+      g%cxp = b200_addr(cxp); g%cyp = b200_addr(cyp); g%cxm = b200_addr(cxm); g%cym = b200_addr(cym)
+      g%tarea = b200_addr(tarea); g%tarear = b200_addr(tarear); g%tinyarea = b200_addr(tinyarea)
+      g%uarea = b200_addr(uarea); g%uarear = b200_addr(uarear); g%fcor = c_loc(fcor_blk)
       g%tmask = c_loc(tmask_i4); g%umask = c_loc(umask_i4)
-      g%HTE = c_loc(HTE); g%HTN = c_loc(HTN)      ! optional: 2-plane metric path (checked bit for bit at init)
+      g%HTE = b200_addr(HTE); g%HTN = b200_addr(HTN)      ! optional: 2-plane metric path (checked bit for bit at init)
 
       call b200_check(evp_b200_init(d, p, g, b200_handle), 'evp_b200_init')
 
@@ -350,14 +363,14 @@
 
       where (iceumask) ; iceumask_i4 = 1 ; elsewhere ; iceumask_i4 = 0 ; end where
 
-      inp%aice = c_loc(aice); inp%vice = c_loc(vice); inp%vsno = c_loc(vsno)
+      inp%aice = b200_addr(aice); inp%vice = b200_addr(vice); inp%vsno = b200_addr(vsno)
 #ifdef ACCESS
-      inp%strairxT = c_loc(strax); inp%strairyT = c_loc(stray)
+      inp%strairxT = b200_addr(strax); inp%strairyT = b200_addr(stray)
 #else
-      inp%strairxT = c_loc(strairxT); inp%strairyT = c_loc(strairyT)
+      inp%strairxT = b200_addr(strairxT); inp%strairyT = b200_addr(strairyT)
 #endif
-      inp%uocn = c_loc(uocn); inp%vocn = c_loc(vocn)
-      inp%ss_tltx = c_loc(ss_tltx); inp%ss_tlty = c_loc(ss_tlty)
+      inp%uocn = b200_addr(uocn); inp%vocn = b200_addr(vocn)
+      inp%ss_tltx = b200_addr(ss_tltx); inp%ss_tlty = b200_addr(ss_tlty)
       inp%aice0 = c_null_ptr; inp%aicen = c_null_ptr; inp%vicen = c_null_ptr
 
       call b200_state_ptrs(st)
@@ -385,24 +398,24 @@
                             aicen(:,:,:,iblk), vicen(:,:,:,iblk), strength(:,:,iblk))
       enddo
 
-      outp%strairx = c_loc(strairx); outp%strairy = c_loc(strairy)
-      outp%strtltx = c_loc(strtltx); outp%strtlty = c_loc(strtlty)
-      outp%strintx = c_loc(strintx); outp%strinty = c_loc(strinty)
-      outp%strocnx = c_loc(strocnx); outp%strocny = c_loc(strocny)
-      outp%strocnxT = c_loc(strocnxT); outp%strocnyT = c_loc(strocnyT)
-      outp%fm = c_loc(fm); outp%prs_sig = c_loc(prs_sig)
-      outp%divu = c_loc(divu); outp%shear = c_loc(shear)
-      outp%rdg_conv = c_loc(rdg_conv); outp%rdg_shear = c_loc(rdg_shear)
-      outp%strength = c_loc(strength)      ! comes back halo-updated, as after :337-338
-      outp%sig1 = c_loc(sig1); outp%sig2 = c_loc(sig2)   ! fused principal-stress epilogue (ice_history :1939)
+      outp%strairx = b200_addr(strairx); outp%strairy = b200_addr(strairy)
+      outp%strtltx = b200_addr(strtltx); outp%strtlty = b200_addr(strtlty)
+      outp%strintx = b200_addr(strintx); outp%strinty = b200_addr(strinty)
+      outp%strocnx = b200_addr(strocnx); outp%strocny = b200_addr(strocny)
+      outp%strocnxT = b200_addr(strocnxT); outp%strocnyT = b200_addr(strocnyT)
+      outp%fm = b200_addr(fm); outp%prs_sig = b200_addr(prs_sig)
+      outp%divu = b200_addr(divu); outp%shear = b200_addr(shear)
+      outp%rdg_conv = b200_addr(rdg_conv); outp%rdg_shear = b200_addr(rdg_shear)
+      outp%strength = b200_addr(strength)      ! comes back halo-updated, as after :337-338
+      outp%sig1 = b200_addr(sig1); outp%sig2 = b200_addr(sig2)   ! fused principal-stress epilogue (ice_history :1939)
 #ifdef AusCOM
-      outp%sicemass = c_loc(sicemass)
+      outp%sicemass = b200_addr(sicemass)
 #else
       outp%sicemass = c_null_ptr
 #endif
 
       ! phase 2 on the device: HALO strength,u,v ; ndte x (stress, stepu, HALO) ; evp_finish ; u2tgrid_vector
-      call b200_check(evp_b200_run(b200_handle, c_loc(strength), st, outp), 'evp_b200_run')
+      call b200_check(evp_b200_run(b200_handle, b200_addr(strength), st, outp), 'evp_b200_run')
 
       if (evp_b200_residency /= 2) iceumask = (iceumask_i4 == 1)
 
@@ -434,20 +447,20 @@
       subroutine evp_velocity_to_host
       use ice_state, only: uvel, vvel
       if (evp_b200_residency /= 2) return
-      call b200_check(evp_b200_download_velocity(b200_handle, c_loc(uvel), c_loc(vvel)), 'evp_b200_download_velocity')
+      call b200_check(evp_b200_download_velocity(b200_handle, b200_addr(uvel), b200_addr(vvel)), 'evp_b200_download_velocity')
       end subroutine evp_velocity_to_host
 
       subroutine b200_state_ptrs(st)
       use ice_state
       use ice_flux
       type (evp_b200_state), intent(out) :: st
-      st%uvel = c_loc(uvel); st%vvel = c_loc(vvel)
-      st%stressp_1 = c_loc(stressp_1); st%stressp_2 = c_loc(stressp_2)
-      st%stressp_3 = c_loc(stressp_3); st%stressp_4 = c_loc(stressp_4)
-      st%stressm_1 = c_loc(stressm_1); st%stressm_2 = c_loc(stressm_2)
-      st%stressm_3 = c_loc(stressm_3); st%stressm_4 = c_loc(stressm_4)
-      st%stress12_1 = c_loc(stress12_1); st%stress12_2 = c_loc(stress12_2)
-      st%stress12_3 = c_loc(stress12_3); st%stress12_4 = c_loc(stress12_4)
+      st%uvel = b200_addr(uvel); st%vvel = b200_addr(vvel)
+      st%stressp_1 = b200_addr(stressp_1); st%stressp_2 = b200_addr(stressp_2)
+      st%stressp_3 = b200_addr(stressp_3); st%stressp_4 = b200_addr(stressp_4)
+      st%stressm_1 = b200_addr(stressm_1); st%stressm_2 = b200_addr(stressm_2)
+      st%stressm_3 = b200_addr(stressm_3); st%stressm_4 = b200_addr(stressm_4)
+      st%stress12_1 = b200_addr(stress12_1); st%stress12_2 = b200_addr(stress12_2)
+      st%stress12_3 = b200_addr(stress12_3); st%stress12_4 = b200_addr(stress12_4)
       st%iceumask = c_loc(iceumask_i4)
       end subroutine b200_state_ptrs
 
