@@ -12,12 +12,16 @@
 //
 //   * a CTA owns a strip of `strip_w` U columns and marches north over `rows` U rows;
 //     thread t holds T column i0+t and U column i0+t (threads 0..strip_w are active, the last
-//     one only supplies the T column east of the strip);
+//     one only supplies the T column east of the strip).  DEFAULT since round 2 (WARPX, 128-thread
+//     CTAs): the CTA's strip is shared out among its warps, each warp owns strip_w / 4 <= 31 columns
+//     of its own (+ the redundant T column east of them) and is autonomous;
 //   * for T row j a thread computes the four-corner strain rates / Delta / stress update of its
 //     T cell from u,v at (i-1..i, j-1..j) -- west values by an offset load that hits L1, south
 //     values carried in registers from the previous row -- and forms str(1:8);
-//   * str(2,4,7,8) of the east neighbour arrive through a double-buffered shared-memory line
-//     (one __syncthreads per row), str(1,5) (+ east 2,7) of the row below are carried in
+//   * str(2,4,7,8) of the east neighbour arrive by warp shuffle (WARPX: no barrier in the row loop;
+//     measured 107.4 vs 113.95 us per launch at 1440 x 1080) or, with one strip per CTA, through a
+//     double-buffered shared-memory line (one __syncthreads per row); str(1,5) (+ east 2,7) of the
+//     row below are carried in
 //     registers, so U(i, j-1) is finished in the same iteration with the reference's summation
 //     order  ((s1 + s2) + s3) + s4  and  ((s5 + s6) + s7) + s8  (:1415-1418);
 //   * u,v and the 12 stresses are ping-ponged (read `old`, write `new`): the first T row of the
