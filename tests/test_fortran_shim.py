@@ -234,3 +234,31 @@ def test_calls_into_the_reference_have_the_right_argument_count():
             seen.add(name)
             assert sig[0] - sig[1] <= nargs <= sig[0], f"{scope.name}: {name} called with {nargs} arguments, takes {sig}"
     assert {"ice_strength", "get_block", "ice_timer_start", "ice_timer_stop", "abort_ice", "b200_check"} <= seen, seen
+
+
+def test_free_form_limits_and_statement_shapes():
+    """Free-form source limits a compiler enforces without extra flags (132 columns, at most 39 continuation lines,
+    balanced parentheses per statement, no tab characters) and every statement of the shim is of a known form."""
+    import fortran_names as F
+    raw = open(SHIM).read().splitlines()
+    assert max(len(ln) for ln in raw) <= 132
+    assert not any("\t" in ln for ln in raw)
+    run = 0
+    for ln in raw:
+        code = F._strip(ln).rstrip()
+        run = run + 1 if code.endswith("&") else 0
+        assert run <= 39
+    forms = [
+        r"^(module|end\s*module|contains|implicit\s+none|save|interface|end\s*interface|end\s*type|end\s*select|end\s*where|elsewhere|else|end\s*if|endif|end\s*do|enddo|return)\b",
+        r"^use\b", r"^import\s*::", r"^type\s*,\s*bind\(c\)\s*::\s*\w+$",
+        r"^(integer|real|logical|character|type)\s*(\(.*?\))?.*::",          # declarations
+        r"^(integer\(c_int\)|integer\(c_int32_t\)|type\(c_ptr\))\s+function\s+\w+\s*\(.*\)(\s*bind\(c,\s*name=@\s*\))?$",
+        r"^subroutine\s+\w+\s*(\(.*\))?$", r"^end\s+(subroutine|function)(\s+\w+)?$",
+        r"^call\s+\w+(\s*\(.*\))?$", r"^if\s*\(.*\)\s*then$", r"^if\s*\(.*\)\s*\S.*$", r"^do\s+\w+\s*=\s*.+,.+$",
+        r"^select\s+case\s*\(.*\)$", r"^case\s*(\(.*\)|default)$", r"^where\s*\(.*\)$",
+        r"^allocate\s*\(.*\)$", r"^write\s*\(.*\).*$",
+        r"^[a-z_]\w*(\s*\(.*\))?(\s*%\s*\w+)*\s*=[^=].*$",                 # assignment
+    ]
+    for st in F.statements(SHIM):
+        assert st.count("(") == st.count(")"), st
+        assert any(re.match(f, st) for f in forms), f"statement of no known form: {st}"
