@@ -415,6 +415,10 @@ def measure(ctx, case, args, ndte, steps, warmup, full):
         ms_loop = ctx.allmax(dyn.subcycle_resident(steps))
         ctx.barrier()
     tm = dyn.timings()
+    try:
+        res["kernel_info"] = {k: int(v) for k, v in dyn.info().items()}   # which subcycle kernel ran (evp_b200_get_info)
+    except Exception as e:   # informative only
+        res["kernel_info"] = {"error": str(e)}
     kernel_s = ms_loop * 1e-3 / ndte
     achieved = bytes_per_sub / kernel_s / 1e9        # whole job, all GPUs
     peak, peak_src = measured_peaks()
@@ -546,6 +550,7 @@ def run_b200(args):
                    "l2": r["l2"],
                    "math_mode": "fma-contracted (<=1e-10 of the unfused oracle)" if args.math_mode else "unfused (bit-exact vs oracle)",
                    "tile": {"threads": args.tile_threads, "rows": args.tile_rows, "variant": args.variant},
+                   "kernel": r.get("kernel_info"),
                    "parallelism": f"{world} y-slab(s), one process per GPU; velocity halo inside the loop: {xname}",
                    "exchange_mode_used": xmode},
         "roofline": {"bound": "hbm", "achieved": r["achieved"], "peak": r["peak"], "unit": "GB/s",
