@@ -321,3 +321,48 @@ def test_reference_create_blocks_one_column_edge_block():
     a = np.zeros(lay.shape, order="F")
     with pytest.raises(RuntimeError, match="not what create_blocks makes"):
         O.ref_halo(a, 2, 3, 2, 2, layout=lay)
+
+
+@pytest.mark.parametrize("name", ["ice_HaloUpdate2DR8", "ice_HaloUpdate2DI4"])
+def test_mpi_halo_update_is_the_serial_one_plus_message_plumbing(name):
+    """oracle/_ref executes the SERIAL build's ice_HaloUpdate (serial/ice_boundary.F90:591-873, 1169-1451); the MPI
+    build's (mpi/ice_boundary.F90:1028-1417, ...) is what a multi-task run of the reference executes.  Text-level pin:
+    every statement of the serial routine appears, in order, in the MPI routine, and what the MPI routine adds is only
+    message plumbing -- request / status arrays, posting the receives, packing + sending, waiting, and unpacking the
+    received values into `array` or into the same tripole buffer the local copies fill.  So the local copies, the
+    tripole buffer arithmetic and the copy-out that the translated reference runs are the MPI build's too."""
+    import difflib
+    import os
+    import re
+    ref = "/root/reference"
+
+    def routine(path):
+        src = open(os.path.join(ref, path)).read().splitlines()
+        a = [i for i, l in enumerate(src) if re.match(r"\s*subroutine\s+" + name + r"\b", l)][0]
+        b = [i for i, l in enumerate(src) if re.match(r"\s*end subroutine\s+" + name + r"\b", l)][0]
+        out = []
+        for l in src[a:b + 1]:
+            l = re.sub(r"\s+", " ", l.split("!")[0].strip().lower())
+            if l:
+                out.append(l)
+        return out
+
+    s, m = routine("serial/ice_boundary.F90"), routine("mpi/ice_boundary.F90")
+    ops = difflib.SequenceMatcher(None, s, m, autojunk=False).get_opcodes()
+    assert {t for t, *_ in ops} == {"equal", "insert"}, [o for o in ops if o[0] not in ("equal", "insert")]
+    kind = "r8" if name.endswith("R8") else "i4"
+    plumbing = [r"^integer \(int_kind\)(, dimension\(:(,:)?\), allocatable)? ::", r"^(snd|rcv)(request|status)(, &)?$",
+                r"^(allocate|deallocate)\(", r"^(snd|rcv)(request|status)\(", r"^if \(ierr > 0\) then$", r"^call abort_ice\(",
+                r"^'ice_haloupdate2d" + kind + r": error (de)?allocating req,status arrays'\)$", r"^return$", r"^end ?if$",
+                r"^do nmsg=1,halo%nummsg(send|recv)$", r"^do n=", r"^end do$", r"^len = halo%size(send|recv)\(nmsg\)$",
+                r"^call mpi_(irecv|isend|waitall)\(", r"^halo%(recv|send)task\(nmsg\), &$", r"^mpitaghalo \+ ",
+                r"^halo%communicator, (snd|rcv)request\(nmsg\), ierr\)$",
+                r"^(isrc|jsrc|srcblock) = halo%sendaddr\(\d,n,nmsg\)$", r"^(idst|jdst|dstblock) = halo%recvaddr\(\d,n,nmsg\)$",
+                r"^bufsend" + kind + r"\(n,nmsg\) = (array\(isrc,jsrc,srcblock\)|fill)$",
+                r"^if \(dstblock > 0\) then$", r"^else if \(dstblock < 0\) then$",
+                r"^array\(idst,jdst,dstblock\) = bufrecv" + kind + r"\(n,nmsg\)$",
+                r"^buftripole" + kind + r"\(idst,jdst\) = bufrecv" + kind + r"\(n,nmsg\)$"]
+    added = [l for t, i1, i2, j1, j2 in ops if t == "insert" for l in m[j1:j2]]
+    assert len(added) > 40
+    for l in added:
+        assert any(re.match(p, l) for p in plumbing), f"MPI-only statement that is not message plumbing: {l}"
